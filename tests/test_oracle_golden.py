@@ -1,0 +1,128 @@
+"""Pins the CPU oracle (oracle/od_oracle.c) to outputs of the reference itself.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py running
+the unmodified reference head (/root/reference) on seeded inputs; see the header
+of od_oracle.c.  Contract: positive masks, rel==1 masks and the
+assignment under the positive mask are exact; float values within 1e-6 relative
+(the reference ran on torch-CPU whose atan/exp differ from glibc in the last bit; values to 1e-5);
+losses within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from oracle import golden_cases as gc
+from oracle import od_oracle as orc
+from sihl_b200 import synth
+
+
+def _geom(name):
+    g = gc.load("geom_" + name)
+    return g, [tuple(x) for x in g["levels"]], int(g["img_wh"][0]), int(g["img_wh"][1])
+
+
+@pytest.mark.parametrize("name", sorted(gc.GEOMETRIES))
+def test_anchor_tables(name):
+    g, levels, W, H = _geom(name)
+    off, sc, an = orc.anchors(levels, W, H)
+    assert off.shape == g["offsets"].shape
+    np.testing.assert_array_equal(sc, g["scales"])
+    np.testing.assert_allclose(off, g["offsets"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(an, g["anchors"], rtol=1e-6, atol=1e-4)
+
+
+def _dense(flat, vals, n, dtype, fill):
+    out = np.full(n, fill, dtype)
+    out[flat] = vals
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(gc.ASSIGN_CASES))
+@pytest.mark.parametrize("relative", [True, False])
+def test_bbox_matching(name, relative):
+    case = gc.ASSIGN_CASES[name]
+    g, levels, W, H = _geom(case["geom"])
+    gold = gc.load(name)
+    gt = gc.case_gt(case)
+    tag = "rel" if relative else "abs"
+    B, A = gt.batch_size, len(g["anchors"])
+    want_v = _dense(gold[f"{tag}_pos_flat"], gold[f"{tag}_pos_val"], B * A, np.float32, 0).reshape(B, A)
+    want_a = _dense(gold[f"{tag}_pos_flat"], gold[f"{tag}_pos_assign"], B * A, np.int64, -1).reshape(B, A)
+    got_a, got_v, _ = orc.assign_batch(g["anchors"], gt.boxes, gt.offsets, 9, relative)
+    if case.get("integer_coords"):
+        # lattice coordinates produce exact ties at the 9th/10th boundary whose winner is
+        # implementation-defined in torch.topk: compare the tie-free part.
+        same = (got_v > 0) == (want_v > 0)
+        assert same.mean() > 0.995
+        ok = same & (want_v > 0)
+        agree = got_a[ok] == want_a[ok]
+        assert agree.mean() > 0.99
+        return
+    np.testing.assert_array_equal(got_v > 0, want_v > 0)
+    if relative:
+        np.testing.assert_array_equal(got_v == 1, want_v == 1)
+    np.testing.assert_array_equal(got_a, want_a)
+    np.testing.assert_allclose(got_v, want_v, rtol=1e-5, atol=1e-7)   # atan last-bit differences amplified by cancellation
+
+
+@pytest.mark.parametrize("name", sorted(gc.TRAIN_CASES))
+def test_train_losses(name):
+    case = gc.TRAIN_CASES[name]
+    g, levels, W, H = _geom(case["geom"])
+    gold = gc.load(name)
+    gt = gc.case_gt(case)
+    maps = gc.train_maps(case)
+    res = orc.train_losses(g["anchors"], g["offsets"], g["scales"], W, H, gt.boxes, gt.classes, gt.offsets,
+                           maps.loc_logits, maps.iou_preds, maps.box_raw, maps.cls_logits, dense_rows=True)
+    got = res["losses"]
+    want = [gold["location_loss"], gold["box_loss"], gold["class_loss"], gold["iou_loss"], gold["loss"]]
+    for gv, wv in zip(got, want):
+        if np.isfinite(wv):
+            assert gv == pytest.approx(float(wv), rel=1e-5)
+        else:
+            assert not np.isfinite(gv)       # no anchor with rel==1: the reference divides by zero (ref :163)
+    if "grad_rows" in gold and gold["grad_rows"].size:
+        np.testing.assert_array_equal(res["pos_index"], gold["grad_rows"])   # row-major (b, a) compaction order
+
+
+@pytest.mark.parametrize("name", sorted(gc.FORWARD_CASES))
+def test_forward_tail(name):
+    case = gc.FORWARD_CASES[name]
+    g, levels, W, H = _geom(case["geom"])
+    gold = gc.load(name)
+    maps = gc.forward_maps(case)
+    K = case["k"]
+    idx, top = orc.topk_rows(maps.loc_logits, K)
+    np.testing.assert_array_equal(idx, gold["idx"])
+    B = idx.shape[0]
+    rows = np.arange(B)[:, None]
+    num, scores, classes, boxes = orc.decode_rows(top, idx, maps.cls_logits[rows, idx], maps.box_raw[rows, idx],
+                                                  g["offsets"], g["scales"], W, H)
+    np.testing.assert_array_equal(num, gold["num_instances"])
+    np.testing.assert_array_equal(classes, gold["classes"])
+    np.testing.assert_allclose(scores, gold["scores"], rtol=1e-6)
+    np.testing.assert_allclose(boxes, gold["boxes"], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", sorted(gc.NMS_CASES))
+def test_nms(name):
+    case = gc.NMS_CASES[name]
+    boxes, scores, classes = gc.nms_inputs(case)
+    keep = orc.batched_nms(boxes, scores, classes, case["thr"])
+    want = gc.load(name)["keep"].astype(np.int64)
+    assert set(keep.tolist()) == set(want.tolist())
+    # torchvision's final sort is not stable; order is pinned only where scores are unique
+    order = np.lexsort((want, -scores[want].astype(np.float64)))
+    np.testing.assert_array_equal(keep, want[order])
+
+
+def test_dense_postprocess_matches_components():
+    levels = synth.level_sizes(128, 128, 3, 7, "floor")
+    off, sc, an = orc.anchors(levels, 128, 128)
+    maps = synth.dense_maps_np(5, 3, len(an), 7, loc_mean=-2.0, loc_std=2.0)
+    num, scores, classes, boxes, ncand = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw, off, sc,
+                                                               128, 128, 0.05, 0.5, 20)
+    assert (num <= 20).all() and (ncand >= num).all()
+    for b in range(3):
+        s = scores[b, :num[b]]
+        assert (np.diff(s) <= 0).all() and (s > 0.05).all()
+        assert (scores[b, num[b]:] == 0).all()
