@@ -1,0 +1,239 @@
+/*
+ * sihl_od.h — C ABI of libsihl_b200.so: the dense tail of sihl's ObjectDetection
+ * head (anchor grid, CIoU top-k assignment, loss reductions + their backward,
+ * top-k decode, dense decode + class-aware NMS) as hand-written sm_100a kernels.
+ *
+ * The reference (jonregef/sihl) is pure Python and has no FFI; its boundary for
+ * this path is the `Head` protocol (ref: src/sihl/heads/__init__.py:28-53) as
+ * implemented by `ObjectDetection` (ref: src/sihl/heads/object_detection.py).
+ * Each entry point below names the reference lines it replaces.  The Python
+ * host side (sihl_b200/heads/object_detection.py) binds these with ctypes; see
+ * INTEGRATION.md for the stub a sihl maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends
+ *    in `_host`; nothing is allocated, freed or retained by the library;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    every call only enqueues work on it and returns (no host synchronisation);
+ *  - return value: 0 = SIHL_OD_OK, otherwise an error code; the message is
+ *    available from sihl_od_last_error_string() (thread-local).  Nothing throws;
+ *  - tensors are dense, row-major, fp32 unless stated; indices follow the
+ *    reference: anchors are level-major, row-major (y outer, x inner), boxes
+ *    are xyxy; ragged ground truth is CSR: gt_boxes [sumG,4], gt_classes
+ *    [sumG] (int64), gt_offsets [B+1] (int32, device);
+ *  - re-entrant: no global mutable state besides the thread-local error text.
+ */
+#ifndef SIHL_OD_H
+#define SIHL_OD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SIHL_OD_API __attribute__((visibility("default")))
+#else
+#define SIHL_OD_API
+#endif
+
+#define SIHL_OD_OK      0
+#define SIHL_OD_EINVAL  1   /* bad argument (mirrors the reference's asserts / torch errors) */
+#define SIHL_OD_ECUDA   2   /* a CUDA runtime call failed */
+
+#define SIHL_OD_MAX_LEVELS 8
+#define SIHL_OD_MAX_TOPK   16
+#define SIHL_OD_NUM_SUMS   8
+
+/* Layout of the fp64 partial-sum vector every loss kernel accumulates into and
+ * the one thing that crosses GPUs (one all-reduce of 8 doubles per step):
+ *   [0] sum BCE-with-logits(loc, rel==1)      ref object_detection.py:160-162
+ *   [1] #(rel == 1)                           ref :159,163
+ *   [2] sum (iou_pred - rel)^2                ref :177-179
+ *   [3] sum rel  (== sum of positive weights) ref :180,197,208
+ *   [4] sum w * CIoU-loss(decoded box, gt)    ref :194-197
+ *   [5] sum w * CE(class logits, gt class)    ref :205-208
+ *   [6] #(rel > 0)  (P, number of positives)  ref :165,182
+ *   [7] reserved (0)                                                          */
+
+SIHL_OD_API int sihl_od_version(void);
+SIHL_OD_API const char *sihl_od_last_error_string(void);
+
+/* ---- a1/a2: anchor grid ---------------------------------------------------
+ * Replaces ObjectDetection.get_offsets_and_scales (ref :83-97) and the anchor
+ * product (ref :134-140).  level_hw_host: HOST array [n_levels][2] = (h_l, w_l).
+ * Outputs [A,4] each, A = sum h_l*w_l; any of them may be NULL. */
+SIHL_OD_API int sihl_od_anchors(const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
+                    float *offsets, float *scales, float *anchors, void *stream);
+
+/* ---- a3/a4: label assignment ----------------------------------------------
+ * Replaces the per-image ObjectDetection.bbox_matching loop (ref :143-148,
+ * :252-284; CIoU from torchvision ops/boxes.py:404-434) in two stages.
+ *
+ * Stage 1, select: per gt, the top-k anchors by clamp(CIoU,0) restricted to
+ * positive values (ties: lowest anchor index), and the gt's best CIoU.
+ *   level_hw_host != NULL: anchors must be the grid produced by sihl_od_anchors
+ *     for these levels; candidates are enumerated from the gt extent (every
+ *     anchor with CIoU > 0 overlaps the gt) and evaluated on the given table.
+ *   level_hw_host == NULL: arbitrary anchors, all A x G pairs are evaluated.
+ * Outputs: sel_anchor int32 [sumG, topk] (-1 = unused slot), sel_val fp32
+ * [sumG, topk] (descending), best_iou fp32 [sumG].  If sums != NULL the 8
+ * doubles are zeroed here (saves a memset launch per step).
+ * Errors: topk outside 1..SIHL_OD_MAX_TOPK, A < topk with sumG > 0 (torch.topk
+ * raises in the reference), n_levels > SIHL_OD_MAX_LEVELS, level sizes that do
+ * not add up to A. */
+SIHL_OD_API int sihl_od_assign_select(const float *anchors, int64_t num_anchors,
+                          const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
+                          const float *gt_boxes, const int32_t *gt_offsets, int batch, int total_gt,
+                          int topk, int32_t *sel_anchor, float *sel_val, float *best_iou,
+                          double *sums, void *stream);
+
+/* Stage 2, resolve (+ fused dense losses): per anchor the maximum over the gts
+ * that selected it (ties: lowest gt index, torch.max), relative IoU =
+ * value / best_iou[gt] (relative != 0) or the value itself.
+ *   assignment int64 [B,A]: gt index within the image, -1 where iou is not > 0
+ *     (canonical form; the reference leaves implementation-defined indices on
+ *     zero-IoU fill slots which nothing downstream reads);
+ *   out_iou fp32 [B,A].
+ * If loc_logits != NULL (and optionally iou_preds) the BCE / MSE reductions of
+ * ref :157-163, :175-180 are accumulated into sums[0..3,6] in the same pass.
+ * Positive compaction (ref :182-184 order = row-major (b,a)): if
+ * tile_pos_count != NULL the kernel writes, per (image, tile), the number of
+ * positives and their flat indices b*A+a in ascending order into
+ * tile_pos_rows [B * n_tiles * tile]; query the geometry with
+ * sihl_od_resolve_tiles().  sihl_od_pos_compact() turns that into pos_index.
+ * If box_raw/cls_logits != NULL (dense maps [B,A,4] / [B,A,C]) the positive
+ * losses of ref :187-208 are fused too (sums[4], sums[5]); this needs offsets,
+ * scales, gt_classes. */
+SIHL_OD_API int sihl_od_resolve_tiles(int64_t num_anchors, int *n_tiles, int *tile);
+
+SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *sel_val, const float *best_iou,
+                           const int32_t *gt_offsets, int batch, int64_t num_anchors, int topk, int relative,
+                           const float *loc_logits, const float *iou_preds,
+                           int64_t *assignment, float *out_iou, double *sums,
+                           int32_t *tile_pos_count, int32_t *tile_pos_rows,
+                           const float *box_raw, const float *cls_logits, int num_classes,
+                           const float *offsets, const float *scales, int img_w, int img_h,
+                           const float *gt_boxes, const int64_t *gt_classes,
+                           void *stream);
+
+/* pos_index int32 [capacity] (flat b*A+a, ascending), pos_total int32 [1],
+ * pos_image_offsets int32 [B+1] (may be NULL).  Entries beyond capacity are
+ * dropped (pos_total still reports the true count). */
+SIHL_OD_API int sihl_od_pos_compact(const int32_t *tile_pos_count, const int32_t *tile_pos_rows, int batch,
+                        int64_t num_anchors, int32_t *pos_index, int64_t capacity, int32_t *pos_total,
+                        int32_t *pos_image_offsets, void *stream);
+
+/* ---- a5-a10: losses ---------------------------------------------------------
+ * Dense losses alone (ref :157-163, :175-180) for callers that already hold
+ * rel_iou.  iou_preds may be NULL (early-out path).  Accumulates into sums. */
+SIHL_OD_API int sihl_od_dense_loss(const float *loc_logits, const float *iou_preds, const float *rel_iou,
+                       int64_t n, double *sums, void *stream);
+
+/* Positive-row losses (ref :187-208; CIoU loss from torchvision
+ * ops/ciou_loss.py:47-64, diou_loss.py:64-91, _utils.py:87-106).
+ * pos_index int32 [P] flat b*A+a; n_pos_dev int32 [1] on the device (the true
+ * count, clamped to capacity) or NULL to use `capacity` rows.
+ * dense_rows != 0: box_raw [B*A,4], cls_logits [B*A,C] addressed by b*A+a;
+ * dense_rows == 0: compact rows [P,4] / [P,C] in pos_index order (what the
+ * reference's box_head / cls_head produce from flat_feats[o2m_mask]).
+ * Either of box_raw / cls_logits may be NULL.  Accumulates sums[4], sums[5]. */
+SIHL_OD_API int sihl_od_pos_loss(const int32_t *pos_index, const int32_t *n_pos_dev, int64_t capacity,
+                     int64_t num_anchors, const float *rel_iou, const int64_t *assignment,
+                     const float *offsets, const float *scales, int img_w, int img_h,
+                     const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                     const float *box_raw, const float *cls_logits, int num_classes, int dense_rows,
+                     double *sums, void *stream);
+
+/* ref :163-172, :180, :197, :208, :210 — losses fp32 [5] =
+ * [location, box, class, iou, total]; early-out when sums[6] == 0. */
+SIHL_OD_API int sihl_od_loss_finalize(const double *sums, float *losses, void *stream);
+
+/* Backward of the four loss terms w.r.t. the head outputs.
+ * grad_terms: device fp32 [4] = upstream gradient of [location, box, class, iou]
+ * loss; NULL means the total loss of ref :210, i.e. {1, 10, 1, 1}.
+ *   dloc[i]  = g0 * (sigmoid(loc) - [rel==1]) / sums[1]
+ *   diou[i]  = g3 * 2 (iou_pred - rel) / sums[3]         (0 if sums[6] == 0)
+ * dbox [P,4] / dcls [P,C] (compact rows) or dense [B*A,..] scattered rows
+ * (dense_rows != 0; non-positive rows are NOT written — zero them first):
+ *   dcls = g2 * w/sums[3] * (softmax - onehot)
+ *   dbox = g1 * w/sums[3] * dCIoU/dpred * scales * exp(raw), alpha constant
+ * (the reference's early-out, ref :165-172, leaves box/class/iou heads without
+ * gradient; callers skip sihl_od_pos_loss_bwd when there are no positives). */
+SIHL_OD_API int sihl_od_dense_loss_bwd(const float *loc_logits, const float *iou_preds, const float *rel_iou, int64_t n,
+                           const double *sums, const float *grad_terms,
+                           float *dloc, float *diou, void *stream);
+
+SIHL_OD_API int sihl_od_pos_loss_bwd(const int32_t *pos_index, const int32_t *n_pos_dev, int64_t capacity,
+                         int64_t num_anchors, const float *rel_iou, const int64_t *assignment,
+                         const float *offsets, const float *scales, int img_w, int img_h,
+                         const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                         const float *box_raw, const float *cls_logits, int num_classes, int dense_rows,
+                         const double *sums, const float *grad_terms,
+                         float *dbox, float *dcls, void *stream);
+
+/* ---- a11: forward tail ------------------------------------------------------
+ * ref :108-109: per image the K largest location logits, sorted descending
+ * (ties: lowest index).  idx int64 [B,K], top_logits fp32 [B,K]. */
+SIHL_OD_API int sihl_od_topk(const float *loc_logits, int batch, int64_t num_anchors, int k,
+                 int64_t *idx, float *top_logits, void *stream);
+
+/* ref :113-121 on gathered rows: scores = sigmoid(top_logits), num_instances =
+ * #(score > 0.5), classes = first argmax of cls_rows [B,K,C], boxes =
+ * (offsets[idx] + scales[idx] * exp(box_rows)) * [W,H,W,H].
+ * num_instances int64 [B], scores [B,K], classes int64 [B,K], boxes [B,K,4]. */
+SIHL_OD_API int sihl_od_decode_rows(const float *top_logits, const int64_t *idx, int batch, int k,
+                        const float *cls_rows, int num_classes, const float *box_rows,
+                        const float *offsets, const float *scales, int img_w, int img_h,
+                        int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
+                        void *stream);
+
+/* ---- a15 (extension, not in the reference): dense decode + class-aware NMS --
+ * Dense decode of every location: class = first argmax over C logits, score =
+ * sigmoid(loc) (the semantics of ref :113,:117), candidate iff score >
+ * score_thr, box decoded as ref :121.  Candidates are appended per image to
+ * cand_* [B, cand_capacity] (unordered); cand_count int32 [B] must be zeroed by
+ * the caller or by passing zero_counts != 0 (costs one tiny launch).
+ * cand_key: uint64 [B,cap] sort key (score desc, location asc); cand_box
+ * [B,cap,4]; cand_cls int32 [B,cap]. */
+SIHL_OD_API int sihl_od_dense_decode(const float *loc_logits, const float *cls_logits, const float *box_raw,
+                         int batch, int64_t num_anchors, int num_classes,
+                         const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
+                         int32_t *cand_count, int64_t cand_capacity,
+                         uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                         void *stream);
+
+/* Class-aware greedy NMS per image over the candidate lists written by
+ * sihl_od_dense_decode, semantics of torchvision _batched_nms_vanilla
+ * (ops/boxes.py:102-120): visit by (score desc, location asc); a kept box
+ * suppresses later boxes of the same class with IoU > iou_thr.  Emits the first
+ * K kept detections per image, zero padded, in the reference forward()'s output
+ * format.  workspace: sihl_od_nms_workspace_bytes(batch, cand_capacity). */
+SIHL_OD_API size_t sihl_od_nms_workspace_bytes(int batch, int64_t cand_capacity);
+
+SIHL_OD_API int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacity,
+                     const uint64_t *cand_key, const float *cand_box, const int32_t *cand_cls,
+                     int batch, float iou_thr, int k,
+                     int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
+                     void *workspace, void *stream);
+
+/* Stand-alone batched NMS with torchvision.ops.batched_nms's signature, over
+ * `n_images` independent segments: boxes [N,4], scores [N], classes int64 [N],
+ * seg_offsets int32 [n_images+1] (device).  keep int64 [N]: per segment, the
+ * kept indices (global, into [0,N)) in (score desc, index asc) order are
+ * written at keep[seg_offsets[s] ...], keep_count int32 [n_images].
+ * classes must lie in [0, 2^32).  workspace: sihl_od_batched_nms_workspace_bytes(N)
+ * bytes (0 when every segment fits on chip; NULL is then accepted). */
+SIHL_OD_API size_t sihl_od_batched_nms_workspace_bytes(int64_t n);
+
+SIHL_OD_API int sihl_od_batched_nms(const float *boxes, const float *scores, const int64_t *classes,
+                        const int32_t *seg_offsets, int n_images, int64_t n,
+                        float iou_thr, int64_t *keep, int32_t *keep_count,
+                        void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIHL_OD_H */

@@ -1,0 +1,452 @@
+// od_assign.cu — CIoU top-k label assignment and the streaming
+// resolve pass with the dense losses (a5/a6), positive compaction (a7) and, for dense
+// maps, the positive-row losses (a8/a9) fused in.
+//
+// Replaces, per training step, the Python loop of B calls to ObjectDetection.bbox_matching
+// (ref: src/sihl/heads/object_detection.py:143-148, :252-284), ~100 ATen launches, ~35
+// [A,G] fp32 temporaries and ~7 host syncs per image, by two launches for the batch.
+//
+// Stage 1 (k_assign_select): one warp per ground-truth box.  CIoU > 0 implies IoU > 0
+// (every subtracted term is >= 0), so only anchors whose cell overlaps the gt can be
+// positive: candidates are enumerated from the gt extent per pyramid level (widened by
+// one cell; the overlap itself is decided by the CIoU arithmetic on the real anchor
+// table), levels are visited in order of decreasing IoU upper bound
+// min(area)/max(area) and skipped once that bound falls below the current k-th value.
+// Lanes append positives to a per-warp shared-memory buffer with ballot/popc; a rank-by-
+// counting pass (lexicographic (value desc, anchor asc)) keeps the top k and yields them
+// sorted.  Bound: FP32 ALU / latency (≈45 flops + 4 IEEE divisions + atanf per pair);
+// compulsory HBM traffic is 16 B per gt in, 8k+4 B per gt out.
+//
+// Stage 2 (k_assign_resolve): one CTA per (image, tile of 1024 anchors).  The image's
+// <= G*k selections are max-reduced into 64-bit keys (value bits << 32 | ~gt) in shared
+// memory — the torch.max rule "largest value, lowest gt index" in one atomicMax — then
+// the CTA streams loc_logits / iou_preds (coalesced 4-byte loads), writes assignment
+// (int64) and rel_iou, and reduces BCE / MSE / counts in registers -> shuffles -> one
+// fp64 atomicAdd per CTA and term.  Bound: HBM, 20 B per anchor.
+#include "od_common.cuh"
+#include "od_pos.cuh"
+
+namespace sihl {
+
+int fill_level_table(const int32_t *level_hw_host, int n_levels, LevelTable *lv);   // od_anchors.cu
+
+// ---------------------------------------------------------------------------
+// Stage 1: select
+// ---------------------------------------------------------------------------
+constexpr int kSelWarps = 8;
+constexpr int kBufCap = 64;
+
+struct SelectParams {
+    LevelTable lv;
+    int use_levels;
+    float img_w, img_h;
+    int num_anchors;
+    int topk;
+};
+
+// Keep the top-k of the warp's buffer, sorted by (value desc, anchor asc); returns the new count.
+__device__ __forceinline__ int select_compress(float *bv, int *bi, int cnt, int topk, int lane)
+{
+    __syncwarp();
+    const bool h0 = lane < cnt, h1 = lane + 32 < cnt;
+    const float v0 = h0 ? bv[lane] : 0.f, v1 = h1 ? bv[lane + 32] : 0.f;
+    const int a0 = h0 ? bi[lane] : 0, a1 = h1 ? bi[lane + 32] : 0;
+    int r0 = 0, r1 = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const float vi = bv[i];
+        const int ai = bi[i];
+        r0 += (vi > v0) || (vi == v0 && ai < a0);
+        r1 += (vi > v1) || (vi == v1 && ai < a1);
+    }
+    __syncwarp();
+    if (h0 && r0 < topk) { bv[r0] = v0; bi[r0] = a0; }
+    if (h1 && r1 < topk) { bv[r1] = v1; bi[r1] = a1; }
+    __syncwarp();
+    return cnt < topk ? cnt : topk;
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32)
+k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4 *__restrict__ gt_boxes,
+                int total_gt, int32_t *__restrict__ sel_anchor, float *__restrict__ sel_val,
+                float *__restrict__ best_iou, double *__restrict__ sums)
+{
+    __shared__ float s_val[kSelWarps][kBufCap];
+    __shared__ int s_idx[kSelWarps][kBufCap];
+
+    if (sums != nullptr && blockIdx.x == 0 && threadIdx.x < SIHL_OD_NUM_SUMS) sums[threadIdx.x] = 0.0;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= total_gt) return;                       // warp-uniform; no block barriers below
+
+    float *bv = s_val[warp];
+    int *bi = s_idx[warp];
+    const int topk = p.topk;
+    const BoxTerms gt = box_terms(to_box(__ldg(gt_boxes + g)));
+    int cnt = 0;
+    float thr = 0.f;                                 // k-th best so far once cnt == topk, else 0
+
+    // Evaluate up to 32 candidates (one per lane) and append the ones that can still make the top k.
+    auto consider = [&](bool valid, int a) {
+        float v = 0.f;
+        if (valid) v = ciou_pair(box_terms(to_box(__ldg(anchors + a))), gt);
+        const bool hit = valid && (thr > 0.f ? v >= thr : v > 0.f);      // clamp(0): non-positives never rank
+        const unsigned m = __ballot_sync(kFullMask, hit);
+        if (m) {
+            if (hit) {
+                const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                bv[pos] = v;
+                bi[pos] = a;
+            }
+            cnt += __popc(m);
+            if (cnt > kBufCap - 32) {
+                cnt = select_compress(bv, bi, cnt, topk, lane);
+                if (cnt == topk) thr = bv[topk - 1];
+            }
+        }
+    };
+
+    if (!p.use_levels) {
+        for (int t0 = 0; t0 < p.num_anchors; t0 += 32) consider(t0 + lane < p.num_anchors, t0 + lane);
+    } else {
+        // IoU <= min(area)/max(area); 0.1 % slack covers the rounding of the anchor table.
+        float bound[SIHL_OD_MAX_LEVELS];
+#pragma unroll
+        for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) {
+            const float cell = (p.img_w / (float)p.lv.w[l]) * (p.img_h / (float)p.lv.h[l]);
+            const float lo = fminf(cell, gt.area), hi = fmaxf(cell, gt.area);
+            bound[l] = (l < p.lv.n) ? ((gt.area > 0.f) ? (lo / hi) * 1.001f : CUDART_INF_F) : -1.f;
+        }
+        for (int it = 0; it < p.lv.n; ++it) {
+            int l = 0;
+            float bmax = -1.f;
+#pragma unroll
+            for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k)
+                if (bound[k] > bmax) { bmax = bound[k]; l = k; }
+            if (cnt >= topk) {
+                cnt = select_compress(bv, bi, cnt, topk, lane);
+                thr = bv[topk - 1];
+                if (bmax < thr) break;               // no remaining level can reach the current k-th value
+            }
+#pragma unroll
+            for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k)
+                if (k == l) bound[k] = -2.f;         // visited
+            const int lw = p.lv.w[l], lh = p.lv.h[l], base = p.lv.base[l];
+            const float sx = p.img_w / (float)lw, sy = p.img_h / (float)lh;
+            const float fw = (float)(lw - 1), fh = (float)(lh - 1);
+            const int j0 = (int)fminf(fmaxf(floorf(gt.x1 / sx) - 1.f, 0.f), fw);
+            const int j1 = (int)fminf(fmaxf(floorf(gt.x2 / sx) + 1.f, 0.f), fw);
+            const int i0 = (int)fminf(fmaxf(floorf(gt.y1 / sy) - 1.f, 0.f), fh);
+            const int i1 = (int)fminf(fmaxf(floorf(gt.y2 / sy) + 1.f, 0.f), fh);
+            const int nj = j1 - j0 + 1, ni = i1 - i0 + 1;
+            if (nj <= 0 || ni <= 0) continue;
+            const int n = ni * nj;
+            const float inv_nj = 1.f / (float)nj;
+            for (int t0 = 0; t0 < n; t0 += 32) {
+                const int t = t0 + lane;
+                const int ri = (int)(((float)t + 0.5f) * inv_nj);     // t / nj (exact: margin 0.5/nj >> ulp)
+                const int rj = t - ri * nj;
+                consider(t < n, base + (i0 + ri) * lw + (j0 + rj));
+            }
+        }
+    }
+
+    cnt = select_compress(bv, bi, cnt, topk, lane);
+    if (lane < topk) {
+        sel_anchor[(int64_t)g * topk + lane] = lane < cnt ? bi[lane] : -1;
+        sel_val[(int64_t)g * topk + lane] = lane < cnt ? bv[lane] : 0.f;
+    }
+    if (lane == 0) best_iou[g] = cnt ? bv[0] : 0.f;                  // ref :277 topk_ious[0]
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2: resolve (+ dense losses, + compaction, + fused positive losses)
+// ---------------------------------------------------------------------------
+constexpr int kTile = 1024;
+constexpr int kResThreads = 256;
+constexpr int kChunks = kTile / kResThreads;
+
+struct ResolveParams {
+    const int32_t *sel_anchor; const float *sel_val; const float *best_iou; const int32_t *gt_offsets;
+    int num_anchors, topk, relative;
+    const float *loc; const float *iou_pred;
+    int64_t *assignment; float *out_iou; double *sums;
+    int32_t *tile_pos_count; int32_t *tile_pos_rows;
+    const float *box_raw; const float *cls; int num_classes;
+    const float4 *offsets; const float4 *scales; float img_w, img_h;
+    const float4 *gt_boxes; const int64_t *gt_classes;
+};
+
+__global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
+{
+    __shared__ unsigned long long s_key[kTile];
+    __shared__ float s_rel[kTile];
+    __shared__ unsigned short s_pos[kTile];
+    __shared__ int s_seg[kChunks * (kResThreads / 32) + 1];
+    __shared__ double s_red[5 * 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, tile = blockIdx.x, n_tiles = gridDim.x;
+    const int A = p.num_anchors, a0 = tile * kTile;
+    const int na = min(kTile, A - a0);
+    const int g0 = __ldg(p.gt_offsets + b), g1 = __ldg(p.gt_offsets + b + 1);
+
+    for (int i = tid; i < kTile; i += kResThreads) s_key[i] = 0ull;
+    __syncthreads();
+    // per anchor: max value over the gts that selected it, ties -> lowest gt (ref :270)
+    const int n_entries = (g1 - g0) * p.topk;
+    const int32_t *sa = p.sel_anchor + (int64_t)g0 * p.topk;
+    const float *sv = p.sel_val + (int64_t)g0 * p.topk;
+    for (int e = tid; e < n_entries; e += kResThreads) {
+        const int a = __ldg(sa + e) - a0;
+        if (a >= 0 && a < na) {
+            const unsigned g = (unsigned)(e / p.topk);
+            const unsigned long long key =
+                ((unsigned long long)__float_as_uint(__ldg(sv + e)) << 32) | (unsigned long long)(0xffffffffu - g);
+            atomicMax(&s_key[a], key);
+        }
+    }
+    __syncthreads();
+
+    float acc_bce = 0.f, acc_one = 0.f, acc_mse = 0.f, acc_rel = 0.f, acc_pos = 0.f;
+    unsigned ballots[kChunks];
+    bool flags[kChunks];
+    const bool want_list = (p.tile_pos_count != nullptr) || (p.box_raw != nullptr) || (p.cls != nullptr);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const int la = c * kResThreads + tid;
+        bool pos = false;
+        if (la < na) {
+            const unsigned long long key = s_key[la];
+            const int64_t flat = (int64_t)b * A + a0 + la;
+            float rel = 0.f;
+            int64_t asg = -1;
+            if (key != 0ull) {
+                const float v = __uint_as_float((unsigned)(key >> 32));
+                const int g = (int)(0xffffffffu - (unsigned)(key & 0xffffffffu));
+                rel = p.relative ? v / __ldg(p.best_iou + g0 + g) : v;          // ref :279-281
+                pos = rel > 0.f;
+                asg = pos ? g : -1;                                              // canonical form (sihl_od.h)
+            }
+            p.assignment[flat] = asg;
+            p.out_iou[flat] = rel;
+            s_rel[la] = rel;
+            if (p.loc != nullptr) {
+                const float t = (rel == 1.0f) ? 1.f : 0.f;                       // ref :159
+                acc_bce += bce_logits(__ldg(p.loc + flat), t);
+                acc_one += t;
+                if (p.iou_pred != nullptr) {
+                    const float d = __ldg(p.iou_pred + flat) - rel;              // ref :177-179
+                    acc_mse += d * d;
+                }
+                acc_rel += rel;
+                acc_pos += pos ? 1.f : 0.f;
+            }
+        }
+        flags[c] = pos;
+        ballots[c] = __ballot_sync(kFullMask, pos);
+        if (want_list && lane == 0) s_seg[c * (kResThreads / 32) + warp] = __popc(ballots[c]);
+    }
+
+    int n_pos = 0;
+    if (want_list) {
+        // ordered compaction: segment (chunk, warp) order == ascending anchor order (ref :182-184)
+        __syncthreads();
+        if (warp == 0) {
+            const int nseg = kChunks * (kResThreads / 32);
+            int x = lane < nseg ? s_seg[lane] : 0;
+            int incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane < nseg) s_seg[lane] = incl - x;
+            if (lane == 31) s_seg[nseg] = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+            if (flags[c]) {
+                const int r = s_seg[c * (kResThreads / 32) + warp] + __popc(ballots[c] & ((1u << lane) - 1u));
+                s_pos[r] = (unsigned short)(c * kResThreads + tid);
+            }
+        __syncthreads();
+        n_pos = s_seg[kChunks * (kResThreads / 32)];
+        if (p.tile_pos_count != nullptr) {
+            const int slot = b * n_tiles + tile;
+            if (tid == 0) p.tile_pos_count[slot] = n_pos;
+            for (int r = tid; r < n_pos; r += kResThreads)
+                p.tile_pos_rows[(int64_t)slot * kTile + r] = (int32_t)((int64_t)b * A + a0 + s_pos[r]);
+        }
+    }
+
+    float acc_box = 0.f, acc_cls = 0.f;
+    if (p.box_raw != nullptr) {                       // thread per positive row
+        for (int r = tid; r < n_pos; r += kResThreads) {
+            const int la = s_pos[r], a = a0 + la;
+            const int64_t flat = (int64_t)b * A + a;
+            const int g = g0 + (int)(0xffffffffu - (unsigned)(s_key[la] & 0xffffffffu));
+            const float l = pos_box_loss(ldg4(p.box_raw + 4 * flat), __ldg(p.offsets + a), __ldg(p.scales + a),
+                                         __ldg(p.gt_boxes + g), p.img_w, p.img_h);
+            acc_box += s_rel[la] * l;
+        }
+    }
+    if (p.cls != nullptr) {                           // 8 lanes per positive row
+        const int gl = lane & 7, grp = tid >> 3, ngrp = kResThreads >> 3;
+        const int rounds = (n_pos + ngrp - 1) / ngrp;
+        for (int it = 0; it < rounds; ++it) {
+            const int r = it * ngrp + grp;
+            const bool ok = r < n_pos;
+            const int la = s_pos[ok ? r : 0], a = a0 + la;
+            const int64_t flat = (int64_t)b * A + a;
+            const int g = g0 + (int)(0xffffffffu - (unsigned)(s_key[la] & 0xffffffffu));
+            float ce = 0.f;
+            if (n_pos > 0) ce = ce_row_group8(p.cls + flat * p.num_classes, p.num_classes, (int)__ldg(p.gt_classes + g), gl);
+            if (ok && gl == 0) acc_cls += s_rel[la] * ce;
+        }
+    }
+
+    if (p.sums != nullptr && (p.loc != nullptr || p.box_raw != nullptr || p.cls != nullptr)) {
+        {
+            double v[5] = {acc_bce, acc_one, acc_mse, acc_rel, acc_pos};
+            const int slot[5] = {0, 1, 2, 3, 6};
+            if (p.loc != nullptr) block_accumulate<5>(v, s_red, p.sums, slot);
+        }
+        {
+            double v[2] = {acc_box, acc_cls};
+            const int slot[2] = {4, 5};
+            if (p.box_raw != nullptr || p.cls != nullptr) block_accumulate<2>(v, s_red, p.sums, slot);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Tile lists -> one ascending pos_index (ref :182-184 row order)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pos_compact(const int32_t *__restrict__ tile_pos_count, const int32_t *__restrict__ tile_pos_rows, int n_tiles,
+              int n_slots, int32_t *__restrict__ pos_index, int64_t capacity, int32_t *__restrict__ pos_total,
+              int32_t *__restrict__ pos_image_offsets)
+{
+    __shared__ int s_red[32];
+    const int slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int before = 0, total = 0;
+    for (int i = tid; i < n_slots; i += blockDim.x) {
+        const int c = __ldg(tile_pos_count + i);
+        total += c;
+        if (i < slot) before += c;
+    }
+    before = warp_sum(before);
+    total = warp_sum(total);
+    if (lane == 0) { s_red[warp] = before; s_red[16 + warp] = total; }
+    __syncthreads();
+    before = 0; total = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { before += s_red[w]; total += s_red[16 + w]; }
+    if (tid == 0) {
+        if (slot == 0 && pos_total) *pos_total = total;
+        if (pos_image_offsets) {
+            if (slot % n_tiles == 0) pos_image_offsets[slot / n_tiles] = before;
+            if (slot == n_slots - 1) pos_image_offsets[n_slots / n_tiles] = total;
+        }
+    }
+    const int n = __ldg(tile_pos_count + slot);
+    for (int r = tid; r < n; r += blockDim.x)
+        if ((int64_t)before + r < capacity) pos_index[before + r] = __ldg(tile_pos_rows + (int64_t)slot * kTile + r);
+}
+
+}  // namespace sihl
+
+using namespace sihl;
+
+extern "C" int sihl_od_assign_select(const float *anchors, int64_t num_anchors, const int32_t *level_hw_host,
+                                     int n_levels, int img_w, int img_h, const float *gt_boxes,
+                                     const int32_t *gt_offsets, int batch, int total_gt, int topk,
+                                     int32_t *sel_anchor, float *sel_val, float *best_iou, double *sums, void *stream)
+{
+    (void)gt_offsets; (void)batch;
+    SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
+    SIHL_CHECK_ARG(total_gt >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
+    SIHL_CHECK_ARG(total_gt == 0 || num_anchors >= topk,
+                   "selected index k out of range: %lld anchors < topk=%d (torch.topk raises in the reference)",
+                   (long long)num_anchors, topk);
+    SelectParams p;
+    p.use_levels = level_hw_host != nullptr;
+    if (p.use_levels) {
+        int rc = fill_level_table(level_hw_host, n_levels, &p.lv);
+        if (rc) return rc;
+        SIHL_CHECK_ARG(p.lv.base[n_levels] == num_anchors, "levels hold %d anchors, table has %lld", p.lv.base[n_levels],
+                       (long long)num_anchors);
+        SIHL_CHECK_ARG(img_w > 0 && img_h > 0, "image size %dx%d", img_w, img_h);
+    } else {
+        p.lv.n = 0;
+        for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) { p.lv.h[l] = p.lv.w[l] = 1; p.lv.base[l] = 0; }
+        p.lv.base[SIHL_OD_MAX_LEVELS] = 0;
+    }
+    p.img_w = (float)img_w; p.img_h = (float)img_h;
+    p.num_anchors = (int)num_anchors; p.topk = topk;
+    if (total_gt == 0 && sums == nullptr) return SIHL_OD_OK;
+    const int blocks = total_gt > 0 ? (total_gt + kSelWarps - 1) / kSelWarps : 1;
+    k_assign_select<<<blocks, kSelWarps * 32, 0, (cudaStream_t)stream>>>(
+        p, reinterpret_cast<const float4 *>(anchors), reinterpret_cast<const float4 *>(gt_boxes), total_gt, sel_anchor,
+        sel_val, best_iou, sums);
+    SIHL_CHECK_LAUNCH("k_assign_select");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_resolve_tiles(int64_t num_anchors, int *n_tiles, int *tile)
+{
+    if (n_tiles) *n_tiles = (int)((num_anchors + kTile - 1) / kTile);
+    if (tile) *tile = kTile;
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *sel_val, const float *best_iou,
+                                      const int32_t *gt_offsets, int batch, int64_t num_anchors, int topk, int relative,
+                                      const float *loc_logits, const float *iou_preds, int64_t *assignment,
+                                      float *out_iou, double *sums, int32_t *tile_pos_count, int32_t *tile_pos_rows,
+                                      const float *box_raw, const float *cls_logits, int num_classes,
+                                      const float *offsets, const float *scales, int img_w, int img_h,
+                                      const float *gt_boxes, const int64_t *gt_classes, void *stream)
+{
+    SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
+    SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
+    SIHL_CHECK_ARG(assignment && out_iou && gt_offsets, "assignment / out_iou / gt_offsets must not be NULL");
+    SIHL_CHECK_ARG((tile_pos_count == nullptr) == (tile_pos_rows == nullptr), "tile_pos_count and tile_pos_rows go together");
+    SIHL_CHECK_ARG(iou_preds == nullptr || loc_logits != nullptr, "iou_preds needs loc_logits");
+    const bool fused = box_raw != nullptr || cls_logits != nullptr;
+    SIHL_CHECK_ARG(!fused || (sums && gt_boxes && gt_classes && offsets && scales && img_w > 0 && img_h > 0),
+                   "fused positive losses need sums, gt, offsets, scales and the image size");
+    SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "num_classes=%d", num_classes);
+    SIHL_CHECK_ARG(loc_logits == nullptr || sums != nullptr, "dense losses need sums");
+    if (batch == 0 || num_anchors == 0) return SIHL_OD_OK;
+    ResolveParams p;
+    p.sel_anchor = sel_anchor; p.sel_val = sel_val; p.best_iou = best_iou; p.gt_offsets = gt_offsets;
+    p.num_anchors = (int)num_anchors; p.topk = topk; p.relative = relative;
+    p.loc = loc_logits; p.iou_pred = iou_preds; p.assignment = assignment; p.out_iou = out_iou; p.sums = sums;
+    p.tile_pos_count = tile_pos_count; p.tile_pos_rows = tile_pos_rows;
+    p.box_raw = box_raw; p.cls = cls_logits; p.num_classes = num_classes;
+    p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
+    p.img_w = (float)img_w; p.img_h = (float)img_h;
+    p.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); p.gt_classes = gt_classes;
+    const dim3 grid((unsigned)((num_anchors + kTile - 1) / kTile), (unsigned)batch);
+    SIHL_CHECK_ARG(batch <= 65535, "batch=%d > 65535", batch);
+    k_assign_resolve<<<grid, kResThreads, 0, (cudaStream_t)stream>>>(p);
+    SIHL_CHECK_LAUNCH("k_assign_resolve");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_pos_compact(const int32_t *tile_pos_count, const int32_t *tile_pos_rows, int batch,
+                                   int64_t num_anchors, int32_t *pos_index, int64_t capacity, int32_t *pos_total,
+                                   int32_t *pos_image_offsets, void *stream)
+{
+    SIHL_CHECK_ARG(tile_pos_count && tile_pos_rows && pos_index, "NULL argument");
+    SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && capacity >= 0, "bad sizes");
+    const int n_tiles = (int)((num_anchors + kTile - 1) / kTile);
+    const int n_slots = batch * n_tiles;
+    if (n_slots == 0) return SIHL_OD_OK;
+    k_pos_compact<<<n_slots, 256, 0, (cudaStream_t)stream>>>(tile_pos_count, tile_pos_rows, n_tiles, n_slots, pos_index,
+                                                              capacity, pos_total, pos_image_offsets);
+    SIHL_CHECK_LAUNCH("k_pos_compact");
+    return SIHL_OD_OK;
+}

@@ -1,0 +1,90 @@
+// od_common.cuh — shared device helpers for libsihl_b200 (sm_100a only).
+//
+// Arithmetic contract: every kernel that produces values compared bit-for-bit
+// with torch-CUDA eager (anchors, CIoU, decoded boxes, sigmoid) is compiled with
+// -fmad=false -prec-div=true -prec-sqrt=true and never --use_fast_math, so each
+// source operator is one IEEE fp32 operation, in the operator order of the
+// torch / torchvision eager code.  Fused multiply-adds appear
+// only where torch's own kernels have them, written explicitly (__fmaf_rn).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/sihl_od.h"
+#include "od_math.h"
+
+namespace sihl {
+
+void set_error(const char *fmt, ...);
+int cuda_status(cudaError_t e, const char *what);
+
+#define SIHL_CHECK_ARG(cond, ...)                          \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            ::sihl::set_error(__VA_ARGS__);                \
+            return SIHL_OD_EINVAL;                         \
+        }                                                  \
+    } while (0)
+
+#define SIHL_CHECK_LAUNCH(what)                                              \
+    do {                                                                     \
+        int _rc = ::sihl::cuda_status(cudaGetLastError(), what);             \
+        if (_rc) return _rc;                                                 \
+    } while (0)
+
+constexpr int kNumSMs = 148;          // B200
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct LevelTable {                   // passed by value as a kernel parameter
+    int n;
+    int h[SIHL_OD_MAX_LEVELS];
+    int w[SIHL_OD_MAX_LEVELS];
+    int base[SIHL_OD_MAX_LEVELS + 1]; // first anchor index of each level
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ Box4 to_box(float4 b) { return Box4{b.x, b.y, b.z, b.w}; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+
+// Block-wide sum of NV doubles per thread -> atomicAdd into dst[slot[i]] by one thread.
+// red: shared double[NV * 32].
+template <int NV>
+__device__ __forceinline__ void block_accumulate(double (&v)[NV], double *red, double *dst, const int (&slot)[NV])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = lane < nwarps ? red[i * 32 + lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0 && x != 0.0) atomicAdd(dst + slot[i], x);
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace sihl

@@ -1,0 +1,343 @@
+// od_infer.cu — inference tail of the detection head (SURVEY.md §8 a11 + the dense
+// decode half of the a15 extension).
+//
+//   k_topk          ref object_detection.py:108-109  torch.topk(loc_logits, K, dim=1)
+//   k_decode_rows   ref :113-121                     sigmoid / count / argmax / box decode on K rows
+//   k_dense_decode  extension: the same per-location decode over ALL locations of the
+//                   dense maps + score threshold, feeding class-aware NMS (od_nms.cu).
+//                   This is the HBM-bound kernel of the path: 4*A*(C+1) B per image are
+//                   read exactly once with coalesced 32-B-sector loads, 8 lanes per row.
+#include "od_common.cuh"
+
+namespace sihl {
+
+// Order-preserving map fp32 -> uint32 (ascending).
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---------------------------------------------------------------------------
+// top-K of one row per CTA: 4-pass MSB radix select for the K-th largest value, one
+// ordered pass that takes everything above it plus the lowest-index elements equal to
+// it, then a bitonic sort of the K winners by (value desc, index asc).
+// ---------------------------------------------------------------------------
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMaxK = 1024;
+
+__global__ void __launch_bounds__(kTopkThreads)
+k_topk(const float *__restrict__ loc, int A, int K, int KP /* pow2 >= K */, int64_t *__restrict__ idx_out,
+       float *__restrict__ val_out)
+{
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_pick[2];               // [0] = digit, [1] = remaining
+    __shared__ int s_warp[33];
+    __shared__ unsigned long long s_sel[kTopkMaxK];
+    __shared__ int s_ngt;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float *row = loc + (int64_t)blockIdx.x * A;
+
+    unsigned prefix = 0, mask = 0, remaining = (unsigned)K;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < A; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            const bool ok = i < A;
+            const unsigned u = ok ? f2ord(__ldg(row + i)) : 0u;
+            const bool in = ok && ((u & mask) == prefix);
+            const unsigned digit = (u >> shift) & 255u;
+            // warp-aggregated histogram update (logits cluster in a few exponent buckets)
+            const unsigned act = __ballot_sync(kFullMask, in);
+            if (in) {
+                const unsigned peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane handles 8 digits, descending: digit = 255 - (lane*8 + j)
+            unsigned c[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = s_hist[255 - (lane * 8 + j)]; tot += c[j]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += y;
+            }
+            unsigned before = incl - tot;          // elements in strictly larger digits handled by lower lanes
+            if (before < remaining && remaining <= incl) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (before < remaining && remaining <= before + c[j]) {
+                        s_pick[0] = 255u - (unsigned)(lane * 8 + j);
+                        s_pick[1] = remaining - before;
+                    }
+                    before += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= s_pick[0] << shift;
+        mask |= 255u << shift;
+        remaining = s_pick[1];
+        __syncthreads();
+    }
+    const unsigned kth = prefix;                 // ord-key of the K-th largest value
+    const int need_eq = (int)remaining;          // how many elements equal to it are taken (lowest index first)
+    if (tid == 0) s_ngt = 0;
+    for (int i = tid; i < KP; i += blockDim.x) s_sel[i] = 0ull;
+    __syncthreads();
+
+    int eq_seen = 0;                             // block-uniform running count of equal elements
+    for (int i0 = 0; i0 < A; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        const unsigned u = (i < A) ? f2ord(__ldg(row + i)) : 0u;
+        const bool gt = (i < A) && u > kth, eq = (i < A) && u == kth;
+        const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+        if (gt) s_sel[atomicAdd(&s_ngt, 1)] = key;           // fewer than K of these by construction
+        // ordered rank among the equal elements
+        const unsigned beq = __ballot_sync(kFullMask, eq);
+        if (lane == 0) s_warp[warp] = __popc(beq);
+        __syncthreads();
+        if (warp == 0) {
+            const int x = lane < nwarps ? s_warp[lane] : 0;
+            int incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane < nwarps) s_warp[lane] = incl - x;
+            if (lane == 31) s_warp[32] = incl;
+        }
+        __syncthreads();
+        if (eq) {
+            const int r = eq_seen + s_warp[warp] + __popc(beq & ((1u << lane) - 1u));
+            if (r < need_eq) s_sel[K - need_eq + r] = key;   // slots [K-need_eq, K) are reserved for the ties
+        }
+        eq_seen += s_warp[32];
+        __syncthreads();
+    }
+
+    // bitonic sort, descending, of KP (>= K) composite keys; the zero padding sinks to the end
+    for (int k = 2; k <= KP; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < KP; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_sel[i], b = s_sel[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { s_sel[i] = b; s_sel[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < K; i += blockDim.x) {
+        const unsigned long long key = s_sel[i];
+        idx_out[(int64_t)blockIdx.x * K + i] = (int64_t)(0xffffffffu - (unsigned)(key & 0xffffffffu));
+        val_out[(int64_t)blockIdx.x * K + i] = ord2f((unsigned)(key >> 32));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// First arg-max over a row of C logits by a group of 8 lanes (4 rows per warp).
+// Lane gl visits c = gl, gl+8, ...; strict '>' keeps the lowest index inside a lane and
+// the cross-lane reduction prefers the lower index on equal values (torch.max, ref :117).
+// ---------------------------------------------------------------------------
+template <int CPL>   // logits per lane when C == 8*CPL (fully unrolled, all loads in flight); 0 = runtime C
+__device__ __forceinline__ int row_argmax8(const float *__restrict__ z, int C, int gl)
+{
+    float best = -CUDART_INF_F;
+    int arg = 0x7fffffff;
+    if (CPL > 0) {
+        float v[CPL > 0 ? CPL : 1];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] = __ldcs(z + gl + 8 * i);      // streamed once: evict-first
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+            if (v[i] > best || arg == 0x7fffffff) { best = v[i]; arg = gl + 8 * i; }
+    } else {
+        for (int c = gl; c < C; c += 8) {
+            const float x = __ldcs(z + c);
+            if (x > best || arg == 0x7fffffff) { best = x; arg = c; }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(kFullMask, best, o);
+        const int oa = __shfl_xor_sync(kFullMask, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    return arg;
+}
+
+// ref :113-121 on the K gathered rows of one image per CTA.
+__global__ void __launch_bounds__(256)
+k_decode_rows(const float *__restrict__ top_logits, const int64_t *__restrict__ idx, int K,
+              const float *__restrict__ cls_rows, int C, const float *__restrict__ box_rows,
+              const float4 *__restrict__ offsets, const float4 *__restrict__ scales, float img_w, float img_h,
+              int64_t *__restrict__ num_instances, float *__restrict__ scores, int64_t *__restrict__ classes,
+              float *__restrict__ boxes)
+{
+    __shared__ int s_count;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    int local = 0;
+    for (int k = tid; k < K; k += blockDim.x) {
+        const int64_t r = (int64_t)b * K + k;
+        const float s = sigmoid_f(__ldg(top_logits + r));                  // ref :113
+        scores[r] = s;
+        local += (s > 0.5f) ? 1 : 0;                                       // ref :114
+        const int a = (int)__ldg(idx + r);
+        const float4 raw = ldg4(box_rows + 4 * r), off = __ldg(offsets + a), sc = __ldg(scales + a);
+        *reinterpret_cast<float4 *>(boxes + 4 * r) =                       // ref :121
+            make_float4(decode_norm(off.x, sc.x, raw.x) * img_w, decode_norm(off.y, sc.y, raw.y) * img_h,
+                        decode_norm(off.z, sc.z, raw.z) * img_w, decode_norm(off.w, sc.w, raw.w) * img_h);
+    }
+    local = warp_sum(local);
+    if ((tid & 31) == 0 && local) atomicAdd(&s_count, local);
+    const int gl = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
+    for (int k0 = 0; k0 < K; k0 += ngrp) {
+        const int k = k0 + grp;
+        const int64_t r = (int64_t)b * K + (k < K ? k : K - 1);
+        const int arg = row_argmax8<0>(cls_rows + r * C, C, gl);           // ref :117
+        if (k < K && gl == 0) classes[r] = arg;
+    }
+    __syncthreads();
+    if (tid == 0) num_instances[b] = s_count;
+}
+
+// ---------------------------------------------------------------------------
+// Dense decode (extension).  Grid-stride over rows (= locations of the whole batch),
+// 8 lanes per row.  Candidates (sigmoid(loc) > thr) are appended to the image's list.
+// ---------------------------------------------------------------------------
+struct DenseDecodeParams {
+    const float *loc; const float *cls; const float *box_raw;
+    int batch, A, C;
+    const float4 *offsets; const float4 *scales; float img_w, img_h, score_thr;
+    int32_t *cand_count; int64_t cap;
+    unsigned long long *cand_key; float4 *cand_box; int32_t *cand_cls;
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(256) k_dense_decode(DenseDecodeParams p)
+{
+    const int gl = threadIdx.x & 7;
+    const int64_t rows = (int64_t)p.batch * p.A;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t rounds = (rows + ngrp - 1) / ngrp;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t row = it * ngrp + grp;
+        const bool ok = row < rows;
+        const int64_t rr = ok ? row : rows - 1;
+        const float x = __ldcs(p.loc + rr);
+        const int arg = row_argmax8<CPL>(p.cls + rr * p.C, p.C, gl);
+        if (ok && gl == 0) {
+            const float s = sigmoid_f(x);
+            if (s > p.score_thr) {
+                const int b = (int)(row / p.A), a = (int)(row - (int64_t)b * p.A);
+                const int slot = atomicAdd(p.cand_count + b, 1);
+                if (slot < p.cap) {
+                    const float4 raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + row);
+                    const float4 off = __ldg(p.offsets + a), sc = __ldg(p.scales + a);
+                    const int64_t o = (int64_t)b * p.cap + slot;
+                    p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) |
+                                    (unsigned long long)(0xffffffffu - (unsigned)a);
+                    p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
+                                                decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
+                    p.cand_cls[o] = arg;
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_zero_i32(int32_t *p, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
+}
+
+}  // namespace sihl
+
+using namespace sihl;
+
+extern "C" int sihl_od_topk(const float *loc_logits, int batch, int64_t num_anchors, int k, int64_t *idx,
+                            float *top_logits, void *stream)
+{
+    SIHL_CHECK_ARG(loc_logits && idx && top_logits, "NULL argument");
+    SIHL_CHECK_ARG(k >= 1 && k <= kTopkMaxK, "k=%d outside 1..%d", k, kTopkMaxK);
+    SIHL_CHECK_ARG(num_anchors >= k && num_anchors < (1ll << 30),
+                   "selected index k out of range: k=%d > %lld locations (torch.topk raises in the reference)", k,
+                   (long long)num_anchors);
+    if (batch <= 0) return SIHL_OD_OK;
+    int kp = 1;
+    while (kp < k) kp <<= 1;
+    k_topk<<<batch, kTopkThreads, 0, (cudaStream_t)stream>>>(loc_logits, (int)num_anchors, k, kp, idx, top_logits);
+    SIHL_CHECK_LAUNCH("k_topk");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_decode_rows(const float *top_logits, const int64_t *idx, int batch, int k,
+                                   const float *cls_rows, int num_classes, const float *box_rows,
+                                   const float *offsets, const float *scales, int img_w, int img_h,
+                                   int64_t *num_instances, float *scores, int64_t *classes, float *boxes, void *stream)
+{
+    SIHL_CHECK_ARG(top_logits && idx && cls_rows && box_rows && offsets && scales, "NULL input");
+    SIHL_CHECK_ARG(num_instances && scores && classes && boxes, "NULL output");
+    SIHL_CHECK_ARG(k >= 1 && num_classes >= 1 && img_w > 0 && img_h > 0, "bad sizes");
+    if (batch <= 0) return SIHL_OD_OK;
+    k_decode_rows<<<batch, 256, 0, (cudaStream_t)stream>>>(
+        top_logits, idx, k, cls_rows, num_classes, box_rows, reinterpret_cast<const float4 *>(offsets),
+        reinterpret_cast<const float4 *>(scales), (float)img_w, (float)img_h, num_instances, scores, classes, boxes);
+    SIHL_CHECK_LAUNCH("k_decode_rows");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_logits, const float *box_raw, int batch,
+                                    int64_t num_anchors, int num_classes, const float *offsets, const float *scales,
+                                    int img_w, int img_h, float score_thr, int32_t *cand_count, int64_t cand_capacity,
+                                    uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                                    void *stream)
+{
+    SIHL_CHECK_ARG(loc_logits && cls_logits && box_raw && offsets && scales, "NULL input");
+    SIHL_CHECK_ARG(cand_count && cand_key && cand_box && cand_cls, "NULL output");
+    SIHL_CHECK_ARG(batch >= 0 && num_anchors > 0 && num_anchors < (1ll << 30) && num_classes >= 1 && cand_capacity >= 1,
+                   "bad sizes");
+    SIHL_CHECK_ARG(img_w > 0 && img_h > 0, "image size %dx%d", img_w, img_h);
+    SIHL_CHECK_ARG(score_thr >= 0.f, "score_thr=%f must be >= 0 (scores are sigmoid outputs)", (double)score_thr);
+    if (batch == 0) return SIHL_OD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (zero_counts) {
+        k_zero_i32<<<(batch + 255) / 256, 256, 0, st>>>(cand_count, batch);
+        SIHL_CHECK_LAUNCH("k_zero_i32");
+    }
+    DenseDecodeParams p;
+    p.loc = loc_logits; p.cls = cls_logits; p.box_raw = box_raw; p.batch = batch; p.A = (int)num_anchors; p.C = num_classes;
+    p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
+    p.img_w = (float)img_w; p.img_h = (float)img_h; p.score_thr = score_thr;
+    p.cand_count = cand_count; p.cap = cand_capacity;
+    p.cand_key = reinterpret_cast<unsigned long long *>(cand_key); p.cand_box = reinterpret_cast<float4 *>(cand_box);
+    p.cand_cls = cand_cls;
+    const int64_t rows = (int64_t)batch * num_anchors;
+    int64_t blocks = (rows * 8 + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 8;          // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    const dim3 grid((unsigned)blocks);
+    if (num_classes == 80) k_dense_decode<10><<<grid, 256, 0, st>>>(p);
+    else if (num_classes == 16) k_dense_decode<2><<<grid, 256, 0, st>>>(p);
+    else if (num_classes == 8) k_dense_decode<1><<<grid, 256, 0, st>>>(p);
+    else k_dense_decode<0><<<grid, 256, 0, st>>>(p);
+    SIHL_CHECK_LAUNCH("k_dense_decode");
+    return SIHL_OD_OK;
+}

@@ -1,0 +1,51 @@
+// od_pos.cuh — device pieces of the positive-row losses, shared by the
+// fused resolve kernel (od_assign.cu) and the stand-alone forward/backward kernels (od_loss.cu).
+#pragma once
+
+#include "od_common.cuh"
+
+namespace sihl {
+
+// ref object_detection.py:189 and :195 — decoded (normalised) prediction and target of one positive.
+__device__ __forceinline__ void pos_boxes(float4 raw, float4 off, float4 sc, float4 gt, float img_w, float img_h,
+                                          Box4 *pred, Box4 *tgt)
+{
+    *pred = Box4{decode_norm(off.x, sc.x, raw.x), decode_norm(off.y, sc.y, raw.y),
+                 decode_norm(off.z, sc.z, raw.z), decode_norm(off.w, sc.w, raw.w)};
+    *tgt = Box4{gt.x / img_w, gt.y / img_h, gt.z / img_w, gt.w / img_h};
+}
+
+// CIoU loss of one positive (thread per row).  ref :189-197.
+__device__ __forceinline__ float pos_box_loss(float4 raw, float4 off, float4 sc, float4 gt, float img_w, float img_h)
+{
+    Box4 pred, tgt;
+    pos_boxes(raw, off, sc, gt, img_w, img_h, &pred, &tgt);
+    return ciou_loss_row(pred, tgt, nullptr);
+}
+
+// Row statistics of a class-logit row by a group of 8 lanes (4 rows per warp): max and
+// sum exp(z - max).  Every lane of the warp must call; lanes of a group share z and C.
+__device__ __forceinline__ void row_softmax_stats8(const float *__restrict__ z, int C, int gl, float *m_out,
+                                                   float *s_out)
+{
+    float m = -CUDART_INF_F;
+    for (int c = gl; c < C; c += 8) m = fmaxf(m, __ldg(z + c));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+    float s = 0.f;
+    for (int c = gl; c < C; c += 8) s += expf(__ldg(z + c) - m);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    *m_out = m;
+    *s_out = s;
+}
+
+// Cross-entropy of one row (ref :205-207): logsumexp(z) - z[target].
+__device__ __forceinline__ float ce_row_group8(const float *__restrict__ z, int C, int target, int gl)
+{
+    float m, s;
+    row_softmax_stats8(z, C, gl, &m, &s);
+    return (logf(s) + m) - __ldg(z + target);
+}
+
+}  // namespace sihl

@@ -1,0 +1,420 @@
+"""Tensor-level entry points of the detection-head path.
+
+Thin hand-off from ``torch.Tensor`` to the C ABI (``include/sihl_od.h``): check
+device / dtype / contiguity, allocate outputs with torch, pass raw device
+pointers and the current CUDA stream.  No arithmetic happens here and there is
+no non-CUDA path: CPU tensors are rejected.
+
+Reference lines (``/root/reference/src/sihl/heads/object_detection.py``) are cited
+per function; the same citations are in the header next to each C entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _native
+
+NUM_SUMS = 8
+MAX_TOPK = 16
+
+
+def _lib():
+    return _native.load()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: Tensor, dtype, name: str, ndim: Optional[int] = None) -> Tensor:
+    if not isinstance(t, Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: sihl_b200 kernels run on CUDA tensors only (got {t.device}); there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _levels_array(levels: Sequence[Tuple[int, int]]) -> np.ndarray:
+    arr = np.ascontiguousarray(np.asarray(levels, dtype=np.int32).reshape(-1, 2))
+    return arr
+
+
+# --------------------------------------------------------------------------- a1/a2
+_anchor_cache: Dict[tuple, Tuple[Tensor, Tensor, Tensor]] = {}
+
+
+def anchor_tables(levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, device,
+                  cache: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """``(offsets, scales, anchors)``, each ``[A,4]`` fp32 — ref :83-97 and :134-140.
+
+    The tables depend only on the feature-map shapes, so they are cached per
+    (levels, image size, device) instead of being rebuilt by ~40 launches per call.
+    """
+    device = torch.device(device)
+    key = (tuple(map(tuple, levels)), int(img_w), int(img_h), device.type, device.index)
+    if cache and key in _anchor_cache:
+        return _anchor_cache[key]
+    hw = _levels_array(levels)
+    A = int((hw[:, 0].astype(np.int64) * hw[:, 1]).sum())
+    with torch.cuda.device(device):
+        out = tuple(torch.empty((A, 4), dtype=torch.float32, device=device) for _ in range(3))
+        rc = _lib().sihl_od_anchors(hw.ctypes.data, len(hw), int(img_w), int(img_h), _p(out[0]), _p(out[1]), _p(out[2]),
+                                    _stream(device))
+    _native.check(rc, "sihl_od_anchors")
+    if cache:
+        _anchor_cache[key] = out
+    return out
+
+
+# --------------------------------------------------------------------------- ground truth
+@dataclass
+class GtBatch:
+    """Ragged ground truth as CSR on the device (what the kernels consume)."""
+    boxes: Tensor      # [sumG, 4] f32 xyxy px
+    classes: Tensor    # [sumG] i64
+    offsets: Tensor    # [B+1] i32
+    counts: List[int]  # host copy of the per-image counts (from tensor shapes: no sync)
+
+    @property
+    def batch_size(self) -> int:
+        return len(self.counts)
+
+    @property
+    def total(self) -> int:
+        return int(sum(self.counts))
+
+    @staticmethod
+    def from_lists(boxes: Sequence[Tensor], classes: Optional[Sequence[Tensor]], device) -> "GtBatch":
+        """ref :127-128 — per-image lists (possibly empty, possibly ``tv_tensors`` subclasses)."""
+        device = torch.device(device)
+        counts = [int(b.shape[0]) for b in boxes]
+        plain = [b.as_subclass(Tensor).reshape(-1, 4) for b in boxes]
+        if plain:
+            cat = torch.cat(plain).to(device=device, dtype=torch.float32).contiguous()
+        else:
+            cat = torch.empty((0, 4), dtype=torch.float32, device=device)
+        if classes is not None:
+            cls = torch.cat([c.as_subclass(Tensor).reshape(-1) for c in classes]) if len(classes) else torch.empty(0)
+            cls = cls.to(device=device, dtype=torch.int64).contiguous()
+            if cls.numel() != cat.shape[0]:
+                raise ValueError("classes and boxes disagree on the number of objects")
+        else:
+            cls = torch.zeros((cat.shape[0],), dtype=torch.int64, device=device)
+        off = np.zeros(len(counts) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(counts)
+        return GtBatch(cat, cls, torch.from_numpy(off).to(device), counts)
+
+
+# --------------------------------------------------------------------------- a3/a4
+def assign_select(anchors: Tensor, levels: Optional[Sequence[Tuple[int, int]]], img_w: int, img_h: int,
+                  gt: GtBatch, topk: int = 9, sums: Optional[Tensor] = None):
+    """Stage 1 of ``bbox_matching`` for the whole batch (ref :263-268, :277).
+
+    ``levels=None`` evaluates all ``A x G`` pairs (arbitrary anchors); otherwise
+    ``anchors`` must be the grid of :func:`anchor_tables` for ``levels``.
+    Returns ``(sel_anchor [sumG,k] i32, sel_val [sumG,k] f32, best_iou [sumG] f32)``.
+    """
+    anchors = _req(anchors, torch.float32, "anchors", 2)
+    dev = anchors.device
+    G = gt.total
+    sel_anchor = torch.empty((G, topk), dtype=torch.int32, device=dev)
+    sel_val = torch.empty((G, topk), dtype=torch.float32, device=dev)
+    best = torch.empty((G,), dtype=torch.float32, device=dev)
+    hw = None if levels is None else _levels_array(levels)
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_assign_select(
+            _p(anchors), anchors.shape[0], None if hw is None else hw.ctypes.data, 0 if hw is None else len(hw),
+            int(img_w), int(img_h), _p(_req(gt.boxes, torch.float32, "gt.boxes", 2)),
+            _p(_req(gt.offsets, torch.int32, "gt.offsets", 1)), gt.batch_size, G, int(topk),
+            _p(sel_anchor), _p(sel_val), _p(best), _p(sums), _stream(dev))
+    _native.check(rc, "sihl_od_assign_select")
+    return sel_anchor, sel_val, best
+
+
+def resolve_tiles(num_anchors: int) -> Tuple[int, int]:
+    n_tiles, tile = C.c_int(0), C.c_int(0)
+    _lib().sihl_od_resolve_tiles(int(num_anchors), C.byref(n_tiles), C.byref(tile))
+    return n_tiles.value, tile.value
+
+
+def assign_resolve(sel, gt: GtBatch, num_anchors: int, topk: int = 9, relative: bool = True,
+                   loc_logits: Optional[Tensor] = None, iou_preds: Optional[Tensor] = None,
+                   sums: Optional[Tensor] = None, want_positives: bool = False,
+                   fused: Optional[dict] = None):
+    """Stage 2 (ref :270-282) with the dense losses (ref :157-163, :175-180) fused when
+    ``loc_logits`` is given.  ``fused`` = dict(box_raw, cls_logits, offsets, scales, img_w, img_h)
+    additionally fuses the positive-row losses over dense maps.
+    Returns dict(assignment, iou, tile_pos_count, tile_pos_rows)."""
+    sel_anchor, sel_val, best = sel
+    dev = sel_anchor.device
+    B, A = gt.batch_size, int(num_anchors)
+    assignment = torch.empty((B, A), dtype=torch.int64, device=dev)
+    out_iou = torch.empty((B, A), dtype=torch.float32, device=dev)
+    tpc = tpr = None
+    if want_positives:
+        n_tiles, tile = resolve_tiles(A)
+        tpc = torch.empty((B * n_tiles,), dtype=torch.int32, device=dev)
+        tpr = torch.empty((B * n_tiles * tile,), dtype=torch.int32, device=dev)
+    f = fused or {}
+    box_raw = f.get("box_raw")
+    cls = f.get("cls_logits")
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_assign_resolve(
+            _p(sel_anchor), _p(sel_val), _p(best), _p(gt.offsets), B, A, int(topk), int(bool(relative)),
+            _p(None if loc_logits is None else _req(loc_logits, torch.float32, "loc_logits")),
+            _p(None if iou_preds is None else _req(iou_preds, torch.float32, "iou_preds")),
+            _p(assignment), _p(out_iou), _p(sums), _p(tpc), _p(tpr),
+            _p(None if box_raw is None else _req(box_raw, torch.float32, "box_raw")),
+            _p(None if cls is None else _req(cls, torch.float32, "cls_logits")),
+            0 if cls is None else int(cls.shape[-1]),
+            _p(f.get("offsets")), _p(f.get("scales")), int(f.get("img_w", 0)), int(f.get("img_h", 0)),
+            _p(gt.boxes), _p(gt.classes), _stream(dev))
+    _native.check(rc, "sihl_od_assign_resolve")
+    return dict(assignment=assignment, iou=out_iou, tile_pos_count=tpc, tile_pos_rows=tpr)
+
+
+def pos_compact(tile_pos_count: Tensor, tile_pos_rows: Tensor, batch: int, num_anchors: int,
+                capacity: Optional[int] = None):
+    """Tile lists -> ``pos_index`` in the row order of ``flat_feats[o2m_mask]`` (ref :182-184).
+    Returns ``(pos_index [capacity] i32, pos_total [1] i32, pos_image_offsets [B+1] i32)``."""
+    dev = tile_pos_count.device
+    cap = int(capacity if capacity is not None else tile_pos_rows.numel())
+    pos_index = torch.empty((max(cap, 1),), dtype=torch.int32, device=dev)
+    total = torch.zeros((1,), dtype=torch.int32, device=dev)
+    img_off = torch.zeros((batch + 1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_pos_compact(_p(tile_pos_count), _p(tile_pos_rows), int(batch), int(num_anchors),
+                                        _p(pos_index), cap, _p(total), _p(img_off), _stream(dev))
+    _native.check(rc, "sihl_od_pos_compact")
+    return pos_index, total, img_off
+
+
+def bbox_matching(anchors: Tensor, gt_boxes: Tensor, topk: int, relative: bool = False,
+                  levels: Optional[Sequence[Tuple[int, int]]] = None, img_size: Optional[Tuple[int, int]] = None):
+    """Drop-in for the static ``ObjectDetection.bbox_matching`` (ref :252-284), one image.
+
+    Returns ``(assignment int64 [A], iou fp32 [A])`` in canonical form: ``assignment`` is -1
+    wherever the returned iou is not > 0 (the reference leaves implementation-defined indices
+    there; nothing downstream reads them — SURVEY.md §3.4).
+    """
+    anchors = _req(anchors, torch.float32, "anchors", 2)
+    gt_boxes = gt_boxes.as_subclass(Tensor).to(device=anchors.device, dtype=torch.float32).reshape(-1, 4)
+    gt = GtBatch.from_lists([gt_boxes], None, anchors.device)
+    A = anchors.shape[0]
+    if gt.total == 0:                                            # ref :258-261
+        return (torch.full((A,), -1, dtype=torch.int64, device=anchors.device),
+                torch.zeros((A,), dtype=torch.float32, device=anchors.device))
+    w, h = img_size if img_size is not None else (0, 0)
+    sel = assign_select(anchors, levels, w, h, gt, topk)
+    out = assign_resolve(sel, gt, A, topk, relative)
+    return out["assignment"][0], out["iou"][0]
+
+
+# --------------------------------------------------------------------------- a5-a10
+def new_sums(device) -> Tensor:
+    return torch.zeros((NUM_SUMS,), dtype=torch.float64, device=device)
+
+
+def dense_loss(loc_logits: Tensor, iou_preds: Optional[Tensor], rel_iou: Tensor, sums: Tensor) -> Tensor:
+    """ref :157-163, :175-180 — accumulates into ``sums`` (fp64 [8])."""
+    dev = rel_iou.device
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_dense_loss(_p(_req(loc_logits, torch.float32, "loc_logits")),
+                                       _p(None if iou_preds is None else _req(iou_preds, torch.float32, "iou_preds")),
+                                       _p(_req(rel_iou, torch.float32, "rel_iou")), rel_iou.numel(), _p(sums), _stream(dev))
+    _native.check(rc, "sihl_od_dense_loss")
+    return sums
+
+
+def _pos_args(pos_index, n_pos_dev, capacity, num_anchors, rel_iou, assignment, offsets, scales, img_w, img_h,
+              gt: GtBatch, box_raw, cls_logits, dense_rows):
+    return [_p(pos_index), _p(n_pos_dev), int(capacity), int(num_anchors), _p(rel_iou), _p(assignment), _p(offsets),
+            _p(scales), int(img_w), int(img_h), _p(gt.boxes), _p(gt.classes), _p(gt.offsets),
+            _p(None if box_raw is None else _req(box_raw, torch.float32, "box_raw")),
+            _p(None if cls_logits is None else _req(cls_logits, torch.float32, "cls_logits")),
+            0 if cls_logits is None else int(cls_logits.shape[-1]), int(bool(dense_rows))]
+
+
+def pos_loss(pos_index: Tensor, n_pos_dev: Optional[Tensor], capacity: int, num_anchors: int, rel_iou: Tensor,
+             assignment: Tensor, offsets: Tensor, scales: Tensor, img_w: int, img_h: int, gt: GtBatch,
+             box_raw: Optional[Tensor], cls_logits: Optional[Tensor], dense_rows: bool, sums: Tensor) -> Tensor:
+    """ref :187-208 — weighted CIoU loss and cross-entropy over the positive rows."""
+    dev = rel_iou.device
+    args = _pos_args(pos_index, n_pos_dev, capacity, num_anchors, rel_iou, assignment, offsets, scales, img_w, img_h,
+                     gt, box_raw, cls_logits, dense_rows)
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_pos_loss(*args, _p(sums), _stream(dev))
+    _native.check(rc, "sihl_od_pos_loss")
+    return sums
+
+
+def loss_finalize(sums: Tensor) -> Tensor:
+    """ref :163-172, :180, :197, :208, :210 -> fp32 [5] = [location, box, class, iou, total]."""
+    out = torch.empty((5,), dtype=torch.float32, device=sums.device)
+    with torch.cuda.device(sums.device):
+        rc = _lib().sihl_od_loss_finalize(_p(sums), _p(out), _stream(sums.device))
+    _native.check(rc, "sihl_od_loss_finalize")
+    return out
+
+
+def dense_loss_bwd(loc_logits: Tensor, iou_preds: Optional[Tensor], rel_iou: Tensor, sums: Tensor,
+                   grad_terms: Optional[Tensor], want_dloc: bool = True, want_diou: bool = True):
+    dev = rel_iou.device
+    dloc = torch.empty_like(loc_logits, dtype=torch.float32) if want_dloc else None
+    diou = torch.empty_like(iou_preds, dtype=torch.float32) if (want_diou and iou_preds is not None) else None
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_dense_loss_bwd(_p(loc_logits), _p(iou_preds), _p(rel_iou), rel_iou.numel(), _p(sums),
+                                           _p(grad_terms), _p(dloc), _p(diou), _stream(dev))
+    _native.check(rc, "sihl_od_dense_loss_bwd")
+    return dloc, diou
+
+
+def pos_loss_bwd(pos_index, n_pos_dev, capacity, num_anchors, rel_iou, assignment, offsets, scales, img_w, img_h,
+                 gt: GtBatch, box_raw, cls_logits, dense_rows, sums, grad_terms, dbox=None, dcls=None):
+    dev = rel_iou.device
+    if dbox is None and box_raw is not None:
+        dbox = torch.zeros_like(box_raw) if dense_rows else torch.empty_like(box_raw)
+    if dcls is None and cls_logits is not None:
+        dcls = torch.zeros_like(cls_logits) if dense_rows else torch.empty_like(cls_logits)
+    args = _pos_args(pos_index, n_pos_dev, capacity, num_anchors, rel_iou, assignment, offsets, scales, img_w, img_h,
+                     gt, box_raw, cls_logits, dense_rows)
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_pos_loss_bwd(*args, _p(sums), _p(grad_terms), _p(dbox), _p(dcls), _stream(dev))
+    _native.check(rc, "sihl_od_pos_loss_bwd")
+    return dbox, dcls
+
+
+# --------------------------------------------------------------------------- a11
+def topk_locations(loc_logits: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """ref :109 — ``loc_logits.topk(k, dim=1)``: ``(values [B,k] f32, indices [B,k] i64)``,
+    sorted descending, exact ties broken towards the lowest index."""
+    loc = _req(loc_logits, torch.float32, "loc_logits", 2)
+    B, A = loc.shape
+    idx = torch.empty((B, k), dtype=torch.int64, device=loc.device)
+    top = torch.empty((B, k), dtype=torch.float32, device=loc.device)
+    with torch.cuda.device(loc.device):
+        rc = _lib().sihl_od_topk(_p(loc), B, A, int(k), _p(idx), _p(top), _stream(loc.device))
+    _native.check(rc, "sihl_od_topk")
+    return top, idx
+
+
+def decode_rows(top_logits: Tensor, idx: Tensor, cls_rows: Tensor, box_rows: Tensor, offsets: Tensor, scales: Tensor,
+                img_w: int, img_h: int):
+    """ref :113-121 — ``(num_instances [B] i64, scores [B,K], classes [B,K] i64, boxes [B,K,4])``."""
+    top = _req(top_logits, torch.float32, "top_logits", 2)
+    B, K = top.shape
+    dev = top.device
+    cls_rows = _req(cls_rows, torch.float32, "cls_rows", 3)
+    num = torch.empty((B,), dtype=torch.int64, device=dev)
+    scores = torch.empty((B, K), dtype=torch.float32, device=dev)
+    classes = torch.empty((B, K), dtype=torch.int64, device=dev)
+    boxes = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_decode_rows(_p(top), _p(_req(idx, torch.int64, "idx", 2)), B, K, _p(cls_rows),
+                                        int(cls_rows.shape[-1]), _p(_req(box_rows, torch.float32, "box_rows", 3)),
+                                        _p(offsets), _p(scales), int(img_w), int(img_h), _p(num), _p(scores),
+                                        _p(classes), _p(boxes), _stream(dev))
+    _native.check(rc, "sihl_od_decode_rows")
+    return num, scores, classes, boxes
+
+
+# --------------------------------------------------------------------------- a15 (extension)
+@dataclass
+class CandidateBuffers:
+    count: Tensor      # [B] i32
+    key: Tensor        # [B, cap] u64 (as int64 storage)
+    box: Tensor        # [B, cap, 4] f32
+    cls: Tensor        # [B, cap] i32
+    capacity: int
+    workspace: Optional[Tensor]
+
+    @staticmethod
+    def allocate(batch: int, capacity: int, device) -> "CandidateBuffers":
+        ws_bytes = int(_lib().sihl_od_nms_workspace_bytes(int(batch), int(capacity)))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device) if ws_bytes else None
+        return CandidateBuffers(torch.zeros((batch,), dtype=torch.int32, device=device),
+                                torch.empty((batch, capacity), dtype=torch.int64, device=device),
+                                torch.empty((batch, capacity, 4), dtype=torch.float32, device=device),
+                                torch.empty((batch, capacity), dtype=torch.int32, device=device), int(capacity), ws)
+
+
+def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offsets: Tensor, scales: Tensor,
+                 img_w: int, img_h: int, score_thr: float, cand: CandidateBuffers, zero_counts: bool = True) -> None:
+    loc = _req(loc_logits, torch.float32, "loc_logits", 2)
+    cls = _req(cls_logits, torch.float32, "cls_logits", 3)
+    box = _req(box_raw, torch.float32, "box_raw", 3)
+    B, A = loc.shape
+    with torch.cuda.device(loc.device):
+        rc = _lib().sihl_od_dense_decode(_p(loc), _p(cls), _p(box), B, A, int(cls.shape[-1]), _p(offsets), _p(scales),
+                                         int(img_w), int(img_h), float(score_thr), _p(cand.count), cand.capacity,
+                                         _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts), _stream(loc.device))
+    _native.check(rc, "sihl_od_dense_decode")
+
+
+def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Optional[tuple] = None):
+    dev = cand.count.device
+    if out is None:
+        out = (torch.empty((batch,), dtype=torch.int64, device=dev), torch.empty((batch, k), dtype=torch.float32, device=dev),
+               torch.empty((batch, k), dtype=torch.int64, device=dev), torch.empty((batch, k, 4), dtype=torch.float32, device=dev))
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_nms_topk(_p(cand.count), cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(batch),
+                                     float(iou_thr), int(k), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                     _p(cand.workspace), _stream(dev))
+    _native.check(rc, "sihl_od_nms_topk")
+    return out
+
+
+def dense_postprocess(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, levels, img_w: int, img_h: int,
+                      score_thr: float = 0.05, iou_thr: float = 0.5, max_instances: int = 100,
+                      cand: Optional[CandidateBuffers] = None):
+    """Extension (no reference counterpart): dense decode of every location + class-aware NMS.
+    Output format of ``ObjectDetection.forward`` (ref :122), zero padded past ``num_instances``."""
+    B, A = loc_logits.shape
+    offsets, scales, _ = anchor_tables(levels, img_w, img_h, loc_logits.device)
+    if cand is None:
+        cand = CandidateBuffers.allocate(B, A, loc_logits.device)
+    dense_decode(loc_logits, cls_logits, box_raw, offsets, scales, img_w, img_h, score_thr, cand)
+    return nms_topk(cand, B, iou_thr, max_instances)
+
+
+def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: float,
+                seg_offsets: Optional[Tensor] = None):
+    """``torchvision.ops.batched_nms`` signature (exact per-class semantics, stable order).
+
+    With ``seg_offsets`` (int32 ``[n_images+1]``) the call handles several images at once and
+    returns ``(keep [N] i64, keep_count [n_images] i32)``; without it, the kept indices of the
+    single segment (one deliberate sync to size the result, like torchvision)."""
+    boxes = _req(boxes, torch.float32, "boxes", 2)
+    scores = _req(scores, torch.float32, "scores", 1)
+    idxs = _req(idxs, torch.int64, "idxs", 1)
+    dev = boxes.device
+    N = scores.numel()
+    single = seg_offsets is None
+    if single:
+        seg_offsets = torch.tensor([0, N], dtype=torch.int32, device=dev)
+    n_images = seg_offsets.numel() - 1
+    keep = torch.empty((max(N, 1),), dtype=torch.int64, device=dev)
+    count = torch.zeros((n_images,), dtype=torch.int32, device=dev)
+    ws_bytes = int(_lib().sihl_od_batched_nms_workspace_bytes(N))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_batched_nms(_p(boxes), _p(scores), _p(idxs), _p(seg_offsets), n_images, N,
+                                        float(iou_threshold), _p(keep), _p(count), _p(ws), _stream(dev))
+    _native.check(rc, "sihl_od_batched_nms")
+    if single:
+        return keep[: int(count.item())]
+    return keep[:N], count
