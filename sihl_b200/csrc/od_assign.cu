@@ -415,8 +415,9 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
     SIHL_CHECK_ARG((tile_pos_count == nullptr) == (tile_pos_rows == nullptr), "tile_pos_count and tile_pos_rows go together");
     SIHL_CHECK_ARG(iou_preds == nullptr || loc_logits != nullptr, "iou_preds needs loc_logits");
     const bool fused = box_raw != nullptr || cls_logits != nullptr;
-    SIHL_CHECK_ARG(!fused || (sums && gt_boxes && gt_classes && offsets && scales && img_w > 0 && img_h > 0),
-                   "fused positive losses need sums, gt, offsets, scales and the image size");
+    // gt_boxes / gt_classes may be NULL when the batch holds no ground truth at all
+    SIHL_CHECK_ARG(!fused || (sums && offsets && scales && img_w > 0 && img_h > 0),
+                   "fused positive losses need sums, offsets, scales and the image size");
     SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "num_classes=%d", num_classes);
     SIHL_CHECK_ARG(loc_logits == nullptr || sums != nullptr, "dense losses need sums");
     if (batch == 0 || num_anchors == 0) return SIHL_OD_OK;

@@ -198,9 +198,10 @@ static int fill_pos(PosParams *p, const int32_t *pos_index, const int32_t *n_pos
 {
     SIHL_CHECK_ARG(pos_index && rel_iou && assignment && gt_offsets, "NULL argument");
     SIHL_CHECK_ARG(capacity >= 0 && num_anchors > 0 && num_anchors < (1ll << 30), "bad sizes");
-    SIHL_CHECK_ARG(box_raw == nullptr || (offsets && scales && gt_boxes && img_w > 0 && img_h > 0),
-                   "box loss needs offsets, scales, gt_boxes and the image size");
-    SIHL_CHECK_ARG(cls_logits == nullptr || (gt_classes && num_classes > 0), "class loss needs gt_classes and num_classes");
+    // gt_boxes / gt_classes may be NULL when the batch holds no ground truth at all (then no row is positive)
+    SIHL_CHECK_ARG(box_raw == nullptr || (offsets && scales && img_w > 0 && img_h > 0),
+                   "box loss needs offsets, scales and the image size");
+    SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "class loss needs num_classes");
     p->pos_index = pos_index; p->n_pos_dev = n_pos_dev; p->capacity = capacity; p->num_anchors = (int)num_anchors;
     p->rel = rel_iou; p->assignment = assignment;
     p->offsets = reinterpret_cast<const float4 *>(offsets); p->scales = reinterpret_cast<const float4 *>(scales);

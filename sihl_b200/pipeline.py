@@ -1,0 +1,135 @@
+"""Steady-state pipeline over dense head outputs: assign + losses and dense decode + NMS
+with every buffer preallocated, two CUDA streams and (optionally) one CUDA graph per step.
+
+This is the whole-batch form of the hot path that ``bench.py`` measures
+(BASELINE.json metric: det-head images/sec, assign + loss + NMS).  Per step and GPU:
+
+  train chain  (stream A): k_assign_select -> k_assign_resolve (dense + positive losses fused)
+                           -> k_loss_finalize                      [3 launches]
+  infer chain  (stream B): k_dense_decode (zeroing its counters in a 1-block launch first)
+                           -> k_nms                                [3 launches]
+
+The two chains share no data, so they run concurrently: the assignment is FP32-ALU/latency
+bound, the dense decode is HBM bound (SURVEY.md §8d caveat).  Across GPUs the only exchange
+is ``sums`` (8 doubles), all-reduced between resolve and finalize when ``world_size > 1``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native, ops
+
+LAUNCHES_PER_STEP = 6     # select, resolve, finalize, zero, dense_decode, nms
+
+
+@dataclass
+class StepInputs:
+    """Device-resident inputs of one step (one batch shard)."""
+    loc_logits: Tensor     # [B, A] f32
+    iou_preds: Tensor      # [B, A] f32
+    box_raw: Tensor        # [B, A, 4] f32
+    cls_logits: Tensor     # [B, A, C] f32
+    gt: ops.GtBatch
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.loc_logits, self.iou_preds, self.box_raw, self.cls_logits, self.gt.boxes, self.gt.classes,
+                    self.gt.offsets))
+
+
+@dataclass
+class StepOutputs:
+    assignment: Tensor     # [B, A] i64
+    rel_iou: Tensor        # [B, A] f32
+    sums: Tensor           # [8] f64
+    losses: Tensor         # [5] f32: location, box, class, iou, total
+    num_instances: Tensor  # [B] i64
+    scores: Tensor         # [B, K] f32
+    classes: Tensor        # [B, K] i64
+    boxes: Tensor          # [B, K, 4] f32
+
+
+class DetectionHeadPipeline:
+    def __init__(self, levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, batch: int, num_classes: int,
+                 max_gt_total: int, device, topk: int = 9, max_instances: int = 100, score_thr: float = 0.05,
+                 iou_thr: float = 0.5, cand_capacity: Optional[int] = None):
+        self.levels = [tuple(int(v) for v in l) for l in levels]
+        self.img_w, self.img_h, self.B, self.C = int(img_w), int(img_h), int(batch), int(num_classes)
+        self.device = torch.device(device)
+        self.topk, self.K, self.score_thr, self.iou_thr = int(topk), int(max_instances), float(score_thr), float(iou_thr)
+        self.offsets, self.scales, self.anchors = ops.anchor_tables(self.levels, img_w, img_h, self.device)
+        self.A = int(self.anchors.shape[0])
+        self._hw = ops._levels_array(self.levels)
+        dev, B, A, K = self.device, self.B, self.A, self.K
+        self.sel_anchor = torch.empty((max_gt_total, topk), dtype=torch.int32, device=dev)
+        self.sel_val = torch.empty((max_gt_total, topk), dtype=torch.float32, device=dev)
+        self.best_iou = torch.empty((max_gt_total,), dtype=torch.float32, device=dev)
+        self.max_gt_total = int(max_gt_total)
+        self.cand = ops.CandidateBuffers.allocate(B, int(cand_capacity or A), dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.lib = _native.load()
+
+    def new_outputs(self) -> StepOutputs:
+        dev, B, A, K = self.device, self.B, self.A, self.K
+        return StepOutputs(
+            assignment=torch.empty((B, A), dtype=torch.int64, device=dev),
+            rel_iou=torch.empty((B, A), dtype=torch.float32, device=dev),
+            sums=torch.zeros((8,), dtype=torch.float64, device=dev),
+            losses=torch.zeros((5,), dtype=torch.float32, device=dev),
+            num_instances=torch.empty((B,), dtype=torch.int64, device=dev),
+            scores=torch.empty((B, K), dtype=torch.float32, device=dev),
+            classes=torch.empty((B, K), dtype=torch.int64, device=dev),
+            boxes=torch.empty((B, K, 4), dtype=torch.float32, device=dev))
+
+    # -- the two chains (enqueue only; no sync) --------------------------------------------
+    def train_chain(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> None:
+        lib, st = self.lib, torch.cuda.current_stream(self.device).cuda_stream
+        gt = x.gt
+        assert gt.total <= self.max_gt_total and gt.batch_size == self.B
+        p = ops._p
+        _native.check(lib.sihl_od_assign_select(
+            p(self.anchors), self.A, self._hw.ctypes.data, len(self._hw), self.img_w, self.img_h, p(gt.boxes),
+            p(gt.offsets), self.B, gt.total, self.topk, p(self.sel_anchor), p(self.sel_val), p(self.best_iou),
+            p(out.sums), st), "sihl_od_assign_select")
+        _native.check(lib.sihl_od_assign_resolve(
+            p(self.sel_anchor), p(self.sel_val), p(self.best_iou), p(gt.offsets), self.B, self.A, self.topk, 1,
+            p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), None, None,
+            p(x.box_raw), p(x.cls_logits), self.C, p(self.offsets), p(self.scales), self.img_w, self.img_h,
+            p(gt.boxes), p(gt.classes), st), "sihl_od_assign_resolve")
+        if finalize:
+            self.finalize(out)
+
+    def finalize(self, out: StepOutputs) -> None:
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self.lib.sihl_od_loss_finalize(ops._p(out.sums), ops._p(out.losses), st), "sihl_od_loss_finalize")
+
+    def infer_chain(self, x: StepInputs, out: StepOutputs) -> None:
+        ops.dense_decode(x.loc_logits, x.cls_logits, x.box_raw, self.offsets, self.scales, self.img_w, self.img_h,
+                         self.score_thr, self.cand, zero_counts=True)
+        ops.nms_topk(self.cand, self.B, self.iou_thr, self.K, (out.num_instances, out.scores, out.classes, out.boxes))
+
+    def step(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> None:
+        """One pass of the hot path over one batch: both chains, concurrently, on two streams."""
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.infer_chain(x, out)
+        self.train_chain(x, out, finalize)
+        main.wait_stream(self.side)
+
+    def capture(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> torch.cuda.CUDAGraph:
+        """Capture :meth:`step` for fixed buffers into a CUDA graph (one host launch per step)."""
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(warm):
+            self.step(x, out, finalize)
+        torch.cuda.current_stream(self.device).wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(x, out, finalize)
+        return graph

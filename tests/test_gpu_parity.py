@@ -202,7 +202,8 @@ def test_loss_backward_vs_reference_autograd(name, dense_rows):
     res, P, pos_index = r["res"], r["P"], r["pos_index"]
     dloc, diou = ops.dense_loss_bwd(loc, iou, res["iou"], r["sums"], None)
     np.testing.assert_allclose(dloc.cpu().numpy().reshape(-1), gold["dloc"].reshape(-1), rtol=2e-5, atol=1e-9)
-    np.testing.assert_allclose(diou.cpu().numpy().reshape(-1), gold["diou"].reshape(-1), rtol=2e-5, atol=1e-9)
+    # rel_iou of the CPU-run reference differs by ~1e-7 absolute (atan last bit); 2*(p-rel)/R inherits it
+    np.testing.assert_allclose(diou.cpu().numpy().reshape(-1), gold["diou"].reshape(-1), rtol=2e-5, atol=2e-8)
     rows = gold["grad_rows"]
     np.testing.assert_array_equal(pos_index.cpu().numpy(), rows)
     if dense_rows:
@@ -227,7 +228,7 @@ def test_dense_loss_standalone_matches_fused():
     sums2 = ops.new_sums(DEV)
     ops.dense_loss(loc, iou, r["res"]["iou"], sums2)
     a, b = r["sums"].cpu().numpy(), sums2.cpu().numpy()
-    np.testing.assert_allclose(b[[0, 1, 2, 3, 6]], a[[0, 1, 2, 3, 6]], rtol=1e-9)
+    np.testing.assert_allclose(b[[0, 1, 2, 3, 6]], a[[0, 1, 2, 3, 6]], rtol=1e-7)   # fp32 partials grouped differently
 
 
 # --------------------------------------------------------------------------- a11
