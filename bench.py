@@ -285,7 +285,7 @@ def run_ours(args, w, world, rank, local_rank):
     # ---- sanity of what was timed (not timed): losses finite, detections present
     losses = outs[0].losses.cpu().tolist()
     P_bar = float(outs[0].sums[6].item()) / B
-    cand_mean = float(pipe.cand.count.float().mean().item())
+    cand_mean = None      # measured in the stand-alone decode loop below (k_nms* zero the counters they consume)
     det_mean = float(outs[(args.steps - 1) % n_sets].num_instances.float().mean().item())
 
     result = {"ms": ms, "value": value, "losses": losses, "P_bar": P_bar, "cand_mean": cand_mean, "det_mean": det_mean}
@@ -317,6 +317,7 @@ def run_ours(args, w, world, rank, local_rank):
     torch.cuda.synchronize()
     if sampler: sampler.mark()
     pipe.cand.count = counts_saved
+    cand_mean = float(scratch[:iters].float().mean().item())
     k_ms = k0.elapsed_time(k1) / iters
     # algorithmic bytes per launch: every class logit and location logit once (4*A*(C+1) per image) + per
     # candidate 16 B raw box read and 28 B (key 8, box 16, class 4) written

@@ -78,13 +78,18 @@ SIHL_OD_API int sihl_od_anchors(const int32_t *level_hw_host, int n_levels, int 
  *     for these levels; candidates are enumerated from the gt extent (every
  *     anchor with CIoU > 0 overlaps the gt) and evaluated on the given table.
  *   level_hw_host == NULL: arbitrary anchors, all A x G pairs are evaluated.
+ * anchor_terms (optional, may be NULL): [A,4] = (area, cx, cy, atan(w/h)) per anchor as
+ * written by sihl_od_anchor_terms() — the per-anchor half of the CIoU hoisted out of the
+ * pair loop (same fp32 operations, so results are unchanged) and cacheable with the tables.
  * Outputs: sel_anchor int32 [sumG, topk] (-1 = unused slot), sel_val fp32
  * [sumG, topk] (descending), best_iou fp32 [sumG].  If sums != NULL the 8
  * doubles are zeroed here (saves a memset launch per step).
  * Errors: topk outside 1..SIHL_OD_MAX_TOPK, A < topk with sumG > 0 (torch.topk
  * raises in the reference), n_levels > SIHL_OD_MAX_LEVELS, level sizes that do
  * not add up to A. */
-SIHL_OD_API int sihl_od_assign_select(const float *anchors, int64_t num_anchors,
+SIHL_OD_API int sihl_od_anchor_terms(const float *anchors, int64_t num_anchors, float *terms, void *stream);
+
+SIHL_OD_API int sihl_od_assign_select(const float *anchors, const float *anchor_terms, int64_t num_anchors,
                           const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
                           const float *gt_boxes, const int32_t *gt_offsets, int batch, int total_gt,
                           int topk, int32_t *sel_anchor, float *sel_val, float *best_iou,
@@ -99,14 +104,14 @@ SIHL_OD_API int sihl_od_assign_select(const float *anchors, int64_t num_anchors,
  *   out_iou fp32 [B,A].
  * If loc_logits != NULL (and optionally iou_preds) the BCE / MSE reductions of
  * ref :157-163, :175-180 are accumulated into sums[0..3,6] in the same pass.
- * Positive compaction (ref :182-184 order = row-major (b,a)): if
- * tile_pos_count != NULL the kernel writes, per (image, tile), the number of
- * positives and their flat indices b*A+a in ascending order into
- * tile_pos_rows [B * n_tiles * tile]; query the geometry with
- * sihl_od_resolve_tiles().  sihl_od_pos_compact() turns that into pos_index.
- * If box_raw/cls_logits != NULL (dense maps [B,A,4] / [B,A,C]) the positive
- * losses of ref :187-208 are fused too (sums[4], sums[5]); this needs offsets,
- * scales, gt_classes. */
+ * Positive lists (ref :182-184 order = row-major (b,a)): if tile_pos_count !=
+ * NULL the kernel writes, per (image, tile), the number of positives and their
+ * flat indices b*A+a in ascending order into tile_pos_rows [B * n_tiles * tile];
+ * query the geometry with sihl_od_resolve_tiles().  sihl_od_pos_compact() turns
+ * the lists into one pos_index (compact rows for the reference's gathered-row
+ * MLPs); sihl_od_pos_loss_tiles() consumes them directly for dense maps.
+ * prefetch_box_raw / prefetch_cls_logits (optional dense maps [B*A,4] / [B*A,C]):
+ * the rows of the positives are prefetched into L2 for that next kernel. */
 SIHL_OD_API int sihl_od_resolve_tiles(int64_t num_anchors, int *n_tiles, int *tile);
 
 SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *sel_val, const float *best_iou,
@@ -114,9 +119,7 @@ SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *s
                            const float *loc_logits, const float *iou_preds,
                            int64_t *assignment, float *out_iou, double *sums,
                            int32_t *tile_pos_count, int32_t *tile_pos_rows,
-                           const float *box_raw, const float *cls_logits, int num_classes,
-                           const float *offsets, const float *scales, int img_w, int img_h,
-                           const float *gt_boxes, const int64_t *gt_classes,
+                           const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
                            void *stream);
 
 /* pos_index int32 [capacity] (flat b*A+a, ascending), pos_total int32 [1],
@@ -146,6 +149,16 @@ SIHL_OD_API int sihl_od_pos_loss(const int32_t *pos_index, const int32_t *n_pos_
                      const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
                      const float *box_raw, const float *cls_logits, int num_classes, int dense_rows,
                      double *sums, void *stream);
+
+/* The same positive-row losses over DENSE maps (box_raw [B*A,4], cls_logits
+ * [B*A,C]) taken straight from the per-tile lists of sihl_od_assign_resolve:
+ * no compaction pass, no host round trip.  Accumulates sums[4], sums[5]. */
+SIHL_OD_API int sihl_od_pos_loss_tiles(const int32_t *tile_pos_count, const int32_t *tile_pos_rows, int batch,
+                           int64_t num_anchors, const float *rel_iou, const int64_t *assignment,
+                           const float *offsets, const float *scales, int img_w, int img_h,
+                           const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                           const float *box_raw, const float *cls_logits, int num_classes,
+                           double *sums, void *stream);
 
 /* ref :163-172, :180, :197, :208, :210 — losses fp32 [5] =
  * [location, box, class, iou, total]; early-out when sums[6] == 0. */
@@ -210,14 +223,16 @@ SIHL_OD_API int sihl_od_dense_decode(const float *loc_logits, const float *cls_l
  * (ops/boxes.py:102-120): visit by (score desc, location asc); a kept box
  * suppresses later boxes of the same class with IoU > iou_thr.  Emits the first
  * K kept detections per image, zero padded, in the reference forward()'s output
- * format.  workspace: sihl_od_nms_workspace_bytes(batch, cand_capacity). */
+ * format.  workspace: sihl_od_nms_workspace_bytes(batch, cand_capacity).
+ * reset_counts != 0: cand_count[b] is zeroed once consumed, so the next
+ * sihl_od_dense_decode needs no zeroing launch. */
 SIHL_OD_API size_t sihl_od_nms_workspace_bytes(int batch, int64_t cand_capacity);
 
 SIHL_OD_API int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacity,
                      const uint64_t *cand_key, const float *cand_box, const int32_t *cand_cls,
                      int batch, float iou_thr, int k,
                      int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
-                     void *workspace, void *stream);
+                     void *workspace, int reset_counts, void *stream);
 
 /* Stand-alone batched NMS with torchvision.ops.batched_nms's signature, over
  * `n_images` independent segments: boxes [N,4], scores [N], classes int64 [N],

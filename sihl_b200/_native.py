@@ -22,9 +22,11 @@ _SIGNATURES = {
     "sihl_od_version": (C.c_int, []),
     "sihl_od_last_error_string": (C.c_char_p, []),
     "sihl_od_anchors": (I, [P, I, I, I, P, P, P, P]),
-    "sihl_od_assign_select": (I, [P, I64, P, I, I, I, P, P, I, I, I, P, P, P, P, P]),
+    "sihl_od_anchor_terms": (I, [P, I64, P, P]),
+    "sihl_od_assign_select": (I, [P, P, I64, P, I, I, I, P, P, I, I, I, P, P, P, P, P]),
     "sihl_od_resolve_tiles": (I, [I64, P, P]),
-    "sihl_od_assign_resolve": (I, [P, P, P, P, I, I64, I, I, P, P, P, P, P, P, P, P, P, I, P, P, I, I, P, P, P]),
+    "sihl_od_assign_resolve": (I, [P, P, P, P, I, I64, I, I, P, P, P, P, P, P, P, P, P, I, P]),
+    "sihl_od_pos_loss_tiles": (I, [P, P, I, I64, P, P, P, P, I, I, P, P, P, P, P, I, P, P]),
     "sihl_od_pos_compact": (I, [P, P, I, I64, P, I64, P, P, P]),
     "sihl_od_dense_loss": (I, [P, P, P, I64, P, P]),
     "sihl_od_pos_loss": (I, [P, P, I64, I64, P, P, P, P, I, I, P, P, P, P, P, I, I, P, P]),
@@ -35,7 +37,7 @@ _SIGNATURES = {
     "sihl_od_decode_rows": (I, [P, P, I, I, P, I, P, P, P, I, I, P, P, P, P, P]),
     "sihl_od_dense_decode": (I, [P, P, P, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_nms_workspace_bytes": (C.c_size_t, [I, I64]),
-    "sihl_od_nms_topk": (I, [P, I64, P, P, P, I, F, I, P, P, P, P, P, P]),
+    "sihl_od_nms_topk": (I, [P, I64, P, P, P, I, F, I, P, P, P, P, P, I, P]),
     "sihl_od_batched_nms_workspace_bytes": (C.c_size_t, [I64]),
     "sihl_od_batched_nms": (I, [P, P, P, P, I, I64, F, P, P, P, P]),
 }
@@ -57,8 +59,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
-        if build_if_missing:
+        override = os.environ.get("SIHL_B200_LIB")      # developer builds (e.g. -DSIHL_PHASE_TIMING)
+        path = override or _build.LIB_PATH
+        if build_if_missing and not override:
             try:
                 path = _build.build()
             except Exception as exc:                       # nvcc absent or compile error

@@ -1,6 +1,5 @@
 // od_assign.cu — CIoU top-k label assignment and the streaming
-// resolve pass with the dense losses (a5/a6), positive compaction (a7) and, for dense
-// maps, the positive-row losses (a8/a9) fused in.
+// resolve pass with the dense losses (a5/a6) and the positive lists (a7) fused in.
 //
 // Replaces, per training step, the Python loop of B calls to ObjectDetection.bbox_matching
 // (ref: src/sihl/heads/object_detection.py:143-148, :252-284), ~100 ATen launches, ~35
@@ -33,13 +32,14 @@ int fill_level_table(const int32_t *level_hw_host, int n_levels, LevelTable *lv)
 // ---------------------------------------------------------------------------
 // Stage 1: select
 // ---------------------------------------------------------------------------
-constexpr int kSelWarps = 8;
+constexpr int kSelWarps = 4;
 constexpr int kBufCap = 64;
 
 struct SelectParams {
     LevelTable lv;
+    float inv_sx[SIHL_OD_MAX_LEVELS], inv_sy[SIHL_OD_MAX_LEVELS];   // cells per pixel (host-computed, only sizes the
+    float cell_area[SIHL_OD_MAX_LEVELS];                            // conservative candidate window / the IoU bound)
     int use_levels;
-    float img_w, img_h;
     int num_anchors;
     int topk;
 };
@@ -52,11 +52,18 @@ __device__ __forceinline__ int select_compress(float *bv, int *bi, int cnt, int 
     const float v0 = h0 ? bv[lane] : 0.f, v1 = h1 ? bv[lane + 32] : 0.f;
     const int a0 = h0 ? bi[lane] : 0, a1 = h1 ? bi[lane + 32] : 0;
     int r0 = 0, r1 = 0;
-    for (int i = 0; i < cnt; ++i) {
-        const float vi = bv[i];
-        const int ai = bi[i];
-        r0 += (vi > v0) || (vi == v0 && ai < a0);
-        r1 += (vi > v1) || (vi == v1 && ai < a1);
+    if (cnt <= 32) {
+        for (int i = 0; i < cnt; ++i) {
+            const float vi = bv[i];
+            r0 += (vi > v0) || (vi == v0 && bi[i] < a0);
+        }
+    } else {
+        for (int i = 0; i < cnt; ++i) {
+            const float vi = bv[i];
+            const int ai = bi[i];
+            r0 += (vi > v0) || (vi == v0 && ai < a0);
+            r1 += (vi > v1) || (vi == v1 && ai < a1);
+        }
     }
     __syncwarp();
     if (h0 && r0 < topk) { bv[r0] = v0; bi[r0] = a0; }
@@ -65,10 +72,12 @@ __device__ __forceinline__ int select_compress(float *bv, int *bi, int cnt, int 
     return cnt < topk ? cnt : topk;
 }
 
-__global__ void __launch_bounds__(kSelWarps * 32)
-k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4 *__restrict__ gt_boxes,
-                int total_gt, int32_t *__restrict__ sel_anchor, float *__restrict__ sel_val,
-                float *__restrict__ best_iou, double *__restrict__ sums)
+// anchor_terms (optional): per anchor (area, cx, cy, atan(w/h)) as sihl_od_anchor_terms writes them —
+// the same fp32 operations box_terms() performs, hoisted out of the pair loop and cached with the tables.
+__global__ void __launch_bounds__(kSelWarps * 32, 10)
+k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4 *__restrict__ anchor_terms,
+                const float4 *__restrict__ gt_boxes, int total_gt, int32_t *__restrict__ sel_anchor,
+                float *__restrict__ sel_val, float *__restrict__ best_iou, double *__restrict__ sums)
 {
     __shared__ float s_val[kSelWarps][kBufCap];
     __shared__ int s_idx[kSelWarps][kBufCap];
@@ -84,13 +93,50 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
     const int topk = p.topk;
     const BoxTerms gt = box_terms(to_box(__ldg(gt_boxes + g)));
     int cnt = 0;
+    bool dirty = false;                              // appended since the last compress
     float thr = 0.f;                                 // k-th best so far once cnt == topk, else 0
 
     // Evaluate up to 32 candidates (one per lane) and append the ones that can still make the top k.
+    // The arithmetic is ciou_pair() (od_math.h) cut in three so that a chunk leaves early when no lane
+    // can still rank: no overlap => CIoU <= 0; IoU < thr => CIoU < thr (CIoU <= IoU).
     auto consider = [&](bool valid, int a) {
-        float v = 0.f;
-        if (valid) v = ciou_pair(box_terms(to_box(__ldg(anchors + a))), gt);
-        const bool hit = valid && (thr > 0.f ? v >= thr : v > 0.f);      // clamp(0): non-positives never rank
+        BoxTerms an;
+        an.x1 = an.y1 = an.x2 = an.y2 = an.area = an.cx = an.cy = an.at = 0.f;
+        if (valid) {
+            const float4 b = __ldg(anchors + a);
+            if (anchor_terms != nullptr) {
+                const float4 t = __ldg(anchor_terms + a);
+                an.x1 = b.x; an.y1 = b.y; an.x2 = b.z; an.y2 = b.w;
+                an.area = t.x; an.cx = t.y; an.cy = t.z; an.at = t.w;
+            } else {
+                an = box_terms(to_box(b));
+            }
+        }
+        const float eps = 1e-7f;
+        float w = fminf(an.x2, gt.x2) - fmaxf(an.x1, gt.x1);
+        float h = fminf(an.y2, gt.y2) - fmaxf(an.y1, gt.y1);
+        w = w < 0.f ? 0.f : w;
+        h = h < 0.f ? 0.f : h;
+        const float inter = w * h;
+        bool live = valid && inter > 0.f;
+        if (!__any_sync(kFullMask, live)) return;
+        const float uni = (an.area + gt.area) - inter;
+        const float iou = inter / uni;
+        live = live && (thr > 0.f ? iou >= thr : true);
+        if (!__any_sync(kFullMask, live)) return;
+        float wi = fmaxf(an.x2, gt.x2) - fminf(an.x1, gt.x1);
+        float hi = fmaxf(an.y2, gt.y2) - fminf(an.y1, gt.y1);
+        wi = wi < 0.f ? 0.f : wi;
+        hi = hi < 0.f ? 0.f : hi;
+        const float diag = ((wi * wi) + (hi * hi)) + eps;
+        const float dx = an.cx - gt.cx, dy = an.cy - gt.cy;
+        const float cd = (dx * dx) + (dy * dy);
+        const float diou = iou - (cd / diag);
+        const float da = an.at - gt.at;
+        const float vv = SIHL_FOUR_OVER_PI2 * (da * da);
+        const float alpha = vv / (((1.f - iou) + vv) + eps);
+        const float v = diou - (alpha * vv);
+        const bool hit = live && (thr > 0.f ? v >= thr : v > 0.f);      // clamp(0): non-positives never rank
         const unsigned m = __ballot_sync(kFullMask, hit);
         if (m) {
             if (hit) {
@@ -99,8 +145,10 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
                 bi[pos] = a;
             }
             cnt += __popc(m);
+            dirty = true;
             if (cnt > kBufCap - 32) {
                 cnt = select_compress(bv, bi, cnt, topk, lane);
+                dirty = false;
                 if (cnt == topk) thr = bv[topk - 1];
             }
         }
@@ -113,9 +161,9 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
         float bound[SIHL_OD_MAX_LEVELS];
 #pragma unroll
         for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) {
-            const float cell = (p.img_w / (float)p.lv.w[l]) * (p.img_h / (float)p.lv.h[l]);
+            const float cell = p.cell_area[l];
             const float lo = fminf(cell, gt.area), hi = fmaxf(cell, gt.area);
-            bound[l] = (l < p.lv.n) ? ((gt.area > 0.f) ? (lo / hi) * 1.001f : CUDART_INF_F) : -1.f;
+            bound[l] = (l < p.lv.n) ? ((gt.area > 0.f) ? __fdividef(lo, hi) * 1.001f : CUDART_INF_F) : -1.f;
         }
         for (int it = 0; it < p.lv.n; ++it) {
             int l = 0;
@@ -124,7 +172,7 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
             for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k)
                 if (bound[k] > bmax) { bmax = bound[k]; l = k; }
             if (cnt >= topk) {
-                cnt = select_compress(bv, bi, cnt, topk, lane);
+                if (dirty) { cnt = select_compress(bv, bi, cnt, topk, lane); dirty = false; }
                 thr = bv[topk - 1];
                 if (bmax < thr) break;               // no remaining level can reach the current k-th value
             }
@@ -132,19 +180,19 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
             for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k)
                 if (k == l) bound[k] = -2.f;         // visited
             const int lw = p.lv.w[l], lh = p.lv.h[l], base = p.lv.base[l];
-            const float sx = p.img_w / (float)lw, sy = p.img_h / (float)lh;
             const float fw = (float)(lw - 1), fh = (float)(lh - 1);
-            const int j0 = (int)fminf(fmaxf(floorf(gt.x1 / sx) - 1.f, 0.f), fw);
-            const int j1 = (int)fminf(fmaxf(floorf(gt.x2 / sx) + 1.f, 0.f), fw);
-            const int i0 = (int)fminf(fmaxf(floorf(gt.y1 / sy) - 1.f, 0.f), fh);
-            const int i1 = (int)fminf(fmaxf(floorf(gt.y2 / sy) + 1.f, 0.f), fh);
+            // window of cells that can overlap the gt, widened by one cell on every side
+            const int j0 = (int)fminf(fmaxf(floorf(gt.x1 * p.inv_sx[l]) - 1.f, 0.f), fw);
+            const int j1 = (int)fminf(fmaxf(floorf(gt.x2 * p.inv_sx[l]) + 1.f, 0.f), fw);
+            const int i0 = (int)fminf(fmaxf(floorf(gt.y1 * p.inv_sy[l]) - 1.f, 0.f), fh);
+            const int i1 = (int)fminf(fmaxf(floorf(gt.y2 * p.inv_sy[l]) + 1.f, 0.f), fh);
             const int nj = j1 - j0 + 1, ni = i1 - i0 + 1;
             if (nj <= 0 || ni <= 0) continue;
             const int n = ni * nj;
-            const float inv_nj = 1.f / (float)nj;
+            const float inv_nj = __fdividef(1.f, (float)nj);
             for (int t0 = 0; t0 < n; t0 += 32) {
                 const int t = t0 + lane;
-                const int ri = (int)(((float)t + 0.5f) * inv_nj);     // t / nj (exact: margin 0.5/nj >> ulp)
+                int ri = (int)(((float)t + 0.5f) * inv_nj);           // t / nj (margin 0.5/nj >> rounding)
                 const int rj = t - ri * nj;
                 consider(t < n, base + (i0 + ri) * lw + (j0 + rj));
             }
@@ -159,12 +207,21 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
     if (lane == 0) best_iou[g] = cnt ? bv[0] : 0.f;                  // ref :277 topk_ious[0]
 }
 
+// Per-anchor terms of the CIoU (box_terms() of od_math.h), cached next to the anchor table.
+__global__ void __launch_bounds__(256) k_anchor_terms(const float4 *__restrict__ anchors, int n, float4 *__restrict__ terms)
+{
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const BoxTerms t = box_terms(to_box(__ldg(anchors + a)));
+        terms[a] = make_float4(t.area, t.cx, t.cy, t.at);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Stage 2: resolve (+ dense losses, + compaction, + fused positive losses)
 // ---------------------------------------------------------------------------
-constexpr int kTile = 1024;
-constexpr int kResThreads = 256;
+constexpr int kResThreads = 128;
 constexpr int kChunks = kTile / kResThreads;
+constexpr int kResWarps = kResThreads / 32;
 
 struct ResolveParams {
     const int32_t *sel_anchor; const float *sel_val; const float *best_iou; const int32_t *gt_offsets;
@@ -172,17 +229,14 @@ struct ResolveParams {
     const float *loc; const float *iou_pred;
     int64_t *assignment; float *out_iou; double *sums;
     int32_t *tile_pos_count; int32_t *tile_pos_rows;
-    const float *box_raw; const float *cls; int num_classes;
-    const float4 *offsets; const float4 *scales; float img_w, img_h;
-    const float4 *gt_boxes; const int64_t *gt_classes;
+    const float *prefetch_box; const float *prefetch_cls; int num_classes;   // L2 hints for k_pos_loss_tiles
 };
 
 __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
 {
     __shared__ unsigned long long s_key[kTile];
-    __shared__ float s_rel[kTile];
     __shared__ unsigned short s_pos[kTile];
-    __shared__ int s_seg[kChunks * (kResThreads / 32) + 1];
+    __shared__ int s_seg[kChunks * kResWarps + 1];
     __shared__ double s_red[5 * 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -190,6 +244,16 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
     const int A = p.num_anchors, a0 = tile * kTile;
     const int na = min(kTile, A - a0);
     const int g0 = __ldg(p.gt_offsets + b), g1 = __ldg(p.gt_offsets + b + 1);
+
+    // issue the streaming loads first: they are independent of the key reduction below
+    float x_loc[kChunks], x_iou[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const int la = c * kResThreads + tid;
+        const int64_t flat = (int64_t)b * A + a0 + (la < na ? la : 0);
+        x_loc[c] = p.loc != nullptr ? __ldcs(p.loc + flat) : 0.f;
+        x_iou[c] = p.iou_pred != nullptr ? __ldcs(p.iou_pred + flat) : 0.f;
+    }
 
     for (int i = tid; i < kTile; i += kResThreads) s_key[i] = 0ull;
     __syncthreads();
@@ -199,10 +263,11 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
     const float *sv = p.sel_val + (int64_t)g0 * p.topk;
     for (int e = tid; e < n_entries; e += kResThreads) {
         const int a = __ldg(sa + e) - a0;
+        const float v = __ldg(sv + e);
         if (a >= 0 && a < na) {
             const unsigned g = (unsigned)(e / p.topk);
             const unsigned long long key =
-                ((unsigned long long)__float_as_uint(__ldg(sv + e)) << 32) | (unsigned long long)(0xffffffffu - g);
+                ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - g);
             atomicMax(&s_key[a], key);
         }
     }
@@ -211,7 +276,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
     float acc_bce = 0.f, acc_one = 0.f, acc_mse = 0.f, acc_rel = 0.f, acc_pos = 0.f;
     unsigned ballots[kChunks];
     bool flags[kChunks];
-    const bool want_list = (p.tile_pos_count != nullptr) || (p.box_raw != nullptr) || (p.cls != nullptr);
+    const bool want_list = p.tile_pos_count != nullptr;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
         const int la = c * kResThreads + tid;
@@ -230,13 +295,21 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
             }
             p.assignment[flat] = asg;
             p.out_iou[flat] = rel;
-            s_rel[la] = rel;
+            if (pos) {                                    // the positive-row kernel gathers these next: warm L2 now
+                if (p.prefetch_box != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.prefetch_box + 4 * flat));
+                if (p.prefetch_cls != nullptr) {
+                    const char *row = reinterpret_cast<const char *>(p.prefetch_cls + flat * p.num_classes);
+                    const int bytes = p.num_classes * 4;
+                    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + bytes - 4));
+                }
+            }
             if (p.loc != nullptr) {
                 const float t = (rel == 1.0f) ? 1.f : 0.f;                       // ref :159
-                acc_bce += bce_logits(__ldg(p.loc + flat), t);
+                acc_bce += bce_logits(x_loc[c], t);
                 acc_one += t;
                 if (p.iou_pred != nullptr) {
-                    const float d = __ldg(p.iou_pred + flat) - rel;              // ref :177-179
+                    const float d = x_iou[c] - rel;                              // ref :177-179
                     acc_mse += d * d;
                 }
                 acc_rel += rel;
@@ -245,7 +318,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         }
         flags[c] = pos;
         ballots[c] = __ballot_sync(kFullMask, pos);
-        if (want_list && lane == 0) s_seg[c * (kResThreads / 32) + warp] = __popc(ballots[c]);
+        if (want_list && lane == 0) s_seg[c * kResWarps + warp] = __popc(ballots[c]);
     }
 
     int n_pos = 0;
@@ -253,7 +326,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         // ordered compaction: segment (chunk, warp) order == ascending anchor order (ref :182-184)
         __syncthreads();
         if (warp == 0) {
-            const int nseg = kChunks * (kResThreads / 32);
+            const int nseg = kChunks * kResWarps;
             int x = lane < nseg ? s_seg[lane] : 0;
             int incl = x;
 #pragma unroll
@@ -268,11 +341,11 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
             if (flags[c]) {
-                const int r = s_seg[c * (kResThreads / 32) + warp] + __popc(ballots[c] & ((1u << lane) - 1u));
+                const int r = s_seg[c * kResWarps + warp] + __popc(ballots[c] & ((1u << lane) - 1u));
                 s_pos[r] = (unsigned short)(c * kResThreads + tid);
             }
         __syncthreads();
-        n_pos = s_seg[kChunks * (kResThreads / 32)];
+        n_pos = s_seg[kChunks * kResWarps];
         if (p.tile_pos_count != nullptr) {
             const int slot = b * n_tiles + tile;
             if (tid == 0) p.tile_pos_count[slot] = n_pos;
@@ -281,43 +354,10 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         }
     }
 
-    float acc_box = 0.f, acc_cls = 0.f;
-    if (p.box_raw != nullptr) {                       // thread per positive row
-        for (int r = tid; r < n_pos; r += kResThreads) {
-            const int la = s_pos[r], a = a0 + la;
-            const int64_t flat = (int64_t)b * A + a;
-            const int g = g0 + (int)(0xffffffffu - (unsigned)(s_key[la] & 0xffffffffu));
-            const float l = pos_box_loss(ldg4(p.box_raw + 4 * flat), __ldg(p.offsets + a), __ldg(p.scales + a),
-                                         __ldg(p.gt_boxes + g), p.img_w, p.img_h);
-            acc_box += s_rel[la] * l;
-        }
-    }
-    if (p.cls != nullptr) {                           // 8 lanes per positive row
-        const int gl = lane & 7, grp = tid >> 3, ngrp = kResThreads >> 3;
-        const int rounds = (n_pos + ngrp - 1) / ngrp;
-        for (int it = 0; it < rounds; ++it) {
-            const int r = it * ngrp + grp;
-            const bool ok = r < n_pos;
-            const int la = s_pos[ok ? r : 0], a = a0 + la;
-            const int64_t flat = (int64_t)b * A + a;
-            const int g = g0 + (int)(0xffffffffu - (unsigned)(s_key[la] & 0xffffffffu));
-            float ce = 0.f;
-            if (n_pos > 0) ce = ce_row_group8(p.cls + flat * p.num_classes, p.num_classes, (int)__ldg(p.gt_classes + g), gl);
-            if (ok && gl == 0) acc_cls += s_rel[la] * ce;
-        }
-    }
-
-    if (p.sums != nullptr && (p.loc != nullptr || p.box_raw != nullptr || p.cls != nullptr)) {
-        {
-            double v[5] = {acc_bce, acc_one, acc_mse, acc_rel, acc_pos};
-            const int slot[5] = {0, 1, 2, 3, 6};
-            if (p.loc != nullptr) block_accumulate<5>(v, s_red, p.sums, slot);
-        }
-        {
-            double v[2] = {acc_box, acc_cls};
-            const int slot[2] = {4, 5};
-            if (p.box_raw != nullptr || p.cls != nullptr) block_accumulate<2>(v, s_red, p.sums, slot);
-        }
+    if (p.sums != nullptr && p.loc != nullptr) {
+        double v[5] = {acc_bce, acc_one, acc_mse, acc_rel, acc_pos};
+        const int slot[5] = {0, 1, 2, 3, 6};
+        block_accumulate<5>(v, s_red, p.sums, slot);
     }
 }
 
@@ -359,10 +399,21 @@ k_pos_compact(const int32_t *__restrict__ tile_pos_count, const int32_t *__restr
 
 using namespace sihl;
 
-extern "C" int sihl_od_assign_select(const float *anchors, int64_t num_anchors, const int32_t *level_hw_host,
-                                     int n_levels, int img_w, int img_h, const float *gt_boxes,
-                                     const int32_t *gt_offsets, int batch, int total_gt, int topk,
-                                     int32_t *sel_anchor, float *sel_val, float *best_iou, double *sums, void *stream)
+extern "C" int sihl_od_anchor_terms(const float *anchors, int64_t num_anchors, float *terms, void *stream)
+{
+    SIHL_CHECK_ARG(anchors && terms && num_anchors >= 0 && num_anchors < (1ll << 30), "bad arguments");
+    if (num_anchors == 0) return SIHL_OD_OK;
+    k_anchor_terms<<<(unsigned)((num_anchors + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(anchors), (int)num_anchors, reinterpret_cast<float4 *>(terms));
+    SIHL_CHECK_LAUNCH("k_anchor_terms");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_assign_select(const float *anchors, const float *anchor_terms, int64_t num_anchors,
+                                     const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
+                                     const float *gt_boxes, const int32_t *gt_offsets, int batch, int total_gt,
+                                     int topk, int32_t *sel_anchor, float *sel_val, float *best_iou, double *sums,
+                                     void *stream)
 {
     (void)gt_offsets; (void)batch;
     SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
@@ -372,24 +423,29 @@ extern "C" int sihl_od_assign_select(const float *anchors, int64_t num_anchors, 
                    (long long)num_anchors, topk);
     SelectParams p;
     p.use_levels = level_hw_host != nullptr;
+    for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) { p.inv_sx[l] = p.inv_sy[l] = 0.f; p.cell_area[l] = 1.f; }
     if (p.use_levels) {
         int rc = fill_level_table(level_hw_host, n_levels, &p.lv);
         if (rc) return rc;
         SIHL_CHECK_ARG(p.lv.base[n_levels] == num_anchors, "levels hold %d anchors, table has %lld", p.lv.base[n_levels],
                        (long long)num_anchors);
         SIHL_CHECK_ARG(img_w > 0 && img_h > 0, "image size %dx%d", img_w, img_h);
+        for (int l = 0; l < n_levels; ++l) {
+            p.inv_sx[l] = (float)p.lv.w[l] / (float)img_w;
+            p.inv_sy[l] = (float)p.lv.h[l] / (float)img_h;
+            p.cell_area[l] = ((float)img_w / (float)p.lv.w[l]) * ((float)img_h / (float)p.lv.h[l]);
+        }
     } else {
         p.lv.n = 0;
         for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) { p.lv.h[l] = p.lv.w[l] = 1; p.lv.base[l] = 0; }
         p.lv.base[SIHL_OD_MAX_LEVELS] = 0;
     }
-    p.img_w = (float)img_w; p.img_h = (float)img_h;
     p.num_anchors = (int)num_anchors; p.topk = topk;
     if (total_gt == 0 && sums == nullptr) return SIHL_OD_OK;
     const int blocks = total_gt > 0 ? (total_gt + kSelWarps - 1) / kSelWarps : 1;
     k_assign_select<<<blocks, kSelWarps * 32, 0, (cudaStream_t)stream>>>(
-        p, reinterpret_cast<const float4 *>(anchors), reinterpret_cast<const float4 *>(gt_boxes), total_gt, sel_anchor,
-        sel_val, best_iou, sums);
+        p, reinterpret_cast<const float4 *>(anchors), reinterpret_cast<const float4 *>(anchor_terms),
+        reinterpret_cast<const float4 *>(gt_boxes), total_gt, sel_anchor, sel_val, best_iou, sums);
     SIHL_CHECK_LAUNCH("k_assign_select");
     return SIHL_OD_OK;
 }
@@ -405,20 +461,14 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
                                       const int32_t *gt_offsets, int batch, int64_t num_anchors, int topk, int relative,
                                       const float *loc_logits, const float *iou_preds, int64_t *assignment,
                                       float *out_iou, double *sums, int32_t *tile_pos_count, int32_t *tile_pos_rows,
-                                      const float *box_raw, const float *cls_logits, int num_classes,
-                                      const float *offsets, const float *scales, int img_w, int img_h,
-                                      const float *gt_boxes, const int64_t *gt_classes, void *stream)
+                                      const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
+                                      void *stream)
 {
     SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
     SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
     SIHL_CHECK_ARG(assignment && out_iou && gt_offsets, "assignment / out_iou / gt_offsets must not be NULL");
     SIHL_CHECK_ARG((tile_pos_count == nullptr) == (tile_pos_rows == nullptr), "tile_pos_count and tile_pos_rows go together");
     SIHL_CHECK_ARG(iou_preds == nullptr || loc_logits != nullptr, "iou_preds needs loc_logits");
-    const bool fused = box_raw != nullptr || cls_logits != nullptr;
-    // gt_boxes / gt_classes may be NULL when the batch holds no ground truth at all
-    SIHL_CHECK_ARG(!fused || (sums && offsets && scales && img_w > 0 && img_h > 0),
-                   "fused positive losses need sums, offsets, scales and the image size");
-    SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "num_classes=%d", num_classes);
     SIHL_CHECK_ARG(loc_logits == nullptr || sums != nullptr, "dense losses need sums");
     if (batch == 0 || num_anchors == 0) return SIHL_OD_OK;
     ResolveParams p;
@@ -426,10 +476,7 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
     p.num_anchors = (int)num_anchors; p.topk = topk; p.relative = relative;
     p.loc = loc_logits; p.iou_pred = iou_preds; p.assignment = assignment; p.out_iou = out_iou; p.sums = sums;
     p.tile_pos_count = tile_pos_count; p.tile_pos_rows = tile_pos_rows;
-    p.box_raw = box_raw; p.cls = cls_logits; p.num_classes = num_classes;
-    p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
-    p.img_w = (float)img_w; p.img_h = (float)img_h;
-    p.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); p.gt_classes = gt_classes;
+    p.prefetch_box = prefetch_box_raw; p.prefetch_cls = num_classes > 0 ? prefetch_cls_logits : nullptr; p.num_classes = num_classes;
     const dim3 grid((unsigned)((num_anchors + kTile - 1) / kTile), (unsigned)batch);
     SIHL_CHECK_ARG(batch <= 65535, "batch=%d > 65535", batch);
     k_assign_resolve<<<grid, kResThreads, 0, (cudaStream_t)stream>>>(p);

@@ -36,6 +36,7 @@ int cuda_status(cudaError_t e, const char *what);
 
 constexpr int kNumSMs = 148;          // B200
 constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kTile = 512;            // anchors per CTA of k_assign_resolve == capacity of one tile's positive list
 
 struct LevelTable {                   // passed by value as a kernel parameter
     int n;
@@ -86,5 +87,6 @@ __device__ __forceinline__ void block_accumulate(double (&v)[NV], double *red, d
     }
     __syncthreads();
 }
+
 
 }  // namespace sihl

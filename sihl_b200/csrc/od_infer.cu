@@ -225,10 +225,29 @@ struct DenseDecodeParams {
     const float *loc; const float *cls; const float *box_raw;
     int batch, A, C;
     const float4 *offsets; const float4 *scales; float img_w, img_h, score_thr;
+    float logit_thr;        // a logit below this cannot pass (conservative pre-filter; the sigmoid test decides)
     int32_t *cand_count; int64_t cap;
     unsigned long long *cand_key; float4 *cand_box; int32_t *cand_cls;
 };
 
+// Candidate test and append for one decoded location (one lane per row).
+__device__ __forceinline__ void emit_candidate(const DenseDecodeParams &p, int64_t row, float x, int arg)
+{
+    const float s = sigmoid_f(x);
+    if (!(s > p.score_thr)) return;
+    const int b = (int)(row / p.A), a = (int)(row - (int64_t)b * p.A);
+    const int slot = atomicAdd(p.cand_count + b, 1);
+    if (slot >= p.cap) return;
+    const float4 raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + row);
+    const float4 off = __ldg(p.offsets + a), sc = __ldg(p.scales + a);
+    const int64_t o = (int64_t)b * p.cap + slot;
+    p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
+    p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
+                                decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
+    p.cand_cls[o] = arg;
+}
+
+// Scalar variant (any C): 8 lanes per row, 4-byte loads.
 template <int CPL>
 __global__ void __launch_bounds__(256) k_dense_decode(DenseDecodeParams p)
 {
@@ -243,24 +262,233 @@ __global__ void __launch_bounds__(256) k_dense_decode(DenseDecodeParams p)
         const int64_t rr = ok ? row : rows - 1;
         const float x = __ldcs(p.loc + rr);
         const int arg = row_argmax8<CPL>(p.cls + rr * p.C, p.C, gl);
-        if (ok && gl == 0) {
-            const float s = sigmoid_f(x);
-            if (s > p.score_thr) {
-                const int b = (int)(row / p.A), a = (int)(row - (int64_t)b * p.A);
-                const int slot = atomicAdd(p.cand_count + b, 1);
-                if (slot < p.cap) {
-                    const float4 raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + row);
-                    const float4 off = __ldg(p.offsets + a), sc = __ldg(p.scales + a);
-                    const int64_t o = (int64_t)b * p.cap + slot;
-                    p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) |
-                                    (unsigned long long)(0xffffffffu - (unsigned)a);
-                    p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
-                                                decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
-                    p.cand_cls[o] = arg;
+        if (ok && gl == 0) emit_candidate(p, row, x, arg);
+    }
+}
+
+// Vector variant (C % 4 == 0): LPR lanes per row, VPL 16-byte loads per lane and row, two rows
+// per group and iteration, i.e. 2*VPL independent LDG.128 in flight per lane before the first
+// use — enough bytes in flight (~160 B/lane) to cover HBM latency at 4 CTAs/SM.
+// Lane gl owns float4 indices gl, gl+LPR, ...: ascending class index inside the lane, so a
+// strict '>' keeps the first maximum; the cross-lane step prefers the lower index on ties.
+template <int LPR, int VPL, bool EXACT>
+__global__ void __launch_bounds__(256) k_dense_decode_v4(DenseDecodeParams p)
+{
+    const int gl = threadIdx.x & (LPR - 1);
+    const int C4 = p.C >> 2;
+    const int64_t rows = (int64_t)p.batch * p.A;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / LPR;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const float4 *cls4 = reinterpret_cast<const float4 *>(p.cls);
+    for (int64_t row0 = grp; row0 < rows; row0 += 2 * ngrp) {       // rows is warp-uniform-safe: see clamp below
+        const int64_t rowA = row0, rowB = row0 + ngrp;
+        const bool okB = rowB < rows;
+        const int64_t rb = okB ? rowB : rowA;
+        float4 va[VPL], vb[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int v = gl + LPR * i;
+            const bool in = EXACT || v < C4;
+            va[i] = in ? __ldcs(cls4 + rowA * C4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[i] = in ? __ldcs(cls4 + rb * C4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float xa = __ldcs(p.loc + rowA), xb = __ldcs(p.loc + rb);
+        float bestA = -CUDART_INF_F, bestB = -CUDART_INF_F;
+        int argA = 0x7fffffff, argB = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int v = gl + LPR * i;
+            if (EXACT || v < C4) {
+                const int c = 4 * v;
+                const float ea[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+                const float eb[4] = {vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (ea[e] > bestA || argA == 0x7fffffff) { bestA = ea[e]; argA = c + e; }
+                    if (eb[e] > bestB || argB == 0x7fffffff) { bestB = eb[e]; argB = c + e; }
                 }
             }
         }
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) {
+            const float oa = __shfl_xor_sync(kFullMask, bestA, o), ob = __shfl_xor_sync(kFullMask, bestB, o);
+            const int ia = __shfl_xor_sync(kFullMask, argA, o), ib = __shfl_xor_sync(kFullMask, argB, o);
+            if (oa > bestA || (oa == bestA && ia < argA)) { bestA = oa; argA = ia; }
+            if (ob > bestB || (ob == bestB && ib < argB)) { bestB = ob; argB = ib; }
+        }
+        if (gl == 0) emit_candidate(p, rowA, xa, argA);
+        if (gl == (LPR > 1 ? 1 : 0) && okB) emit_candidate(p, rowB, xb, argB);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Bulk-async variant (C % 4 == 0, C <= 128): the class-logit map is streamed through shared
+// memory by the TMA unit — cp.async.bulk of 64 consecutive rows (64*C*4 B, contiguous in
+// HBM) + their 64 location logits per stage, completion signalled on an mbarrier — in a
+// ring of kStages stages per CTA, persistent CTAs striding over the chunks.  Bytes in flight
+// are set by the ring (2 CTAs x 4 stages x 20 KB per SM at C = 80), not by what the compiler
+// keeps in registers, and every byte is read from HBM exactly once.  Consumers: 4 lanes per
+// row, conflict-free LDS.128, first-argmax as above.
+// ---------------------------------------------------------------------------
+constexpr int kChunkRows = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Candidates found while streaming are only *staged* in shared memory (row, logit, class, raw
+// box): the global atomic that allocates the output slot and the dependent stores would put a
+// ~2 us round trip on the critical path of every 64-row chunk.  The stage list is flushed by
+// the whole CTA, all candidates in parallel, when it runs full and at the end.
+constexpr int kStageCap = 512;
+
+struct StagedCand {
+    float4 raw;
+    int row_lo, row_hi;      // 64-bit row index
+    float x;
+    int arg;
+};
+
+__device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const StagedCand *list, int count)
+{
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const StagedCand c = list[i];
+        const int64_t row = ((int64_t)c.row_hi << 32) | (unsigned)c.row_lo;
+        const float s = sigmoid_f(c.x);
+        const int b = (int)(row / p.A), a = (int)(row - (int64_t)b * p.A);
+        const int slot = atomicAdd(p.cand_count + b, 1);
+        if (slot >= p.cap) continue;
+        const float4 off = __ldg(p.offsets + a), sc = __ldg(p.scales + a);
+        const int64_t o = (int64_t)b * p.cap + slot;
+        p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
+        p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, c.raw.x) * p.img_w, decode_norm(off.y, sc.y, c.raw.y) * p.img_h,
+                                    decode_norm(off.z, sc.z, c.raw.z) * p.img_w, decode_norm(off.w, sc.w, c.raw.w) * p.img_h);
+        p.cand_cls[o] = c.arg;
+    }
+}
+
+template <int VPL, bool EXACT>
+__global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, int stages, int n_chunks)
+{
+    extern __shared__ __align__(128) unsigned char s_ring[];
+    __shared__ StagedCand s_list[kStageCap];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, gl = tid & 3, r = tid >> 2;
+    const int C4 = p.C >> 2;
+    const int64_t rows = (int64_t)p.batch * p.A;
+    // per stage: 64 rows of class logits | 64 raw boxes | 64 location logits
+    const uint32_t cls_bytes = (uint32_t)kChunkRows * (uint32_t)p.C * 4u, box_bytes = kChunkRows * 16u, loc_bytes = kChunkRows * 4u;
+    const uint32_t stage_bytes = cls_bytes + box_bytes + loc_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + (size_t)stages * stage_bytes);
+
+    auto issue = [&](int stage, int chunk) {                      // one elected thread
+        const int64_t row0 = (int64_t)chunk * kChunkRows;
+        const int64_t n = rows - row0 < kChunkRows ? rows - row0 : kChunkRows;
+        unsigned char *dst = s_ring + (size_t)stage * stage_bytes;
+        const uint32_t cb = (uint32_t)n * (uint32_t)p.C * 4u, bb = (uint32_t)n * 16u;
+        const bool full = n == kChunkRows;                        // partial tail: loc is read directly (16-B size rule)
+        mbar_expect_tx(bars + stage, cb + bb + (full ? loc_bytes : 0u));
+        bulk_g2s(dst, p.cls + row0 * p.C, cb, bars + stage);
+        bulk_g2s(dst + cls_bytes, p.box_raw + row0 * 4, bb, bars + stage);
+        if (full) bulk_g2s(dst + cls_bytes + box_bytes, p.loc + row0, loc_bytes, bars + stage);
+    };
+
+    if (tid == 0) {
+        s_count = 0;
+        for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < stages; ++s) {
+            const int c = blockIdx.x + s * gridDim.x;
+            if (c < n_chunks) issue(s, c);
+        }
+
+    // sigmoid(x) > thr is monotone in x: compare logits against the smallest logit whose sigmoid passes
+    const float x_thr = p.logit_thr;
+    for (int k = 0;; ++k) {
+        const int c = blockIdx.x + k * gridDim.x;
+        if (c >= n_chunks) break;
+        const int s = k % stages;
+        mbar_wait(bars + s, (uint32_t)((k / stages) & 1));
+        const int64_t row = (int64_t)c * kChunkRows + r;
+        const bool ok = row < rows;
+        const unsigned char *base = s_ring + (size_t)s * stage_bytes;
+        const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
+        float best = -CUDART_INF_F;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int v = gl + 4 * i;
+            if (EXACT || v < C4) {
+                const float4 q = src[v];
+                const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (e[j] > best || arg == 0x7fffffff) { best = e[j]; arg = 4 * v + j; }
+            }
+        }
+#pragma unroll
+        for (int o = 2; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(kFullMask, best, o);
+            const int oa = __shfl_xor_sync(kFullMask, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (gl == 0 && ok) {
+            const bool full = rows - (int64_t)c * kChunkRows >= kChunkRows;
+            const float x = full ? reinterpret_cast<const float *>(base + cls_bytes + box_bytes)[r] : __ldcs(p.loc + row);
+            if (x >= x_thr && sigmoid_f(x) > p.score_thr) {
+                const int i = atomicAdd(&s_count, 1);             // < kStageCap: flushed below before it can overflow
+                StagedCand sc;
+                sc.raw = reinterpret_cast<const float4 *>(base + cls_bytes)[r];
+                sc.row_lo = (int)(row & 0xffffffff); sc.row_hi = (int)(row >> 32);
+                sc.x = x; sc.arg = arg;
+                s_list[i] = sc;
+            }
+        }
+        __syncthreads();                                          // every lane is done with stage s
+        if (tid == 0) {
+            const int next = c + stages * gridDim.x;
+            if (next < n_chunks) issue(s, next);
+        }
+        if (s_count > kStageCap - kChunkRows) {                   // block-uniform: read after the barrier
+            flush_staged(p, s_list, s_count);
+            __syncthreads();
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    flush_staged(p, s_list, s_count);
 }
 
 __global__ void k_zero_i32(int32_t *p, int n)
@@ -326,18 +554,89 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
     p.loc = loc_logits; p.cls = cls_logits; p.box_raw = box_raw; p.batch = batch; p.A = (int)num_anchors; p.C = num_classes;
     p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
     p.img_w = (float)img_w; p.img_h = (float)img_h; p.score_thr = score_thr;
+    {   // logit(thr) minus a safety margin: only saves the exp for the bulk of the rows
+        const double t = (double)score_thr;
+        p.logit_thr = (t <= 0.0) ? -HUGE_VALF : (t >= 1.0 ? HUGE_VALF : (float)(log(t / (1.0 - t)) - 1e-3 * (1.0 + fabs(log(t / (1.0 - t))))));
+    }
     p.cand_count = cand_count; p.cap = cand_capacity;
     p.cand_key = reinterpret_cast<unsigned long long *>(cand_key); p.cand_box = reinterpret_cast<float4 *>(cand_box);
     p.cand_cls = cand_cls;
     const int64_t rows = (int64_t)batch * num_anchors;
-    int64_t blocks = (rows * 8 + 255) / 256;
-    const int64_t cap = (int64_t)kNumSMs * 8;          // 8 resident CTAs of 256 threads per SM
-    if (blocks > cap) blocks = cap;
-    const dim3 grid((unsigned)blocks);
-    if (num_classes == 80) k_dense_decode<10><<<grid, 256, 0, st>>>(p);
-    else if (num_classes == 16) k_dense_decode<2><<<grid, 256, 0, st>>>(p);
-    else if (num_classes == 8) k_dense_decode<1><<<grid, 256, 0, st>>>(p);
-    else k_dense_decode<0><<<grid, 256, 0, st>>>(p);
+    const bool aligned = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0);
+    const int c4 = num_classes / 4;
+    const bool loc_aligned = (reinterpret_cast<uintptr_t>(loc_logits) & 15u) == 0;
+    if (aligned && loc_aligned && c4 <= 32 && rows >= 4 * kChunkRows) {
+        const int vpl = (c4 + 3) / 4;
+        const bool exact = vpl * 4 == c4;
+        const size_t stage_bytes = (size_t)kChunkRows * num_classes * 4 + kChunkRows * 16 + kChunkRows * 4;
+        int stages = (int)((92 * 1024) / stage_bytes);
+        stages = stages > 4 ? 4 : (stages < 2 ? 2 : stages);
+        const size_t smem = stages * stage_bytes + stages * sizeof(uint64_t);
+        const int n_chunks = (int)((rows + kChunkRows - 1) / kChunkRows);
+        int blocks = kNumSMs * 2;
+        if (blocks > n_chunks) blocks = n_chunks;
+#define SIHL_DT(VPL)                                                                                              \
+    do {                                                                                                          \
+        auto kern = exact ? k_dense_decode_tma<VPL, true> : k_dense_decode_tma<VPL, false>;                       \
+        int rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),  \
+                             "cudaFuncSetAttribute(k_dense_decode_tma)");                                         \
+        if (rc) return rc;                                                                                        \
+        kern<<<blocks, 256, smem, st>>>(p, stages, n_chunks);                                                     \
+    } while (0)
+        switch (vpl) {
+            case 1: SIHL_DT(1); break;
+            case 2: SIHL_DT(2); break;
+            case 3: SIHL_DT(3); break;
+            case 4: SIHL_DT(4); break;
+            case 5: SIHL_DT(5); break;
+            case 6: SIHL_DT(6); break;
+            case 7: SIHL_DT(7); break;
+            default: SIHL_DT(8); break;
+        }
+#undef SIHL_DT
+    } else if (aligned && c4 <= 32 * 8) {
+        // 4 lanes per row up to C = 128, a full warp per row beyond; grid = 4 resident CTAs per SM
+        const int lpr = c4 <= 32 ? 4 : 32;
+        int64_t blocks = (rows * lpr / 2 + 255) / 256;
+        const int64_t cap = (int64_t)kNumSMs * 4;
+        if (blocks > cap) blocks = cap;
+        const dim3 grid((unsigned)(blocks < 1 ? 1 : blocks));
+        const int vpl = (c4 + lpr - 1) / lpr;
+        const bool exact = vpl * lpr == c4;
+#define SIHL_DD(LPR, VPL)                                                                    \
+    if (exact) k_dense_decode_v4<LPR, VPL, true><<<grid, 256, 0, st>>>(p);                   \
+    else k_dense_decode_v4<LPR, VPL, false><<<grid, 256, 0, st>>>(p)
+        if (lpr == 4) {
+            switch (vpl) {
+                case 1: SIHL_DD(4, 1); break;
+                case 2: SIHL_DD(4, 2); break;
+                case 3: SIHL_DD(4, 3); break;
+                case 4: SIHL_DD(4, 4); break;
+                case 5: SIHL_DD(4, 5); break;
+                case 6: SIHL_DD(4, 6); break;
+                case 7: SIHL_DD(4, 7); break;
+                default: SIHL_DD(4, 8); break;
+            }
+        } else {
+            switch (vpl) {
+                case 2: SIHL_DD(32, 2); break;
+                case 3: SIHL_DD(32, 3); break;
+                case 4: SIHL_DD(32, 4); break;
+                case 5: SIHL_DD(32, 5); break;
+                case 6: SIHL_DD(32, 6); break;
+                case 7: SIHL_DD(32, 7); break;
+                default: SIHL_DD(32, 8); break;
+            }
+        }
+#undef SIHL_DD
+    } else {
+        int64_t blocks = (rows * 8 + 255) / 256;
+        const int64_t cap = (int64_t)kNumSMs * 8;          // 8 resident CTAs of 256 threads per SM
+        if (blocks > cap) blocks = cap;
+        const dim3 grid((unsigned)(blocks < 1 ? 1 : blocks));
+        k_dense_decode<0><<<grid, 256, 0, st>>>(p);
+    }
     SIHL_CHECK_LAUNCH("k_dense_decode");
     return SIHL_OD_OK;
 }

@@ -100,6 +100,65 @@ __global__ void __launch_bounds__(kLossThreads) k_pos_loss(PosParams p)
     block_accumulate<2>(v, s_red, p.sums, slot);
 }
 
+// Positive-row losses straight from the per-tile lists k_assign_resolve leaves behind (dense
+// maps only): one CTA per (image, tile), one group of lanes per positive.  No compaction, no
+// host round trip; the class-logit row (the only DRAM-latency hop) is requested before the
+// assignment -> gt chain is followed.
+constexpr int kPosTileThreads = 256;
+
+struct PosTileParams {
+    const int32_t *tile_pos_count; const int32_t *tile_pos_rows; int n_tiles; int num_anchors;
+    const float *rel; const int64_t *assignment;
+    const float4 *offsets; const float4 *scales; float img_w, img_h;
+    const float4 *gt_boxes; const int64_t *gt_classes; const int32_t *gt_offsets;
+    const float *box_raw; const float *cls; int num_classes; int cls_vec4;
+    double *sums;
+};
+
+__global__ void __launch_bounds__(kPosTileThreads) k_pos_loss_tiles(PosTileParams p)
+{
+    __shared__ double s_red[2 * 32];
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    const int32_t *rows = p.tile_pos_rows + (int64_t)slot * kTile;
+    const int lpr = p.cls_vec4 ? 4 : 8;                           // lanes per positive row
+    const int gl = tid & (lpr - 1), grp = tid / lpr, ngrp = kPosTileThreads / lpr;
+    // first-round row index fetched before the count is known (entries past the count are stale but
+    // always valid indices): one global round trip less on the critical path
+    const int32_t flat_first = __ldg(rows + grp);
+    const int n = __ldg(p.tile_pos_count + slot);
+    if (n == 0) return;                                           // block-uniform
+    const int b = slot / p.n_tiles, A = p.num_anchors;
+    const int g0 = __ldg(p.gt_offsets + b);
+    float acc_box = 0.f, acc_cls = 0.f;
+    for (int r0 = 0; r0 < n; r0 += ngrp) {
+        const int r = r0 + grp;
+        const bool ok = r < n;
+        const int64_t flat = ok ? (r0 == 0 ? flat_first : __ldg(rows + r)) : __ldg(rows);
+        const int a = (int)(flat - (int64_t)b * A);
+        const int64_t asg = __ldg(p.assignment + flat);
+        const float w = __ldg(p.rel + flat);
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), off = raw, sc = raw;
+        if (p.box_raw != nullptr && gl == 0) { raw = ldg4(p.box_raw + 4 * flat); off = __ldg(p.offsets + a); sc = __ldg(p.scales + a); }
+        float m = 0.f, se = 1.f;
+        if (p.cls != nullptr) {
+            if (p.cls_vec4) row_softmax_stats4v(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+            else row_softmax_stats8(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+        }
+        const int g = g0 + (int)asg;
+        if (ok && gl == 0) {
+            if (p.cls != nullptr) {
+                const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + (int)__ldg(p.gt_classes + g));
+                acc_cls += w * ce;                                // ref :208
+            }
+            if (p.box_raw != nullptr)
+                acc_box += w * pos_box_loss(raw, off, sc, __ldg(p.gt_boxes + g), p.img_w, p.img_h);   // ref :197
+        }
+    }
+    double v[2] = {acc_box, acc_cls};
+    const int slot_idx[2] = {4, 5};
+    block_accumulate<2>(v, s_red, p.sums, slot_idx);
+}
+
 __global__ void k_loss_finalize(const double *__restrict__ sums, float *__restrict__ losses)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -286,5 +345,34 @@ extern "C" int sihl_od_pos_loss_bwd(const int32_t *pos_index, const int32_t *n_p
     p.sums = const_cast<double *>(sums); p.grad_terms = grad_terms; p.dbox = dbox; p.dcls = dcls;
     k_pos_loss_bwd<<<grid_for(capacity, 1) * (dcls ? 4 : 1), kLossThreads, 0, (cudaStream_t)stream>>>(p);
     SIHL_CHECK_LAUNCH("k_pos_loss_bwd");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_pos_loss_tiles(const int32_t *tile_pos_count, const int32_t *tile_pos_rows, int batch,
+                                      int64_t num_anchors, const float *rel_iou, const int64_t *assignment,
+                                      const float *offsets, const float *scales, int img_w, int img_h,
+                                      const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                                      const float *box_raw, const float *cls_logits, int num_classes, double *sums,
+                                      void *stream)
+{
+    SIHL_CHECK_ARG(tile_pos_count && tile_pos_rows && rel_iou && assignment && gt_offsets && sums, "NULL argument");
+    SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
+    SIHL_CHECK_ARG(box_raw == nullptr || (offsets && scales && img_w > 0 && img_h > 0),
+                   "box loss needs offsets, scales and the image size");
+    SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "class loss needs num_classes");
+    const int n_tiles = (int)((num_anchors + kTile - 1) / kTile);
+    const int n_slots = batch * n_tiles;
+    if (n_slots == 0 || (box_raw == nullptr && cls_logits == nullptr)) return SIHL_OD_OK;
+    PosTileParams p;
+    p.tile_pos_count = tile_pos_count; p.tile_pos_rows = tile_pos_rows; p.n_tiles = n_tiles; p.num_anchors = (int)num_anchors;
+    p.rel = rel_iou; p.assignment = assignment;
+    p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
+    p.img_w = (float)img_w; p.img_h = (float)img_h;
+    p.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); p.gt_classes = gt_classes; p.gt_offsets = gt_offsets;
+    p.box_raw = box_raw; p.cls = cls_logits; p.num_classes = num_classes;
+    p.cls_vec4 = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
+    p.sums = sums;
+    k_pos_loss_tiles<<<n_slots, kPosTileThreads, 0, (cudaStream_t)stream>>>(p);
+    SIHL_CHECK_LAUNCH("k_pos_loss_tiles");
     return SIHL_OD_OK;
 }

@@ -19,9 +19,20 @@
 
 namespace sihl {
 
+// Developer instrumentation (compiled out unless -DSIHL_PHASE_TIMING): SM clock of block 0 /
+// thread 0 at phase boundaries, read back with sihl_od_debug_phases().
+#ifdef SIHL_PHASE_TIMING
+__device__ long long g_phase_clock[16];
+#define SIHL_PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clock[i] = clock64(); } while (0)
+#else
+#define SIHL_PHASE(i) do { } while (0)
+#endif
+
 constexpr int kNmsThreads = 1024;
 constexpr int kSmemItems = 4096;          // per-image candidates held on chip
 constexpr int kBigSegment = 512;
+constexpr int kSmallItems = 256;          // lists up to this size take the single-pass rank-sort kernel
+constexpr int kSmallThreads = 4 * kSmallItems;   // four lanes per candidate
 constexpr size_t kSmemItemBytes = 41;     // key 8 + box 16 + val 4 + area 4 + slot 4 + seg 4 + dead 1
 constexpr size_t kWsItemBytes = 48;       // workspace stride per item (keeps every image 16-B aligned)
 
@@ -126,6 +137,8 @@ struct NmsParams {
     int K; int64_t *num_instances; float *out_scores; int64_t *out_classes; float4 *out_boxes;   // mode 0
     int64_t *keep; int32_t *keep_count;                                                           // mode 1
     unsigned char *workspace; size_t ws_stride;   // mode 0: bytes per image; mode 1: unused (offset = 2*seg start)
+    int skip_small;
+    int reset_counts;          // mode 0: zero cand_count[img] once consumed (saves the next step's memset launch)
 };
 
 __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
@@ -143,6 +156,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
         src0 = __ldg(p.seg_offsets + img);
         n = __ldg(p.seg_offsets + img + 1) - src0;
     }
+    if (p.skip_small && n <= kSmallItems) return;          // handled by k_nms_small
     int np = 2;
     while (np < n) np <<= 1;
     int n_kept = 0;
@@ -249,7 +263,10 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
 
     if (p.mode == 0) {
         const int m = n_kept < p.K ? n_kept : p.K;
-        if (tid == 0) p.num_instances[img] = m;
+        if (tid == 0) {
+            p.num_instances[img] = m;
+            if (p.reset_counts) const_cast<int32_t *>(p.cand_count)[img] = 0;
+        }
         for (int k = m + tid; k < p.K; k += blockDim.x) {
             const int64_t o = (int64_t)img * p.K + k;
             p.out_scores[o] = 0.f;
@@ -261,6 +278,172 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
     }
 }
 
+// Short lists (n <= kSmallItems, the common case after a 0.05 score threshold).  Four lanes per
+// candidate; ONE counting pass over shared memory yields, per candidate, its rank r in
+// (score desc, index asc) order, its class-major position q, and the start / length of its
+// class segment.  Suppression is then a per-candidate bitmask of earlier same-class boxes with
+// IoU > thr (all pairs in parallel, no serial dependence), resolved by one lane per segment with
+// pure bit operations — the greedy chain costs a few cycles per box instead of a shared-memory
+// round trip per kept box.  Segments longer than 32 fall back to the broadcast loop of k_nms.
+__global__ void __launch_bounds__(kSmallThreads) k_nms_small(NmsParams p)
+{
+    __shared__ unsigned long long s_key[kSmallItems];
+    __shared__ unsigned s_cls[kSmallItems];        // by slot
+    __shared__ float4 s_box[kSmallItems];          // by q
+    __shared__ float s_area[kSmallItems];          // by q
+    __shared__ unsigned s_mask[kSmallItems];       // by q: earlier boxes of the segment that suppress q (if kept)
+    __shared__ unsigned s_keep[kSmallItems];       // by segment start: kept bits of the segment
+    __shared__ unsigned char s_dead[kSmallItems];  // by q (only for segments longer than 32)
+    __shared__ unsigned short s_q_of_r[kSmallItems], s_slot_of_r[kSmallItems], s_seg0_of_q[kSmallItems], s_len_of_q[kSmallItems];
+    __shared__ int s_warp[33];
+    __shared__ int s_big;
+
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int item = tid >> 2, sub = tid & 3;
+    SIHL_PHASE(0);
+    int n, src0;
+    if (p.mode == 0) {
+        const int c = __ldg(p.cand_count + img);
+        n = (int)(c < p.cap ? c : p.cap);
+        src0 = 0;
+    } else {
+        src0 = __ldg(p.seg_offsets + img);
+        n = __ldg(p.seg_offsets + img + 1) - src0;
+    }
+    if (n > kSmallItems) return;                   // k_nms takes it
+    SIHL_PHASE(1);
+    int n_kept = 0;
+    if (n > 0) {
+        const bool have = item < n;
+        unsigned long long key = 0ull;
+        unsigned cls = 0;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have) {
+            if (p.mode == 0) {
+                key = __ldg(p.cand_key + (int64_t)img * p.cap + item);
+                cls = (unsigned)__ldg(p.cand_cls + (int64_t)img * p.cap + item);
+                bx = __ldg(p.cand_box + (int64_t)img * p.cap + item);
+            } else {
+                key = ((unsigned long long)f2ord_nms(__ldg(p.scores + src0 + item)) << 32) |
+                      (unsigned long long)(0xffffffffu - (unsigned)item);
+                cls = (unsigned)__ldg(p.classes + src0 + item);
+                bx = __ldg(p.boxes + src0 + item);
+            }
+            if (sub == 0) { s_key[item] = key; s_cls[item] = cls; }
+        }
+        if (tid == 0) s_big = 0;
+        __syncthreads();
+        SIHL_PHASE(2);
+        // one pass: r = #better keys; seg0 = #smaller classes; k = #better keys of the same class; len = #same class
+        int r = 0, seg0 = 0, k = 0, len = 0;
+        if (have) {
+#pragma unroll 4
+            for (int j = sub; j < n; j += 4) {
+                const unsigned long long kj = s_key[j];
+                const unsigned cj = s_cls[j];
+                const bool better = kj > key, same = cj == cls;
+                r += better;
+                seg0 += cj < cls;
+                k += same && better;
+                len += same;
+            }
+        }
+#pragma unroll
+        for (int o = 2; o > 0; o >>= 1) {
+            r += __shfl_xor_sync(kFullMask, r, o);
+            seg0 += __shfl_xor_sync(kFullMask, seg0, o);
+            k += __shfl_xor_sync(kFullMask, k, o);
+            len += __shfl_xor_sync(kFullMask, len, o);
+        }
+        const int q = seg0 + k;
+        if (have && sub == 0) {
+            s_box[q] = bx;
+            s_area[q] = (bx.z - bx.x) * (bx.w - bx.y);
+            s_q_of_r[r] = (unsigned short)q;
+            s_slot_of_r[r] = (unsigned short)item;
+            s_seg0_of_q[q] = (unsigned short)seg0;
+            s_len_of_q[q] = (unsigned short)len;
+            s_dead[q] = 0;
+            if (len > 32) s_big = 1;
+        }
+        __syncthreads();
+        SIHL_PHASE(3);
+        // suppressor masks: the 4 lanes of a candidate split its earlier same-class boxes
+        unsigned mask = 0;
+        if (have && len <= 32) {
+            const float area = (bx.z - bx.x) * (bx.w - bx.y);
+            for (int j = sub; j < k; j += 4)
+                if (iou_gt(s_box[seg0 + j], s_area[seg0 + j], bx, area, p.iou_thr)) mask |= 1u << j;
+        }
+        mask |= __shfl_xor_sync(kFullMask, mask, 1);
+        mask |= __shfl_xor_sync(kFullMask, mask, 2);
+        if (have && sub == 0) s_mask[q] = mask;
+        __syncthreads();
+        SIHL_PHASE(4);
+        if (have && sub == 0 && k == 0 && len <= 32) {          // segment leader: greedy pass on bits only
+            unsigned kept = 1u;
+            for (int i = 1; i < len; ++i)
+                if ((s_mask[seg0 + i] & kept) == 0u) kept |= 1u << i;
+            s_keep[seg0] = kept;
+        }
+        __syncthreads();
+        if (s_big) {                                             // rare: a class with more than 32 candidates
+            const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+            for (int qq = warp; qq < n; qq += nwarps) {          // a warp per long segment, found by its leader
+                const int q0 = s_seg0_of_q[qq], m = s_len_of_q[qq];
+                if (qq != q0 || m <= 32) continue;
+                for (int i = 0; i + 1 < m; ++i) {
+                    __syncwarp();
+                    if (s_dead[q0 + i]) continue;
+                    const float4 bi = s_box[q0 + i];
+                    const float ai = s_area[q0 + i];
+                    for (int j = i + 1 + lane; j < m; j += 32)
+                        if (!s_dead[q0 + j] && iou_gt(bi, ai, s_box[q0 + j], s_area[q0 + j], p.iou_thr)) s_dead[q0 + j] = 1;
+                }
+            }
+            __syncthreads();
+        }
+        SIHL_PHASE(5);
+        // survivors in rank order
+        n_kept = block_ordered_compact(
+            n, s_warp,
+            [&](int rr) {
+                const int qq = s_q_of_r[rr], q0 = s_seg0_of_q[qq];
+                return s_len_of_q[qq] <= 32 ? ((s_keep[q0] >> (qq - q0)) & 1u) != 0u : s_dead[qq] == 0;
+            },
+            [&](int rr, int kk) {
+                const int qq = s_q_of_r[rr], slot = s_slot_of_r[rr];
+                if (p.mode == 0) {
+                    if (kk < p.K) {
+                        const int64_t o = (int64_t)img * p.K + kk;
+                        p.out_scores[o] = __uint_as_float((unsigned)(s_key[slot] >> 32));
+                        p.out_classes[o] = (int64_t)s_cls[slot];
+                        p.out_boxes[o] = s_box[qq];
+                    }
+                } else {
+                    p.keep[src0 + kk] = (int64_t)src0 + slot;
+                }
+            });
+    }
+    SIHL_PHASE(6);
+    if (p.mode == 0) {
+        const int m = n_kept < p.K ? n_kept : p.K;
+        if (tid == 0) {
+            p.num_instances[img] = m;
+            if (p.reset_counts) const_cast<int32_t *>(p.cand_count)[img] = 0;
+        }
+        for (int kk = m + tid; kk < p.K; kk += blockDim.x) {
+            const int64_t o = (int64_t)img * p.K + kk;
+            p.out_scores[o] = 0.f;
+            p.out_classes[o] = 0;
+            p.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else if (tid == 0) {
+        p.keep_count[img] = n_kept;
+    }
+    SIHL_PHASE(7);
+}
+
 static int pow2ceil(int64_t n)
 {
     int p = 2;
@@ -268,7 +451,7 @@ static int pow2ceil(int64_t n)
     return p;
 }
 
-static int launch_nms(const NmsParams &p, int n_images, cudaStream_t st)
+static int launch_nms(const NmsParams &p, int n_images, int64_t max_items, cudaStream_t st)
 {
     static thread_local bool attr_set = false;
     const size_t smem = (size_t)kSmemItems * kSmemItemBytes;
@@ -278,8 +461,15 @@ static int launch_nms(const NmsParams &p, int n_images, cudaStream_t st)
         if (rc) return rc;
         attr_set = true;
     }
-    k_nms<<<n_images, kNmsThreads, smem, st>>>(p);
-    SIHL_CHECK_LAUNCH("k_nms");
+    // short lists (the common case) in a light kernel; k_nms returns at once for those
+    k_nms_small<<<n_images, kSmallThreads, 0, st>>>(p);
+    SIHL_CHECK_LAUNCH("k_nms_small");
+    NmsParams big = p;
+    big.skip_small = 1;
+    if (max_items > kSmallItems) {
+        k_nms<<<n_images, kNmsThreads, smem, st>>>(big);
+        SIHL_CHECK_LAUNCH("k_nms");
+    }
     return SIHL_OD_OK;
 }
 
@@ -298,7 +488,7 @@ extern "C" size_t sihl_od_nms_workspace_bytes(int batch, int64_t cand_capacity)
 extern "C" int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacity, const uint64_t *cand_key,
                                 const float *cand_box, const int32_t *cand_cls, int batch, float iou_thr, int k,
                                 int64_t *num_instances, float *scores, int64_t *classes, float *boxes, void *workspace,
-                                void *stream)
+                                int reset_counts, void *stream)
 {
     SIHL_CHECK_ARG(cand_count && cand_key && cand_box && cand_cls, "NULL input");
     SIHL_CHECK_ARG(num_instances && scores && classes && boxes, "NULL output");
@@ -310,12 +500,12 @@ extern "C" int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacity
     p.cand_count = cand_count; p.cap = cand_capacity;
     p.cand_key = reinterpret_cast<const unsigned long long *>(cand_key);
     p.cand_box = reinterpret_cast<const float4 *>(cand_box); p.cand_cls = cand_cls;
-    p.mode = 0; p.iou_thr = iou_thr; p.K = k;
+    p.mode = 0; p.iou_thr = iou_thr; p.K = k; p.reset_counts = reset_counts;
     p.num_instances = num_instances; p.out_scores = scores; p.out_classes = classes;
     p.out_boxes = reinterpret_cast<float4 *>(boxes);
     p.workspace = static_cast<unsigned char *>(workspace);
     p.ws_stride = (size_t)pow2ceil(cand_capacity) * kWsItemBytes;
-    return launch_nms(p, batch, (cudaStream_t)stream);
+    return launch_nms(p, batch, cand_capacity, (cudaStream_t)stream);
 }
 
 extern "C" size_t sihl_od_batched_nms_workspace_bytes(int64_t n)
@@ -338,5 +528,12 @@ extern "C" int sihl_od_batched_nms(const float *boxes, const float *scores, cons
     p.boxes = reinterpret_cast<const float4 *>(boxes); p.scores = scores; p.classes = classes; p.seg_offsets = seg_offsets;
     p.mode = 1; p.iou_thr = iou_thr; p.keep = keep; p.keep_count = keep_count;
     p.workspace = static_cast<unsigned char *>(workspace); p.ws_stride = 0;
-    return launch_nms(p, n_images, (cudaStream_t)stream);
+    return launch_nms(p, n_images, n, (cudaStream_t)stream);
 }
+
+#ifdef SIHL_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int sihl_od_debug_phases(long long *out_host)
+{
+    return cudaMemcpyFromSymbol(out_host, sihl::g_phase_clock, sizeof(long long) * 16) == cudaSuccess ? 0 : 2;
+}
+#endif

@@ -214,7 +214,8 @@ class ObjectDetection(nn.Module):
         num_anchors = anchors.shape[0]
         gt = ops.GtBatch.from_lists(boxes, classes, device)
         assert gt.batch_size == batch_size, (gt.batch_size, batch_size)
-        sel = ops.assign_select(anchors, levels, width, height, gt, self.topk)
+        sel = ops.assign_select(anchors, levels, width, height, gt, self.topk,
+                                terms=ops.anchor_terms(levels, width, height, device))
         res = ops.assign_resolve(sel, gt, num_anchors, self.topk, True, want_positives=True)
         pos_index, pos_total, _ = ops.pos_compact(res["tile_pos_count"], res["tile_pos_rows"], batch_size, num_anchors)
         # the one host sync of the step: P sizes the gathered rows (the reference syncs ~7x per image)

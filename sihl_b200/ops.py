@@ -54,7 +54,7 @@ def _levels_array(levels: Sequence[Tuple[int, int]]) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- a1/a2
-_anchor_cache: Dict[tuple, Tuple[Tensor, Tensor, Tensor]] = {}
+_anchor_cache: Dict[tuple, Tuple[Tensor, Tensor, Tensor, Tensor]] = {}
 
 
 def anchor_tables(levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, device,
@@ -67,17 +67,29 @@ def anchor_tables(levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, dev
     device = torch.device(device)
     key = (tuple(map(tuple, levels)), int(img_w), int(img_h), device.type, device.index)
     if cache and key in _anchor_cache:
-        return _anchor_cache[key]
+        return _anchor_cache[key][:3]
     hw = _levels_array(levels)
     A = int((hw[:, 0].astype(np.int64) * hw[:, 1]).sum())
     with torch.cuda.device(device):
         out = tuple(torch.empty((A, 4), dtype=torch.float32, device=device) for _ in range(3))
         rc = _lib().sihl_od_anchors(hw.ctypes.data, len(hw), int(img_w), int(img_h), _p(out[0]), _p(out[1]), _p(out[2]),
                                     _stream(device))
-    _native.check(rc, "sihl_od_anchors")
+        _native.check(rc, "sihl_od_anchors")
+        terms = torch.empty((A, 4), dtype=torch.float32, device=device)
+        rc = _lib().sihl_od_anchor_terms(_p(out[2]), A, _p(terms), _stream(device))
+        _native.check(rc, "sihl_od_anchor_terms")
     if cache:
-        _anchor_cache[key] = out
+        _anchor_cache[key] = out + (terms,)
     return out
+
+
+def anchor_terms(levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, device) -> Tensor:
+    """Per-anchor CIoU terms ``[A,4]`` = (area, cx, cy, atan(w/h)) of the cached grid (the per-anchor
+    half of torchvision's ``complete_box_iou``, hoisted out of the pair loop)."""
+    device = torch.device(device)
+    anchor_tables(levels, img_w, img_h, device)
+    key = (tuple(map(tuple, levels)), int(img_w), int(img_h), device.type, device.index)
+    return _anchor_cache[key][3]
 
 
 # --------------------------------------------------------------------------- ground truth
@@ -121,7 +133,7 @@ class GtBatch:
 
 # --------------------------------------------------------------------------- a3/a4
 def assign_select(anchors: Tensor, levels: Optional[Sequence[Tuple[int, int]]], img_w: int, img_h: int,
-                  gt: GtBatch, topk: int = 9, sums: Optional[Tensor] = None):
+                  gt: GtBatch, topk: int = 9, sums: Optional[Tensor] = None, terms: Optional[Tensor] = None):
     """Stage 1 of ``bbox_matching`` for the whole batch (ref :263-268, :277).
 
     ``levels=None`` evaluates all ``A x G`` pairs (arbitrary anchors); otherwise
@@ -137,7 +149,7 @@ def assign_select(anchors: Tensor, levels: Optional[Sequence[Tuple[int, int]]], 
     hw = None if levels is None else _levels_array(levels)
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_assign_select(
-            _p(anchors), anchors.shape[0], None if hw is None else hw.ctypes.data, 0 if hw is None else len(hw),
+            _p(anchors), _p(terms), anchors.shape[0], None if hw is None else hw.ctypes.data, 0 if hw is None else len(hw),
             int(img_w), int(img_h), _p(_req(gt.boxes, torch.float32, "gt.boxes", 2)),
             _p(_req(gt.offsets, torch.int32, "gt.offsets", 1)), gt.batch_size, G, int(topk),
             _p(sel_anchor), _p(sel_val), _p(best), _p(sums), _stream(dev))
@@ -157,7 +169,7 @@ def assign_resolve(sel, gt: GtBatch, num_anchors: int, topk: int = 9, relative: 
                    fused: Optional[dict] = None):
     """Stage 2 (ref :270-282) with the dense losses (ref :157-163, :175-180) fused when
     ``loc_logits`` is given.  ``fused`` = dict(box_raw, cls_logits, offsets, scales, img_w, img_h)
-    additionally fuses the positive-row losses over dense maps.
+    additionally runs the positive-row losses over dense maps from the per-tile lists.
     Returns dict(assignment, iou, tile_pos_count, tile_pos_rows)."""
     sel_anchor, sel_val, best = sel
     dev = sel_anchor.device
@@ -170,20 +182,21 @@ def assign_resolve(sel, gt: GtBatch, num_anchors: int, topk: int = 9, relative: 
         tpc = torch.empty((B * n_tiles,), dtype=torch.int32, device=dev)
         tpr = torch.empty((B * n_tiles * tile,), dtype=torch.int32, device=dev)
     f = fused or {}
-    box_raw = f.get("box_raw")
-    cls = f.get("cls_logits")
+    if f and tpc is None:
+        n_tiles, tile = resolve_tiles(A)
+        tpc = torch.empty((B * n_tiles,), dtype=torch.int32, device=dev)
+        tpr = torch.empty((B * n_tiles * tile,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_assign_resolve(
             _p(sel_anchor), _p(sel_val), _p(best), _p(gt.offsets), B, A, int(topk), int(bool(relative)),
             _p(None if loc_logits is None else _req(loc_logits, torch.float32, "loc_logits")),
             _p(None if iou_preds is None else _req(iou_preds, torch.float32, "iou_preds")),
-            _p(assignment), _p(out_iou), _p(sums), _p(tpc), _p(tpr),
-            _p(None if box_raw is None else _req(box_raw, torch.float32, "box_raw")),
-            _p(None if cls is None else _req(cls, torch.float32, "cls_logits")),
-            0 if cls is None else int(cls.shape[-1]),
-            _p(f.get("offsets")), _p(f.get("scales")), int(f.get("img_w", 0)), int(f.get("img_h", 0)),
-            _p(gt.boxes), _p(gt.classes), _stream(dev))
-    _native.check(rc, "sihl_od_assign_resolve")
+            _p(assignment), _p(out_iou), _p(sums), _p(tpc), _p(tpr), _p(f.get("box_raw")), _p(f.get("cls_logits")),
+            0 if f.get("cls_logits") is None else int(f["cls_logits"].shape[-1]), _stream(dev))
+        _native.check(rc, "sihl_od_assign_resolve")
+        if f:
+            pos_loss_tiles(tpc, tpr, B, A, out_iou, assignment, f["offsets"], f["scales"], f["img_w"], f["img_h"], gt,
+                           f.get("box_raw"), f.get("cls_logits"), sums)
     return dict(assignment=assignment, iou=out_iou, tile_pos_count=tpc, tile_pos_rows=tpr)
 
 
@@ -259,6 +272,22 @@ def pos_loss(pos_index: Tensor, n_pos_dev: Optional[Tensor], capacity: int, num_
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_pos_loss(*args, _p(sums), _stream(dev))
     _native.check(rc, "sihl_od_pos_loss")
+    return sums
+
+
+def pos_loss_tiles(tile_pos_count: Tensor, tile_pos_rows: Tensor, batch: int, num_anchors: int, rel_iou: Tensor,
+                   assignment: Tensor, offsets: Tensor, scales: Tensor, img_w: int, img_h: int, gt: GtBatch,
+                   box_raw: Optional[Tensor], cls_logits: Optional[Tensor], sums: Tensor) -> Tensor:
+    """ref :187-208 over dense maps, straight from the per-tile positive lists (no compaction)."""
+    dev = rel_iou.device
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_pos_loss_tiles(
+            _p(tile_pos_count), _p(tile_pos_rows), int(batch), int(num_anchors), _p(rel_iou), _p(assignment), _p(offsets),
+            _p(scales), int(img_w), int(img_h), _p(gt.boxes), _p(gt.classes), _p(gt.offsets),
+            _p(None if box_raw is None else _req(box_raw, torch.float32, "box_raw")),
+            _p(None if cls_logits is None else _req(cls_logits, torch.float32, "cls_logits")),
+            0 if cls_logits is None else int(cls_logits.shape[-1]), _p(sums), _stream(dev))
+    _native.check(rc, "sihl_od_pos_loss_tiles")
     return sums
 
 
@@ -365,7 +394,8 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
     _native.check(rc, "sihl_od_dense_decode")
 
 
-def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Optional[tuple] = None):
+def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Optional[tuple] = None,
+             reset_counts: bool = False):
     dev = cand.count.device
     if out is None:
         out = (torch.empty((batch,), dtype=torch.int64, device=dev), torch.empty((batch, k), dtype=torch.float32, device=dev),
@@ -373,7 +403,7 @@ def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Op
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_nms_topk(_p(cand.count), cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(batch),
                                      float(iou_thr), int(k), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
-                                     _p(cand.workspace), _stream(dev))
+                                     _p(cand.workspace), int(reset_counts), _stream(dev))
     _native.check(rc, "sihl_od_nms_topk")
     return out
 

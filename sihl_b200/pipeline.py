@@ -4,10 +4,10 @@ with every buffer preallocated, two CUDA streams and (optionally) one CUDA graph
 This is the whole-batch form of the hot path that ``bench.py`` measures
 (BASELINE.json metric: det-head images/sec, assign + loss + NMS).  Per step and GPU:
 
-  train chain  (stream A): k_assign_select -> k_assign_resolve (dense + positive losses fused)
-                           -> k_loss_finalize                      [3 launches]
-  infer chain  (stream B): k_dense_decode (zeroing its counters in a 1-block launch first)
-                           -> k_nms                                [3 launches]
+  train chain  (stream A): k_assign_select -> k_assign_resolve (dense losses fused)
+                           -> k_pos_loss_tiles -> k_loss_finalize  [4 launches]
+  infer chain  (stream B): k_dense_decode_tma -> k_nms_small -> k_nms (long lists only)
+                                                                   [3 launches]
 
 The two chains share no data, so they run concurrently: the assignment is FP32-ALU/latency
 bound, the dense decode is HBM bound (SURVEY.md §8d caveat).  Across GPUs the only exchange
@@ -23,7 +23,7 @@ from torch import Tensor
 
 from . import _native, ops
 
-LAUNCHES_PER_STEP = 6     # select, resolve, finalize, zero, dense_decode, nms
+LAUNCHES_PER_STEP = 7     # select, resolve, pos_loss_tiles, finalize | dense_decode, nms_small, nms (returns at once for short lists)
 
 
 @dataclass
@@ -62,6 +62,7 @@ class DetectionHeadPipeline:
         self.device = torch.device(device)
         self.topk, self.K, self.score_thr, self.iou_thr = int(topk), int(max_instances), float(score_thr), float(iou_thr)
         self.offsets, self.scales, self.anchors = ops.anchor_tables(self.levels, img_w, img_h, self.device)
+        self.terms = ops.anchor_terms(self.levels, img_w, img_h, self.device)
         self.A = int(self.anchors.shape[0])
         self._hw = ops._levels_array(self.levels)
         dev, B, A, K = self.device, self.B, self.A, self.K
@@ -69,6 +70,9 @@ class DetectionHeadPipeline:
         self.sel_val = torch.empty((max_gt_total, topk), dtype=torch.float32, device=dev)
         self.best_iou = torch.empty((max_gt_total,), dtype=torch.float32, device=dev)
         self.max_gt_total = int(max_gt_total)
+        n_tiles, tile = ops.resolve_tiles(A)
+        self.tile_pos_count = torch.zeros((B * n_tiles,), dtype=torch.int32, device=dev)
+        self.tile_pos_rows = torch.zeros((B * n_tiles * tile,), dtype=torch.int32, device=dev)
         self.cand = ops.CandidateBuffers.allocate(B, int(cand_capacity or A), dev)
         self.side = torch.cuda.Stream(device=dev)
         self.lib = _native.load()
@@ -92,14 +96,17 @@ class DetectionHeadPipeline:
         assert gt.total <= self.max_gt_total and gt.batch_size == self.B
         p = ops._p
         _native.check(lib.sihl_od_assign_select(
-            p(self.anchors), self.A, self._hw.ctypes.data, len(self._hw), self.img_w, self.img_h, p(gt.boxes),
+            p(self.anchors), p(self.terms), self.A, self._hw.ctypes.data, len(self._hw), self.img_w, self.img_h, p(gt.boxes),
             p(gt.offsets), self.B, gt.total, self.topk, p(self.sel_anchor), p(self.sel_val), p(self.best_iou),
             p(out.sums), st), "sihl_od_assign_select")
         _native.check(lib.sihl_od_assign_resolve(
             p(self.sel_anchor), p(self.sel_val), p(self.best_iou), p(gt.offsets), self.B, self.A, self.topk, 1,
-            p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), None, None,
-            p(x.box_raw), p(x.cls_logits), self.C, p(self.offsets), p(self.scales), self.img_w, self.img_h,
-            p(gt.boxes), p(gt.classes), st), "sihl_od_assign_resolve")
+            p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), p(self.tile_pos_count),
+            p(self.tile_pos_rows), p(x.box_raw), p(x.cls_logits), self.C, st), "sihl_od_assign_resolve")
+        _native.check(lib.sihl_od_pos_loss_tiles(
+            p(self.tile_pos_count), p(self.tile_pos_rows), self.B, self.A, p(out.rel_iou), p(out.assignment),
+            p(self.offsets), p(self.scales), self.img_w, self.img_h, p(gt.boxes), p(gt.classes), p(gt.offsets),
+            p(x.box_raw), p(x.cls_logits), self.C, p(out.sums), st), "sihl_od_pos_loss_tiles")
         if finalize:
             self.finalize(out)
 
@@ -108,9 +115,11 @@ class DetectionHeadPipeline:
         _native.check(self.lib.sihl_od_loss_finalize(ops._p(out.sums), ops._p(out.losses), st), "sihl_od_loss_finalize")
 
     def infer_chain(self, x: StepInputs, out: StepOutputs) -> None:
+        # the candidate counters start at zero and k_nms* re-zero them once consumed: no memset launch
         ops.dense_decode(x.loc_logits, x.cls_logits, x.box_raw, self.offsets, self.scales, self.img_w, self.img_h,
-                         self.score_thr, self.cand, zero_counts=True)
-        ops.nms_topk(self.cand, self.B, self.iou_thr, self.K, (out.num_instances, out.scores, out.classes, out.boxes))
+                         self.score_thr, self.cand, zero_counts=False)
+        ops.nms_topk(self.cand, self.B, self.iou_thr, self.K, (out.num_instances, out.scores, out.classes, out.boxes),
+                     reset_counts=True)
 
     def step(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> None:
         """One pass of the hot path over one batch: both chains, concurrently, on two streams."""
