@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--serial", action="store_true", help="run both chains on one stream")
+    ap.add_argument("--lanes", type=int, default=3, help="steps in flight (independent scratch + stream each)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=20)
@@ -210,51 +211,69 @@ def run_ours(args, w, world, rank, local_rank):
     dev = torch.device("cuda", local_rank)
     H, W, B, C, G, K = w["height"], w["width"], w["batch"], w["classes"], w["gt"], w["k"]
     levels = synth.level_sizes(H, W)
-    pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR)
+    n_lanes = max(1, args.lanes)
+    pipes = [DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR) for _ in range(n_lanes)]
+    pipe = pipes[0]
     A = pipe.A
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + 1000 * rank)
     n_sets = 3
-    sets, outs = [], []
+    sets = []
     for _ in range(n_sets):
         boxes, classes, offsets = synth.gt_batch_torch(gen, B, H, W, C, G, dev)
         loc, iou, box, cls = synth.dense_maps_torch(gen, B, A, C, dev)
         sets.append(StepInputs(loc, iou, box, cls, ops.GtBatch(boxes, classes, offsets, [G] * B)))
-        outs.append(pipe.new_outputs())
+    # every (lane, input set) pair owns its outputs: steps in flight on different lanes never share a buffer
+    outs = [[pipes[ln].new_outputs() for _ in range(n_sets)] for ln in range(n_lanes)]
     torch.cuda.synchronize()
 
     multi = world > 1
     use_graph = not args.no_graph
+    main = torch.cuda.current_stream(dev)
+    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
 
-    def plain_step(i):
+    def plain_step(ln, i):
         if args.serial:
-            pipe.infer_chain(sets[i], outs[i]); pipe.train_chain(sets[i], outs[i], finalize=not multi)
+            pipes[ln].infer_chain(sets[i], outs[ln][i]); pipes[ln].train_chain(sets[i], outs[ln][i], finalize=not multi)
         else:
-            pipe.step(sets[i], outs[i], finalize=not multi)
+            pipes[ln].step(sets[i], outs[ln][i], finalize=not multi)
 
     graphs = None
     if use_graph and not args.serial:
-        graphs = [pipe.capture(sets[i], outs[i], finalize=not multi) for i in range(n_sets)]
+        graphs = []
+        for ln in range(n_lanes):
+            with torch.cuda.stream(lane_streams[ln]):
+                graphs.append([pipes[ln].capture(sets[i], outs[ln][i], finalize=not multi) for i in range(n_sets)])
+        torch.cuda.synchronize()
 
-    prev = {"work": None}
+    prev = [None] * n_lanes
 
     def run_step(s):
-        i = s % n_sets
-        if graphs is not None:
-            graphs[i].replay()
-        else:
-            plain_step(i)
-        if multi:
-            # the all-reduce of step s overlaps the kernels of step s+1; its finalize follows one step later
-            if prev["work"] is not None:
-                j, work = prev["work"]
-                work.wait(); pipe.finalize(outs[j])
-            prev["work"] = (i, dist.all_reduce(outs[i].sums, op=dist.ReduceOp.SUM, async_op=True))
+        """Step s goes to lane s % n_lanes: consecutive steps overlap (the HBM-bound decode of one step runs
+        next to the latency-bound assignment / NMS kernels of its neighbours)."""
+        ln, i = s % n_lanes, s % n_sets
+        with torch.cuda.stream(lane_streams[ln]):
+            if multi and prev[ln] is not None:        # finish this lane's previous step: all-reduced sums -> losses
+                j, work = prev[ln]
+                work.wait(); pipes[ln].finalize(outs[ln][j]); prev[ln] = None
+            if graphs is not None:
+                graphs[ln][i].replay()
+            else:
+                plain_step(ln, i)
+            if multi:
+                prev[ln] = (i, dist.all_reduce(outs[ln][i].sums, op=dist.ReduceOp.SUM, async_op=True))
 
     def drain():
-        if prev["work"] is not None:
-            j, work = prev["work"]
-            work.wait(); pipe.finalize(outs[j]); prev["work"] = None
+        for ln in range(n_lanes):
+            with torch.cuda.stream(lane_streams[ln]):
+                if prev[ln] is not None:
+                    j, work = prev[ln]
+                    work.wait(); pipes[ln].finalize(outs[ln][j]); prev[ln] = None
+            main.wait_stream(lane_streams[ln])
+
+    def fork():
+        for st in lane_streams:
+            st.wait_stream(main)
 
     def barrier():
         if multi:
@@ -262,17 +281,19 @@ def run_ours(args, w, world, rank, local_rank):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    fork()
     for s in range(max(args.warmup, 3)):
         run_step(s)
     drain()
     barrier()
     if sampler: sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(main)
+    fork()
     for s in range(args.steps):
         run_step(s)
     drain()
-    e1.record()
+    e1.record(main)
     barrier()
     if sampler: sampler.mark()
     ms = e0.elapsed_time(e1)
@@ -281,12 +302,13 @@ def run_ours(args, w, world, rank, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = B * world * args.steps / (ms * 1e-3)
+    outs0 = outs[0]
 
     # ---- sanity of what was timed (not timed): losses finite, detections present
-    losses = outs[0].losses.cpu().tolist()
-    P_bar = float(outs[0].sums[6].item()) / B
+    losses = outs0[0].losses.cpu().tolist()
+    P_bar = float(outs0[0].sums[6].item()) / (B * (world if multi else 1))
     cand_mean = None      # measured in the stand-alone decode loop below (k_nms* zero the counters they consume)
-    det_mean = float(outs[(args.steps - 1) % n_sets].num_instances.float().mean().item())
+    det_mean = float(outs0[0].num_instances.float().mean().item())
 
     result = {"ms": ms, "value": value, "losses": losses, "P_bar": P_bar, "cand_mean": cand_mean, "det_mean": det_mean}
     if rank != 0:
@@ -343,7 +365,7 @@ def run_ours(args, w, world, rank, local_rank):
     # ---- end to end: host (pinned) inputs -> H2D -> step -> D2H of losses + detections, every step
     e2e = None
     if not args.skip_e2e:
-        e2e = run_e2e(args, pipe, sets[0], outs[0], world, multi, dev, sampler)
+        e2e = run_e2e(args, pipe, sets[0], outs0[0], world, multi, dev, sampler)
 
     cpu = None
     if not multi and not args.skip_cpu_baseline:
@@ -357,7 +379,8 @@ def run_ours(args, w, world, rank, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, args, world, {"cuda_graph": graphs is not None, "streams": 1 if args.serial else 2,
+        "config": config_dict(w, args, world, {"cuda_graph": graphs is not None, "streams_per_step": 1 if args.serial else 2,
+                                                "steps_in_flight": n_lanes,
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
         "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "roofline_step": roofline_step,

@@ -56,7 +56,8 @@ extern "C" {
  *   [4] sum w * CIoU-loss(decoded box, gt)    ref :194-197
  *   [5] sum w * CE(class logits, gt class)    ref :205-208
  *   [6] #(rel > 0)  (P, number of positives)  ref :165,182
- *   [7] reserved (0)                                                          */
+ *   [7] scratch: number of 32-row positive chunks published for
+ *       sihl_od_pos_loss_tiles (not a loss term)                              */
 
 SIHL_OD_API int sihl_od_version(void);
 SIHL_OD_API const char *sihl_od_last_error_string(void);
@@ -111,7 +112,11 @@ SIHL_OD_API int sihl_od_assign_select(const float *anchors, const float *anchor_
  * the lists into one pos_index (compact rows for the reference's gathered-row
  * MLPs); sihl_od_pos_loss_tiles() consumes them directly for dense maps.
  * prefetch_box_raw / prefetch_cls_logits (optional dense maps [B*A,4] / [B*A,C]):
- * the rows of the positives are prefetched into L2 for that next kernel. */
+ * the rows of the positives are prefetched into L2 for that next kernel.
+ * pos_chunks (optional, int32 [B * n_tiles * tile / 32]): work list of 32-row chunks
+ * of the positive lists for sihl_od_pos_loss_tiles; its length is kept in sums[7].
+ * tile_pos_aux (optional, int32 [B * n_tiles * tile * 2]): per listed positive the
+ * pair (global gt index, rel_iou bits), parallel to tile_pos_rows. */
 SIHL_OD_API int sihl_od_resolve_tiles(int64_t num_anchors, int *n_tiles, int *tile);
 
 SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *sel_val, const float *best_iou,
@@ -120,7 +125,7 @@ SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *s
                            int64_t *assignment, float *out_iou, double *sums,
                            int32_t *tile_pos_count, int32_t *tile_pos_rows,
                            const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
-                           void *stream);
+                           int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream);
 
 /* pos_index int32 [capacity] (flat b*A+a, ascending), pos_total int32 [1],
  * pos_image_offsets int32 [B+1] (may be NULL).  Entries beyond capacity are
@@ -151,14 +156,18 @@ SIHL_OD_API int sihl_od_pos_loss(const int32_t *pos_index, const int32_t *n_pos_
                      double *sums, void *stream);
 
 /* The same positive-row losses over DENSE maps (box_raw [B*A,4], cls_logits
- * [B*A,C]) taken straight from the per-tile lists of sihl_od_assign_resolve:
- * no compaction pass, no host round trip.  Accumulates sums[4], sums[5]. */
-SIHL_OD_API int sihl_od_pos_loss_tiles(const int32_t *tile_pos_count, const int32_t *tile_pos_rows, int batch,
-                           int64_t num_anchors, const float *rel_iou, const int64_t *assignment,
+ * [B*A,C]) taken straight from the per-tile lists of sihl_od_assign_resolve: no
+ * compaction pass, no host round trip.  pos_chunks / tile_pos_rows / tile_pos_aux
+ * are what sihl_od_assign_resolve published (the chunk count lives in sums[7]).
+ * Accumulates sums[4], sums[5].  If losses != NULL (with done_counter, a
+ * zero-initialised uint32 the kernel resets itself) the last CTA also performs
+ * sihl_od_loss_finalize — one launch less on a single GPU. */
+SIHL_OD_API int sihl_od_pos_loss_tiles(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
+                           const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
                            const float *offsets, const float *scales, int img_w, int img_h,
                            const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
                            const float *box_raw, const float *cls_logits, int num_classes,
-                           double *sums, void *stream);
+                           double *sums, float *losses, uint32_t *done_counter, void *stream);
 
 /* ref :163-172, :180, :197, :208, :210 — losses fp32 [5] =
  * [location, box, class, iou, total]; early-out when sums[6] == 0. */

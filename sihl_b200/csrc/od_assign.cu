@@ -7,10 +7,11 @@
 //
 // Stage 1 (k_assign_select): one warp per ground-truth box.  CIoU > 0 implies IoU > 0
 // (every subtracted term is >= 0), so only anchors whose cell overlaps the gt can be
-// positive: candidates are enumerated from the gt extent per pyramid level (widened by
-// one cell; the overlap itself is decided by the CIoU arithmetic on the real anchor
-// table), levels are visited in order of decreasing IoU upper bound
-// min(area)/max(area) and skipped once that bound falls below the current k-th value.
+// positive, and CIoU <= IoU - rho^2/c^2 bounds the distance between the centres: per
+// pyramid level the candidates are the cells of a small window around the gt (overlap
+// window intersected with the centre-distance window, both with slack; the decision is
+// always the exact CIoU arithmetic on the real anchor table).  The windows of all
+// levels form one flat candidate range that the warp sweeps 32 at a time.
 // Lanes append positives to a per-warp shared-memory buffer with ballot/popc; a rank-by-
 // counting pass (lexicographic (value desc, anchor asc)) keeps the top k and yields them
 // sorted.  Bound: FP32 ALU / latency (≈45 flops + 4 IEEE divisions + atanf per pair);
@@ -32,13 +33,16 @@ int fill_level_table(const int32_t *level_hw_host, int n_levels, LevelTable *lv)
 // ---------------------------------------------------------------------------
 // Stage 1: select
 // ---------------------------------------------------------------------------
+#ifdef SIHL_PHASE_TIMING
+__device__ unsigned g_sel_dbg[3 * 16384];     // per gt: start (globaltimer ns, low bits), cycles, candidates evaluated
+#endif
 constexpr int kSelWarps = 4;
 constexpr int kBufCap = 64;
 
 struct SelectParams {
     LevelTable lv;
     float inv_sx[SIHL_OD_MAX_LEVELS], inv_sy[SIHL_OD_MAX_LEVELS];   // cells per pixel (host-computed, only sizes the
-    float cell_area[SIHL_OD_MAX_LEVELS];                            // conservative candidate window / the IoU bound)
+    float cell_w[SIHL_OD_MAX_LEVELS], cell_h[SIHL_OD_MAX_LEVELS];   // conservative candidate windows)
     int use_levels;
     int num_anchors;
     int topk;
@@ -74,13 +78,14 @@ __device__ __forceinline__ int select_compress(float *bv, int *bi, int cnt, int 
 
 // anchor_terms (optional): per anchor (area, cx, cy, atan(w/h)) as sihl_od_anchor_terms writes them —
 // the same fp32 operations box_terms() performs, hoisted out of the pair loop and cached with the tables.
-__global__ void __launch_bounds__(kSelWarps * 32, 10)
+__global__ void __launch_bounds__(kSelWarps * 32)
 k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4 *__restrict__ anchor_terms,
                 const float4 *__restrict__ gt_boxes, int total_gt, int32_t *__restrict__ sel_anchor,
                 float *__restrict__ sel_val, float *__restrict__ best_iou, double *__restrict__ sums)
 {
     __shared__ float s_val[kSelWarps][kBufCap];
     __shared__ int s_idx[kSelWarps][kBufCap];
+    __shared__ int4 s_tab[kSelWarps][SIHL_OD_MAX_LEVELS];
 
     if (sums != nullptr && blockIdx.x == 0 && threadIdx.x < SIHL_OD_NUM_SUMS) sums[threadIdx.x] = 0.0;
 
@@ -88,6 +93,12 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
     const int g = blockIdx.x * kSelWarps + warp;
     if (g >= total_gt) return;                       // warp-uniform; no block barriers below
 
+#ifdef SIHL_PHASE_TIMING
+    const long long dbg_c0 = clock64();
+    unsigned long long dbg_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    unsigned dbg_chunks = 0;
+#endif
     float *bv = s_val[warp];
     int *bi = s_idx[warp];
     const int topk = p.topk;
@@ -100,6 +111,9 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
     // The arithmetic is ciou_pair() (od_math.h) cut in three so that a chunk leaves early when no lane
     // can still rank: no overlap => CIoU <= 0; IoU < thr => CIoU < thr (CIoU <= IoU).
     auto consider = [&](bool valid, int a) {
+#ifdef SIHL_PHASE_TIMING
+        ++dbg_chunks;
+#endif
         BoxTerms an;
         an.x1 = an.y1 = an.x2 = an.y2 = an.area = an.cx = an.cy = an.at = 0.f;
         if (valid) {
@@ -157,45 +171,62 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
     if (!p.use_levels) {
         for (int t0 = 0; t0 < p.num_anchors; t0 += 32) consider(t0 + lane < p.num_anchors, t0 + lane);
     } else {
-        // IoU <= min(area)/max(area); 0.1 % slack covers the rounding of the anchor table.
-        float bound[SIHL_OD_MAX_LEVELS];
-#pragma unroll
-        for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) {
-            const float cell = p.cell_area[l];
-            const float lo = fminf(cell, gt.area), hi = fmaxf(cell, gt.area);
-            bound[l] = (l < p.lv.n) ? ((gt.area > 0.f) ? __fdividef(lo, hi) * 1.001f : CUDART_INF_F) : -1.f;
-        }
-        for (int it = 0; it < p.lv.n; ++it) {
-            int l = 0;
-            float bmax = -1.f;
-#pragma unroll
-            for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k)
-                if (bound[k] > bmax) { bmax = bound[k]; l = k; }
-            if (cnt >= topk) {
-                if (dirty) { cnt = select_compress(bv, bi, cnt, topk, lane); dirty = false; }
-                thr = bv[topk - 1];
-                if (bmax < thr) break;               // no remaining level can reach the current k-th value
-            }
-#pragma unroll
-            for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k)
-                if (k == l) bound[k] = -2.f;         // visited
-            const int lw = p.lv.w[l], lh = p.lv.h[l], base = p.lv.base[l];
+        // Candidate windows, one pyramid level per lane.  A positive CIoU needs BOTH
+        //  (i)  overlap (CIoU <= IoU): cells from floor(x1/sx) to floor(x2/sx), widened by one, and
+        //  (ii) rho^2 / c^2 < IoU (CIoU <= IoU - rho^2/c^2) with IoU <= min(area)/max(area) and, for
+        //       overlapping boxes, c^2 <= (Wg+sx)^2 + (Hg+sy)^2: the cell centre lies within
+        //       R = sqrt(IoU_max * c_max^2) of the gt centre in x and in y.
+        // Both are supersets evaluated with slack (2 % + 0.01 px on R, one cell on the overlap window); the
+        // decision itself is always the exact CIoU arithmetic on the real anchor table above.
+        int4 *tab = s_tab[warp];
+        int n_l = 0;
+        if (lane < p.lv.n) {
+            const int l = lane;
+            const int lw = p.lv.w[l], lh = p.lv.h[l];
+            const float isx = p.inv_sx[l], isy = p.inv_sy[l], sx = p.cell_w[l], sy = p.cell_h[l];
             const float fw = (float)(lw - 1), fh = (float)(lh - 1);
-            // window of cells that can overlap the gt, widened by one cell on every side
-            const int j0 = (int)fminf(fmaxf(floorf(gt.x1 * p.inv_sx[l]) - 1.f, 0.f), fw);
-            const int j1 = (int)fminf(fmaxf(floorf(gt.x2 * p.inv_sx[l]) + 1.f, 0.f), fw);
-            const int i0 = (int)fminf(fmaxf(floorf(gt.y1 * p.inv_sy[l]) - 1.f, 0.f), fh);
-            const int i1 = (int)fminf(fmaxf(floorf(gt.y2 * p.inv_sy[l]) + 1.f, 0.f), fh);
-            const int nj = j1 - j0 + 1, ni = i1 - i0 + 1;
-            if (nj <= 0 || ni <= 0) continue;
-            const int n = ni * nj;
-            const float inv_nj = __fdividef(1.f, (float)nj);
-            for (int t0 = 0; t0 < n; t0 += 32) {
-                const int t = t0 + lane;
-                int ri = (int)(((float)t + 0.5f) * inv_nj);           // t / nj (margin 0.5/nj >> rounding)
-                const int rj = t - ri * nj;
-                consider(t < n, base + (i0 + ri) * lw + (j0 + rj));
+            float jlo = floorf(gt.x1 * isx) - 1.f, jhi = floorf(gt.x2 * isx) + 1.f;
+            float ilo = floorf(gt.y1 * isy) - 1.f, ihi = floorf(gt.y2 * isy) + 1.f;
+            if (gt.area > 0.f) {
+                const float cell = sx * sy;
+                const float iou_max = __fdividef(fminf(cell, gt.area), fmaxf(cell, gt.area));
+                const float wg = fabsf(gt.x2 - gt.x1) + sx, hg = fabsf(gt.y2 - gt.y1) + sy;
+                const float R = sqrtf(iou_max * ((wg * wg) + (hg * hg) + 1.f)) * 1.02f + 0.01f;
+                jlo = fmaxf(jlo, floorf((gt.cx - R) * isx - 0.5f));
+                jhi = fminf(jhi, floorf((gt.cx + R) * isx - 0.5f) + 1.f);
+                ilo = fmaxf(ilo, floorf((gt.cy - R) * isy - 0.5f));
+                ihi = fminf(ihi, floorf((gt.cy + R) * isy - 0.5f) + 1.f);
             }
+            const int j0 = (int)fminf(fmaxf(jlo, 0.f), fw), j1 = (int)fminf(fmaxf(jhi, 0.f), fw);
+            const int i0 = (int)fminf(fmaxf(ilo, 0.f), fh), i1 = (int)fminf(fmaxf(ihi, 0.f), fh);
+            const bool empty = !(jhi >= 0.f) || !(jlo <= fw) || !(ihi >= 0.f) || !(ilo <= fh) || j1 < j0 || i1 < i0;
+            const int nj = empty ? 0 : j1 - j0 + 1, ni = empty ? 0 : i1 - i0 + 1;
+            n_l = ni * nj;
+            tab[l] = make_int4(p.lv.base[l] + i0 * lw + j0, nj, lw, __float_as_int(__fdividef(1.f, (float)(nj > 0 ? nj : 1))));
+        }
+        int incl = n_l;                              // inclusive prefix of the window sizes over the level lanes
+#pragma unroll
+        for (int o = 1; o < SIHL_OD_MAX_LEVELS; o <<= 1) {
+            const int y = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += y;
+        }
+        int pre[SIHL_OD_MAX_LEVELS];                 // pre[k] = first flat candidate index of level k+1
+#pragma unroll
+        for (int k = 0; k < SIHL_OD_MAX_LEVELS; ++k) pre[k] = __shfl_sync(kFullMask, incl, k);
+        const int total = pre[SIHL_OD_MAX_LEVELS - 1];
+        __syncwarp();
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            const bool valid = t < total;
+            int l = 0, first = 0;
+#pragma unroll
+            for (int k = 0; k < SIHL_OD_MAX_LEVELS - 1; ++k)
+                if (t >= pre[k]) { l = k + 1; first = pre[k]; }
+            const int4 e = tab[valid ? l : 0];
+            const int tl = t - first;
+            const int ri = (int)(((float)tl + 0.5f) * __int_as_float(e.w));     // tl / nj (margin 0.5/nj >> rounding)
+            const int rj = tl - ri * e.y;
+            consider(valid, e.x + ri * e.z + rj);
         }
     }
 
@@ -205,6 +236,13 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
         sel_val[(int64_t)g * topk + lane] = lane < cnt ? bv[lane] : 0.f;
     }
     if (lane == 0) best_iou[g] = cnt ? bv[0] : 0.f;                  // ref :277 topk_ious[0]
+#ifdef SIHL_PHASE_TIMING
+    if (lane == 0 && g < 16384) {
+        g_sel_dbg[3 * g] = (unsigned)(dbg_t0 & 0xffffffffu);
+        g_sel_dbg[3 * g + 1] = (unsigned)(clock64() - dbg_c0);
+        g_sel_dbg[3 * g + 2] = dbg_chunks;
+    }
+#endif
 }
 
 // Per-anchor terms of the CIoU (box_terms() of od_math.h), cached next to the anchor table.
@@ -219,6 +257,12 @@ __global__ void __launch_bounds__(256) k_anchor_terms(const float4 *__restrict__
 // ---------------------------------------------------------------------------
 // Stage 2: resolve (+ dense losses, + compaction, + fused positive losses)
 // ---------------------------------------------------------------------------
+#ifdef SIHL_PHASE_TIMING
+__device__ long long g_res_phase[8 * 16];
+#define SIHL_RP(i) do { if ((blockIdx.x == 0 || blockIdx.x == 16) && blockIdx.y < 4 && threadIdx.x == 0) g_res_phase[((blockIdx.x ? 4 : 0) + blockIdx.y) * 16 + (i)] = clock64(); } while (0)
+#else
+#define SIHL_RP(i) do { } while (0)
+#endif
 constexpr int kResThreads = 128;
 constexpr int kChunks = kTile / kResThreads;
 constexpr int kResWarps = kResThreads / 32;
@@ -230,11 +274,14 @@ struct ResolveParams {
     int64_t *assignment; float *out_iou; double *sums;
     int32_t *tile_pos_count; int32_t *tile_pos_rows;
     const float *prefetch_box; const float *prefetch_cls; int num_classes;   // L2 hints for k_pos_loss_tiles
+    int32_t *pos_chunks;       // work list for k_pos_loss_tiles: (slot << 10 | first_row / 32 << 6 | rows - 1)
+    int2 *tile_pos_aux;        // per listed positive: (global gt index, rel bits) — saves that kernel two dependent hops
 };
 
 __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
 {
-    __shared__ unsigned long long s_key[kTile];
+    __shared__ unsigned s_v[kTile], s_g[kTile];
+    __shared__ float s_rel[kTile];
     __shared__ unsigned short s_pos[kTile];
     __shared__ int s_seg[kChunks * kResWarps + 1];
     __shared__ double s_red[5 * 32];
@@ -243,6 +290,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
     const int b = blockIdx.y, tile = blockIdx.x, n_tiles = gridDim.x;
     const int A = p.num_anchors, a0 = tile * kTile;
     const int na = min(kTile, A - a0);
+    SIHL_RP(0);
     const int g0 = __ldg(p.gt_offsets + b), g1 = __ldg(p.gt_offsets + b + 1);
 
     // issue the streaming loads first: they are independent of the key reduction below
@@ -255,23 +303,47 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         x_iou[c] = p.iou_pred != nullptr ? __ldcs(p.iou_pred + flat) : 0.f;
     }
 
-    for (int i = tid; i < kTile; i += kResThreads) s_key[i] = 0ull;
+    for (int i = tid; i < kTile; i += kResThreads) { s_v[i] = 0u; s_g[i] = 0xffffffffu; }
     __syncthreads();
-    // per anchor: max value over the gts that selected it, ties -> lowest gt (ref :270)
+    SIHL_RP(1);
+    // per anchor: max value over the gts that selected it, ties -> lowest gt (ref :270), as two passes
+    // of native 32-bit shared-memory atomics (max of the value bits, then min of the gt among the maxima)
     const int n_entries = (g1 - g0) * p.topk;
     const int32_t *sa = p.sel_anchor + (int64_t)g0 * p.topk;
     const float *sv = p.sel_val + (int64_t)g0 * p.topk;
-    for (int e = tid; e < n_entries; e += kResThreads) {
-        const int a = __ldg(sa + e) - a0;
-        const float v = __ldg(sv + e);
-        if (a >= 0 && a < na) {
-            const unsigned g = (unsigned)(e / p.topk);
-            const unsigned long long key =
-                ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - g);
-            atomicMax(&s_key[a], key);
+    constexpr int kEntryBatch = 8;                                   // loads in flight per thread
+    for (int e0 = 0; e0 < n_entries; e0 += kEntryBatch * kResThreads) {
+        int ea[kEntryBatch];
+        unsigned ev[kEntryBatch];
+#pragma unroll
+        for (int u = 0; u < kEntryBatch; ++u) {                         // all loads first: one L2 round trip per batch
+            const int e = e0 + u * kResThreads + tid;
+            const bool in = e < n_entries;
+            ea[u] = in ? __ldg(sa + e) - a0 : -1;
+            ev[u] = in ? __float_as_uint(__ldg(sv + e)) : 0u;           // values are > 0: bit order == value order
         }
+#pragma unroll
+        for (int u = 0; u < kEntryBatch; ++u)
+            if (ea[u] >= 0 && ea[u] < na) atomicMax(&s_v[ea[u]], ev[u]);
     }
     __syncthreads();
+    for (int e0 = 0; e0 < n_entries; e0 += kEntryBatch * kResThreads) {
+        int ea[kEntryBatch];
+        unsigned ev[kEntryBatch];
+#pragma unroll
+        for (int u = 0; u < kEntryBatch; ++u) {
+            const int e = e0 + u * kResThreads + tid;
+            const bool in = e < n_entries;
+            ea[u] = in ? __ldg(sa + e) - a0 : -1;
+            ev[u] = in ? __float_as_uint(__ldg(sv + e)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kEntryBatch; ++u)
+            if (ea[u] >= 0 && ea[u] < na && s_v[ea[u]] == ev[u])
+                atomicMin(&s_g[ea[u]], (unsigned)((e0 + u * kResThreads + tid) / p.topk));
+    }
+    __syncthreads();
+    SIHL_RP(2);
 
     float acc_bce = 0.f, acc_one = 0.f, acc_mse = 0.f, acc_rel = 0.f, acc_pos = 0.f;
     unsigned ballots[kChunks];
@@ -282,19 +354,20 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         const int la = c * kResThreads + tid;
         bool pos = false;
         if (la < na) {
-            const unsigned long long key = s_key[la];
+            const unsigned vb = s_v[la];
             const int64_t flat = (int64_t)b * A + a0 + la;
             float rel = 0.f;
             int64_t asg = -1;
-            if (key != 0ull) {
-                const float v = __uint_as_float((unsigned)(key >> 32));
-                const int g = (int)(0xffffffffu - (unsigned)(key & 0xffffffffu));
+            if (vb != 0u) {
+                const float v = __uint_as_float(vb);
+                const int g = (int)s_g[la];
                 rel = p.relative ? v / __ldg(p.best_iou + g0 + g) : v;          // ref :279-281
                 pos = rel > 0.f;
                 asg = pos ? g : -1;                                              // canonical form (sihl_od.h)
             }
             p.assignment[flat] = asg;
             p.out_iou[flat] = rel;
+            s_rel[la] = rel;
             if (pos) {                                    // the positive-row kernel gathers these next: warm L2 now
                 if (p.prefetch_box != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.prefetch_box + 4 * flat));
                 if (p.prefetch_cls != nullptr) {
@@ -321,6 +394,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         if (want_list && lane == 0) s_seg[c * kResWarps + warp] = __popc(ballots[c]);
     }
 
+    SIHL_RP(3);
     int n_pos = 0;
     if (want_list) {
         // ordered compaction: segment (chunk, warp) order == ascending anchor order (ref :182-184)
@@ -349,16 +423,37 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
         if (p.tile_pos_count != nullptr) {
             const int slot = b * n_tiles + tile;
             if (tid == 0) p.tile_pos_count[slot] = n_pos;
-            for (int r = tid; r < n_pos; r += kResThreads)
-                p.tile_pos_rows[(int64_t)slot * kTile + r] = (int32_t)((int64_t)b * A + a0 + s_pos[r]);
+            // reserve ceil(n_pos/32) entries of the chunk list; the counter lives in sums[7] (zeroed by
+            // k_assign_select together with the loss sums; integers are exact in fp64).  The atomic's
+            // round trip overlaps the list writes below.
+            const int nchunk = (n_pos + 31) >> 5;
+            double base_d = 0.0;
+            const bool publish = p.pos_chunks != nullptr && n_pos > 0 && warp == 0;
+            if (publish && lane == 0) base_d = atomicAdd(p.sums + 7, (double)nchunk);
+            for (int r = tid; r < n_pos; r += kResThreads) {
+                const int la = s_pos[r];
+                p.tile_pos_rows[(int64_t)slot * kTile + r] = (int32_t)((int64_t)b * A + a0 + la);
+                if (p.tile_pos_aux != nullptr) {
+                    p.tile_pos_aux[(int64_t)slot * kTile + r] = make_int2(g0 + (int)s_g[la], __float_as_int(s_rel[la]));
+                }
+            }
+            if (publish) {
+                const int base = __shfl_sync(kFullMask, (int)base_d, 0);
+                if (lane < nchunk) {
+                    const int rows = min(32, n_pos - 32 * lane);
+                    p.pos_chunks[base + lane] = (slot << 10) | (lane << 6) | (rows - 1);
+                }
+            }
         }
     }
 
+    SIHL_RP(4);
     if (p.sums != nullptr && p.loc != nullptr) {
-        double v[5] = {acc_bce, acc_one, acc_mse, acc_rel, acc_pos};
+        float v[5] = {acc_bce, acc_one, acc_mse, acc_rel, acc_pos};
         const int slot[5] = {0, 1, 2, 3, 6};
-        block_accumulate<5>(v, s_red, p.sums, slot);
+        block_accumulate_f<5>(v, s_red, p.sums, slot);
     }
+    SIHL_RP(5);
 }
 
 // ---------------------------------------------------------------------------
@@ -423,7 +518,7 @@ extern "C" int sihl_od_assign_select(const float *anchors, const float *anchor_t
                    (long long)num_anchors, topk);
     SelectParams p;
     p.use_levels = level_hw_host != nullptr;
-    for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) { p.inv_sx[l] = p.inv_sy[l] = 0.f; p.cell_area[l] = 1.f; }
+    for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) { p.inv_sx[l] = p.inv_sy[l] = 0.f; p.cell_w[l] = p.cell_h[l] = 1.f; }
     if (p.use_levels) {
         int rc = fill_level_table(level_hw_host, n_levels, &p.lv);
         if (rc) return rc;
@@ -433,7 +528,8 @@ extern "C" int sihl_od_assign_select(const float *anchors, const float *anchor_t
         for (int l = 0; l < n_levels; ++l) {
             p.inv_sx[l] = (float)p.lv.w[l] / (float)img_w;
             p.inv_sy[l] = (float)p.lv.h[l] / (float)img_h;
-            p.cell_area[l] = ((float)img_w / (float)p.lv.w[l]) * ((float)img_h / (float)p.lv.h[l]);
+            p.cell_w[l] = (float)img_w / (float)p.lv.w[l];
+            p.cell_h[l] = (float)img_h / (float)p.lv.h[l];
         }
     } else {
         p.lv.n = 0;
@@ -462,7 +558,7 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
                                       const float *loc_logits, const float *iou_preds, int64_t *assignment,
                                       float *out_iou, double *sums, int32_t *tile_pos_count, int32_t *tile_pos_rows,
                                       const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
-                                      void *stream)
+                                      int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream)
 {
     SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
     SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
@@ -477,6 +573,11 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
     p.loc = loc_logits; p.iou_pred = iou_preds; p.assignment = assignment; p.out_iou = out_iou; p.sums = sums;
     p.tile_pos_count = tile_pos_count; p.tile_pos_rows = tile_pos_rows;
     p.prefetch_box = prefetch_box_raw; p.prefetch_cls = num_classes > 0 ? prefetch_cls_logits : nullptr; p.num_classes = num_classes;
+    SIHL_CHECK_ARG(pos_chunks == nullptr || (tile_pos_count != nullptr && sums != nullptr), "pos_chunks needs the tile lists and sums");
+    SIHL_CHECK_ARG(pos_chunks == nullptr || (int64_t)batch * ((num_anchors + kTile - 1) / kTile) < (1 << 21), "too many tiles for the chunk list");
+    p.pos_chunks = pos_chunks;
+    SIHL_CHECK_ARG(tile_pos_aux == nullptr || tile_pos_count != nullptr, "tile_pos_aux needs the tile lists");
+    p.tile_pos_aux = reinterpret_cast<int2 *>(tile_pos_aux);
     const dim3 grid((unsigned)((num_anchors + kTile - 1) / kTile), (unsigned)batch);
     SIHL_CHECK_ARG(batch <= 65535, "batch=%d > 65535", batch);
     k_assign_resolve<<<grid, kResThreads, 0, (cudaStream_t)stream>>>(p);
@@ -498,3 +599,14 @@ extern "C" int sihl_od_pos_compact(const int32_t *tile_pos_count, const int32_t 
     SIHL_CHECK_LAUNCH("k_pos_compact");
     return SIHL_OD_OK;
 }
+
+#ifdef SIHL_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int sihl_od_debug_resolve(long long *out_host)
+{
+    return cudaMemcpyFromSymbol(out_host, sihl::g_res_phase, sizeof(long long) * 128) == cudaSuccess ? 0 : 2;
+}
+extern "C" __attribute__((visibility("default"))) int sihl_od_debug_select(unsigned *out_host, int n)
+{
+    return cudaMemcpyFromSymbol(out_host, sihl::g_sel_dbg, sizeof(unsigned) * 3 * n) == cudaSuccess ? 0 : 2;
+}
+#endif

@@ -89,4 +89,30 @@ __device__ __forceinline__ void block_accumulate(double (&v)[NV], double *red, d
 }
 
 
+// Block-wide sum of NV floats per thread (each the sum of a handful of elements): fp32 inside a warp,
+// fp64 across warps and into dst[slot[i]] — one shared-memory hop, one atomicAdd per CTA and term.
+// red: shared double[NV * 32].
+template <int NV>
+__device__ __forceinline__ void block_accumulate_f(float (&v)[NV], double *red, double *dst, const int (&slot)[NV])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 32 + warp] = (double)v[i];
+    }
+    __syncthreads();
+    // lane i of warp 0 finishes term i: a handful of fp64 adds, then one atomicAdd per CTA and term
+    if (warp == 0 && lane < NV) {
+        double x = 0.0;
+        for (int w = 0; w < nwarps; ++w) x += red[lane * 32 + w];
+        int sl = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (lane == i) sl = slot[i];
+        if (x != 0.0) atomicAdd(dst + sl, x);
+    }
+}
+
 }  // namespace sihl

@@ -101,67 +101,102 @@ __global__ void __launch_bounds__(kLossThreads) k_pos_loss(PosParams p)
 }
 
 // Positive-row losses straight from the per-tile lists k_assign_resolve leaves behind (dense
-// maps only): one CTA per (image, tile), one group of lanes per positive.  No compaction, no
-// host round trip; the class-logit row (the only DRAM-latency hop) is requested before the
-// assignment -> gt chain is followed.
-constexpr int kPosTileThreads = 256;
+// maps only).  Work items are 32-row chunks of those lists, published by k_assign_resolve in
+// pos_chunks (count in sums[7]): coarse-level tiles hold several hundred positives, fine-level
+// tiles a handful, so chunking the lists balances the CTAs and no CTA ever starts empty.  One CTA
+// of 128 threads takes one chunk per round, 4 (or 8) lanes per row.  No compaction, no host
+// round trip; the class-logit row was prefetched into L2 by k_assign_resolve.
+// The last CTA to finish may also fold k_loss_finalize in (single-GPU case).
+constexpr int kPosTileThreads = 128;
+#ifdef SIHL_PHASE_TIMING
+__device__ unsigned long long g_pos_blk[4 * 4096];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SIHL_PT(i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_pos_blk[4 * blockIdx.x + (i)] = gtimer(); } while (0)
+#else
+#define SIHL_PT(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ void finalize_losses(const double *sums, float *losses);
 
 struct PosTileParams {
-    const int32_t *tile_pos_count; const int32_t *tile_pos_rows; int n_tiles; int num_anchors;
-    const float *rel; const int64_t *assignment;
+    const int32_t *pos_chunks; const int32_t *tile_pos_rows; const int2 *tile_pos_aux; int n_tiles; int num_anchors;
     const float4 *offsets; const float4 *scales; float img_w, img_h;
     const float4 *gt_boxes; const int64_t *gt_classes; const int32_t *gt_offsets;
     const float *box_raw; const float *cls; int num_classes; int cls_vec4;
     double *sums;
+    float *losses; unsigned *done_counter;       // optional fused finalize
 };
 
-__global__ void __launch_bounds__(kPosTileThreads) k_pos_loss_tiles(PosTileParams p)
+__global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileParams p)
 {
     __shared__ double s_red[2 * 32];
-    const int slot = blockIdx.x, tid = threadIdx.x;
-    const int32_t *rows = p.tile_pos_rows + (int64_t)slot * kTile;
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    SIHL_PT(0);
+    // the first descriptor is fetched together with the list length (stale entries are harmless: they are
+    // only used when blockIdx.x < n_chunks)
+    int desc = __ldg(p.pos_chunks + blockIdx.x);
+    const int n_chunks = (int)p.sums[7];
     const int lpr = p.cls_vec4 ? 4 : 8;                           // lanes per positive row
     const int gl = tid & (lpr - 1), grp = tid / lpr, ngrp = kPosTileThreads / lpr;
-    // first-round row index fetched before the count is known (entries past the count are stale but
-    // always valid indices): one global round trip less on the critical path
-    const int32_t flat_first = __ldg(rows + grp);
-    const int n = __ldg(p.tile_pos_count + slot);
-    if (n == 0) return;                                           // block-uniform
-    const int b = slot / p.n_tiles, A = p.num_anchors;
-    const int g0 = __ldg(p.gt_offsets + b);
+    const int A = p.num_anchors;
     float acc_box = 0.f, acc_cls = 0.f;
-    for (int r0 = 0; r0 < n; r0 += ngrp) {
-        const int r = r0 + grp;
-        const bool ok = r < n;
-        const int64_t flat = ok ? (r0 == 0 ? flat_first : __ldg(rows + r)) : __ldg(rows);
-        const int a = (int)(flat - (int64_t)b * A);
-        const int64_t asg = __ldg(p.assignment + flat);
-        const float w = __ldg(p.rel + flat);
-        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), off = raw, sc = raw;
-        if (p.box_raw != nullptr && gl == 0) { raw = ldg4(p.box_raw + 4 * flat); off = __ldg(p.offsets + a); sc = __ldg(p.scales + a); }
-        float m = 0.f, se = 1.f;
-        if (p.cls != nullptr) {
-            if (p.cls_vec4) row_softmax_stats4v(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
-            else row_softmax_stats8(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
-        }
-        const int g = g0 + (int)asg;
-        if (ok && gl == 0) {
-            if (p.cls != nullptr) {
-                const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + (int)__ldg(p.gt_classes + g));
-                acc_cls += w * ce;                                // ref :208
+    for (int w = blockIdx.x; w < n_chunks; w += gridDim.x) {
+        if (w != (int)blockIdx.x) desc = __ldg(p.pos_chunks + w);
+        const int slot = desc >> 10, r_begin = ((desc >> 6) & 15) * 32, n = (desc & 63) + 1;
+        const int b = slot / p.n_tiles;
+        const int32_t *rows = p.tile_pos_rows + (int64_t)slot * kTile + r_begin;
+        const int2 *aux = p.tile_pos_aux + (int64_t)slot * kTile + r_begin;
+        for (int r0 = 0; r0 < n; r0 += ngrp) {                    // one round with 4 lanes per row
+            const int r = r0 + grp;
+            const bool ok = r < n;
+            const int64_t flat = __ldg(rows + (ok ? r : 0));
+            const int2 ga = __ldg(aux + (ok ? r : 0));
+            const int g = ga.x;
+            const float wgt = __int_as_float(ga.y);
+            const int a = (int)(flat - (int64_t)b * A);
+            // everything below depends only on (flat, g): one round of independent loads
+            const int tgt = p.cls != nullptr ? (int)__ldg(p.gt_classes + g) : 0;
+            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), off = raw, sc = raw, gtb = raw;
+            if (p.box_raw != nullptr && gl == 0) {
+                raw = ldg4(p.box_raw + 4 * flat); off = __ldg(p.offsets + a); sc = __ldg(p.scales + a); gtb = __ldg(p.gt_boxes + g);
             }
-            if (p.box_raw != nullptr)
-                acc_box += w * pos_box_loss(raw, off, sc, __ldg(p.gt_boxes + g), p.img_w, p.img_h);   // ref :197
+            float m = 0.f, se = 1.f;
+            if (p.cls != nullptr) {
+                if (p.cls_vec4) row_softmax_stats4v(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+                else row_softmax_stats8(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+            }
+            if (ok && gl == 0) {
+                if (p.cls != nullptr) {
+                    const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + tgt);
+                    acc_cls += wgt * ce;                          // ref :208
+                }
+                if (p.box_raw != nullptr) acc_box += wgt * pos_box_loss(raw, off, sc, gtb, p.img_w, p.img_h);   // ref :197
+            }
         }
     }
+    SIHL_PT(1);
     double v[2] = {acc_box, acc_cls};
     const int slot_idx[2] = {4, 5};
     block_accumulate<2>(v, s_red, p.sums, slot_idx);
+    SIHL_PT(2);
+    if (p.losses != nullptr) {                                    // last CTA out computes the five losses
+        if (tid == 0) {
+            __threadfence();
+            s_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last && tid == 0) {
+            __threadfence();
+            finalize_losses(const_cast<const double *>(reinterpret_cast<volatile double *>(p.sums)), p.losses);
+            *p.done_counter = 0u;
+        }
+    }
+    SIHL_PT(3);
 }
 
-__global__ void k_loss_finalize(const double *__restrict__ sums, float *__restrict__ losses)
+__device__ __forceinline__ void finalize_losses(const double *sums, float *losses)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double loc = sums[0] / sums[1];                         // ref :163 (0/0 and x/0 as in the reference)
     if (sums[6] == 0.0) {                                         // ref :165-172, rel_iou.max() == 0
         losses[0] = (float)loc; losses[1] = 0.f; losses[2] = 0.f; losses[3] = 0.f; losses[4] = (float)loc;
@@ -170,6 +205,11 @@ __global__ void k_loss_finalize(const double *__restrict__ sums, float *__restri
     const double iou = sums[2] / sums[3], box = sums[4] / sums[3], cls = sums[5] / sums[3];
     losses[0] = (float)loc; losses[1] = (float)box; losses[2] = (float)cls; losses[3] = (float)iou;
     losses[4] = (float)(loc + 10.0 * box + cls + iou);           // ref :210
+}
+
+__global__ void k_loss_finalize(const double *__restrict__ sums, float *__restrict__ losses)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) finalize_losses(sums, losses);
 }
 
 __global__ void __launch_bounds__(kLossThreads)
@@ -348,31 +388,44 @@ extern "C" int sihl_od_pos_loss_bwd(const int32_t *pos_index, const int32_t *n_p
     return SIHL_OD_OK;
 }
 
-extern "C" int sihl_od_pos_loss_tiles(const int32_t *tile_pos_count, const int32_t *tile_pos_rows, int batch,
-                                      int64_t num_anchors, const float *rel_iou, const int64_t *assignment,
+extern "C" int sihl_od_pos_loss_tiles(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
+                                      const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
                                       const float *offsets, const float *scales, int img_w, int img_h,
                                       const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
                                       const float *box_raw, const float *cls_logits, int num_classes, double *sums,
-                                      void *stream)
+                                      float *losses, uint32_t *done_counter, void *stream)
 {
-    SIHL_CHECK_ARG(tile_pos_count && tile_pos_rows && rel_iou && assignment && gt_offsets && sums, "NULL argument");
+    (void)gt_offsets;
+    SIHL_CHECK_ARG(pos_chunks && tile_pos_rows && tile_pos_aux && sums, "NULL argument");
     SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
     SIHL_CHECK_ARG(box_raw == nullptr || (offsets && scales && img_w > 0 && img_h > 0),
                    "box loss needs offsets, scales and the image size");
     SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "class loss needs num_classes");
+    SIHL_CHECK_ARG((losses == nullptr) == (done_counter == nullptr), "losses and done_counter go together");
     const int n_tiles = (int)((num_anchors + kTile - 1) / kTile);
-    const int n_slots = batch * n_tiles;
-    if (n_slots == 0 || (box_raw == nullptr && cls_logits == nullptr)) return SIHL_OD_OK;
+    const int64_t n_slots = (int64_t)batch * n_tiles;
+    if (n_slots == 0) return SIHL_OD_OK;
     PosTileParams p;
-    p.tile_pos_count = tile_pos_count; p.tile_pos_rows = tile_pos_rows; p.n_tiles = n_tiles; p.num_anchors = (int)num_anchors;
-    p.rel = rel_iou; p.assignment = assignment;
+    p.pos_chunks = pos_chunks; p.tile_pos_rows = tile_pos_rows; p.tile_pos_aux = reinterpret_cast<const int2 *>(tile_pos_aux);
+    p.n_tiles = n_tiles; p.num_anchors = (int)num_anchors;
     p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
     p.img_w = (float)img_w; p.img_h = (float)img_h;
     p.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); p.gt_classes = gt_classes; p.gt_offsets = gt_offsets;
     p.box_raw = box_raw; p.cls = cls_logits; p.num_classes = num_classes;
     p.cls_vec4 = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
-    p.sums = sums;
-    k_pos_loss_tiles<<<n_slots, kPosTileThreads, 0, (cudaStream_t)stream>>>(p);
+    p.sums = sums; p.losses = losses; p.done_counter = done_counter;
+    // persistent grid: up to 12 CTAs of 128 threads per SM, never more than the chunk-list capacity
+    int64_t blocks = n_slots * (kTile / 32);
+    const int64_t cap = (int64_t)kNumSMs * 12;
+    if (blocks > cap) blocks = cap;
+    k_pos_loss_tiles<<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p);
     SIHL_CHECK_LAUNCH("k_pos_loss_tiles");
     return SIHL_OD_OK;
 }
+
+#ifdef SIHL_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int sihl_od_debug_pos_blocks(unsigned long long *out_host, int n)
+{
+    return cudaMemcpyFromSymbol(out_host, sihl::g_pos_blk, sizeof(unsigned long long) * 4 * n) == cudaSuccess ? 0 : 2;
+}
+#endif

@@ -32,7 +32,7 @@ constexpr int kNmsThreads = 1024;
 constexpr int kSmemItems = 4096;          // per-image candidates held on chip
 constexpr int kBigSegment = 512;
 constexpr int kSmallItems = 256;          // lists up to this size take the single-pass rank-sort kernel
-constexpr int kSmallThreads = 4 * kSmallItems;   // four lanes per candidate
+static_assert(4 * kSmallItems == kNmsThreads, "short-list path: four lanes per candidate");
 constexpr size_t kSmemItemBytes = 41;     // key 8 + box 16 + val 4 + area 4 + slot 4 + seg 4 + dead 1
 constexpr size_t kWsItemBytes = 48;       // workspace stride per item (keeps every image 16-B aligned)
 
@@ -141,7 +141,7 @@ struct NmsParams {
     int reset_counts;          // mode 0: zero cand_count[img] once consumed (saves the next step's memset launch)
 };
 
-__global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
+__device__ __forceinline__ void nms_big_body(const NmsParams &p)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ int s_warp[33];
@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
         src0 = __ldg(p.seg_offsets + img);
         n = __ldg(p.seg_offsets + img + 1) - src0;
     }
-    if (p.skip_small && n <= kSmallItems) return;          // handled by k_nms_small
     int np = 2;
     while (np < n) np <<= 1;
     int n_kept = 0;
@@ -285,7 +284,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
 // IoU > thr (all pairs in parallel, no serial dependence), resolved by one lane per segment with
 // pure bit operations — the greedy chain costs a few cycles per box instead of a shared-memory
 // round trip per kept box.  Segments longer than 32 fall back to the broadcast loop of k_nms.
-__global__ void __launch_bounds__(kSmallThreads) k_nms_small(NmsParams p)
+__device__ __forceinline__ void nms_small_body(const NmsParams &p)
 {
     __shared__ unsigned long long s_key[kSmallItems];
     __shared__ unsigned s_cls[kSmallItems];        // by slot
@@ -310,7 +309,6 @@ __global__ void __launch_bounds__(kSmallThreads) k_nms_small(NmsParams p)
         src0 = __ldg(p.seg_offsets + img);
         n = __ldg(p.seg_offsets + img + 1) - src0;
     }
-    if (n > kSmallItems) return;                   // k_nms takes it
     SIHL_PHASE(1);
     int n_kept = 0;
     if (n > 0) {
@@ -444,6 +442,20 @@ __global__ void __launch_bounds__(kSmallThreads) k_nms_small(NmsParams p)
     SIHL_PHASE(7);
 }
 
+// One launch for both paths: the list length (known only on the device) picks the body.
+__global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
+{
+    int n;
+    if (p.mode == 0) {
+        const int c = __ldg(p.cand_count + blockIdx.x);
+        n = (int)(c < p.cap ? c : p.cap);
+    } else {
+        n = __ldg(p.seg_offsets + blockIdx.x + 1) - __ldg(p.seg_offsets + blockIdx.x);
+    }
+    if (n <= kSmallItems) nms_small_body(p);
+    else nms_big_body(p);
+}
+
 static int pow2ceil(int64_t n)
 {
     int p = 2;
@@ -453,23 +465,18 @@ static int pow2ceil(int64_t n)
 
 static int launch_nms(const NmsParams &p, int n_images, int64_t max_items, cudaStream_t st)
 {
+    // dynamic shared memory only when a list can exceed the short-list path
+    const size_t smem = max_items > kSmallItems ? (size_t)kSmemItems * kSmemItemBytes : 0;
     static thread_local bool attr_set = false;
-    const size_t smem = (size_t)kSmemItems * kSmemItemBytes;
-    if (!attr_set) {
-        int rc = cuda_status(cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    if (smem && !attr_set) {
+        int rc = cuda_status(cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)((size_t)kSmemItems * kSmemItemBytes)),
                              "cudaFuncSetAttribute(k_nms)");
         if (rc) return rc;
         attr_set = true;
     }
-    // short lists (the common case) in a light kernel; k_nms returns at once for those
-    k_nms_small<<<n_images, kSmallThreads, 0, st>>>(p);
-    SIHL_CHECK_LAUNCH("k_nms_small");
-    NmsParams big = p;
-    big.skip_small = 1;
-    if (max_items > kSmallItems) {
-        k_nms<<<n_images, kNmsThreads, smem, st>>>(big);
-        SIHL_CHECK_LAUNCH("k_nms");
-    }
+    k_nms<<<n_images, kNmsThreads, smem, st>>>(p);
+    SIHL_CHECK_LAUNCH("k_nms");
     return SIHL_OD_OK;
 }
 

@@ -182,20 +182,24 @@ def assign_resolve(sel, gt: GtBatch, num_anchors: int, topk: int = 9, relative: 
         tpc = torch.empty((B * n_tiles,), dtype=torch.int32, device=dev)
         tpr = torch.empty((B * n_tiles * tile,), dtype=torch.int32, device=dev)
     f = fused or {}
-    if f and tpc is None:
+    chunks = aux = None
+    if f:
         n_tiles, tile = resolve_tiles(A)
-        tpc = torch.empty((B * n_tiles,), dtype=torch.int32, device=dev)
-        tpr = torch.empty((B * n_tiles * tile,), dtype=torch.int32, device=dev)
+        if tpc is None:
+            tpc = torch.empty((B * n_tiles,), dtype=torch.int32, device=dev)
+            tpr = torch.zeros((B * n_tiles * tile,), dtype=torch.int32, device=dev)
+        chunks = torch.zeros((B * n_tiles * (tile // 32),), dtype=torch.int32, device=dev)
+        aux = torch.zeros((B * n_tiles * tile, 2), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_assign_resolve(
             _p(sel_anchor), _p(sel_val), _p(best), _p(gt.offsets), B, A, int(topk), int(bool(relative)),
             _p(None if loc_logits is None else _req(loc_logits, torch.float32, "loc_logits")),
             _p(None if iou_preds is None else _req(iou_preds, torch.float32, "iou_preds")),
             _p(assignment), _p(out_iou), _p(sums), _p(tpc), _p(tpr), _p(f.get("box_raw")), _p(f.get("cls_logits")),
-            0 if f.get("cls_logits") is None else int(f["cls_logits"].shape[-1]), _stream(dev))
+            0 if f.get("cls_logits") is None else int(f["cls_logits"].shape[-1]), _p(chunks), _p(aux), _stream(dev))
         _native.check(rc, "sihl_od_assign_resolve")
         if f:
-            pos_loss_tiles(tpc, tpr, B, A, out_iou, assignment, f["offsets"], f["scales"], f["img_w"], f["img_h"], gt,
+            pos_loss_tiles(chunks, tpr, aux, B, A, f["offsets"], f["scales"], f["img_w"], f["img_h"], gt,
                            f.get("box_raw"), f.get("cls_logits"), sums)
     return dict(assignment=assignment, iou=out_iou, tile_pos_count=tpc, tile_pos_rows=tpr)
 
@@ -275,18 +279,20 @@ def pos_loss(pos_index: Tensor, n_pos_dev: Optional[Tensor], capacity: int, num_
     return sums
 
 
-def pos_loss_tiles(tile_pos_count: Tensor, tile_pos_rows: Tensor, batch: int, num_anchors: int, rel_iou: Tensor,
-                   assignment: Tensor, offsets: Tensor, scales: Tensor, img_w: int, img_h: int, gt: GtBatch,
-                   box_raw: Optional[Tensor], cls_logits: Optional[Tensor], sums: Tensor) -> Tensor:
-    """ref :187-208 over dense maps, straight from the per-tile positive lists (no compaction)."""
-    dev = rel_iou.device
+def pos_loss_tiles(pos_chunks: Tensor, tile_pos_rows: Tensor, tile_pos_aux: Tensor, batch: int, num_anchors: int,
+                   offsets: Tensor, scales: Tensor, img_w: int, img_h: int, gt: GtBatch,
+                   box_raw: Optional[Tensor], cls_logits: Optional[Tensor], sums: Tensor,
+                   losses: Optional[Tensor] = None, done_counter: Optional[Tensor] = None) -> Tensor:
+    """ref :187-208 over dense maps, straight from the per-tile positive lists (no compaction);
+    ``pos_chunks`` is the work list ``assign_resolve`` published (length in ``sums[7]``)."""
+    dev = sums.device
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_pos_loss_tiles(
-            _p(tile_pos_count), _p(tile_pos_rows), int(batch), int(num_anchors), _p(rel_iou), _p(assignment), _p(offsets),
+            _p(pos_chunks), _p(tile_pos_rows), _p(tile_pos_aux), int(batch), int(num_anchors), _p(offsets),
             _p(scales), int(img_w), int(img_h), _p(gt.boxes), _p(gt.classes), _p(gt.offsets),
             _p(None if box_raw is None else _req(box_raw, torch.float32, "box_raw")),
             _p(None if cls_logits is None else _req(cls_logits, torch.float32, "cls_logits")),
-            0 if cls_logits is None else int(cls_logits.shape[-1]), _p(sums), _stream(dev))
+            0 if cls_logits is None else int(cls_logits.shape[-1]), _p(sums), _p(losses), _p(done_counter), _stream(dev))
     _native.check(rc, "sihl_od_pos_loss_tiles")
     return sums
 

@@ -5,9 +5,8 @@ This is the whole-batch form of the hot path that ``bench.py`` measures
 (BASELINE.json metric: det-head images/sec, assign + loss + NMS).  Per step and GPU:
 
   train chain  (stream A): k_assign_select -> k_assign_resolve (dense losses fused)
-                           -> k_pos_loss_tiles -> k_loss_finalize  [4 launches]
-  infer chain  (stream B): k_dense_decode_tma -> k_nms_small -> k_nms (long lists only)
-                                                                   [3 launches]
+                           -> k_pos_loss_tiles (last CTA finalizes) [3 launches]
+  infer chain  (stream B): k_dense_decode_tma -> k_nms              [2 launches]
 
 The two chains share no data, so they run concurrently: the assignment is FP32-ALU/latency
 bound, the dense decode is HBM bound (SURVEY.md §8d caveat).  Across GPUs the only exchange
@@ -23,7 +22,7 @@ from torch import Tensor
 
 from . import _native, ops
 
-LAUNCHES_PER_STEP = 7     # select, resolve, pos_loss_tiles, finalize | dense_decode, nms_small, nms (returns at once for short lists)
+LAUNCHES_PER_STEP = 5     # select, resolve, pos_loss_tiles (+finalize) | dense_decode, nms
 
 
 @dataclass
@@ -73,6 +72,9 @@ class DetectionHeadPipeline:
         n_tiles, tile = ops.resolve_tiles(A)
         self.tile_pos_count = torch.zeros((B * n_tiles,), dtype=torch.int32, device=dev)
         self.tile_pos_rows = torch.zeros((B * n_tiles * tile,), dtype=torch.int32, device=dev)
+        self.pos_chunks = torch.zeros((B * n_tiles * (tile // 32),), dtype=torch.int32, device=dev)
+        self.tile_pos_aux = torch.zeros((B * n_tiles * tile, 2), dtype=torch.int32, device=dev)
+        self.done_counter = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.cand = ops.CandidateBuffers.allocate(B, int(cand_capacity or A), dev)
         self.side = torch.cuda.Stream(device=dev)
         self.lib = _native.load()
@@ -102,13 +104,14 @@ class DetectionHeadPipeline:
         _native.check(lib.sihl_od_assign_resolve(
             p(self.sel_anchor), p(self.sel_val), p(self.best_iou), p(gt.offsets), self.B, self.A, self.topk, 1,
             p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), p(self.tile_pos_count),
-            p(self.tile_pos_rows), p(x.box_raw), p(x.cls_logits), self.C, st), "sihl_od_assign_resolve")
+            p(self.tile_pos_rows), p(x.box_raw), p(x.cls_logits), self.C, p(self.pos_chunks), p(self.tile_pos_aux), st),
+            "sihl_od_assign_resolve")
+        # single GPU: the last CTA of the positive-loss kernel also finalizes the five losses
         _native.check(lib.sihl_od_pos_loss_tiles(
-            p(self.tile_pos_count), p(self.tile_pos_rows), self.B, self.A, p(out.rel_iou), p(out.assignment),
+            p(self.pos_chunks), p(self.tile_pos_rows), p(self.tile_pos_aux), self.B, self.A,
             p(self.offsets), p(self.scales), self.img_w, self.img_h, p(gt.boxes), p(gt.classes), p(gt.offsets),
-            p(x.box_raw), p(x.cls_logits), self.C, p(out.sums), st), "sihl_od_pos_loss_tiles")
-        if finalize:
-            self.finalize(out)
+            p(x.box_raw), p(x.cls_logits), self.C, p(out.sums), p(out.losses) if finalize else None,
+            p(self.done_counter) if finalize else None, st), "sihl_od_pos_loss_tiles")
 
     def finalize(self, out: StepOutputs) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -45,10 +45,10 @@ def k_select(i):
     lib.sihl_od_assign_select(p(pipe.anchors), p(pipe.terms), pipe.A, pipe._hw.ctypes.data, len(pipe._hw), W, H, p(gt.boxes), p(gt.offsets), B, gt.total, 9, p(pipe.sel_anchor), p(pipe.sel_val), p(pipe.best_iou), p(out.sums), st)
 def k_resolve(i):
     x, out = sets[i], outs[i]; gt = x.gt; p = ops._p; st = torch.cuda.current_stream().cuda_stream
-    lib.sihl_od_assign_resolve(p(pipe.sel_anchor), p(pipe.sel_val), p(pipe.best_iou), p(gt.offsets), B, pipe.A, 9, 1, p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), p(pipe.tile_pos_count), p(pipe.tile_pos_rows), p(x.box_raw), p(x.cls_logits), C, st)
+    lib.sihl_od_assign_resolve(p(pipe.sel_anchor), p(pipe.sel_val), p(pipe.best_iou), p(gt.offsets), B, pipe.A, 9, 1, p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), p(pipe.tile_pos_count), p(pipe.tile_pos_rows), p(x.box_raw), p(x.cls_logits), C, p(pipe.pos_chunks), p(pipe.tile_pos_aux), st)
 def k_pos(i):
     x, out = sets[i], outs[i]; gt = x.gt; p = ops._p; st = torch.cuda.current_stream().cuda_stream
-    lib.sihl_od_pos_loss_tiles(p(pipe.tile_pos_count), p(pipe.tile_pos_rows), B, pipe.A, p(out.rel_iou), p(out.assignment), p(pipe.offsets), p(pipe.scales), W, H, p(gt.boxes), p(gt.classes), p(gt.offsets), p(x.box_raw), p(x.cls_logits), C, p(out.sums), st)
+    lib.sihl_od_pos_loss_tiles(p(pipe.pos_chunks), p(pipe.tile_pos_rows), p(pipe.tile_pos_aux), B, pipe.A, p(pipe.offsets), p(pipe.scales), W, H, p(gt.boxes), p(gt.classes), p(gt.offsets), p(x.box_raw), p(x.cls_logits), C, p(out.sums), p(out.losses), p(pipe.done_counter), st)
 def k_decode(i):
     x = sets[i]
     ops.dense_decode(x.loc_logits, x.cls_logits, x.box_raw, pipe.offsets, pipe.scales, W, H, 0.05, pipe.cand, zero_counts=False)
@@ -60,6 +60,17 @@ res = {}
 res["train_chain"] = timeit(capture(lambda i: pipe.train_chain(sets[i], outs[i])))
 res["infer_chain"] = timeit(capture(lambda i: pipe.infer_chain(sets[i], outs[i])))
 res["both_2streams"] = timeit(capture(lambda i: pipe.step(sets[i], outs[i])))
+lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+pipe.side = torch.cuda.Stream(device=dev, priority=0)
+hp = torch.cuda.Stream(device=dev, priority=-1)
+def step_hp(i):
+    cur = torch.cuda.current_stream(); hp.wait_stream(cur)
+    with torch.cuda.stream(hp): pipe.step(sets[i], outs[i])
+    cur.wait_stream(hp)
+res["both_train_high_prio"] = timeit(capture(step_hp))
+pipe.side = torch.cuda.Stream(device=dev, priority=-1)
+res["both_infer_high_prio"] = timeit(capture(lambda i: pipe.step(sets[i], outs[i])))
+pipe.side = torch.cuda.Stream(device=dev)
 res["both_serial"] = timeit(capture(lambda i: (pipe.infer_chain(sets[i], outs[i]), pipe.train_chain(sets[i], outs[i]))))
 res["select"] = timeit(capture(k_select))
 res["select+resolve"] = timeit(capture(lambda i: (k_select(i), k_resolve(i))))
@@ -68,3 +79,34 @@ res["decode"] = timeit(capture(k_decode))
 res["decode+nms"] = timeit(capture(lambda i: (k_decode(i), k_nms(i))))
 for k, v in res.items():
     print(f"{k:22s} {v:8.2f} us")
+
+# ---- cross-step overlap: independent pipelines (own scratch) on independent streams, steps alternate
+def lanes_experiment(n_lanes):
+    pipes = [pipe] + [DetectionHeadPipeline(levels, W, H, B, C, B * G, dev) for _ in range(n_lanes - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+    graphs = []
+    for ln in range(n_lanes):
+        gl = []
+        for i in range(3):
+            o = pipes[ln].new_outputs()
+            with torch.cuda.stream(streams[ln]):
+                gl.append(pipes[ln].capture(sets[i], o))
+        graphs.append(gl)
+    torch.cuda.synchronize()
+    def run(n):
+        for s in range(n):
+            ln = s % n_lanes
+            with torch.cuda.stream(streams[ln]):
+                graphs[ln][s % 3].replay()
+    run(60); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream()
+    e0.record(cur)
+    for st in streams: st.wait_event(e0)
+    n = 900
+    run(n)
+    for st in streams: cur.wait_stream(st)
+    e1.record(cur); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+for nl in (1, 2, 3, 4):
+    print(f"lanes={nl}: {lanes_experiment(nl):8.2f} us/step")
