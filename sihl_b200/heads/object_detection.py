@@ -297,7 +297,7 @@ class _RunningMean:
         return self
 
     def update(self, value: Tensor) -> None:
-        v = float(value)
+        v = float(value.detach()) if hasattr(value, "detach") else float(value)
         if v == v:                       # ignore NaN
             self.total, self.count = self.total + v, self.count + 1
 

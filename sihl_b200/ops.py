@@ -248,11 +248,13 @@ def new_sums(device) -> Tensor:
 
 def dense_loss(loc_logits: Tensor, iou_preds: Optional[Tensor], rel_iou: Tensor, sums: Tensor) -> Tensor:
     """ref :157-163, :175-180 — accumulates into ``sums`` (fp64 [8])."""
-    dev = rel_iou.device
+    loc = _req(loc_logits, torch.float32, "loc_logits")
+    rel = _req(rel_iou, torch.float32, "rel_iou")
+    iou = None if iou_preds is None else _req(iou_preds, torch.float32, "iou_preds")
+    sums = _req(sums, torch.float64, "sums")
+    dev = rel.device
     with torch.cuda.device(dev):
-        rc = _lib().sihl_od_dense_loss(_p(_req(loc_logits, torch.float32, "loc_logits")),
-                                       _p(None if iou_preds is None else _req(iou_preds, torch.float32, "iou_preds")),
-                                       _p(_req(rel_iou, torch.float32, "rel_iou")), rel_iou.numel(), _p(sums), _stream(dev))
+        rc = _lib().sihl_od_dense_loss(_p(loc), _p(iou), _p(rel), rel.numel(), _p(sums), _stream(dev))
     _native.check(rc, "sihl_od_dense_loss")
     return sums
 
