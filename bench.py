@@ -232,43 +232,52 @@ def run_ours(args, w, world, rank, local_rank):
     main = torch.cuda.current_stream(dev)
     lane_streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
 
-    def plain_step(ln, i):
+    # multi-GPU: one NCCL communicator per lane (collectives of different lanes may be in flight at once)
+    groups = [dist.new_group(ranks=list(range(world)), backend="nccl") for _ in range(n_lanes)] if multi else None
+    if multi:
+        for ln in range(n_lanes):                      # create the communicators eagerly, outside any capture
+            dist.all_reduce(torch.zeros(8, dtype=torch.float64, device=dev), group=groups[ln])
+        torch.cuda.synchronize()
+
+    def full_step(ln, i):
+        """One step incl. the cross-GPU exchange: 8 fp64 sums all-reduced between the loss kernels and finalize."""
+        out = outs[ln][i]
         if args.serial:
-            pipes[ln].infer_chain(sets[i], outs[ln][i]); pipes[ln].train_chain(sets[i], outs[ln][i], finalize=not multi)
+            pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not multi)
         else:
-            pipes[ln].step(sets[i], outs[ln][i], finalize=not multi)
+            pipes[ln].step(sets[i], out, finalize=not multi)
+        if multi:
+            dist.all_reduce(out.sums, op=dist.ReduceOp.SUM, group=groups[ln])
+            pipes[ln].finalize(out)
 
     graphs = None
     if use_graph and not args.serial:
         graphs = []
         for ln in range(n_lanes):
             with torch.cuda.stream(lane_streams[ln]):
-                graphs.append([pipes[ln].capture(sets[i], outs[ln][i], finalize=not multi) for i in range(n_sets)])
+                lane_graphs = []
+                for i in range(n_sets):
+                    full_step(ln, i)                       # warm-up outside capture
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=lane_streams[ln]):
+                        full_step(ln, i)                   # NCCL all-reduce is captured as a graph node
+                    lane_graphs.append(g)
+                graphs.append(lane_graphs)
         torch.cuda.synchronize()
-
-    prev = [None] * n_lanes
 
     def run_step(s):
         """Step s goes to lane s % n_lanes: consecutive steps overlap (the HBM-bound decode of one step runs
         next to the latency-bound assignment / NMS kernels of its neighbours)."""
         ln, i = s % n_lanes, s % n_sets
         with torch.cuda.stream(lane_streams[ln]):
-            if multi and prev[ln] is not None:        # finish this lane's previous step: all-reduced sums -> losses
-                j, work = prev[ln]
-                work.wait(); pipes[ln].finalize(outs[ln][j]); prev[ln] = None
             if graphs is not None:
                 graphs[ln][i].replay()
             else:
-                plain_step(ln, i)
-            if multi:
-                prev[ln] = (i, dist.all_reduce(outs[ln][i].sums, op=dist.ReduceOp.SUM, async_op=True))
+                full_step(ln, i)
 
     def drain():
         for ln in range(n_lanes):
-            with torch.cuda.stream(lane_streams[ln]):
-                if prev[ln] is not None:
-                    j, work = prev[ln]
-                    work.wait(); pipes[ln].finalize(outs[ln][j]); prev[ln] = None
             main.wait_stream(lane_streams[ln])
 
     def fork():
@@ -312,7 +321,9 @@ def run_ours(args, w, world, rank, local_rank):
 
     result = {"ms": ms, "value": value, "losses": losses, "P_bar": P_bar, "cand_mean": cand_mean, "det_mean": det_mean}
     if rank != 0:
-        if sampler: sampler.stop()
+        # the other ranks only take part in the collective part of the end-to-end measurement
+        if not args.skip_e2e:
+            run_e2e(args, pipe, sets[0], outs0[0], world, multi, dev, None)
         return
 
     # ---- roofline of the dominant kernel (k_dense_decode), timed alone on the launching stream
