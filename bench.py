@@ -352,9 +352,9 @@ def run_ours(args, w, world, rank, local_rank):
     pipe.cand.count = counts_saved
     cand_mean = float(scratch[:iters].float().mean().item())
     k_ms = k0.elapsed_time(k1) / iters
-    # algorithmic bytes per launch: every class logit and location logit once (4*A*(C+1) per image) + per
-    # candidate 16 B raw box read and 28 B (key 8, box 16, class 4) written
-    decode_bytes = B * 4 * A * (C + 1) + B * cand_mean * (16 + 28)
+    # algorithmic bytes per launch (SURVEY.md §8d inference figure): every class logit, raw box and location
+    # logit read once (4*A*(C+5) per image) + 28 B (key 8, box 16, class 4) written per candidate
+    decode_bytes = B * 4 * A * (C + 5) + B * cand_mean * 28
     achieved = decode_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     try:
