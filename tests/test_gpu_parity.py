@@ -351,3 +351,81 @@ def test_full_size_properties():
         oa, ov, _ = orc.bbox_matching(an_np, gt_np.boxes[b * G:(b + 1) * G], 9, True)
         np.testing.assert_array_equal(a1[b].cpu().numpy(), oa)
         np.testing.assert_allclose(v1[b].cpu().numpy(), ov, rtol=1e-5, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- configs[3] / configs[4]
+def test_crowd_config_assign_parity():
+    """configs[3]: 1024x1024, 500 gt / image — pruned select == all-pairs select == C oracle."""
+    W = H = 1024
+    levels = synth.level_sizes(H, W)
+    off, sc, anchors = ops.anchor_tables(levels, W, H, DEV)
+    assert anchors.shape[0] == 21824
+    gt_np = synth.gt_batch_np(31, 3, H, W, 80, 500, counts=[500, 0, 377])
+    gt = _gt_dev(gt_np)
+    a1, v1, s1 = _assign(anchors, levels, W, H, gt, True, brute=False)
+    a2, v2, s2 = _assign(anchors, levels, W, H, gt, True, brute=True)
+    assert torch.equal(a1, a2) and torch.equal(v1, v2) and all(torch.equal(x, y) for x, y in zip(s1, s2))
+    oa, ov, _ = orc.assign_batch(anchors.cpu().numpy(), gt_np.boxes, gt_np.offsets, 9, True)
+    np.testing.assert_array_equal(a1.cpu().numpy(), oa)
+    np.testing.assert_allclose(v1.cpu().numpy(), ov, rtol=1e-5, atol=1e-7)
+    for b, (bx, _) in enumerate(gt_np.per_image()):
+        ra, rv = tr.canonical(*tr.match_one(anchors, _t(bx).reshape(-1, 4), 9, True))
+        assert torch.equal(a1[b], ra) and torch.equal(v1[b], rv)
+
+
+def test_crowd_config_nms_30k_candidates():
+    """configs[3]: NMS over 30 000 pre-NMS candidates of one image, 80 classes (workspace path)."""
+    boxes, scores, classes = synth.nms_candidates_np(555, 30000, 1024, 80)
+    keep = ops.batched_nms(_t(boxes), _t(scores), _t(classes), 0.5).cpu().numpy()
+    np.testing.assert_array_equal(keep, orc.batched_nms(boxes, scores, classes, 0.5))
+
+
+@pytest.mark.parametrize("size,batch", [(640, 3), (1280, 2)])
+def test_inference_sweep_postprocess(size, batch):
+    """configs[4]: decode + NMS at 640-1280 px with loc ~ N(-4, 2^2) (about 30 % of the locations pass 0.05)."""
+    levels = synth.level_sizes(size, size)
+    off, sc, an = orc.anchors(levels, size, size)
+    A, C = len(an), 80
+    maps = synth.dense_maps_np(900 + size, batch, A, C, loc_mean=-4.0, loc_std=2.0)
+    loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(maps.cls_logits)
+    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, size, size, 0.05, 0.5, 100)
+    o_num, o_scores, o_cls, o_boxes, ncand = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw, off, sc,
+                                                                    size, size, 0.05, 0.5, 100)
+    assert ncand.min() > 0.2 * A
+    np.testing.assert_array_equal(num.cpu().numpy(), o_num)
+    np.testing.assert_array_equal(classes.cpu().numpy(), o_cls)
+    np.testing.assert_allclose(scores.cpu().numpy(), o_scores, rtol=1e-6)
+    np.testing.assert_allclose(boxes.cpu().numpy(), o_boxes, rtol=1e-5, atol=1e-4)
+
+
+def test_pipeline_matches_unfused_ops_and_is_replayable():
+    """The bench pipeline (graphs, two streams, fused finalize, counter recycling) gives the same numbers as the
+    step-by-step ops, and the same numbers again on every replay."""
+    from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs
+    W = H = 320
+    B, C, G = 4, 80, 30
+    levels = synth.level_sizes(H, W)
+    pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, DEV)
+    gt_np = synth.gt_batch_np(12, B, H, W, C, G, ragged=False)
+    maps = synth.dense_maps_np(13, B, pipe.A, C, loc_mean=-3.0, loc_std=2.0)
+    gt = _gt_dev(gt_np)
+    x = StepInputs(_t(maps.loc_logits), _t(maps.iou_preds), _t(maps.box_raw), _t(maps.cls_logits), gt)
+    out = pipe.new_outputs()
+    graph = pipe.capture(x, out)
+    results = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        results.append([t.clone() for t in (out.losses, out.assignment, out.rel_iou, out.num_instances, out.scores, out.classes, out.boxes)])
+    for r in results[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(results[0][1:], r[1:]))           # everything but the float sums is deterministic
+        torch.testing.assert_close(results[0][0], r[0], rtol=1e-6, atol=0)
+    off, sc, an = orc.anchors(levels, W, H)
+    want = orc.train_losses(an, off, sc, W, H, gt_np.boxes, gt_np.classes, gt_np.offsets, maps.loc_logits, maps.iou_preds,
+                            maps.box_raw, maps.cls_logits, dense_rows=True)
+    np.testing.assert_array_equal(results[0][1].cpu().numpy(), want["assignment"])
+    np.testing.assert_allclose(results[0][0].cpu().numpy(), want["losses"], rtol=1e-5)
+    o_num, o_scores, o_cls, o_boxes, _ = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw, off, sc, W, H, 0.05, 0.5, 100)
+    np.testing.assert_array_equal(results[0][3].cpu().numpy(), o_num)
+    np.testing.assert_array_equal(results[0][5].cpu().numpy(), o_cls)
+    np.testing.assert_allclose(results[0][6].cpu().numpy(), o_boxes, rtol=1e-5, atol=1e-4)
