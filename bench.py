@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--serial", action="store_true", help="run both chains on one stream")
-    ap.add_argument("--lanes", type=int, default=0, help="steps in flight (independent scratch + stream each); 0 = 3 on one GPU, 4 across GPUs")
+    ap.add_argument("--lanes", type=int, default=0, help="steps in flight (independent scratch + stream each); 0 = 4")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=20)
@@ -211,7 +211,7 @@ def run_ours(args, w, world, rank, local_rank):
     dev = torch.device("cuda", local_rank)
     H, W, B, C, G, K = w["height"], w["width"], w["batch"], w["classes"], w["gt"], w["k"]
     levels = synth.level_sizes(H, W)
-    n_lanes = args.lanes if args.lanes > 0 else (3 if world == 1 else 4)
+    n_lanes = args.lanes if args.lanes > 0 else 4
     pipes = [DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR) for _ in range(n_lanes)]
     pipe = pipes[0]
     A = pipe.A

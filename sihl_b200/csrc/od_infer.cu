@@ -446,25 +446,35 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
         const bool ok = row < rows;
         const unsigned char *base = s_ring + (size_t)s * stage_bytes;
         const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
-        float best = -CUDART_INF_F;
-        int arg = 0x7fffffff;
+        // first arg-max of the row in two cheap steps: the row maximum (max tree + 2 shuffles), then the
+        // lowest class index whose logit equals it (reverse predicated scan + 2 shuffles); half the
+        // instructions of a running (value, index) comparison.  NaN logits never win (as before).
+        float4 q[VPL];
+        float m = -CUDART_INF_F;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int v = gl + 4 * i;
             if (EXACT || v < C4) {
-                const float4 q = src[v];
-                const float e[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (e[j] > best || arg == 0x7fffffff) { best = e[j]; arg = 4 * v + j; }
+                q[i] = src[v];
+                m = fmaxf(m, fmaxf(fmaxf(q[i].x, q[i].y), fmaxf(q[i].z, q[i].w)));
             }
         }
+        m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
+        int arg = 0x7fffffff;
 #pragma unroll
-        for (int o = 2; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(kFullMask, best, o);
-            const int oa = __shfl_xor_sync(kFullMask, arg, o);
-            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        for (int i = VPL - 1; i >= 0; --i) {
+            const int v = gl + 4 * i;
+            if (EXACT || v < C4) {
+                if (q[i].w == m) arg = 4 * v + 3;
+                if (q[i].z == m) arg = 4 * v + 2;
+                if (q[i].y == m) arg = 4 * v + 1;
+                if (q[i].x == m) arg = 4 * v;
+            }
         }
+        arg = min(arg, __shfl_xor_sync(kFullMask, arg, 1));
+        arg = min(arg, __shfl_xor_sync(kFullMask, arg, 2));
+        if (arg == 0x7fffffff) arg = 0;                           // all-NaN row
         if (gl == 0 && ok) {
             const bool full = rows - (int64_t)c * kChunkRows >= kChunkRows;
             const float x = full ? reinterpret_cast<const float *>(base + cls_bytes + box_bytes)[r] : __ldcs(p.loc + row);

@@ -137,7 +137,6 @@ struct NmsParams {
     int K; int64_t *num_instances; float *out_scores; int64_t *out_classes; float4 *out_boxes;   // mode 0
     int64_t *keep; int32_t *keep_count;                                                           // mode 1
     unsigned char *workspace; size_t ws_stride;   // mode 0: bytes per image; mode 1: unused (offset = 2*seg start)
-    int skip_small;
     int reset_counts;          // mode 0: zero cand_count[img] once consumed (saves the next step's memset launch)
 };
 

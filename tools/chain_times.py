@@ -1,7 +1,7 @@
 """Developer probe (not part of the product): time the two chains of the pipeline separately
 and together with CUDA-graph replay, rotating input sets.  python tools_chain_times.py"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sihl_b200 import ops, synth
 from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs

@@ -1,8 +1,8 @@
 """Developer probe: per-gt cycles of k_assign_select / per-phase clocks of k_nms_small (needs tools_build_dbg.sh)."""
 import ctypes as C, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-os.environ["SIHL_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sihl_b200/lib/libsihl_b200_dbg.so")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["SIHL_B200_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sihl_b200/lib/libsihl_b200_dbg.so")
 import torch
 from sihl_b200 import ops, synth, _native
 from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs
