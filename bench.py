@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=0, help="steps in flight (independent scratch + stream each); 0 = 4")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-gpu-eager", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=8, help="images per CPU-baseline pass")
     return ap.parse_args()
@@ -385,6 +386,11 @@ def run_ours(args, w, world, rank, local_rank):
                "sample": f"{r['sample_images']} images of {args.workload} x {r['steps']} passes (assign + losses + dense decode "
                          f"+ per-class NMS) with the reference's torch/torchvision operator sequence, {r['cores']} threads"}
 
+    # ---- the reference's operator sequence as torch eager on THIS GPU (the bar SURVEY.md §2b names)
+    eager = None
+    if not multi and not args.skip_gpu_eager:
+        eager = gpu_eager_reference(w, sets[0], levels, dev)
+
     clocks = sampler.stop() if sampler else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -395,10 +401,32 @@ def run_ours(args, w, world, rank, local_rank):
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
         "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "roofline_step": roofline_step,
-        "cpu_baseline": cpu, "clocks": clocks, "losses_check": losses,
+        "cpu_baseline": cpu, "gpu_eager_reference": eager, "clocks": clocks, "losses_check": losses,
     }
     print(json.dumps(line), flush=True)
     return result
+
+
+def gpu_eager_reference(w, x, levels, dev, passes=2):
+    """oracle/torch_restatement.py (the reference's torch/torchvision operator sequence, per-image Python loop and
+    host syncs included) on the same GPU and the same resident inputs: the eager-PyTorch bar for this path."""
+    import torch
+    from oracle import torch_restatement as tr
+    H, W, B, K, G = w["height"], w["width"], w["batch"], w["k"], w["gt"]
+    boxes = [x.gt.boxes[b * G:(b + 1) * G] for b in range(B)]
+    classes = [x.gt.classes[b * G:(b + 1) * G] for b in range(B)]
+    best = None
+    with torch.no_grad():
+        for _ in range(passes + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tr.train_losses(levels, W, H, boxes, classes, x.loc_logits, x.iou_preds, x.box_raw, x.cls_logits, TOPK)
+            tr.dense_postprocess(levels, W, H, x.loc_logits, x.box_raw, x.cls_logits, SCORE_THR, IOU_THR, K)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return {"value": B / best, "unit": UNIT, "ms_per_step": best * 1e3,
+            "kind": "torch eager on the same GPU: the reference's operator sequence (oracle/torch_restatement.py), best of %d" % passes}
 
 
 def run_e2e(args, pipe, x, out, world, multi, dev, sampler):

@@ -3,10 +3,13 @@
 //
 //   k_topk          ref object_detection.py:108-109  torch.topk(loc_logits, K, dim=1)
 //   k_decode_rows   ref :113-121                     sigmoid / count / argmax / box decode on K rows
-//   k_dense_decode  extension: the same per-location decode over ALL locations of the
+//   k_dense_decode* extension: the same per-location decode over ALL locations of the
 //                   dense maps + score threshold, feeding class-aware NMS (od_nms.cu).
-//                   This is the HBM-bound kernel of the path: 4*A*(C+1) B per image are
-//                   read exactly once with coalesced 32-B-sector loads, 8 lanes per row.
+//                   This is the HBM-bound kernel of the path: 4*A*(C+5) B per image are read
+//                   exactly once.  Three variants, picked by sihl_od_dense_decode():
+//                     _tma  C % 4 == 0, C <= 128: TMA bulk copies into a shared-memory ring
+//                     _v4   C % 4 == 0, larger C: 16-byte loads, 4 or 32 lanes per row
+//                     plain any C: 4-byte loads, 8 lanes per row
 #include <cstdlib>
 
 #include "od_common.cuh"
