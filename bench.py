@@ -243,13 +243,17 @@ def run_ours(args, w, world, rank, local_rank):
     def full_step(ln, i):
         """One step incl. the cross-GPU exchange: 8 fp64 sums all-reduced between the loss kernels and finalize."""
         out = outs[ln][i]
-        if args.serial:
-            pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not multi)
-        else:
-            pipes[ln].step(sets[i], out, finalize=not multi)
-        if multi:
+
+        def exchange():                               # right after the loss kernels, next to the inference chain
             dist.all_reduce(out.sums, op=dist.ReduceOp.SUM, group=groups[ln])
             pipes[ln].finalize(out)
+
+        if args.serial:
+            pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not multi)
+            if multi:
+                exchange()
+        else:
+            pipes[ln].step(sets[i], out, finalize=not multi, after_train=exchange if multi else None)
 
     graphs = None
     if use_graph and not args.serial:

@@ -19,10 +19,30 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    """Compile ``od_oracle.c`` into ``oracle/_ref/`` (gcc, a second or two)."""
+    """Compile ``od_oracle.c`` into ``oracle/_ref/`` (gcc, a second or two).  Content-stamped and file-locked so
+    that copies with fresh file times and concurrent ranks do the right thing."""
+    import fcntl
+    import hashlib
     src = os.path.join(_HERE, "od_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    with open(src, "rb") as fh:
+        fp = hashlib.sha256(fh.read()).hexdigest()
+    stamp = os.path.join(_HERE, "_ref", "libod_oracle.stamp")
+
+    def fresh():
+        try:
+            return os.path.exists(_LIB_PATH) and open(stamp).read().strip() == fp
+        except OSError:
+            return False
+
+    if not force and fresh():
+        return _LIB_PATH
+    os.makedirs(os.path.join(_HERE, "_ref"), exist_ok=True)
+    with open(os.path.join(_HERE, "_ref", ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or not fresh():
+            subprocess.check_call(["make", "-C", _HERE, "-B", "-s"], stdout=subprocess.DEVNULL)
+            with open(stamp, "w") as fh:
+                fh.write(fp + "\n")
     return _LIB_PATH
 
 

@@ -124,13 +124,17 @@ class DetectionHeadPipeline:
         ops.nms_topk(self.cand, self.B, self.iou_thr, self.K, (out.num_instances, out.scores, out.classes, out.boxes),
                      reset_counts=True)
 
-    def step(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> None:
-        """One pass of the hot path over one batch: both chains, concurrently, on two streams."""
+    def step(self, x: StepInputs, out: StepOutputs, finalize: bool = True, after_train=None) -> None:
+        """One pass of the hot path over one batch: both chains, concurrently, on two streams.
+        ``after_train`` (optional callable) runs on the train stream right after the loss kernels — the
+        multi-GPU all-reduce of ``out.sums`` + finalize go there, overlapping the inference chain."""
         main = torch.cuda.current_stream(self.device)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             self.infer_chain(x, out)
         self.train_chain(x, out, finalize)
+        if after_train is not None:
+            after_train()
         main.wait_stream(self.side)
 
     def capture(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> torch.cuda.CUDAGraph:
