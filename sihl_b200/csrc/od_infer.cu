@@ -384,13 +384,27 @@ struct StagedCand {
 
 __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const StagedCand *list, int count)
 {
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const StagedCand c = list[i];
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < count; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool have = i < count;
+        StagedCand c = list[have ? i : 0];
         const int64_t row = ((int64_t)c.row_hi << 32) | (unsigned)c.row_lo;
-        const float s = sigmoid_f(c.x);
         const int b = (int)(row / p.A), a = (int)(row - (int64_t)b * p.A);
-        const int slot = atomicAdd(p.cand_count + b, 1);
-        if (slot >= p.cap) continue;
+        // one returning atomic per (warp, image) instead of one per candidate: neighbours in the list come from
+        // the same 64-row chunk, i.e. almost always the same image (same-address atomics serialise in L2)
+        const unsigned act = __ballot_sync(kFullMask, have);
+        int slot = 0;
+        if (have) {
+            const unsigned peers = __match_any_sync(act, b);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            slot = base + __popc(peers & ((1u << lane) - 1u));
+        }
+        if (!have || slot >= p.cap) continue;
+        const float s = sigmoid_f(c.x);
         const float4 off = __ldg(p.offsets + a), sc = __ldg(p.scales + a);
         const int64_t o = (int64_t)b * p.cap + slot;
         p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);

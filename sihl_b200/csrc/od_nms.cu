@@ -33,7 +33,7 @@ constexpr int kSmemItems = 4096;          // per-image candidates held on chip
 constexpr int kBigSegment = 512;
 constexpr int kSmallItems = 256;          // lists up to this size take the single-pass rank-sort kernel
 static_assert(4 * kSmallItems == kNmsThreads, "short-list path: four lanes per candidate");
-constexpr size_t kSmemItemBytes = 41;     // key 8 + box 16 + val 4 + area 4 + slot 4 + seg 4 + dead 1
+constexpr size_t kSmemItemBytes = 47;     // dynamic shared memory per on-chip candidate: max over the two long-list layouts (41, 47)
 constexpr size_t kWsItemBytes = 48;       // workspace stride per item (keeps every image 16-B aligned)
 
 __device__ __forceinline__ unsigned f2ord_nms(float f)
@@ -441,18 +441,332 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
     SIHL_PHASE(7);
 }
 
-// One launch for both paths: the list length (known only on the device) picks the body.
+// Medium and long lists (n > kSmallItems).  No global sort: candidates are bucketed by class through a small
+// shared-memory hash table (count -> exclusive scan -> scatter), ranked INSIDE their class by counting
+// (sum_c n_c^2 comparisons instead of n log^2 n sort stages with a barrier each), suppressed per class by one
+// warp, and only the survivors are sorted by score (bitonic) for the output order.  Arrays live in shared
+// memory up to kSmemItems candidates, in the global workspace beyond.  Returns false when the list defeats the
+// table (more than kHashSlots/2 distinct classes): the caller then takes the two-sort path (nms_big_body).
+constexpr int kHashSlots = 1024;
+constexpr unsigned kHashEmpty = 0xffffffffu;
+constexpr size_t kMedItemBytes = 47;      // U_key 8 + F_key 8 + F_box 16 + U_slot 4 + F_slot 4 + F_area 4 + B_id 2 + F_dead 1
+static_assert(kMedItemBytes <= kSmemItemBytes && kMedItemBytes <= kWsItemBytes, "long-list layouts must fit the shared/workspace strides");
+
+struct MedArrays {
+    unsigned long long *u_key;   // bucketed by class, unordered inside a bucket; later: survivors to sort
+    unsigned long long *f_key;   // by q (class-major, score-descending inside a class)
+    float4 *f_box;
+    unsigned *u_slot, *f_slot;
+    float *f_area;
+    unsigned short *b_id;        // hash slot of candidate i
+    unsigned char *f_dead;
+};
+
+__device__ __forceinline__ MedArrays carve_med(unsigned char *base, int n_al)
+{
+    MedArrays a;
+    a.u_key = reinterpret_cast<unsigned long long *>(base);
+    a.f_key = reinterpret_cast<unsigned long long *>(base + (size_t)n_al * 8);
+    a.f_box = reinterpret_cast<float4 *>(base + (size_t)n_al * 16);
+    a.u_slot = reinterpret_cast<unsigned *>(base + (size_t)n_al * 32);
+    a.f_slot = reinterpret_cast<unsigned *>(base + (size_t)n_al * 36);
+    a.f_area = reinterpret_cast<float *>(base + (size_t)n_al * 40);
+    a.b_id = reinterpret_cast<unsigned short *>(base + (size_t)n_al * 44);
+    a.f_dead = base + (size_t)n_al * 46;
+    return a;
+}
+
+// SMEM: the arrays are in shared memory (tells the compiler the address space: generic loads from shared are
+// several times slower than LDS and do not pipeline in the counting loops).
+template <bool SMEM>
+__device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int src0, unsigned char *base, int n_al,
+                                                int *s_warp, unsigned *h_cls, int *h_cnt, int *h_start, int *n_kept_out)
+{
+    if (SMEM) __builtin_assume(__isShared(base));
+    else __builtin_assume(__isGlobal(base));
+    __builtin_assume(__isShared(h_cls));
+    __builtin_assume(__isShared(h_cnt));
+    __builtin_assume(__isShared(h_start));
+    int &s_distinct = h_start[0];                    // scratch until the scan overwrites h_start
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const MedArrays ar = carve_med(base, n_al);
+
+    auto key_of = [&](int i) -> unsigned long long {
+        if (p.mode == 0) return __ldg(p.cand_key + (int64_t)img * p.cap + i);
+        return ((unsigned long long)f2ord_nms(__ldg(p.scores + src0 + i)) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    };
+    auto cls_of = [&](int i) -> unsigned {
+        return p.mode == 0 ? (unsigned)__ldg(p.cand_cls + (int64_t)img * p.cap + i) : (unsigned)__ldg(p.classes + src0 + i);
+    };
+
+    SIHL_PHASE(0);
+    for (int h = tid; h < kHashSlots; h += blockDim.x) { h_cls[h] = kHashEmpty; h_cnt[h] = 0; }
+    if (tid == 0) s_distinct = 0;
+    __syncthreads();
+    // 1. class -> hash slot, per-slot counts
+    for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned c = cls_of(i);
+        unsigned h = (c * 2654435761u) >> 22;                      // 10 bits
+        for (int probe = 0; probe < kHashSlots; ++probe) {
+            const unsigned prev = atomicCAS(&h_cls[h], kHashEmpty, c);
+            if (prev == kHashEmpty) { atomicAdd(&s_distinct, 1); break; }
+            if (prev == c) break;
+            h = (h + 1) & (kHashSlots - 1);
+        }
+        ar.b_id[i] = (unsigned short)h;
+        atomicAdd(&h_cnt[h], 1);
+    }
+    __syncthreads();
+    if (s_distinct > kHashSlots / 2) return false;                // block-uniform
+    SIHL_PHASE(1);
+    // 2. exclusive scan of the slot counts (one slot per thread)
+    {
+        const int c = tid < kHashSlots ? h_cnt[tid] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int x = lane < nwarps ? s_warp[lane] : 0;
+            int wi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFullMask, wi, o);
+                if (lane >= o) wi += y;
+            }
+            s_warp[lane] = wi - x;
+        }
+        __syncthreads();
+        if (tid < kHashSlots) { h_start[tid] = s_warp[warp] + incl - c; h_cnt[tid] = 0; }     // h_cnt becomes the fill cursor
+    }
+    __syncthreads();
+    SIHL_PHASE(2);
+    // 3. scatter (key, slot) into the class buckets
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int h = ar.b_id[i];
+        const int pos = h_start[h] + atomicAdd(&h_cnt[h], 1);
+        ar.u_key[pos] = key_of(i);
+        ar.u_slot[pos] = (unsigned)i;
+    }
+    __syncthreads();
+    SIHL_PHASE(3);
+    // 4. rank inside the bucket by counting -> class-major position q; gather the box
+    for (int pp = tid; pp < n; pp += blockDim.x) {
+        const unsigned long long key = ar.u_key[pp];
+        const unsigned slot = ar.u_slot[pp];
+        const int h = ar.b_id[slot];
+        const int s0 = h_start[h], e0 = s0 + h_cnt[h];
+        int rank = 0;
+        for (int j = s0; j < e0; ++j) rank += ar.u_key[j] > key;
+        const int q = s0 + rank;
+        const float4 bx = p.mode == 0 ? __ldg(p.cand_box + (int64_t)img * p.cap + slot) : __ldg(p.boxes + src0 + slot);
+        ar.f_key[q] = key;
+        ar.f_slot[q] = slot;
+        ar.f_box[q] = bx;
+        ar.f_area[q] = (bx.z - bx.x) * (bx.w - bx.y);
+        ar.f_dead[q] = 0;
+    }
+    __syncthreads();
+    SIHL_PHASE(4);
+    // 5. suppression inside each class.  Segments of up to 64 boxes: every box gets the bitmask of the earlier
+    //    boxes of its class that overlap it (all pairs in parallel, u_key is free to hold the masks), then one
+    //    lane per class runs the greedy chain on bits.  Longer segments: one warp per class, the kept box is
+    //    broadcast and 32 later boxes are tested per step.
+    unsigned long long *mask = ar.u_key;
+    for (int q = tid; q < n; q += blockDim.x) {
+        const int h = ar.b_id[ar.f_slot[q]];
+        const int s0 = h_start[h], m = h_cnt[h];
+        unsigned long long bits = 0ull;
+        if (m <= 64) {
+            const float4 bq = ar.f_box[q];
+            const float aq = ar.f_area[q];
+            for (int j = s0; j < q; ++j)
+                if (iou_gt(ar.f_box[j], ar.f_area[j], bq, aq, p.iou_thr)) bits |= 1ull << (j - s0);
+        }
+        mask[q] = bits;
+    }
+    __syncthreads();
+    for (int h = tid; h < kHashSlots; h += blockDim.x) {          // one lane per class: greedy on bits
+        const int m = h_cnt[h];
+        if (m < 2 || m > 64) continue;
+        const int s0 = h_start[h];
+        unsigned long long kept = 1ull;
+        for (int i = 1; i < m; ++i) {
+            if ((mask[s0 + i] & kept) == 0ull) kept |= 1ull << i;
+            else ar.f_dead[s0 + i] = 1;
+        }
+    }
+    for (int h = warp; h < kHashSlots; h += nwarps) {             // long segments
+        const int m = h_cnt[h];
+        if (m <= 64) continue;
+        const int q0 = h_start[h];
+        for (int i = 0; i + 1 < m; ++i) {
+            __syncwarp();
+            if (ar.f_dead[q0 + i]) continue;
+            const float4 bi = ar.f_box[q0 + i];
+            const float ai = ar.f_area[q0 + i];
+            for (int j = i + 1 + lane; j < m; j += 32)
+                if (!ar.f_dead[q0 + j] && iou_gt(bi, ai, ar.f_box[q0 + j], ar.f_area[q0 + j], p.iou_thr)) ar.f_dead[q0 + j] = 1;
+        }
+    }
+    __syncthreads();
+    // 6. survivors -> u_key/u_slot (ballot compaction), then ordered by (score desc, index asc) WITHOUT a sort:
+    //    mode 0 needs the K best only -> radix select of the K-th score + rank-by-counting of the few above it;
+    //    mode 1 needs all of them     -> rank-by-counting over the survivors (bitonic only beyond 4096 of them).
+    //    (Barrier-heavy sorts are slow here: every __syncthreads drains the shared-memory stores of 32 warps.)
+    SIHL_PHASE(5);
+    const int n_kept = block_ordered_compact(
+        n, s_warp, [&](int q) { return ar.f_dead[q] == 0; },
+        [&](int q, int k) { ar.u_key[k] = ar.f_key[q]; ar.u_slot[k] = (unsigned)q; });
+    __syncthreads();
+    SIHL_PHASE(6);
+    auto emit = [&](int k_src, int rank) {                       // survivor k_src goes to output position rank
+        const unsigned q = ar.u_slot[k_src], slot = ar.f_slot[q];
+        if (p.mode == 0) {
+            const int64_t o = (int64_t)img * p.K + rank;
+            p.out_scores[o] = __uint_as_float((unsigned)(ar.u_key[k_src] >> 32));
+            p.out_classes[o] = (int64_t)h_cls[ar.b_id[slot]];
+            p.out_boxes[o] = ar.f_box[q];
+        } else {
+            p.keep[src0 + rank] = (int64_t)src0 + slot;
+        }
+    };
+    const int want = p.mode == 0 ? (n_kept < p.K ? n_kept : p.K) : n_kept;
+    if (p.mode == 1 && n_kept > 4096) {
+        int np = 2;
+        while (np < n_kept) np <<= 1;
+        for (int k = n_kept + tid; k < np; k += blockDim.x) { ar.u_key[k] = 0ull; ar.u_slot[k] = 0u; }
+        __syncthreads();
+        bitonic_kv<true>(ar.u_key, ar.u_slot, np);
+        for (int k = tid; k < n_kept; k += blockDim.x) emit(k, k);
+    } else {
+        // threshold: with more survivors than outputs, only keys >= the want-th largest score can be emitted
+        unsigned thr_hi = 0u;                                    // compare on the score word
+        if (n_kept > want) {
+            unsigned *hist = reinterpret_cast<unsigned *>(h_cnt);    // 1024 ints of scratch, free by now
+            unsigned prefix = 0, mask = 0, remaining = (unsigned)want;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+                __syncthreads();
+                for (int k0 = 0; k0 < n_kept; k0 += blockDim.x) {
+                    const int k = k0 + tid;
+                    const bool ok = k < n_kept;
+                    const unsigned u = ok ? (unsigned)(ar.u_key[k] >> 32) : 0u;
+                    const bool in = ok && ((u & mask) == prefix);
+                    const unsigned digit = (u >> shift) & 255u;
+                    const unsigned act = __ballot_sync(kFullMask, in);
+                    if (in) {
+                        const unsigned peers = __match_any_sync(act, digit);
+                        if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned c[8], tot = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { c[j] = hist[255 - (lane * 8 + j)]; tot += c[j]; }
+                    unsigned incl = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(kFullMask, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    unsigned before = incl - tot;
+                    if (before < remaining && remaining <= incl) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (before < remaining && remaining <= before + c[j]) {
+                                hist[256] = 255u - (unsigned)(lane * 8 + j);
+                                hist[257] = remaining - before;
+                            }
+                            before += c[j];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= hist[256] << shift;
+                mask |= 255u << shift;
+                remaining = hist[257];
+                __syncthreads();
+            }
+            thr_hi = prefix;
+        }
+        // rank-by-counting among the survivors that can make it (all of them when n_kept == want).  They are
+        // compacted first (f_key is free by now) so that a few full warps do the counting instead of one lane
+        // in every warp, and they only need to be ranked among themselves: everything else is smaller.
+        unsigned long long *pass_key = ar.f_key;
+        unsigned *pass_src = reinterpret_cast<unsigned *>(ar.f_area);
+        __syncthreads();
+        const int n_pass = block_ordered_compact(
+            n_kept, s_warp, [&](int k) { return (unsigned)(ar.u_key[k] >> 32) >= thr_hi; },
+            [&](int k, int r) { pass_key[r] = ar.u_key[k]; pass_src[r] = (unsigned)k; });
+        __syncthreads();
+        for (int r = tid; r < n_pass; r += blockDim.x) {
+            const unsigned long long key = pass_key[r];
+            int rank = 0;
+            for (int j = 0; j < n_pass; ++j) rank += pass_key[j] > key;
+            if (rank < want) emit((int)pass_src[r], rank);
+        }
+    }
+    SIHL_PHASE(7);
+    SIHL_PHASE(8);
+    *n_kept_out = n_kept;
+    return true;
+}
+
+// One launch for every path: the list length (known only on the device) picks the body.
 __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
 {
-    int n;
+    extern __shared__ __align__(16) unsigned char s_dyn_top[];
+    __shared__ int s_warp_top[33];
+    __shared__ unsigned s_hcls[kHashSlots];
+    __shared__ int s_hcnt[kHashSlots], s_hstart[kHashSlots];
+    int n, src0;
     if (p.mode == 0) {
         const int c = __ldg(p.cand_count + blockIdx.x);
         n = (int)(c < p.cap ? c : p.cap);
+        src0 = 0;
     } else {
-        n = __ldg(p.seg_offsets + blockIdx.x + 1) - __ldg(p.seg_offsets + blockIdx.x);
+        src0 = __ldg(p.seg_offsets + blockIdx.x);
+        n = __ldg(p.seg_offsets + blockIdx.x + 1) - src0;
     }
-    if (n <= kSmallItems) nms_small_body(p);
-    else nms_big_body(p);
+    if (n <= kSmallItems) { nms_small_body(p); return; }
+    int n_al = 2;
+    while (n_al < n) n_al <<= 1;
+    int n_kept = 0;
+    bool done;
+    if (n_al <= kSmemItems) {
+        done = nms_medium_body<true>(p, n, src0, s_dyn_top, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &n_kept);
+    } else {
+        unsigned char *ws = p.workspace + (p.mode == 0 ? (size_t)blockIdx.x * p.ws_stride : (size_t)2 * src0 * kWsItemBytes);
+        done = nms_medium_body<false>(p, n, src0, ws, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &n_kept);
+    }
+    if (done) {
+        const int img = blockIdx.x, tid = threadIdx.x;
+        if (p.mode == 0) {
+            const int m = n_kept < p.K ? n_kept : p.K;
+            if (tid == 0) {
+                p.num_instances[img] = m;
+                if (p.reset_counts) const_cast<int32_t *>(p.cand_count)[img] = 0;
+            }
+            for (int k = m + tid; k < p.K; k += blockDim.x) {
+                const int64_t o = (int64_t)img * p.K + k;
+                p.out_scores[o] = 0.f;
+                p.out_classes[o] = 0;
+                p.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else if (tid == 0) {
+            p.keep_count[img] = n_kept;
+        }
+        return;
+    }
+    __syncthreads();
+    nms_big_body(p);
 }
 
 static int pow2ceil(int64_t n)
