@@ -324,7 +324,6 @@ def run_ours(args, w, world, rank, local_rank):
     cand_mean = None      # measured in the stand-alone decode loop below (k_nms* zero the counters they consume)
     det_mean = float(outs0[0].num_instances.float().mean().item())
 
-    result = {"ms": ms, "value": value, "losses": losses, "P_bar": P_bar, "cand_mean": cand_mean, "det_mean": det_mean}
     if rank != 0:
         # the other ranks only take part in the collective part of the end-to-end measurement
         if not args.skip_e2e:
@@ -408,7 +407,6 @@ def run_ours(args, w, world, rank, local_rank):
         "cpu_baseline": cpu, "gpu_eager_reference": eager, "clocks": clocks, "losses_check": losses,
     }
     print(json.dumps(line), flush=True)
-    return result
 
 
 def gpu_eager_reference(w, x, levels, dev, passes=2):

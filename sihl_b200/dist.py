@@ -5,7 +5,7 @@ ranks (one process per GPU) and the only exchange is the 8 fp64 loss partial sum
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist

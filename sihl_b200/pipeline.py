@@ -15,7 +15,7 @@ is ``sums`` (8 doubles), all-reduced between resolve and finalize when ``world_s
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor

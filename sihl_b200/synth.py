@@ -17,7 +17,7 @@ redrawn when a side collapses below 1 px, non-integer coordinates;
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
