@@ -347,12 +347,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+// Streamed exactly once: tag the lines evict-first so the scan does not push the L2-resident working set of the
+// concurrently running kernels (anchor tables, selections, candidate and positive lists) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -428,6 +437,7 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
     const uint32_t stage_bytes = cls_bytes + box_bytes + loc_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + (size_t)stages * stage_bytes);
 
+    const uint64_t policy = l2_evict_first_policy();
     auto issue = [&](int stage, int chunk) {                      // one elected thread
         const int64_t row0 = (int64_t)chunk * kChunkRows;
         const int64_t n = rows - row0 < kChunkRows ? rows - row0 : kChunkRows;
@@ -435,9 +445,9 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
         const uint32_t cb = (uint32_t)n * (uint32_t)p.C * 4u, bb = (uint32_t)n * 16u;
         const bool full = n == kChunkRows;                        // partial tail: loc is read directly (16-B size rule)
         mbar_expect_tx(bars + stage, cb + bb + (full ? loc_bytes : 0u));
-        bulk_g2s(dst, p.cls + row0 * p.C, cb, bars + stage);
-        bulk_g2s(dst + cls_bytes, p.box_raw + row0 * 4, bb, bars + stage);
-        if (full) bulk_g2s(dst + cls_bytes + box_bytes, p.loc + row0, loc_bytes, bars + stage);
+        bulk_g2s(dst, p.cls + row0 * p.C, cb, bars + stage, policy);
+        bulk_g2s(dst + cls_bytes, p.box_raw + row0 * 4, bb, bars + stage, policy);
+        if (full) bulk_g2s(dst + cls_bytes + box_bytes, p.loc + row0, loc_bytes, bars + stage, policy);
     };
 
     if (tid == 0) {
@@ -459,10 +469,12 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
         if (c >= n_chunks) break;
         const int s = k % stages;
         mbar_wait(bars + s, (uint32_t)((k / stages) & 1));
-        const int64_t row = (int64_t)c * kChunkRows + r;
-        const bool ok = row < rows;
         const unsigned char *base = s_ring + (size_t)s * stage_bytes;
-        const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
+#pragma unroll 1
+        for (int rr = r; rr < kChunkRows; rr += 64) {             // 256 threads cover 64 rows per pass
+        const int64_t row = (int64_t)c * kChunkRows + rr;
+        const bool ok = row < rows;
+        const float4 *src = reinterpret_cast<const float4 *>(base) + rr * C4;
         // first arg-max of the row in two cheap steps: the row maximum (max tree + 2 shuffles), then the
         // lowest class index whose logit equals it (reverse predicated scan + 2 shuffles); half the
         // instructions of a running (value, index) comparison.  NaN logits never win (as before).
@@ -494,15 +506,16 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
         if (arg == 0x7fffffff) arg = 0;                           // all-NaN row
         if (gl == 0 && ok) {
             const bool full = rows - (int64_t)c * kChunkRows >= kChunkRows;
-            const float x = full ? reinterpret_cast<const float *>(base + cls_bytes + box_bytes)[r] : __ldcs(p.loc + row);
+            const float x = full ? reinterpret_cast<const float *>(base + cls_bytes + box_bytes)[rr] : __ldcs(p.loc + row);
             if (x >= x_thr && sigmoid_f(x) > p.score_thr) {
                 const int i = atomicAdd(&s_count, 1);             // < kStageCap: flushed below before it can overflow
                 StagedCand sc;
-                sc.raw = reinterpret_cast<const float4 *>(base + cls_bytes)[r];
+                sc.raw = reinterpret_cast<const float4 *>(base + cls_bytes)[rr];
                 sc.row_lo = (int)(row & 0xffffffff); sc.row_hi = (int)(row >> 32);
                 sc.x = x; sc.arg = arg;
                 s_list[i] = sc;
             }
+        }
         }
         __syncthreads();                                          // every lane is done with stage s
         if (tid == 0) {
