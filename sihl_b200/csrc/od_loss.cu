@@ -147,32 +147,28 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
         const int b = slot / p.n_tiles;
         const int32_t *rows = p.tile_pos_rows + (int64_t)slot * kTile + r_begin;
         const int2 *aux = p.tile_pos_aux + (int64_t)slot * kTile + r_begin;
-        for (int r0 = 0; r0 < n; r0 += ngrp) {                    // one round with 4 lanes per row
-            const int r = r0 + grp;
-            const bool ok = r < n;
-            const int64_t flat = __ldg(rows + (ok ? r : 0));
-            const int2 ga = __ldg(aux + (ok ? r : 0));
-            const int g = ga.x;
-            const float wgt = __int_as_float(ga.y);
-            const int a = (int)(flat - (int64_t)b * A);
-            // everything below depends only on (flat, g): one round of independent loads
-            const int tgt = p.cls != nullptr ? (int)__ldg(p.gt_classes + g) : 0;
-            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), off = raw, sc = raw, gtb = raw;
-            if (p.box_raw != nullptr && gl == 0) {
-                raw = ldg4(p.box_raw + 4 * flat); off = __ldg(p.offsets + a); sc = __ldg(p.scales + a); gtb = __ldg(p.gt_boxes + g);
-            }
-            float m = 0.f, se = 1.f;
-            if (p.cls != nullptr) {
+        if (p.cls != nullptr) {
+            for (int r0 = 0; r0 < n; r0 += ngrp) {                // class loss: one round with 4 lanes per row
+                const int r = r0 + grp;
+                const bool ok = r < n;
+                const int64_t flat = __ldg(rows + (ok ? r : 0));
+                const int2 ga = __ldg(aux + (ok ? r : 0));
+                const int tgt = (int)__ldg(p.gt_classes + ga.x);
+                float m, se;
                 if (p.cls_vec4) row_softmax_stats4v(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
                 else row_softmax_stats8(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
-            }
-            if (ok && gl == 0) {
-                if (p.cls != nullptr) {
+                if (ok && gl == 0) {
                     const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + tgt);
-                    acc_cls += wgt * ce;                          // ref :208
+                    acc_cls += __int_as_float(ga.y) * ce;         // ref :208
                 }
-                if (p.box_raw != nullptr) acc_box += wgt * pos_box_loss(raw, off, sc, gtb, p.img_w, p.img_h);   // ref :197
             }
+        }
+        if (p.box_raw != nullptr && tid < n) {                    // box loss: one lane per row (a chunk has <= 32 rows)
+            const int64_t flat = __ldg(rows + tid);
+            const int2 ga = __ldg(aux + tid);
+            const int a = (int)(flat - (int64_t)b * A);
+            acc_box += __int_as_float(ga.y) * pos_box_loss(ldg4(p.box_raw + 4 * flat), __ldg(p.offsets + a), __ldg(p.scales + a),
+                                                           __ldg(p.gt_boxes + ga.x), p.img_w, p.img_h);      // ref :197
         }
     }
     SIHL_PT(1);
