@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--serial", action="store_true", help="run both chains on one stream")
     ap.add_argument("--lanes", type=int, default=0, help="steps in flight (independent scratch + stream each); 0 = 4")
+    ap.add_argument("--decode-mode", default="dense", choices=["dense", "candidate_first"],
+                    help="inference chain of the timed step: dense class-map scan (TMA ring, the roofline kernel) or the "
+                         "candidate-first gather (same outputs, ~30x fewer bytes at 2 %% candidates)")
+    ap.add_argument("--skip-candidate-first", action="store_true", help="do not also time the candidate-first variant")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-gpu-eager", action="store_true")
@@ -213,9 +217,7 @@ def run_ours(args, w, world, rank, local_rank):
     H, W, B, C, G, K = w["height"], w["width"], w["batch"], w["classes"], w["gt"], w["k"]
     levels = synth.level_sizes(H, W)
     n_lanes = args.lanes if args.lanes > 0 else 4
-    pipes = [DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR) for _ in range(n_lanes)]
-    pipe = pipes[0]
-    A = pipe.A
+    A = synth.num_anchors(levels)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + 1000 * rank)
     n_sets = 3
@@ -224,8 +226,6 @@ def run_ours(args, w, world, rank, local_rank):
         boxes, classes, offsets = synth.gt_batch_torch(gen, B, H, W, C, G, dev)
         loc, iou, box, cls = synth.dense_maps_torch(gen, B, A, C, dev)
         sets.append(StepInputs(loc, iou, box, cls, ops.GtBatch(boxes, classes, offsets, [G] * B)))
-    # every (lane, input set) pair owns its outputs: steps in flight on different lanes never share a buffer
-    outs = [[pipes[ln].new_outputs() for _ in range(n_sets)] for ln in range(n_lanes)]
     torch.cuda.synchronize()
 
     multi = world > 1
@@ -240,81 +240,96 @@ def run_ours(args, w, world, rank, local_rank):
             dist.all_reduce(torch.zeros(8, dtype=torch.float64, device=dev), group=groups[ln])
         torch.cuda.synchronize()
 
-    def full_step(ln, i):
-        """One step incl. the cross-GPU exchange: 8 fp64 sums all-reduced between the loss kernels and finalize."""
-        out = outs[ln][i]
-
-        def exchange():                               # right after the loss kernels, next to the inference chain
-            dist.all_reduce(out.sums, op=dist.ReduceOp.SUM, group=groups[ln])
-            pipes[ln].finalize(out)
-
-        if args.serial:
-            pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not multi)
-            if multi:
-                exchange()
-        else:
-            pipes[ln].step(sets[i], out, finalize=not multi, after_train=exchange if multi else None)
-
-    graphs = None
-    if use_graph and not args.serial:
-        graphs = []
-        for ln in range(n_lanes):
-            with torch.cuda.stream(lane_streams[ln]):
-                lane_graphs = []
-                for i in range(n_sets):
-                    full_step(ln, i)                       # warm-up outside capture
-                    torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=lane_streams[ln]):
-                        full_step(ln, i)                   # NCCL all-reduce is captured as a graph node
-                    lane_graphs.append(g)
-                graphs.append(lane_graphs)
-        torch.cuda.synchronize()
-
-    def run_step(s):
-        """Step s goes to lane s % n_lanes: consecutive steps overlap (the HBM-bound decode of one step runs
-        next to the latency-bound assignment / NMS kernels of its neighbours)."""
-        ln, i = s % n_lanes, s % n_sets
-        with torch.cuda.stream(lane_streams[ln]):
-            if graphs is not None:
-                graphs[ln][i].replay()
-            else:
-                full_step(ln, i)
-
-    def drain():
-        for ln in range(n_lanes):
-            main.wait_stream(lane_streams[ln])
-
-    def fork():
-        for st in lane_streams:
-            st.wait_stream(main)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
 
     def barrier():
         if multi:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    fork()
-    for s in range(max(args.warmup, 3)):
-        run_step(s)
-    drain()
-    barrier()
-    if sampler: sampler.mark()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
-    fork()
-    for s in range(args.steps):
-        run_step(s)
-    drain()
-    e1.record(main)
-    barrier()
-    if sampler: sampler.mark()
-    ms = e0.elapsed_time(e1)
-    if multi:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def timed_steps(mode, steps, warmup):
+        """Build the lanes for one decode mode, replay `warmup` + `steps` steps, return (ms, pipes, outs, graphs)."""
+        pipes = [DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
+                 for _ in range(n_lanes)]
+        # every (lane, input set) pair owns its outputs: steps in flight on different lanes never share a buffer
+        outs = [[pipes[ln].new_outputs() for _ in range(n_sets)] for ln in range(n_lanes)]
+        torch.cuda.synchronize()
+        return _timed_steps(pipes, outs, steps, warmup)
+
+    def _timed_steps(pipes, outs, n_steps, n_warmup):
+        def full_step(ln, i):
+            """One step incl. the cross-GPU exchange: 8 fp64 sums all-reduced between the loss kernels and finalize."""
+            out = outs[ln][i]
+
+            def exchange():                               # right after the loss kernels, next to the inference chain
+                dist.all_reduce(out.sums, op=dist.ReduceOp.SUM, group=groups[ln])
+                pipes[ln].finalize(out)
+
+            if args.serial:
+                pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not multi)
+                if multi:
+                    exchange()
+            else:
+                pipes[ln].step(sets[i], out, finalize=not multi, after_train=exchange if multi else None)
+
+        graphs = None
+        if use_graph and not args.serial:
+            graphs = []
+            for ln in range(n_lanes):
+                with torch.cuda.stream(lane_streams[ln]):
+                    lane_graphs = []
+                    for i in range(n_sets):
+                        full_step(ln, i)                       # warm-up outside capture
+                        torch.cuda.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=lane_streams[ln]):
+                            full_step(ln, i)                   # NCCL all-reduce is captured as a graph node
+                        lane_graphs.append(g)
+                    graphs.append(lane_graphs)
+            torch.cuda.synchronize()
+
+        def run_step(s):
+            """Step s goes to lane s % n_lanes: consecutive steps overlap (the HBM-bound decode of one step runs
+            next to the latency-bound assignment / NMS kernels of its neighbours)."""
+            ln, i = s % n_lanes, s % n_sets
+            with torch.cuda.stream(lane_streams[ln]):
+                if graphs is not None:
+                    graphs[ln][i].replay()
+                else:
+                    full_step(ln, i)
+
+        def drain():
+            for ln in range(n_lanes):
+                main.wait_stream(lane_streams[ln])
+
+        def fork():
+            for st in lane_streams:
+                st.wait_stream(main)
+
+        fork()
+        for s in range(n_warmup):
+            run_step(s)
+        drain()
+        barrier()
+        if sampler: sampler.mark()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        fork()
+        for s in range(n_steps):
+            run_step(s)
+        drain()
+        e1.record(main)
+        barrier()
+        if sampler: sampler.mark()
+        ms = e0.elapsed_time(e1)
+        if multi:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, pipes, outs, graphs
+
+    ms, pipes, outs, graphs = timed_steps(args.decode_mode, args.steps, max(args.warmup, 3))
+    pipe = pipes[0]
     value = B * world * args.steps / (ms * 1e-3)
     outs0 = outs[0]
 
@@ -323,6 +338,19 @@ def run_ours(args, w, world, rank, local_rank):
     P_bar = float(outs0[0].sums[6].item()) / (B * (world if multi else 1))
     cand_mean = None      # measured in the stand-alone decode loop below (k_nms* zero the counters they consume)
     det_mean = float(outs0[0].num_instances.float().mean().item())
+
+    # ---- the other decode variant on the same inputs (same outputs; reported next to `value`, never instead of it)
+    other = None
+    if not args.skip_candidate_first:
+        other_mode = "candidate_first" if args.decode_mode == "dense" else "dense"
+        o_steps = max(3, min(args.steps, 1000))
+        o_ms, o_pipes, o_outs, _ = timed_steps(other_mode, o_steps, max(min(args.warmup, 100), 3))
+        same = all(torch.equal(a, b) for a, b in zip(
+            (outs0[0].num_instances, outs0[0].scores, outs0[0].classes, outs0[0].boxes, outs0[0].assignment),
+            (o_outs[0][0].num_instances, o_outs[0][0].scores, o_outs[0][0].classes, o_outs[0][0].boxes, o_outs[0][0].assignment)))
+        other = {"decode_mode": other_mode, "value": B * world * o_steps / (o_ms * 1e-3), "unit": UNIT, "steps": o_steps,
+                 "ms_per_step": o_ms / o_steps, "outputs_equal_to_timed_mode": bool(same)}
+        del o_pipes, o_outs
 
     if rank != 0:
         # the other ranks only take part in the collective part of the end-to-end measurement
@@ -400,11 +428,12 @@ def run_ours(args, w, world, rank, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_dict(w, args, world, {"cuda_graph": graphs is not None, "streams_per_step": 1 if args.serial else 2,
-                                                "steps_in_flight": n_lanes,
+                                                "steps_in_flight": n_lanes, "decode_mode": args.decode_mode,
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
         "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "roofline_step": roofline_step,
-        "cpu_baseline": cpu, "gpu_eager_reference": eager, "clocks": clocks, "losses_check": losses,
+        "other_decode_mode": other, "cpu_baseline": cpu, "gpu_eager_reference": eager, "clocks": clocks,
+        "losses_check": losses,
     }
     print(json.dumps(line), flush=True)
 

@@ -227,6 +227,19 @@ SIHL_OD_API int sihl_od_dense_decode(const float *loc_logits, const float *cls_l
                          uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
                          void *stream);
 
+/* Candidate-first variant of the same operation (same arguments, same outputs;
+ * the candidate lists are unordered in both).  score = sigmoid(loc) does not
+ * depend on the class logits (ref :113 vs :117), so the kernel streams only the
+ * location map and gathers the class row + raw box of the locations that pass:
+ * 4*A + n_cand*(4C+16) bytes read per image instead of 4*A*(C+5).  Preferred
+ * while fewer than about half of the locations pass the threshold. */
+SIHL_OD_API int sihl_od_candidate_decode(const float *loc_logits, const float *cls_logits, const float *box_raw,
+                         int batch, int64_t num_anchors, int num_classes,
+                         const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
+                         int32_t *cand_count, int64_t cand_capacity,
+                         uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                         void *stream);
+
 /* Class-aware greedy NMS per image over the candidate lists written by
  * sihl_od_dense_decode, semantics of torchvision _batched_nms_vanilla
  * (ops/boxes.py:102-120): visit by (score desc, location asc); a kept box

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "sihl_od_topk": (I, [P, I, I64, I, P, P, P]),
     "sihl_od_decode_rows": (I, [P, P, I, I, P, I, P, P, P, I, I, P, P, P, P, P]),
     "sihl_od_dense_decode": (I, [P, P, P, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
+    "sihl_od_candidate_decode": (I, [P, P, P, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_nms_workspace_bytes": (C.c_size_t, [I, I64]),
     "sihl_od_nms_topk": (I, [P, I64, P, P, P, I, F, I, P, P, P, P, P, I, P]),
     "sihl_od_batched_nms_workspace_bytes": (C.c_size_t, [I64]),

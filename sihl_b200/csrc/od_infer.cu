@@ -464,11 +464,10 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
 
     // sigmoid(x) > thr is monotone in x: compare logits against the smallest logit whose sigmoid passes
     const float x_thr = p.logit_thr;
-    for (int k = 0;; ++k) {
-        const int c = blockIdx.x + k * gridDim.x;
-        if (c >= n_chunks) break;
-        const int s = k % stages;
-        mbar_wait(bars + s, (uint32_t)((k / stages) & 1));
+    int s = 0;                                                    // ring slot and its phase, carried (no k % stages,
+    uint32_t phase = 0;                                           // k / stages: a runtime divisor costs ~35 instructions)
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        mbar_wait(bars + s, phase);
         const unsigned char *base = s_ring + (size_t)s * stage_bytes;
 #pragma unroll 1
         for (int rr = r; rr < kChunkRows; rr += 64) {             // 256 threads cover 64 rows per pass
@@ -528,9 +527,112 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
             if (tid == 0) s_count = 0;
             __syncthreads();
         }
+        if (++s == stages) { s = 0; phase ^= 1u; }
     }
     __syncthreads();
     flush_staged(p, s_list, s_count);
+}
+
+// ---------------------------------------------------------------------------
+// Candidate-first variant.  score = sigmoid(loc) does not depend on the class logits
+// (ref :113,:117), so only the rows that pass the threshold need their C class logits and
+// their raw box: the kernel streams the location map (4 B per location, coalesced), and
+// gathers 4C+16 B per *candidate*.  Same outputs as the dense variants (the lists are
+// unordered in both).  Compulsory traffic 4*A + cand*(4C+16+28) per image — 30x less than
+// the dense scan at 2 % candidates; it loses to the TMA stream once most rows pass.
+//
+// One warp per block of 32 consecutive rows.  Lane = row for the threshold test and the slot
+// allocation (one returning atomic per (warp, image)); then the candidates are taken four
+// at a time by the warp's four 8-lane groups: lane j of a group loads float4s j, j+8, ...
+// of the class row (128 contiguous bytes per group and load), first-argmax = row maximum
+// (3 shuffles) then lowest index equal to it (3 shuffles), like the TMA consumer.
+// VEC = 4: 16-byte loads (C % 4 == 0, aligned); VEC = 1: any C.
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
+{
+    const int lane = threadIdx.x & 31, gq = lane >> 3, gl = lane & 7;
+    const int64_t rows = (int64_t)p.batch * p.A;
+    const int64_t n_blocks = (rows + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int CV = p.C / VEC;                                      // vectors per row (VEC == 1: CV == C)
+    for (int64_t blk = warp0; blk < n_blocks; blk += n_warps) {
+        const int64_t row = (blk << 5) + lane;
+        const bool in = row < rows;
+        const float x = in ? __ldcs(p.loc + row) : -CUDART_INF_F;
+        float s = 0.f;
+        bool cand = false;
+        if (in && x >= p.logit_thr) { s = sigmoid_f(x); cand = s > p.score_thr; }
+        const unsigned m = __ballot_sync(kFullMask, cand);
+        if (m == 0u) continue;
+        const int b = in ? (int)(row / p.A) : 0;
+        const int a = in ? (int)(row - (int64_t)b * p.A) : 0;
+        int slot = 0;
+        if (cand) {                                                // the atomic's round trip overlaps the row gathers
+            const unsigned peers = __match_any_sync(m, b);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            slot = base + __popc(peers & ((1u << lane) - 1u));
+        }
+        const int n_cand = __popc(m);
+        for (int j0 = 0; j0 < n_cand; j0 += 4) {
+            const int j = j0 + gq;
+            const bool have = j < n_cand;
+            const int src = have ? (int)__fns(m, 0, j + 1) : (__ffs(m) - 1);     // lane that owns the j-th candidate
+            const int64_t crow = (blk << 5) + src;
+            float best = -CUDART_INF_F;
+            int arg = 0x7fffffff;
+            if (VEC == 4) {
+                const float4 *src4 = reinterpret_cast<const float4 *>(p.cls) + crow * CV;
+                for (int v0 = 0; v0 < CV; v0 += 32) {              // 4 loads in flight per lane and pass
+                    float4 q[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int v = v0 + gl + 8 * i;
+                        q[i] = (have && v < CV) ? __ldcs(src4 + v) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = 4 * (v0 + gl + 8 * i);
+                        const float e[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (e[k] > best) { best = e[k]; arg = c + k; }     // ascending index inside the lane: first max
+                    }
+                }
+            } else {
+                const float *srow = p.cls + crow * p.C;
+                for (int c = gl; c < (have ? p.C : 0); c += 8) {
+                    const float e = __ldcs(srow + c);
+                    if (e > best) { best = e; arg = c; }
+                }
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {                      // inside the 8-lane group
+                const float ob = __shfl_xor_sync(kFullMask, best, o);
+                const int oa = __shfl_xor_sync(kFullMask, arg, o);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            // -inf rows (arg still unset when every logit is -inf or NaN): first index whose logit equals the
+            // maximum is 0 for an all -inf row; NaN never wins — same convention as the dense variants
+            if (arg == 0x7fffffff) arg = 0;
+            const float cs = __shfl_sync(kFullMask, s, src);
+            const int ca = __shfl_sync(kFullMask, a, src), cb = __shfl_sync(kFullMask, b, src);
+            const int cslot = __shfl_sync(kFullMask, slot, src);
+            if (have && gl == 0 && cslot < p.cap) {
+                const float4 raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + crow);
+                const float4 off = __ldg(p.offsets + ca), sc = __ldg(p.scales + ca);
+                const int64_t o = (int64_t)cb * p.cap + cslot;
+                p.cand_key[o] = ((unsigned long long)__float_as_uint(cs) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ca);
+                p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
+                                            decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
+                p.cand_cls[o] = arg;
+            }
+        }
+    }
 }
 
 __global__ void k_zero_i32(int32_t *p, int n)
@@ -574,25 +676,27 @@ extern "C" int sihl_od_decode_rows(const float *top_logits, const int64_t *idx, 
     return SIHL_OD_OK;
 }
 
-extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_logits, const float *box_raw, int batch,
-                                    int64_t num_anchors, int num_classes, const float *offsets, const float *scales,
-                                    int img_w, int img_h, float score_thr, int32_t *cand_count, int64_t cand_capacity,
-                                    uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
-                                    void *stream)
+// Argument checks, optional counter zeroing and the parameter block shared by the dense and the
+// candidate-first decode.  Returns 1 when there is nothing to do (batch == 0).
+static int decode_prologue(const float *loc_logits, const float *cls_logits, const float *box_raw, int batch,
+                           int64_t num_anchors, int num_classes, const float *offsets, const float *scales,
+                           int img_w, int img_h, float score_thr, int32_t *cand_count, int64_t cand_capacity,
+                           uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts, cudaStream_t st,
+                           DenseDecodeParams *out, int *nothing)
 {
+    *nothing = 0;
     SIHL_CHECK_ARG(loc_logits && cls_logits && box_raw && offsets && scales, "NULL input");
     SIHL_CHECK_ARG(cand_count && cand_key && cand_box && cand_cls, "NULL output");
     SIHL_CHECK_ARG(batch >= 0 && num_anchors > 0 && num_anchors < (1ll << 30) && num_classes >= 1 && cand_capacity >= 1,
                    "bad sizes");
     SIHL_CHECK_ARG(img_w > 0 && img_h > 0, "image size %dx%d", img_w, img_h);
     SIHL_CHECK_ARG(score_thr >= 0.f, "score_thr=%f must be >= 0 (scores are sigmoid outputs)", (double)score_thr);
-    if (batch == 0) return SIHL_OD_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+    if (batch == 0) { *nothing = 1; return SIHL_OD_OK; }
     if (zero_counts) {
         k_zero_i32<<<(batch + 255) / 256, 256, 0, st>>>(cand_count, batch);
         SIHL_CHECK_LAUNCH("k_zero_i32");
     }
-    DenseDecodeParams p;
+    DenseDecodeParams &p = *out;
     p.loc = loc_logits; p.cls = cls_logits; p.box_raw = box_raw; p.batch = batch; p.A = (int)num_anchors; p.C = num_classes;
     p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
     p.img_w = (float)img_w; p.img_h = (float)img_h; p.score_thr = score_thr;
@@ -603,6 +707,21 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
     p.cand_count = cand_count; p.cap = cand_capacity;
     p.cand_key = reinterpret_cast<unsigned long long *>(cand_key); p.cand_box = reinterpret_cast<float4 *>(cand_box);
     p.cand_cls = cand_cls;
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_logits, const float *box_raw, int batch,
+                                    int64_t num_anchors, int num_classes, const float *offsets, const float *scales,
+                                    int img_w, int img_h, float score_thr, int32_t *cand_count, int64_t cand_capacity,
+                                    uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                                    void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DenseDecodeParams p;
+    int nothing = 0;
+    int rc0 = decode_prologue(loc_logits, cls_logits, box_raw, batch, num_anchors, num_classes, offsets, scales, img_w, img_h,
+                              score_thr, cand_count, cand_capacity, cand_key, cand_box, cand_cls, zero_counts, st, &p, &nothing);
+    if (rc0 || nothing) return rc0;
     const int64_t rows = (int64_t)batch * num_anchors;
     const bool aligned = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0);
@@ -685,5 +804,30 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
         k_dense_decode<0><<<grid, 256, 0, st>>>(p);
     }
     SIHL_CHECK_LAUNCH("k_dense_decode");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_candidate_decode(const float *loc_logits, const float *cls_logits, const float *box_raw, int batch,
+                                        int64_t num_anchors, int num_classes, const float *offsets, const float *scales,
+                                        int img_w, int img_h, float score_thr, int32_t *cand_count, int64_t cand_capacity,
+                                        uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                                        void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    DenseDecodeParams p;
+    int nothing = 0;
+    int rc0 = decode_prologue(loc_logits, cls_logits, box_raw, batch, num_anchors, num_classes, offsets, scales, img_w, img_h,
+                              score_thr, cand_count, cand_capacity, cand_key, cand_box, cand_cls, zero_counts, st, &p, &nothing);
+    if (rc0 || nothing) return rc0;
+    const int64_t rows = (int64_t)batch * num_anchors;
+    const int64_t row_blocks = (rows + 31) / 32;                   // one warp per 32 rows, 8 warps per CTA
+    int64_t blocks = (row_blocks + 7) / 8;
+    const int64_t cap = (int64_t)kNumSMs * 6;                      // 40 registers: 6 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    const bool vec = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
+    SIHL_CHECK_ARG((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0, "box_raw must be 16-byte aligned");
+    if (vec) k_candidate_decode<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else k_candidate_decode<1><<<(unsigned)blocks, 256, 0, st>>>(p);
+    SIHL_CHECK_LAUNCH("k_candidate_decode");
     return SIHL_OD_OK;
 }

@@ -389,17 +389,27 @@ class CandidateBuffers:
                                 torch.empty((batch, capacity), dtype=torch.int32, device=device), int(capacity), ws)
 
 
+DECODE_MODES = ("dense", "candidate_first")
+
+
 def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offsets: Tensor, scales: Tensor,
-                 img_w: int, img_h: int, score_thr: float, cand: CandidateBuffers, zero_counts: bool = True) -> None:
+                 img_w: int, img_h: int, score_thr: float, cand: CandidateBuffers, zero_counts: bool = True,
+                 mode: str = "dense") -> None:
+    """Fill the per-image candidate lists.  ``mode="dense"`` streams every class row (TMA ring, HBM bound);
+    ``mode="candidate_first"`` streams only the location map and gathers the rows that pass the threshold
+    (same lists up to order; far fewer bytes while candidates are sparse)."""
     loc = _req(loc_logits, torch.float32, "loc_logits", 2)
     cls = _req(cls_logits, torch.float32, "cls_logits", 3)
     box = _req(box_raw, torch.float32, "box_raw", 3)
+    if mode not in DECODE_MODES:
+        raise ValueError(f"mode={mode!r}: expected one of {DECODE_MODES}")
     B, A = loc.shape
+    name = "sihl_od_dense_decode" if mode == "dense" else "sihl_od_candidate_decode"
     with torch.cuda.device(loc.device):
-        rc = _lib().sihl_od_dense_decode(_p(loc), _p(cls), _p(box), B, A, int(cls.shape[-1]), _p(offsets), _p(scales),
-                                         int(img_w), int(img_h), float(score_thr), _p(cand.count), cand.capacity,
-                                         _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts), _stream(loc.device))
-    _native.check(rc, "sihl_od_dense_decode")
+        rc = getattr(_lib(), name)(_p(loc), _p(cls), _p(box), B, A, int(cls.shape[-1]), _p(offsets), _p(scales),
+                                   int(img_w), int(img_h), float(score_thr), _p(cand.count), cand.capacity,
+                                   _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts), _stream(loc.device))
+    _native.check(rc, name)
 
 
 def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Optional[tuple] = None,
@@ -418,14 +428,15 @@ def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Op
 
 def dense_postprocess(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, levels, img_w: int, img_h: int,
                       score_thr: float = 0.05, iou_thr: float = 0.5, max_instances: int = 100,
-                      cand: Optional[CandidateBuffers] = None):
+                      cand: Optional[CandidateBuffers] = None, mode: str = "dense"):
     """Extension (no reference counterpart): dense decode of every location + class-aware NMS.
-    Output format of ``ObjectDetection.forward`` (ref :122), zero padded past ``num_instances``."""
+    Output format of ``ObjectDetection.forward`` (ref :122), zero padded past ``num_instances``.
+    ``mode``: see :func:`dense_decode` (identical results)."""
     B, A = loc_logits.shape
     offsets, scales, _ = anchor_tables(levels, img_w, img_h, loc_logits.device)
     if cand is None:
         cand = CandidateBuffers.allocate(B, A, loc_logits.device)
-    dense_decode(loc_logits, cls_logits, box_raw, offsets, scales, img_w, img_h, score_thr, cand)
+    dense_decode(loc_logits, cls_logits, box_raw, offsets, scales, img_w, img_h, score_thr, cand, mode=mode)
     return nms_topk(cand, B, iou_thr, max_instances)
 
 

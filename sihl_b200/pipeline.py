@@ -6,7 +6,7 @@ This is the whole-batch form of the hot path that ``bench.py`` measures
 
   train chain  (stream A): k_assign_select -> k_assign_resolve (dense losses fused)
                            -> k_pos_loss_tiles (last CTA finalizes) [3 launches]
-  infer chain  (stream B): k_dense_decode_tma -> k_nms              [2 launches]
+  infer chain  (stream B): k_dense_decode_tma (or k_candidate_decode, ``decode_mode``) -> k_nms  [2 launches]
 
 The two chains share no data, so they run concurrently: the assignment is FP32-ALU/latency
 bound, the dense decode is HBM bound (SURVEY.md §8d caveat).  Across GPUs the only exchange
@@ -55,7 +55,10 @@ class StepOutputs:
 class DetectionHeadPipeline:
     def __init__(self, levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, batch: int, num_classes: int,
                  max_gt_total: int, device, topk: int = 9, max_instances: int = 100, score_thr: float = 0.05,
-                 iou_thr: float = 0.5, cand_capacity: Optional[int] = None):
+                 iou_thr: float = 0.5, cand_capacity: Optional[int] = None, decode_mode: str = "dense"):
+        if decode_mode not in ops.DECODE_MODES:
+            raise ValueError(f"decode_mode={decode_mode!r}: expected one of {ops.DECODE_MODES}")
+        self.decode_mode = decode_mode
         self.levels = [tuple(int(v) for v in l) for l in levels]
         self.img_w, self.img_h, self.B, self.C = int(img_w), int(img_h), int(batch), int(num_classes)
         self.device = torch.device(device)
@@ -120,7 +123,7 @@ class DetectionHeadPipeline:
     def infer_chain(self, x: StepInputs, out: StepOutputs) -> None:
         # the candidate counters start at zero and k_nms* re-zero them once consumed: no memset launch
         ops.dense_decode(x.loc_logits, x.cls_logits, x.box_raw, self.offsets, self.scales, self.img_w, self.img_h,
-                         self.score_thr, self.cand, zero_counts=False)
+                         self.score_thr, self.cand, zero_counts=False, mode=self.decode_mode)
         ops.nms_topk(self.cand, self.B, self.iou_thr, self.K, (out.num_instances, out.scores, out.classes, out.boxes),
                      reset_counts=True)
 

@@ -309,12 +309,13 @@ def test_nms_idempotent_and_one_class():
 
 @pytest.mark.parametrize("geom,C,B,loc_mean,loc_std", [("test_128", 16, 5, -2.0, 2.0), ("cfg0_320", 10, 3, -2.0, 2.0),
                                                         ("cfg1_640", 80, 4, -5.0, 1.0), ("cfg1_640", 80, 2, -4.0, 2.0)])
-def test_dense_postprocess(geom, C, B, loc_mean, loc_std):
+@pytest.mark.parametrize("mode", ops.DECODE_MODES)
+def test_dense_postprocess(geom, C, B, loc_mean, loc_std, mode):
     g, levels, W, H = _geom(geom)
     A = len(g["anchors"])
     maps = synth.dense_maps_np(4242, B, A, C, loc_mean, loc_std)
     loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(maps.cls_logits)
-    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, W, H, 0.05, 0.5, 100)
+    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, W, H, 0.05, 0.5, 100, mode=mode)
     o_num, o_scores, o_cls, o_boxes, ncand = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw,
                                                                     g["offsets"], g["scales"], W, H, 0.05, 0.5, 100)
     np.testing.assert_array_equal(num.cpu().numpy(), o_num)
@@ -324,6 +325,48 @@ def test_dense_postprocess(geom, C, B, loc_mean, loc_std):
     t_num, t_scores, t_cls, t_boxes = tr.dense_postprocess(levels, W, H, loc, box, cls, 0.05, 0.5, 100)
     assert torch.equal(num, t_num) and torch.equal(classes, t_cls)
     assert torch.equal(scores, t_scores) and torch.equal(boxes, t_boxes)
+
+
+def _candidate_sets(cand: ops.CandidateBuffers, B):
+    n = cand.count.cpu().numpy()
+    key, box, cls = cand.key.cpu().numpy(), cand.box.cpu().numpy(), cand.cls.cpu().numpy()
+    out = []
+    for b in range(B):
+        order = np.argsort(key[b, :n[b]].view(np.uint64))
+        out.append((key[b, :n[b]][order], box[b, :n[b]][order], cls[b, :n[b]][order]))
+    return n, out
+
+
+@pytest.mark.parametrize("C,thr,loc_mean", [(80, 0.05, -5.0), (80, 0.05, -1.0), (10, 0.3, 0.0), (7, 0.05, -2.0), (3, 0.0, 0.0),
+                                            (132, 0.05, -2.0), (80, 1.0, 0.0)])
+def test_candidate_first_lists_equal_dense_lists(C, thr, loc_mean):
+    """Both decode variants fill the same candidate lists (as sets: slot order comes from atomics) — every class count
+    path (16-byte rows, scalar rows, C > 128), duplicated row maxima (first index wins), thresholds 0 and 1."""
+    levels = synth.level_sizes(256, 320)
+    W, H, B = 320, 256, 3
+    off, sc, anchors = ops.anchor_tables(levels, W, H, DEV)
+    A = anchors.shape[0]
+    maps = synth.dense_maps_np(99 + C, B, A, C, loc_mean, 2.0)
+    cls_np = maps.cls_logits.copy()
+    cls_np[:, ::3, C // 2] = cls_np[:, ::3].max(axis=-1)                  # exact ties between two classes on every third row
+    cls_np[0, 5] = -np.inf                                                # all -inf row: class 0
+    loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(cls_np)
+    lists = {}
+    for mode in ops.DECODE_MODES:
+        cand = ops.CandidateBuffers.allocate(B, A, DEV)
+        ops.dense_decode(loc, cls, box, off, sc, W, H, thr, cand, mode=mode)
+        lists[mode] = _candidate_sets(cand, B)
+    n_d, l_d = lists["dense"]
+    n_c, l_c = lists["candidate_first"]
+    np.testing.assert_array_equal(n_d, n_c)
+    want_n = (torch.sigmoid(loc) > thr).sum(dim=1).cpu().numpy()
+    np.testing.assert_array_equal(n_c, want_n)
+    for b in range(B):
+        for x, y in zip(l_d[b], l_c[b]):
+            np.testing.assert_array_equal(x, y)
+        rows = (0xFFFFFFFF - (l_c[b][0].view(np.uint64) & np.uint64(0xFFFFFFFF))).astype(np.int64)
+        first_max = np.argmax(cls_np[b, rows], axis=-1)                   # numpy argmax: first maximum
+        np.testing.assert_array_equal(l_c[b][2], first_max)
 
 
 # --------------------------------------------------------------------------- full size (config[1]) properties
@@ -380,15 +423,16 @@ def test_crowd_config_nms_30k_candidates():
     np.testing.assert_array_equal(keep, orc.batched_nms(boxes, scores, classes, 0.5))
 
 
+@pytest.mark.parametrize("mode", ops.DECODE_MODES)
 @pytest.mark.parametrize("size,batch", [(640, 3), (1280, 2)])
-def test_inference_sweep_postprocess(size, batch):
+def test_inference_sweep_postprocess(size, batch, mode):
     """configs[4]: decode + NMS at 640-1280 px with loc ~ N(-4, 2^2) (about 30 % of the locations pass 0.05)."""
     levels = synth.level_sizes(size, size)
     off, sc, an = orc.anchors(levels, size, size)
     A, C = len(an), 80
     maps = synth.dense_maps_np(900 + size, batch, A, C, loc_mean=-4.0, loc_std=2.0)
     loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(maps.cls_logits)
-    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, size, size, 0.05, 0.5, 100)
+    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, size, size, 0.05, 0.5, 100, mode=mode)
     o_num, o_scores, o_cls, o_boxes, ncand = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw, off, sc,
                                                                     size, size, 0.05, 0.5, 100)
     assert ncand.min() > 0.2 * A
@@ -398,14 +442,15 @@ def test_inference_sweep_postprocess(size, batch):
     np.testing.assert_allclose(boxes.cpu().numpy(), o_boxes, rtol=1e-5, atol=1e-4)
 
 
-def test_pipeline_matches_unfused_ops_and_is_replayable():
+@pytest.mark.parametrize("mode", ops.DECODE_MODES)
+def test_pipeline_matches_unfused_ops_and_is_replayable(mode):
     """The bench pipeline (graphs, two streams, fused finalize, counter recycling) gives the same numbers as the
     step-by-step ops, and the same numbers again on every replay."""
     from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs
     W = H = 320
     B, C, G = 4, 80, 30
     levels = synth.level_sizes(H, W)
-    pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, DEV)
+    pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, DEV, decode_mode=mode)
     gt_np = synth.gt_batch_np(12, B, H, W, C, G, ragged=False)
     maps = synth.dense_maps_np(13, B, pipe.A, C, loc_mean=-3.0, loc_std=2.0)
     gt = _gt_dev(gt_np)
