@@ -37,6 +37,7 @@ int fill_level_table(const int32_t *level_hw_host, int n_levels, LevelTable *lv)
 __device__ unsigned g_sel_dbg[3 * 16384];     // per gt: start (globaltimer ns, low bits), cycles, candidates evaluated
 #endif
 constexpr int kSelWarps = 4;
+constexpr int kSelMinBlocks = 12;     // <= 40 registers: the 1600 CTAs of cfg1 (6400 gts) fit in one wave of 148 x 12
 constexpr int kBufCap = 64;
 
 struct SelectParams {
@@ -48,43 +49,48 @@ struct SelectParams {
     int topk;
 };
 
-// Keep the top-k of the warp's buffer, sorted by (value desc, anchor asc); returns the new count.
-__device__ __forceinline__ int select_compress(float *bv, int *bi, int cnt, int topk, int lane)
+// Buffer entries are 64-bit keys: CIoU bits << 32 | ~anchor.  Values are > 0, so the unsigned order of the keys is
+// (value desc, anchor asc) — the lexicographic rule of torch.topk ties in one integer comparison.
+__device__ __forceinline__ unsigned long long sel_key(float v, int a)
+{
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
+}
+__device__ __forceinline__ float sel_key_val(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ int sel_key_anchor(unsigned long long k) { return (int)(0xffffffffu - (unsigned)k); }
+
+// Keep the top-k of the warp's buffer, sorted descending (rank by counting; keys are distinct); returns the new count.
+__device__ __forceinline__ int select_compress(unsigned long long *bk, int cnt, int topk, int lane)
 {
     __syncwarp();
     const bool h0 = lane < cnt, h1 = lane + 32 < cnt;
-    const float v0 = h0 ? bv[lane] : 0.f, v1 = h1 ? bv[lane + 32] : 0.f;
-    const int a0 = h0 ? bi[lane] : 0, a1 = h1 ? bi[lane + 32] : 0;
+    const unsigned long long k0 = h0 ? bk[lane] : 0ull, k1 = h1 ? bk[lane + 32] : 0ull;
     int r0 = 0, r1 = 0;
     if (cnt <= 32) {
-        for (int i = 0; i < cnt; ++i) {
-            const float vi = bv[i];
-            r0 += (vi > v0) || (vi == v0 && bi[i] < a0);
-        }
+#pragma unroll 4
+        for (int i = 0; i < cnt; ++i) r0 += bk[i] > k0;
     } else {
+#pragma unroll 4
         for (int i = 0; i < cnt; ++i) {
-            const float vi = bv[i];
-            const int ai = bi[i];
-            r0 += (vi > v0) || (vi == v0 && ai < a0);
-            r1 += (vi > v1) || (vi == v1 && ai < a1);
+            const unsigned long long ki = bk[i];
+            r0 += ki > k0;
+            r1 += ki > k1;
         }
     }
     __syncwarp();
-    if (h0 && r0 < topk) { bv[r0] = v0; bi[r0] = a0; }
-    if (h1 && r1 < topk) { bv[r1] = v1; bi[r1] = a1; }
+    if (h0 && r0 < topk) bk[r0] = k0;
+    if (h1 && r1 < topk) bk[r1] = k1;
     __syncwarp();
     return cnt < topk ? cnt : topk;
 }
 
 // anchor_terms (optional): per anchor (area, cx, cy, atan(w/h)) as sihl_od_anchor_terms writes them —
 // the same fp32 operations box_terms() performs, hoisted out of the pair loop and cached with the tables.
-__global__ void __launch_bounds__(kSelWarps * 32)
+__global__ void __launch_bounds__(kSelWarps * 32, kSelMinBlocks)
 k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4 *__restrict__ anchor_terms,
                 const float4 *__restrict__ gt_boxes, int total_gt, int32_t *__restrict__ sel_anchor,
                 float *__restrict__ sel_val, float *__restrict__ best_iou, double *__restrict__ sums)
 {
-    __shared__ float s_val[kSelWarps][kBufCap];
-    __shared__ int s_idx[kSelWarps][kBufCap];
+    __shared__ unsigned long long s_key[kSelWarps][kBufCap];
     __shared__ int4 s_tab[kSelWarps][SIHL_OD_MAX_LEVELS];
 
     if (sums != nullptr && blockIdx.x == 0 && threadIdx.x < SIHL_OD_NUM_SUMS) sums[threadIdx.x] = 0.0;
@@ -99,12 +105,10 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     unsigned dbg_chunks = 0;
 #endif
-    float *bv = s_val[warp];
-    int *bi = s_idx[warp];
+    unsigned long long *bk = s_key[warp];
     const int topk = p.topk;
     const BoxTerms gt = box_terms(to_box(__ldg(gt_boxes + g)));
     int cnt = 0;
-    bool dirty = false;                              // appended since the last compress
     float thr = 0.f;                                 // k-th best so far once cnt == topk, else 0
 
     // Evaluate up to 32 candidates (one per lane) and append the ones that can still make the top k.
@@ -153,17 +157,11 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
         const bool hit = live && (thr > 0.f ? v >= thr : v > 0.f);      // clamp(0): non-positives never rank
         const unsigned m = __ballot_sync(kFullMask, hit);
         if (m) {
-            if (hit) {
-                const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-                bv[pos] = v;
-                bi[pos] = a;
-            }
+            if (hit) bk[cnt + __popc(m & ((1u << lane) - 1u))] = sel_key(v, a);
             cnt += __popc(m);
-            dirty = true;
             if (cnt > kBufCap - 32) {
-                cnt = select_compress(bv, bi, cnt, topk, lane);
-                dirty = false;
-                if (cnt == topk) thr = bv[topk - 1];
+                cnt = select_compress(bk, cnt, topk, lane);
+                if (cnt == topk) thr = sel_key_val(bk[topk - 1]);
             }
         }
     };
@@ -230,12 +228,14 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
         }
     }
 
-    cnt = select_compress(bv, bi, cnt, topk, lane);
+    cnt = select_compress(bk, cnt, topk, lane);
+    const unsigned long long mine = lane < cnt ? bk[lane] : 0ull;
+    const int my_anchor = lane < cnt ? sel_key_anchor(mine) : -1;
     if (lane < topk) {
-        sel_anchor[(int64_t)g * topk + lane] = lane < cnt ? bi[lane] : -1;
-        sel_val[(int64_t)g * topk + lane] = lane < cnt ? bv[lane] : 0.f;
+        sel_anchor[(int64_t)g * topk + lane] = my_anchor;
+        sel_val[(int64_t)g * topk + lane] = lane < cnt ? sel_key_val(mine) : 0.f;
     }
-    if (lane == 0) best_iou[g] = cnt ? bv[0] : 0.f;                  // ref :277 topk_ious[0]
+    if (lane == 0) best_iou[g] = cnt ? sel_key_val(mine) : 0.f;      // ref :277 topk_ious[0]
 #ifdef SIHL_PHASE_TIMING
     if (lane == 0 && g < 16384) {
         g_sel_dbg[3 * g] = (unsigned)(dbg_t0 & 0xffffffffu);
@@ -274,6 +274,7 @@ struct ResolveParams {
     int64_t *assignment; float *out_iou; double *sums;
     int32_t *tile_pos_count; int32_t *tile_pos_rows;
     const float *prefetch_box; const float *prefetch_cls; int num_classes;   // L2 hints for k_pos_loss_tiles
+    float inv_topk;            // 1 / topk: e / topk == (int)((e + 0.5f) * inv_topk) for e < 2^21 (checked for topk <= 64)
     int32_t *pos_chunks;       // work list for k_pos_loss_tiles: (slot << 10 | first_row / 32 << 6 | rows - 1)
     int2 *tile_pos_aux;        // per listed positive: (global gt index, rel bits) — saves that kernel two dependent hops
 };
@@ -312,9 +313,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
     const int32_t *sa = p.sel_anchor + (int64_t)g0 * p.topk;
     const float *sv = p.sel_val + (int64_t)g0 * p.topk;
     constexpr int kEntryBatch = 8;                                   // loads in flight per thread
-    for (int e0 = 0; e0 < n_entries; e0 += kEntryBatch * kResThreads) {
-        int ea[kEntryBatch];
-        unsigned ev[kEntryBatch];
+    auto load_batch = [&](int e0, int (&ea)[kEntryBatch], unsigned (&ev)[kEntryBatch]) {
 #pragma unroll
         for (int u = 0; u < kEntryBatch; ++u) {                         // all loads first: one L2 round trip per batch
             const int e = e0 + u * kResThreads + tid;
@@ -322,25 +321,43 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
             ea[u] = in ? __ldg(sa + e) - a0 : -1;
             ev[u] = in ? __float_as_uint(__ldg(sv + e)) : 0u;           // values are > 0: bit order == value order
         }
+    };
+    auto pass_max = [&](const int (&ea)[kEntryBatch], const unsigned (&ev)[kEntryBatch]) {
 #pragma unroll
         for (int u = 0; u < kEntryBatch; ++u)
             if (ea[u] >= 0 && ea[u] < na) atomicMax(&s_v[ea[u]], ev[u]);
-    }
-    __syncthreads();
-    for (int e0 = 0; e0 < n_entries; e0 += kEntryBatch * kResThreads) {
-        int ea[kEntryBatch];
-        unsigned ev[kEntryBatch];
-#pragma unroll
-        for (int u = 0; u < kEntryBatch; ++u) {
-            const int e = e0 + u * kResThreads + tid;
-            const bool in = e < n_entries;
-            ea[u] = in ? __ldg(sa + e) - a0 : -1;
-            ev[u] = in ? __float_as_uint(__ldg(sv + e)) : 0u;
-        }
+    };
+    auto pass_min = [&](int e0, const int (&ea)[kEntryBatch], const unsigned (&ev)[kEntryBatch]) {
 #pragma unroll
         for (int u = 0; u < kEntryBatch; ++u)
-            if (ea[u] >= 0 && ea[u] < na && s_v[ea[u]] == ev[u])
-                atomicMin(&s_g[ea[u]], (unsigned)((e0 + u * kResThreads + tid) / p.topk));
+            if (ea[u] >= 0 && ea[u] < na && s_v[ea[u]] == ev[u]) {
+                const int e = e0 + u * kResThreads + tid;
+                // e / topk without the ~20-instruction integer division: exact for e < 2^21 and topk <= 64
+                const int g = e < (1 << 21) ? (int)(((float)e + 0.5f) * p.inv_topk) : e / p.topk;
+                atomicMin(&s_g[ea[u]], (unsigned)g);
+            }
+    };
+    if (n_entries <= kEntryBatch * kResThreads) {                    // one batch (<= 1024 selections per image: cfg1 has
+        int ea[kEntryBatch];                                         // 900): the entries stay in registers for pass two
+        unsigned ev[kEntryBatch];
+        load_batch(0, ea, ev);
+        pass_max(ea, ev);
+        __syncthreads();
+        pass_min(0, ea, ev);
+    } else {
+        for (int e0 = 0; e0 < n_entries; e0 += kEntryBatch * kResThreads) {
+            int ea[kEntryBatch];
+            unsigned ev[kEntryBatch];
+            load_batch(e0, ea, ev);
+            pass_max(ea, ev);
+        }
+        __syncthreads();
+        for (int e0 = 0; e0 < n_entries; e0 += kEntryBatch * kResThreads) {
+            int ea[kEntryBatch];
+            unsigned ev[kEntryBatch];
+            load_batch(e0, ea, ev);
+            pass_min(e0, ea, ev);
+        }
     }
     __syncthreads();
     SIHL_RP(2);
@@ -379,7 +396,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
             }
             if (p.loc != nullptr) {
                 const float t = (rel == 1.0f) ? 1.f : 0.f;                       // ref :159
-                acc_bce += bce_logits(x_loc[c], t);
+                acc_bce += bce_logits_fast(x_loc[c], t);
                 acc_one += t;
                 if (p.iou_pred != nullptr) {
                     const float d = x_iou[c] - rel;                              // ref :177-179
@@ -569,6 +586,7 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
     if (batch == 0 || num_anchors == 0) return SIHL_OD_OK;
     ResolveParams p;
     p.sel_anchor = sel_anchor; p.sel_val = sel_val; p.best_iou = best_iou; p.gt_offsets = gt_offsets;
+    p.inv_topk = 1.f / (float)topk;
     p.num_anchors = (int)num_anchors; p.topk = topk; p.relative = relative;
     p.loc = loc_logits; p.iou_pred = iou_preds; p.assignment = assignment; p.out_iou = out_iou; p.sums = sums;
     p.tile_pos_count = tile_pos_count; p.tile_pos_rows = tile_pos_rows;

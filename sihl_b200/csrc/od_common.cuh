@@ -64,6 +64,33 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
+// binary_cross_entropy_with_logits term (od_math.h bce_logits) for the fused resolve pass, where it is 13 % of the
+// kernel's instructions: log1p(e^-|x|) with y = e^-|x| from ex2.approx and, for y < 0.223 (|x| > 1.5: all but a
+// handful of the locations of a detection head whose location logits sit around -5), the alternating series
+// y - y^2/2 + ... - y^8/8 (truncation <= y^8/9 = 7e-7 relative) in 8 FMAs; the exact libdevice path otherwise.
+// The location loss is held to 1e-5 relative (north_star), not to bit equality; sihl_od_dense_loss keeps the
+// libdevice form.
+__device__ __forceinline__ float bce_logits_fast(float x, float t)
+{
+    const float ax = fabsf(x);
+    const float y = __expf(-ax);
+    float l;
+    if (y < 0.223f) {
+        float q = -0.125f;
+        q = __fmaf_rn(q, y, 0.14285714285714285f);
+        q = __fmaf_rn(q, y, -0.16666666666666666f);
+        q = __fmaf_rn(q, y, 0.2f);
+        q = __fmaf_rn(q, y, -0.25f);
+        q = __fmaf_rn(q, y, 0.33333333333333333f);
+        q = __fmaf_rn(q, y, -0.5f);
+        q = __fmaf_rn(q, y, 1.f);
+        l = q * y;
+    } else {
+        l = log1pf(expf(-ax));
+    }
+    return (1.f - t) * x + (fmaxf(-x, 0.f) + l);
+}
+
 // Block-wide sum of NV doubles per thread -> atomicAdd into dst[slot[i]] by one thread.
 // red: shared double[NV * 32].
 template <int NV>

@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
                 const int2 ga = __ldg(aux + (ok ? r : 0));
                 const int tgt = (int)__ldg(p.gt_classes + ga.x);
                 float m, se;
-                if (p.cls_vec4) row_softmax_stats4v(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
-                else row_softmax_stats8(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+                if (p.cls_vec4) row_softmax_stats4v<true>(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+                else row_softmax_stats8<true>(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
                 if (ok && gl == 0) {
                     const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + tgt);
                     acc_cls += __int_as_float(ga.y) * ce;         // ref :208
