@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
         if (in && x >= p.logit_thr) { s = sigmoid_f(x); cand = s > p.score_thr; }
         const unsigned m = __ballot_sync(kFullMask, cand);
         if (m == 0u) continue;
-        const int b = in ? (int)(row / p.A) : 0;
+        const int b = !in ? 0 : (rows < (1ll << 31) ? (int)((unsigned)row / (unsigned)p.A) : (int)(row / p.A));
         const int a = in ? (int)(row - (int64_t)b * p.A) : 0;
         int slot = 0;
         if (cand) {                                                // the atomic's round trip overlaps the row gathers
@@ -577,11 +577,17 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             base = __shfl_sync(peers, base, leader);
             slot = base + __popc(peers & ((1u << lane) - 1u));
         }
-        const int n_cand = __popc(m);
-        for (int j0 = 0; j0 < n_cand; j0 += 4) {
-            const int j = j0 + gq;
-            const bool have = j < n_cand;
-            const int src = have ? (int)__fns(m, 0, j + 1) : (__ffs(m) - 1);     // lane that owns the j-th candidate
+        const int first = __ffs(m) - 1;
+        for (unsigned rem = m; rem != 0u;) {                       // four candidates per pass: peel the four lowest set bits
+            int src = first;                                       // lane that owns this group's candidate
+            bool have = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (rem != 0u) {
+                    if (gq == k) { src = __ffs(rem) - 1; have = true; }
+                    rem &= rem - 1u;
+                }
+            }
             const int64_t crow = (blk << 5) + src;
             float best = -CUDART_INF_F;
             int arg = 0x7fffffff;

@@ -36,10 +36,12 @@ def _p(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def _req(t: Tensor, dtype, name: str, ndim: Optional[int] = None) -> Tensor:
+def _req(t: Tensor, dtype, name: str, ndim: Optional[int] = None, pinned_ok: bool = False) -> Tensor:
+    """``pinned_ok``: a page-locked host tensor is accepted as well — under unified addressing the kernels read it
+    in place over PCIe (only for maps that a kernel *gathers* a few rows of; the compute is still on the GPU)."""
     if not isinstance(t, Tensor):
         raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
-    if not t.is_cuda:
+    if not t.is_cuda and not (pinned_ok and t.is_pinned()):
         raise RuntimeError(f"{name}: sihl_b200 kernels run on CUDA tensors only (got {t.device}); there is no CPU path")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
@@ -397,12 +399,14 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
                  mode: str = "dense") -> None:
     """Fill the per-image candidate lists.  ``mode="dense"`` streams every class row (TMA ring, HBM bound);
     ``mode="candidate_first"`` streams only the location map and gathers the rows that pass the threshold
-    (same lists up to order; far fewer bytes while candidates are sparse)."""
-    loc = _req(loc_logits, torch.float32, "loc_logits", 2)
-    cls = _req(cls_logits, torch.float32, "cls_logits", 3)
-    box = _req(box_raw, torch.float32, "box_raw", 3)
+    (same lists up to order; far fewer bytes while candidates are sparse).  In that mode ``cls_logits`` and
+    ``box_raw`` may be pinned host tensors: the candidates' rows are then read in place over PCIe (zero-copy)."""
     if mode not in DECODE_MODES:
         raise ValueError(f"mode={mode!r}: expected one of {DECODE_MODES}")
+    host_ok = mode == "candidate_first"        # gathers rows: the class / box maps may stay in pinned host memory
+    loc = _req(loc_logits, torch.float32, "loc_logits", 2)
+    cls = _req(cls_logits, torch.float32, "cls_logits", 3, pinned_ok=host_ok)
+    box = _req(box_raw, torch.float32, "box_raw", 3, pinned_ok=host_ok)
     B, A = loc.shape
     name = "sihl_od_dense_decode" if mode == "dense" else "sihl_od_candidate_decode"
     with torch.cuda.device(loc.device):

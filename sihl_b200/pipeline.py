@@ -27,7 +27,9 @@ LAUNCHES_PER_STEP = 5     # select, resolve, pos_loss_tiles (+finalize) | dense_
 
 @dataclass
 class StepInputs:
-    """Device-resident inputs of one step (one batch shard)."""
+    """Inputs of one step (one batch shard), device resident — except that ``box_raw`` / ``cls_logits`` may be pinned
+    host tensors when the pipeline runs ``decode_mode="candidate_first"``: both chains only gather rows of them
+    (positives, candidates), which the kernels then read in place over PCIe instead of uploading the whole maps."""
     loc_logits: Tensor     # [B, A] f32
     iou_preds: Tensor      # [B, A] f32
     box_raw: Tensor        # [B, A, 4] f32
@@ -100,6 +102,10 @@ class DetectionHeadPipeline:
         gt = x.gt
         assert gt.total <= self.max_gt_total and gt.batch_size == self.B
         p = ops._p
+        # host-resident class / box maps (pinned): k_pos_loss_tiles gathers the positives' rows in place over PCIe;
+        # the L2 prefetch hints of k_assign_resolve only make sense for device memory
+        maps_on_device = x.cls_logits.is_cuda and x.box_raw.is_cuda
+        assert maps_on_device or (x.cls_logits.is_pinned() and x.box_raw.is_pinned()), "host maps must be pinned"
         _native.check(lib.sihl_od_assign_select(
             p(self.anchors), p(self.terms), self.A, self._hw.ctypes.data, len(self._hw), self.img_w, self.img_h, p(gt.boxes),
             p(gt.offsets), self.B, gt.total, self.topk, p(self.sel_anchor), p(self.sel_val), p(self.best_iou),
@@ -107,7 +113,8 @@ class DetectionHeadPipeline:
         _native.check(lib.sihl_od_assign_resolve(
             p(self.sel_anchor), p(self.sel_val), p(self.best_iou), p(gt.offsets), self.B, self.A, self.topk, 1,
             p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), p(self.tile_pos_count),
-            p(self.tile_pos_rows), p(x.box_raw), p(x.cls_logits), self.C, p(self.pos_chunks), p(self.tile_pos_aux), st),
+            p(self.tile_pos_rows), p(x.box_raw) if maps_on_device else None, p(x.cls_logits) if maps_on_device else None,
+            self.C, p(self.pos_chunks), p(self.tile_pos_aux), st),
             "sihl_od_assign_resolve")
         # single GPU: the last CTA of the positive-loss kernel also finalizes the five losses
         _native.check(lib.sihl_od_pos_loss_tiles(

@@ -474,3 +474,31 @@ def test_pipeline_matches_unfused_ops_and_is_replayable(mode):
     np.testing.assert_array_equal(results[0][3].cpu().numpy(), o_num)
     np.testing.assert_array_equal(results[0][5].cpu().numpy(), o_cls)
     np.testing.assert_allclose(results[0][6].cpu().numpy(), o_boxes, rtol=1e-5, atol=1e-4)
+
+
+def test_pipeline_reads_pinned_host_maps_in_place():
+    """candidate-first pipeline with the class / box maps left in pinned host memory (the kernels gather the rows of the
+    positives and of the candidates over PCIe): bit-identical to the run on device-resident maps."""
+    from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs
+    W = H = 320
+    B, C, G = 3, 80, 25
+    levels = synth.level_sizes(H, W)
+    pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, DEV, decode_mode="candidate_first")
+    gt = _gt_dev(synth.gt_batch_np(21, B, H, W, C, G, ragged=True))
+    maps = synth.dense_maps_np(22, B, pipe.A, C, loc_mean=-3.0, loc_std=2.0)
+    loc, iou = _t(maps.loc_logits), _t(maps.iou_preds)
+    outs = []
+    for on_host in (False, True):
+        box = torch.from_numpy(maps.box_raw).pin_memory() if on_host else _t(maps.box_raw)
+        cls = torch.from_numpy(maps.cls_logits).pin_memory() if on_host else _t(maps.cls_logits)
+        out = pipe.new_outputs()
+        pipe.step(StepInputs(loc, iou, box, cls, gt), out)
+        torch.cuda.synchronize()
+        outs.append(out)
+    a, b = outs
+    for name in ("assignment", "rel_iou", "num_instances", "scores", "classes", "boxes"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    torch.testing.assert_close(a.losses, b.losses, rtol=1e-6, atol=0)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):          # the dense scan streams everything: device only
+        ops.dense_decode(loc, torch.from_numpy(maps.cls_logits).pin_memory(), _t(maps.box_raw), pipe.offsets, pipe.scales,
+                         W, H, 0.05, pipe.cand, mode="dense")
