@@ -127,6 +127,24 @@ SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *s
                            const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
                            int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream);
 
+/* ---- N1: the un-clamped assignment of QuadrilateralDetection ---
+ * ref: src/sihl/heads/quadrilateral_detection.py:266-294 (bbox_matching) and the
+ * per-image loop :165-172, for a whole batch in two launches.  Arbitrary anchors
+ * [A,4] (xyxy px), gt boxes in CSR form.  Every gt selects exactly topk anchors
+ * by raw CIoU (no clamp; ties: lowest anchor); per anchor the maximum over the
+ * selecting gts' values and one zero per non-selecting gt (ties: lowest gt).
+ *   assignment int64 [B,A]: gt index within the image where rel_iou > 0, else -1
+ *     (canonical: the reference stores the index of an arbitrary zero entry there
+ *     and reads assignment only where rel_iou > 0, :188,:201);
+ *   o2o_mask uint8 [B,A] (torch.bool storage): the anchor is some gt's best match;
+ *   o2m_iou fp32 [B,A]; rel_iou fp32 [B,A] = nan_to_num(o2m_iou / best_iou[gt]).
+ * Workspaces: sel_anchor int32 [sumG,topk], sel_val fp32 [sumG,topk] (the per-gt
+ * top-k, descending — also an output), anchor_terms fp32 [A,4]. */
+SIHL_OD_API int sihl_od_quad_matching(const float *anchors, int64_t num_anchors, const float *gt_boxes,
+                          const int32_t *gt_offsets, int batch, int total_gt, int topk,
+                          int64_t *assignment, uint8_t *o2o_mask, float *o2m_iou, float *rel_iou,
+                          int32_t *sel_anchor, float *sel_val, float *anchor_terms, void *stream);
+
 /* pos_index int32 [capacity] (flat b*A+a, ascending), pos_total int32 [1],
  * pos_image_offsets int32 [B+1] (may be NULL).  Entries beyond capacity are
  * dropped (pos_total still reports the true count). */

@@ -50,6 +50,28 @@ NMS_CASES = {
 }
 
 
+# N1: QuadrilateralDetection.bbox_matching (levels 3..5 like the reference default; "tiny" = gts far smaller than every
+# anchor, where each gt's best CIoU is negative and the un-clamped top-k / all-selected paths are exercised)
+QUAD_CASES = {
+    "quad_128": dict(height=128, width=128, bottom=3, top=5, counts=[0, 1, 3, 7], seed=501),
+    "quad_320": dict(height=320, width=320, bottom=3, top=5, counts=[20, 5], seed=502),
+    "quad_tiny": dict(height=128, width=160, bottom=3, top=5, counts=[1, 2, 9], seed=503, tiny=True),
+}
+
+
+def quad_gt(case) -> synth.GtBatch:
+    gt = synth.gt_batch_np(case["seed"], len(case["counts"]), case["height"], case["width"], 4, 0, ragged=True,
+                           counts=case["counts"])
+    if case.get("tiny"):
+        rng = np.random.RandomState(case["seed"] + 3)
+        n = len(gt.boxes)
+        cx, cy = rng.uniform(4, case["width"] - 4, n), rng.uniform(4, case["height"] - 4, n)
+        w, h = rng.uniform(1.5, 4.0, n), rng.uniform(1.5, 4.0, n)
+        b = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+        gt = synth.GtBatch(b, gt.classes, gt.offsets)
+    return gt
+
+
 def geom_levels(g):
     return synth.level_sizes(g["height"], g["width"], g["bottom"], g["top"], g["mode"])
 

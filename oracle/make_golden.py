@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
 from sihl_b200 import synth  # noqa: E402
-from oracle.golden_cases import (ASSIGN_CASES, FORWARD_CASES, GEOMETRIES, GOLDEN_DIR, NMS_CASES, TRAIN_CASES,  # noqa: E402
-                                 case_gt, forward_maps, geom_levels, nms_inputs, train_maps)
+from oracle.golden_cases import (ASSIGN_CASES, FORWARD_CASES, GEOMETRIES, GOLDEN_DIR, NMS_CASES, QUAD_CASES,  # noqa: E402
+                                 TRAIN_CASES, case_gt, forward_maps, geom_levels, nms_inputs, quad_gt, train_maps)
 
 class _Table(nn.Module):
     """Stands in for an MLP head: row id rides in channel 0 of the features."""
@@ -158,6 +158,30 @@ def make_nms(name, case):
     save(name, keep=keep.astype(np.int32), keep_coordinate_trick=keep_trick.astype(np.int32))
 
 
+def make_quad(name, case):
+    """N1: the reference's QuadrilateralDetection — anchors as training_step builds them (ref :154-163, verbatim) and
+    bbox_matching (ref :266-294) per image; outputs stored in canonical form (assignment only where rel_iou > 0)."""
+    Q = ref_loader.QuadrilateralDetection()
+    H, W, bottom, top = case["height"], case["width"], case["bottom"], case["top"]
+    head = Q([3] + [8] * top, 4, bottom_level=bottom, top_level=top, num_channels=8, num_layers=1)
+    sizes = [(H, W)] + [(-(-H // 2 ** l), -(-W // 2 ** l)) for l in range(1, top + 1)]
+    inputs = [torch.zeros(1, 1, h, w) for h, w in sizes]
+    rel_offsets, levels = head.get_offsets_and_levels(inputs)                                    # ref :156
+    directions = torch.tensor([[-1, -1, 1, 1]])                                                  # ref :157
+    scale = torch.sigmoid(levels - head.top_level)                                               # ref :158
+    anchors = (rel_offsets[:, :4] + directions * scale) * torch.tensor([[W, H] * 2])             # ref :159-161
+    gt = quad_gt(case)
+    asg, o2o, iou, rel = [], [], [], []
+    for bx, _ in gt.per_image():
+        a, o, i, r = Q.bbox_matching(anchors, torch.from_numpy(bx).reshape(-1, 4), head.topk)    # ref :165-168
+        assert not torch.isnan(i).any() and not torch.isnan(r).any()
+        a = a.clone(); a[~(r > 0)] = -1
+        asg.append(a.numpy()); o2o.append(o.numpy()); iou.append((i + 0.0).numpy()); rel.append((r + 0.0).numpy())
+    save(name, anchors=anchors.numpy().astype(np.float32), level_sizes=np.asarray(sizes[bottom:top + 1], np.int32),
+         assignment=np.stack(asg).astype(np.int64), o2o=np.stack(o2o), iou=np.stack(iou).astype(np.float32),
+         rel=np.stack(rel).astype(np.float32), topk=np.int32(head.topk))
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden vectors can only be generated in the authoring container")
@@ -171,6 +195,8 @@ def main():
         make_forward(name, case)
     for name, case in NMS_CASES.items():
         make_nms(name, case)
+    for name, case in QUAD_CASES.items():
+        make_quad(name, case)
 
 
 if __name__ == "__main__":

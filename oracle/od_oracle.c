@@ -27,6 +27,7 @@
  * the contract for losses is 1e-5 relative, not bit equality).
  */
 #define _GNU_SOURCE
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -181,6 +182,69 @@ ORC_API int orc_bbox_matching(const float *anchors, int64_t A, const float *gt, 
     }
     if (best_iou) memcpy(best_iou, best, sizeof(float) * (size_t)G);
     free(atan_a); free(max_v); free(max_g); free(best);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* N1: QuadrilateralDetection.bbox_matching, the un-clamped variant.   */
+/* ref: src/sihl/heads/quadrilateral_detection.py:266-294.             */
+/* Every gt selects exactly k anchors by raw CIoU (:277-278; ties:     */
+/* lowest anchor index).  Per anchor, ref :283 takes the max over gts  */
+/* of iou * is_topk_match: the selected values and one zero per gt     */
+/* that did not select it.  Canonical form as above: assignment = -1   */
+/* wherever rel_iou is not > 0 (there the reference holds the index of */
+/* an arbitrary zero entry; it only reads assignment[rel_iou > 0],     */
+/* :188,:201); iou and rel_iou are 0 there exactly as in the reference.*/
+/* ------------------------------------------------------------------ */
+static inline float orc_nan_to_num0(float x)
+{
+    if (x != x) return 0.f;
+    if (isinf(x)) return x > 0 ? FLT_MAX : -FLT_MAX;
+    return x;
+}
+
+ORC_API int orc_quad_matching(const float *anchors, int64_t A, const float *gt, int64_t G, int topk,
+                              int64_t *assignment, uint8_t *o2o, float *out_iou, float *out_rel)
+{
+    for (int64_t a = 0; a < A; ++a) { assignment[a] = -1; o2o[a] = 0; out_iou[a] = 0.f; out_rel[a] = 0.f; }   /* :271-276 */
+    if (G == 0) return 0;
+    if (topk <= 0 || topk > 64 || A < topk) return -1;
+    float *atan_a = (float *)malloc(sizeof(float) * (size_t)A);
+    for (int64_t a = 0; a < A; ++a) atan_a[a] = orc_box_atan(anchors + 4 * a);
+    float *max_v = (float *)malloc(sizeof(float) * (size_t)A);      /* max over the selecting gts */
+    int64_t *max_g = (int64_t *)malloc(sizeof(int64_t) * (size_t)A);
+    int64_t *n_sel = (int64_t *)calloc((size_t)A, sizeof(int64_t));
+    float *best = (float *)calloc((size_t)G, sizeof(float));
+    for (int64_t a = 0; a < A; ++a) max_g[a] = -1;
+    for (int64_t g = 0; g < G; ++g) {
+        const float *gb = gt + 4 * g;
+        float atan_g = orc_box_atan(gb);
+        float tv[64]; int64_t ti[64]; int n = 0;
+        for (int64_t a = 0; a < A; ++a) {
+            float v = orc_ciou_pair(anchors + 4 * a, gb, atan_a[a], atan_g) + 0.f;   /* -0 -> +0 */
+            if (v != v) continue;                            /* outside the defined domain */
+            if (n == topk && !(v > tv[n - 1])) continue;     /* equal value, higher index: loses */
+            int p = (n < topk) ? n++ : topk - 1;
+            while (p > 0 && v > tv[p - 1]) { tv[p] = tv[p - 1]; ti[p] = ti[p - 1]; --p; }
+            tv[p] = v; ti[p] = a;
+        }
+        best[g] = n ? tv[0] : 0.f;                           /* :289 topk_ious[0] */
+        if (n) o2o[ti[0]] = 1;                               /* :279-280, :286 */
+        for (int s2 = 0; s2 < n; ++s2) {
+            int64_t a = ti[s2];
+            ++n_sel[a];
+            if (max_g[a] < 0 || tv[s2] > max_v[a]) { max_v[a] = tv[s2]; max_g[a] = g; }   /* ascending g: lowest gt on ties */
+        }
+    }
+    for (int64_t a = 0; a < A; ++a) {
+        if (max_g[a] < 0) continue;
+        if (max_v[a] > 0.f || n_sel[a] == G) {               /* otherwise an unselected gt's zero is the max */
+            out_iou[a] = max_v[a];
+            out_rel[a] = orc_nan_to_num0(max_v[a] / best[max_g[a]]);                 /* :290-293 */
+            if (out_rel[a] > 0.f) assignment[a] = max_g[a];
+        }
+    }
+    free(atan_a); free(max_v); free(max_g); free(n_sel); free(best);
     return 0;
 }
 

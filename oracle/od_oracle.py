@@ -94,6 +94,17 @@ def bbox_matching(anchors_px, gt, topk: int = 9, relative: bool = True):
     return assign, iou, best
 
 
+def quad_matching(anchors_px, gt, topk: int = 9):
+    """Canonical ``QuadrilateralDetection.bbox_matching`` -> (assignment i64, o2o bool, iou f32, rel f32), each [A]."""
+    an, gt = _f32(anchors_px), _f32(gt).reshape(-1, 4)
+    A, G = len(an), len(gt)
+    assign, o2o = np.empty(A, np.int64), np.zeros(A, np.uint8)
+    iou, rel = np.empty(A, np.float32), np.empty(A, np.float32)
+    rc = lib().orc_quad_matching(_p(an), C.c_int64(A), _p(gt), C.c_int64(G), int(topk), _p(assign), _p(o2o), _p(iou), _p(rel))
+    assert rc == 0, rc
+    return assign, o2o.astype(bool), iou, rel
+
+
 def assign_batch(anchors_px, gt_boxes, gt_offsets, topk: int = 9, relative: bool = True):
     an, gt, off = _f32(anchors_px), _f32(gt_boxes).reshape(-1, 4), _i32(gt_offsets)
     A, B = len(an), len(off) - 1

@@ -65,3 +65,20 @@ def load_module():
 def ObjectDetection():
     """The reference class itself (call it to construct a head)."""
     return load_module().ObjectDetection
+
+
+_quad_module = None
+
+
+def QuadrilateralDetection():
+    """The reference ``QuadrilateralDetection`` class, loaded straight from its file."""
+    global _quad_module
+    if _quad_module is None:
+        path = os.path.join(REFERENCE_ROOT, "src", "sihl", "heads", "quadrilateral_detection.py")
+        if not os.path.isfile(path):
+            raise FileNotFoundError(f"reference source not found at {path}")
+        _stub_torchmetrics()
+        spec = importlib.util.spec_from_file_location("_sihl_reference_quadrilateral_detection", path)
+        _quad_module = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_quad_module)
+    return _quad_module.QuadrilateralDetection

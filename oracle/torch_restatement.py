@@ -74,6 +74,39 @@ def match_one(anchors: Tensor, gt: Tensor, topk: int = 9, relative: bool = True)
     return assign, out
 
 
+def quad_match_one(anchors: Tensor, gt: Tensor, topk: int = 9) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """ref quadrilateral_detection.py:266-294, raw output (operator for operator)."""
+    A, G = anchors.shape[0], gt.shape[0]
+    dev = anchors.device
+    assign = torch.full((A,), -1, device=dev)                               # :271
+    o2o = torch.zeros((A,), dtype=torch.bool, device=dev)
+    iou = torch.zeros((A,), device=dev)
+    rel = torch.zeros((A,), device=dev)
+    if G == 0:
+        return assign, o2o, iou, rel
+    ciou = tvops.complete_box_iou(anchors, gt)                              # :277 (no clamp)
+    top_val, top_idx = torch.topk(ciou, k=topk, dim=0)                      # :278
+    best_match = torch.zeros((A, G), dtype=torch.bool, device=dev)
+    best_match.scatter_(0, top_idx[0:1], True)                              # :279-280
+    chosen = torch.zeros((A, G), dtype=torch.bool, device=dev)
+    chosen.scatter_(0, top_idx, True)                                       # :281-282
+    row_max, row_arg = torch.max(ciou * chosen.float(), dim=1)              # :283
+    hit = chosen.any(dim=1)                                                 # :284
+    assign[hit] = row_arg[hit]                                              # :285
+    o2o = best_match.any(dim=1)                                             # :286
+    iou[hit] = row_max[hit]                                                 # :287
+    denom = top_val[0][row_arg]                                             # :289-290
+    rel[hit] = (row_max[hit] / denom[hit]).nan_to_num(0)                    # :291-293
+    return assign, o2o, iou, rel
+
+
+def quad_canonical(assign: Tensor, o2o: Tensor, iou: Tensor, rel: Tensor):
+    """Canonical form of the four outputs: assignment defined only where rel_iou > 0; signed zeros folded."""
+    assign = assign.clone()
+    assign[~(rel > 0)] = -1
+    return assign, o2o, iou + 0.0, rel + 0.0
+
+
 def canonical(assign: Tensor, iou: Tensor) -> Tuple[Tensor, Tensor]:
     """SURVEY.md §3.4 contract: assignment is defined only where iou > 0."""
     assign = assign.clone()

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "sihl_od_assign_select": (I, [P, P, I64, P, I, I, I, P, P, I, I, I, P, P, P, P, P]),
     "sihl_od_resolve_tiles": (I, [I64, P, P]),
     "sihl_od_assign_resolve": (I, [P, P, P, P, I, I64, I, I, P, P, P, P, P, P, P, P, P, I, P, P, P]),
+    "sihl_od_quad_matching": (I, [P, I64, P, P, I, I, I, P, P, P, P, P, P, P, P]),
     "sihl_od_pos_loss_tiles": (I, [P, P, P, I, I64, P, P, I, I, P, P, P, P, P, I, P, P, P, P]),
     "sihl_od_pos_compact": (I, [P, P, I, I64, P, I64, P, P, P]),
     "sihl_od_dense_loss": (I, [P, P, P, I64, P, P]),

@@ -243,6 +243,30 @@ def bbox_matching(anchors: Tensor, gt_boxes: Tensor, topk: int, relative: bool =
     return out["assignment"][0], out["iou"][0]
 
 
+# --------------------------------------------------------------------------- N1: un-clamped variant (QuadrilateralDetection)
+def quad_bbox_matching(anchors: Tensor, gt: GtBatch, topk: int = 9) -> Dict[str, Tensor]:
+    """``QuadrilateralDetection.bbox_matching`` (ref quadrilateral_detection.py:266-294) for a whole batch, i.e. the
+    per-image loop + stacks of ref :165-172.  ``anchors`` fp32 [A,4] xyxy px (arbitrary), ``gt`` the per-image boxes
+    (``quads_to_boxes`` of the quads).  Returns dict(assignment i64 [B,A] canonical, o2o_mask bool [B,A],
+    iou f32 [B,A], rel_iou f32 [B,A], sel_anchor i32 [sumG,k], sel_val f32 [sumG,k])."""
+    anchors = _req(anchors, torch.float32, "anchors", 2)
+    dev = anchors.device
+    B, A, G = gt.batch_size, anchors.shape[0], gt.total
+    assignment = torch.empty((B, A), dtype=torch.int64, device=dev)
+    o2o = torch.empty((B, A), dtype=torch.bool, device=dev)
+    iou = torch.empty((B, A), dtype=torch.float32, device=dev)
+    rel = torch.empty((B, A), dtype=torch.float32, device=dev)
+    sel_anchor = torch.empty((G, topk), dtype=torch.int32, device=dev)
+    sel_val = torch.empty((G, topk), dtype=torch.float32, device=dev)
+    terms = torch.empty((A, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib().sihl_od_quad_matching(
+            _p(anchors), A, _p(_req(gt.boxes, torch.float32, "gt.boxes", 2)), _p(_req(gt.offsets, torch.int32, "gt.offsets", 1)),
+            B, G, int(topk), _p(assignment), _p(o2o), _p(iou), _p(rel), _p(sel_anchor), _p(sel_val), _p(terms), _stream(dev))
+    _native.check(rc, "sihl_od_quad_matching")
+    return dict(assignment=assignment, o2o_mask=o2o, iou=iou, rel_iou=rel, sel_anchor=sel_anchor, sel_val=sel_val)
+
+
 # --------------------------------------------------------------------------- a5-a10
 def new_sums(device) -> Tensor:
     return torch.zeros((NUM_SUMS,), dtype=torch.float64, device=device)

@@ -502,3 +502,64 @@ def test_pipeline_reads_pinned_host_maps_in_place():
     with pytest.raises(RuntimeError, match="CUDA tensors only"):          # the dense scan streams everything: device only
         ops.dense_decode(loc, torch.from_numpy(maps.cls_logits).pin_memory(), _t(maps.box_raw), pipe.offsets, pipe.scales,
                          W, H, 0.05, pipe.cand, mode="dense")
+
+
+# --------------------------------------------------------------------------- N1: QuadrilateralDetection.bbox_matching
+def _quad_check_vs_restatement(anchors_dev, boxes_np_list, topk=9):
+    from sihl_b200.heads import quadrilateral_detection as qd
+    boxes = [_t(b).reshape(-1, 4) for b in boxes_np_list]
+    a, o, i, r = qd.batched_bbox_matching(anchors_dev, boxes, topk)
+    for b, bx in enumerate(boxes):
+        ra, ro, ri, rr = tr.quad_canonical(*tr.quad_match_one(anchors_dev, bx, topk))     # the reference's operators on this GPU
+        assert torch.equal(a[b], ra), b
+        assert torch.equal(o[b], ro), b
+        assert torch.equal(i[b], ri) and torch.equal(r[b], rr), b                           # bit-exact values
+    return a, o, i, r
+
+
+@pytest.mark.parametrize("name", sorted(gc.QUAD_CASES))
+def test_quad_matching(name):
+    """Un-clamped four-output assignment (ref quadrilateral_detection.py:266-294) vs the golden outputs of the reference
+    (CPU), the C oracle, and the reference's operator sequence on the same GPU (bit-exact)."""
+    case, g = gc.QUAD_CASES[name], gc.load(name)
+    gt = gc.quad_gt(case)
+    anchors = _t(g["anchors"])
+    per_image = [bx for bx, _ in gt.per_image()]
+    a, o, i, r = _quad_check_vs_restatement(anchors, per_image, int(g["topk"]))
+    np.testing.assert_array_equal(a.cpu().numpy(), g["assignment"])
+    np.testing.assert_array_equal(o.cpu().numpy(), g["o2o"])
+    np.testing.assert_allclose(i.cpu().numpy(), g["iou"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(r.cpu().numpy(), g["rel"], rtol=1e-5, atol=1e-7)
+    for b, bx in enumerate(per_image):
+        oa, oo, oi, orr = orc.quad_matching(g["anchors"], bx, int(g["topk"]))
+        np.testing.assert_array_equal(a[b].cpu().numpy(), oa)
+        np.testing.assert_array_equal(o[b].cpu().numpy(), oo)
+        np.testing.assert_allclose(i[b].cpu().numpy(), oi, rtol=1e-5, atol=1e-7)
+
+
+def test_quad_matching_corner_cases_and_full_size():
+    from sihl_b200.heads import quadrilateral_detection as qd
+    # (i) one distant gt: every candidate is negative, its 9 selections get rel = v / best >= 1 (the reference's rule)
+    sizes = [(16, 16), (8, 8), (4, 4)]
+    anchors = qd.quad_anchors(sizes, range(3, 6), 5, 128, 128, DEV)
+    far = np.array([[900.0, 900.0, 903.0, 904.0]], np.float32)
+    a, o, i, r = _quad_check_vs_restatement(anchors, [far])
+    assert int((r > 0).sum()) == 9 and bool((i[r > 0] < 0).all()) and int(o.sum()) == 1 and float(r.max()) > 1
+    # (ii) A == topk: every gt selects every anchor, no zero entry takes part in the max
+    few = anchors[:9].contiguous()
+    gts = np.array([[200, 200, 204, 203], [2, 2, 38, 41], [60, 60, 100, 90]], np.float32)
+    _quad_check_vs_restatement(few, [gts, gts[:1], gts[:0]])
+    with pytest.raises(ops._native.NativeError, match="selected index k out of range"):
+        qd.bbox_matching(anchors[:5].contiguous(), _t(gts), 9)
+    # (iii) config[1]-sized: 640^2, levels 3..7 (A = 8525 anchors), 64 images x <= 100 gts; spot-check images vs the restatement
+    levels = synth.level_sizes(640, 640)
+    big = qd.quad_anchors(levels, range(3, 8), 7, 640, 640, DEV)
+    gt_np = synth.gt_batch_np(77, 64, 640, 640, 80, 100, ragged=True)
+    per_image = [bx for bx, _ in gt_np.per_image()]
+    a, o, i, r = qd.batched_bbox_matching(big, [_t(b).reshape(-1, 4) for b in per_image], 9)
+    assert a.shape == (64, 8525) and ((r > 0) == (a >= 0)).all()
+    counts = torch.tensor([len(b) for b in per_image], device=DEV)
+    assert torch.equal(o.sum(dim=1), torch.minimum(counts, o.sum(dim=1))) and (o.sum(dim=1) <= counts).all()
+    for b in (0, 31, 63):
+        ra, ro, ri, rr = tr.quad_canonical(*tr.quad_match_one(big, _t(per_image[b]).reshape(-1, 4), 9))
+        assert torch.equal(a[b], ra) and torch.equal(o[b], ro) and torch.equal(i[b], ri) and torch.equal(r[b], rr)

@@ -126,3 +126,30 @@ def test_dense_postprocess_matches_components():
         s = scores[b, :num[b]]
         assert (np.diff(s) <= 0).all() and (s > 0.05).all()
         assert (scores[b, num[b]:] == 0).all()
+
+
+# --------------------------------------------------------------------------- N1: QuadrilateralDetection.bbox_matching
+@pytest.mark.parametrize("name", sorted(gc.QUAD_CASES))
+def test_quad_matching_vs_reference_golden(name):
+    """oracle vs the reference's QuadrilateralDetection.bbox_matching (ref quadrilateral_detection.py:266-294) on the
+    reference's own anchors: assignment (canonical) and the best-match mask exact, iou / rel_iou to 1e-5."""
+    g, gt = gc.load(name), gc.quad_gt(gc.QUAD_CASES[name])
+    for b, (bx, _) in enumerate(gt.per_image()):
+        a, o, i, r = orc.quad_matching(g["anchors"], bx, int(g["topk"]))
+        np.testing.assert_array_equal(a, g["assignment"][b])
+        np.testing.assert_array_equal(o, g["o2o"][b])
+        np.testing.assert_allclose(i, g["iou"][b], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(r, g["rel"][b], rtol=1e-5, atol=1e-7)
+    if name == "quad_tiny":
+        assert (g["iou"] < 0).any()            # the un-clamped branch (a gt's only candidates are negative) is covered
+
+
+def test_quad_matching_every_gt_selects_every_anchor():
+    """A == topk: every gt selects every anchor, so no zero entry takes part in the per-anchor max (ref :283)."""
+    rng = np.random.RandomState(5)
+    anchors = np.array([[0, 0, 40, 40], [30, 30, 90, 80], [5, 50, 60, 100]], np.float32)
+    gts = np.array([[200, 200, 204, 203], [2, 2, 38, 41]], np.float32)
+    a, o, i, r = orc.quad_matching(anchors, gts, 3)
+    assert o.sum() >= 1 and (i != 0).all()      # values come from the selected entries, negative ones included
+    assert ((r > 0) == (a >= 0)).all()
+    del rng

@@ -74,3 +74,22 @@ def test_forward_tail_equals_the_reference_forward(name):
     assert torch.equal(num, t(gold["num_instances"])) and torch.equal(cls, t(gold["classes"]).long())
     assert torch.equal(scores, t(gold["scores"])) and torch.equal(boxes, t(gold["boxes"]))
     assert torch.equal(idx, t(gold["idx"]).long())
+
+
+@pytest.mark.parametrize("name", sorted(gc.QUAD_CASES))
+def test_quad_match_one_is_the_reference_quad_bbox_matching(name):
+    """N1: tr.quad_match_one == QuadrilateralDetection.bbox_matching (ref quadrilateral_detection.py:266-294), raw
+    outputs, and the sihl_b200 anchor helper == the reference's inline anchor construction (ref :156-161)."""
+    Q = ref_loader.QuadrilateralDetection()
+    case, gold = gc.QUAD_CASES[name], gc.load(name)
+    anchors = torch.from_numpy(gold["anchors"])
+    for bx, _ in gc.quad_gt(case).per_image():
+        t = torch.from_numpy(bx).reshape(-1, 4)
+        want = Q.bbox_matching(anchors, t, 9)
+        got = tr.quad_match_one(anchors, t, 9)
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
+    from sihl_b200.heads.quadrilateral_detection import quad_anchors
+    sizes = [tuple(int(v) for v in s) for s in gold["level_sizes"]]
+    mine = quad_anchors(sizes, range(case["bottom"], case["top"] + 1), case["top"], case["width"], case["height"], "cpu")
+    assert torch.equal(mine, anchors)
