@@ -126,6 +126,104 @@ __device__ __forceinline__ bool iou_gt(float4 a, float area_a, float4 b, float a
     return inter / ((area_a + area_b) - inter) > thr;
 }
 
+__device__ __forceinline__ float4 shfl4(float4 v, int src)
+{
+    return make_float4(__shfl_sync(kFullMask, v.x, src), __shfl_sync(kFullMask, v.y, src), __shfl_sync(kFullMask, v.z, src),
+                       __shfl_sync(kFullMask, v.w, src));
+}
+
+// Greedy suppression inside one 32-box chunk of a score-ordered class segment, by one warp (lane = box).
+// `dead` = already suppressed by an earlier chunk.  Returns the kept bits of the chunk (same value in every lane):
+// all 32 x 31 / 2 pairs are tested in parallel (boxes broadcast by shuffles), then the greedy chain runs on bits.
+__device__ __forceinline__ unsigned chunk_greedy(float4 bi, float ai, bool dead, float thr, int lane)
+{
+    unsigned over = 0u;                                   // earlier boxes of the chunk that overlap this one
+#pragma unroll 4
+    for (int l = 0; l < 31; ++l) {
+        const float4 bl = shfl4(bi, l);
+        const float al = __shfl_sync(kFullMask, ai, l);
+        if (l < lane && iou_gt(bl, al, bi, ai, thr)) over |= 1u << l;
+    }
+    const unsigned alive = __ballot_sync(kFullMask, !dead);
+    unsigned kept = 0u;
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l) {
+        const unsigned ol = __shfl_sync(kFullMask, over, l);
+        if (((alive >> l) & 1u) && (ol & kept) == 0u) kept |= 1u << l;
+    }
+    return kept;
+}
+
+// One warp, one class segment [q0, q0 + m) in score order: chunks of 32 boxes; the kept boxes of a chunk then
+// suppress the later boxes of the segment (32 at a time).  m^2/2 pair tests like the serial formulation, but
+// m/32 dependent steps instead of m.
+__device__ __forceinline__ void warp_segment_nms(const float4 *box, const float *area, unsigned char *dead_flag, int q0, int m,
+                                                 float thr, int lane)
+{
+    for (int c0 = 0; c0 < m; c0 += 32) {
+        __syncwarp();
+        const int i = c0 + lane;
+        const bool valid = i < m;
+        const float4 bi = valid ? box[q0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float ai = valid ? area[q0 + i] : 0.f;
+        const bool dead = valid ? dead_flag[q0 + i] != 0 : true;
+        const unsigned kept = chunk_greedy(bi, ai, dead, thr, lane);
+        if (valid && !dead && !((kept >> lane) & 1u)) dead_flag[q0 + i] = 1;
+        for (int j0 = c0 + 32; j0 < m; j0 += 32) {
+            const int j = j0 + lane;
+            const bool live = j < m && dead_flag[q0 + j] == 0;
+            const float4 bj = live ? box[q0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float aj = live ? area[q0 + j] : 0.f;
+            bool kill = false;
+            for (unsigned k = kept; k != 0u; k &= k - 1u) {              // warp-uniform
+                const int l = __ffs(k) - 1;
+                const float4 bl = shfl4(bi, l);
+                const float al = __shfl_sync(kFullMask, ai, l);
+                if (live && !kill && iou_gt(bl, al, bj, aj, thr)) kill = true;
+            }
+            if (kill) dead_flag[q0 + j] = 1;
+        }
+    }
+}
+
+// The whole CTA, one very long class segment: warp 0 resolves a chunk of 32 boxes and publishes its kept boxes in
+// shared memory; every thread then tests its share of the later boxes against them.  2 barriers per 32 boxes.
+struct ChunkScratch { float4 box[32]; float area[32]; unsigned kept; int n_big; int big[32]; };
+
+__device__ __forceinline__ void cta_segment_nms(const float4 *box, const float *area, unsigned char *dead_flag, int q0, int m,
+                                                float thr, ChunkScratch *sc)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c0 = 0; c0 < m; c0 += 32) {
+        __syncthreads();                                                  // flags of the previous pass are visible
+        if (warp == 0) {
+            const int i = c0 + lane;
+            const bool valid = i < m;
+            const float4 bi = valid ? box[q0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ai = valid ? area[q0 + i] : 0.f;
+            const bool dead = valid ? dead_flag[q0 + i] != 0 : true;
+            const unsigned kept = chunk_greedy(bi, ai, dead, thr, lane);
+            if (valid && !dead && !((kept >> lane) & 1u)) dead_flag[q0 + i] = 1;
+            sc->box[lane] = bi;
+            sc->area[lane] = ai;
+            if (lane == 0) sc->kept = kept;
+        }
+        __syncthreads();
+        const unsigned kept = sc->kept;
+        if (kept == 0u) continue;                                         // block-uniform
+        for (int j = c0 + 32 + tid; j < m; j += blockDim.x) {
+            if (dead_flag[q0 + j]) continue;
+            const float4 bj = box[q0 + j];
+            const float aj = area[q0 + j];
+            for (unsigned k = kept; k != 0u; k &= k - 1u) {
+                const int l = __ffs(k) - 1;
+                if (iou_gt(sc->box[l], sc->area[l], bj, aj, thr)) { dead_flag[q0 + j] = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 struct NmsParams {
     // mode 0: candidate lists written by k_dense_decode
     const int32_t *cand_count; int64_t cap;
@@ -447,6 +545,7 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
 // warp, and only the survivors are sorted by score (bitonic) for the output order.  Arrays live in shared
 // memory up to kSmemItems candidates, in the global workspace beyond.  Returns false when the list defeats the
 // table (more than kHashSlots/2 distinct classes): the caller then takes the two-sort path (nms_big_body).
+constexpr int kWarpSegment = 2048;        // class segments up to this length are suppressed by one warp, longer ones by the CTA
 constexpr int kHashSlots = 1024;
 constexpr unsigned kHashEmpty = 0xffffffffu;
 constexpr size_t kMedItemBytes = 47;      // U_key 8 + F_key 8 + F_box 16 + U_slot 4 + F_slot 4 + F_area 4 + B_id 2 + F_dead 1
@@ -480,7 +579,8 @@ __device__ __forceinline__ MedArrays carve_med(unsigned char *base, int n_al)
 // several times slower than LDS and do not pipeline in the counting loops).
 template <bool SMEM>
 __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int src0, unsigned char *base, int n_al,
-                                                int *s_warp, unsigned *h_cls, int *h_cnt, int *h_start, int *n_kept_out)
+                                                int *s_warp, unsigned *h_cls, int *h_cnt, int *h_start, ChunkScratch *chunk_scratch,
+                                                int *n_kept_out)
 {
     if (SMEM) __builtin_assume(__isShared(base));
     else __builtin_assume(__isGlobal(base));
@@ -577,6 +677,7 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
     //    lane per class runs the greedy chain on bits.  Longer segments: one warp per class, the kept box is
     //    broadcast and 32 later boxes are tested per step.
     unsigned long long *mask = ar.u_key;
+    if (tid == 0) chunk_scratch->n_big = 0;                       // visible after the barrier below
     for (int q = tid; q < n; q += blockDim.x) {
         const int h = ar.b_id[ar.f_slot[q]];
         const int s0 = h_start[h], m = h_cnt[h];
@@ -592,6 +693,10 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
     __syncthreads();
     for (int h = tid; h < kHashSlots; h += blockDim.x) {          // one lane per class: greedy on bits
         const int m = h_cnt[h];
+        if (m > kWarpSegment) {                                    // rare: remember it for the CTA-wide pass below
+            const int k = atomicAdd(&chunk_scratch->n_big, 1);
+            if (k < 32) chunk_scratch->big[k] = h;
+        }
         if (m < 2 || m > 64) continue;
         const int s0 = h_start[h];
         unsigned long long kept = 1ull;
@@ -600,20 +705,25 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
             else ar.f_dead[s0 + i] = 1;
         }
     }
-    for (int h = warp; h < kHashSlots; h += nwarps) {             // long segments
+    for (int h = warp; h < kHashSlots; h += nwarps) {             // long segments: one warp each, 32-box chunks
         const int m = h_cnt[h];
-        if (m <= 64) continue;
-        const int q0 = h_start[h];
-        for (int i = 0; i + 1 < m; ++i) {
-            __syncwarp();
-            if (ar.f_dead[q0 + i]) continue;
-            const float4 bi = ar.f_box[q0 + i];
-            const float ai = ar.f_area[q0 + i];
-            for (int j = i + 1 + lane; j < m; j += 32)
-                if (!ar.f_dead[q0 + j] && iou_gt(bi, ai, ar.f_box[q0 + j], ar.f_area[q0 + j], p.iou_thr)) ar.f_dead[q0 + j] = 1;
-        }
+        if (m <= 64 || m > kWarpSegment) continue;
+        warp_segment_nms(ar.f_box, ar.f_area, ar.f_dead, h_start[h], m, p.iou_thr, lane);
     }
     __syncthreads();
+    const int n_big = chunk_scratch->n_big;                       // very long segments: the whole CTA, one after another
+    if (n_big > 0) {                                              // (block-uniform)
+        if (n_big <= 32) {
+            for (int k = 0; k < n_big; ++k) {
+                const int h = chunk_scratch->big[k];               // (cta_segment_nms only touches box / area / kept)
+                cta_segment_nms(ar.f_box, ar.f_area, ar.f_dead, h_start[h], h_cnt[h], p.iou_thr, chunk_scratch);
+            }
+        } else {
+            for (int h = 0; h < kHashSlots; ++h)
+                if (h_cnt[h] > kWarpSegment)
+                    cta_segment_nms(ar.f_box, ar.f_area, ar.f_dead, h_start[h], h_cnt[h], p.iou_thr, chunk_scratch);
+        }
+    }
     // 6. survivors -> u_key/u_slot (ballot compaction), then ordered by (score desc, index asc) WITHOUT a sort:
     //    mode 0 needs the K best only -> radix select of the K-th score + rank-by-counting of the few above it;
     //    mode 1 needs all of them     -> rank-by-counting over the survivors (bitonic only beyond 4096 of them).
@@ -726,6 +836,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
     __shared__ int s_warp_top[33];
     __shared__ unsigned s_hcls[kHashSlots];
     __shared__ int s_hcnt[kHashSlots], s_hstart[kHashSlots];
+    __shared__ ChunkScratch s_chunk;
     int n, src0;
     if (p.mode == 0) {
         const int c = __ldg(p.cand_count + blockIdx.x);
@@ -741,10 +852,10 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
     int n_kept = 0;
     bool done;
     if (n_al <= kSmemItems) {
-        done = nms_medium_body<true>(p, n, src0, s_dyn_top, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &n_kept);
+        done = nms_medium_body<true>(p, n, src0, s_dyn_top, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &s_chunk, &n_kept);
     } else {
         unsigned char *ws = p.workspace + (p.mode == 0 ? (size_t)blockIdx.x * p.ws_stride : (size_t)2 * src0 * kWsItemBytes);
-        done = nms_medium_body<false>(p, n, src0, ws, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &n_kept);
+        done = nms_medium_body<false>(p, n, src0, ws, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &s_chunk, &n_kept);
     }
     if (done) {
         const int img = blockIdx.x, tid = threadIdx.x;
