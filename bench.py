@@ -58,6 +58,9 @@ def parse_args():
                     help="inference chain of the timed step: dense class-map scan (TMA ring, the roofline kernel) or the "
                          "candidate-first gather (same outputs, ~30x fewer bytes at 2 %% candidates)")
     ap.add_argument("--skip-candidate-first", action="store_true", help="do not also time the candidate-first variant")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU exchange of the 8 loss sums: inside the loss kernel over NVLink peer memory (fused) "
+                         "or an NCCL all-reduce node + a finalize launch per step (nccl)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-gpu-eager", action="store_true")
@@ -84,7 +87,9 @@ def config_dict(w, args, world, extra=None):
         "image": [w["height"], w["width"]], "levels": [list(l) for l in levels], "anchors": synth.num_anchors(levels),
         "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world, "classes": w["classes"], "gt_per_image": w["gt"],
         "max_instances": w["k"], "topk": TOPK, "score_thr": SCORE_THR, "iou_thr": IOU_THR,
-        "parallelism": f"batch-sharded x{world}, all-reduce of 8 fp64 loss sums" if world > 1 else "single GPU",
+        "parallelism": (f"batch-sharded x{world}, 8 fp64 loss sums all-reduced " +
+                        ("inside the loss kernel over NVLink peer memory" if args.allreduce == "fused" else "by NCCL"))
+        if world > 1 else "single GPU",
         "cache": "3 rotating input sets of 188 MB each (> 126 MB L2), no flush needed",
     }
     cfg.update(extra or {})
@@ -242,6 +247,18 @@ def run_ours(args, w, world, rank, local_rank):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    fused = multi and args.allreduce == "fused"
+    exchanges = []
+
+    def attach(pipes):
+        """fused exchange: one region per pipeline (= per step in flight); collective across the ranks"""
+        if fused:
+            from sihl_b200.dist import PeerExchange
+            ex = PeerExchange(dev, n_regions=len(pipes))
+            exchanges.append(ex)
+            for i, pp in enumerate(pipes):
+                pp.attach_exchange(ex, i)
+        return pipes
 
     def barrier():
         if multi:
@@ -250,8 +267,8 @@ def run_ours(args, w, world, rank, local_rank):
 
     def timed_steps(mode, steps, warmup):
         """Build the lanes for one decode mode, replay `warmup` + `steps` steps, return (ms, pipes, outs, graphs)."""
-        pipes = [DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
-                 for _ in range(n_lanes)]
+        pipes = attach([DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
+                        for _ in range(n_lanes)])
         # every (lane, input set) pair owns its outputs: steps in flight on different lanes never share a buffer
         outs = [[pipes[ln].new_outputs() for _ in range(n_sets)] for ln in range(n_lanes)]
         torch.cuda.synchronize()
@@ -266,12 +283,13 @@ def run_ours(args, w, world, rank, local_rank):
                 dist.all_reduce(out.sums, op=dist.ReduceOp.SUM, group=groups[ln])
                 pipes[ln].finalize(out)
 
+            separate = multi and not fused                # NCCL all-reduce node + finalize launch after the loss kernel
             if args.serial:
-                pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not multi)
-                if multi:
+                pipes[ln].infer_chain(sets[i], out); pipes[ln].train_chain(sets[i], out, finalize=not separate)
+                if separate:
                     exchange()
             else:
-                pipes[ln].step(sets[i], out, finalize=not multi, after_train=exchange if multi else None)
+                pipes[ln].step(sets[i], out, finalize=not separate, after_train=exchange if separate else None)
 
         graphs = None
         if use_graph and not args.serial:
@@ -340,6 +358,19 @@ def run_ours(args, w, world, rank, local_rank):
     cand_mean = None      # measured in the stand-alone decode loop below (k_nms* zero the counters they consume)
     det_mean = float(outs0[0].num_instances.float().mean().item())
 
+    # ---- fused exchange vs NCCL: the same step with an NCCL all-reduce + finalize launch must give the same losses
+    allreduce_check = None
+    if fused:
+        chk = DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=args.decode_mode)
+        chk_out = chk.new_outputs()
+        chk.step(sets[0], chk_out, finalize=False)
+        dist.all_reduce(chk_out.sums, op=dist.ReduceOp.SUM)
+        chk.finalize(chk_out)
+        torch.cuda.synchronize()
+        allreduce_check = {"nccl_losses": chk_out.losses.cpu().tolist(),
+                           "fused_equals_nccl": bool(torch.allclose(chk_out.losses, outs0[0].losses, rtol=1e-6, atol=0))}
+        del chk, chk_out
+
     # ---- the other decode variant on the same inputs (same outputs; reported next to `value`, never instead of it)
     other = None
     if not args.skip_candidate_first:
@@ -357,9 +388,9 @@ def run_ours(args, w, world, rank, local_rank):
         """`e2e` = host maps read in place (candidate-first pipelines); `e2e_full_upload` = every map uploaded."""
         from sihl_b200.pipeline import DetectionHeadPipeline as _P
         n_e2e = max(1, args.e2e_lanes)
-        mk = lambda mode: [_P(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
-                           for _ in range(n_e2e)]
-        full, _ = run_e2e(args, mk(args.decode_mode)[:2], sets[0], world, multi, dev, smp)
+        mk = lambda mode: attach([_P(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
+                                  for _ in range(n_e2e)])
+        full, _ = run_e2e(args, mk(args.decode_mode), sets[0], world, multi, dev, smp)
         ref = (outs0[0].num_instances, outs0[0].scores, outs0[0].classes, outs0[0].boxes, outs0[0].assignment,
                outs0[0].rel_iou)
         sparse, cf_out = run_e2e(args, mk("candidate_first"), sets[0], world, multi, dev, smp, host_maps=True,
@@ -373,6 +404,8 @@ def run_ours(args, w, world, rank, local_rank):
         # the other ranks only take part in the collective part of the end-to-end measurement
         if not args.skip_e2e:
             both_e2e(None, 0.0)
+        for ex in exchanges:
+            ex.close()
         return
 
     # ---- roofline of the dominant kernel (k_dense_decode), timed alone on the launching stream
@@ -439,6 +472,8 @@ def run_ours(args, w, world, rank, local_rank):
     if not multi and not args.skip_gpu_eager:
         eager = gpu_eager_reference(w, sets[0], levels, dev)
 
+    for ex in exchanges:
+        ex.close()
     clocks = sampler.stop() if sampler else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -448,7 +483,8 @@ def run_ours(args, w, world, rank, local_rank):
                                                 "steps_in_flight": n_lanes, "decode_mode": args.decode_mode,
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
-        "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "roofline_step": roofline_step,
+        "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi and not fused else 0)) * args.steps,
+        "allreduce": (args.allreduce if multi else None), "allreduce_check": allreduce_check, "roofline": roofline, "roofline_step": roofline_step,
         "other_decode_mode": other, "cpu_baseline": cpu, "gpu_eager_reference": eager, "clocks": clocks,
         "losses_check": losses,
     }
@@ -529,8 +565,9 @@ def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathere
         st, pipe, out = ln["stream"], ln["pipe"], ln["out"]
         with torch.cuda.stream(st):
             st.wait_event(ln["ready"])
-            pipe.step(ln["slot"], out, finalize=not multi)
-            if multi:
+            separate = multi and pipe._exchange is None      # no fused exchange attached: NCCL all-reduce + finalize
+            pipe.step(ln["slot"], out, finalize=not separate)
+            if separate:
                 dist.all_reduce(out.sums, op=dist.ReduceOp.SUM)
                 pipe.finalize(out)
             ln["done"].record(st)

@@ -45,6 +45,8 @@ extern "C" {
 
 #define SIHL_OD_MAX_LEVELS 8
 #define SIHL_OD_MAX_TOPK   16
+#define SIHL_OD_MAX_PEERS  16      /* GPUs of one node taking part in the fused loss-sum exchange */
+#define SIHL_OD_IPC_HANDLE_BYTES 64
 #define SIHL_OD_NUM_SUMS   8
 
 /* Layout of the fp64 partial-sum vector every loss kernel accumulates into and
@@ -186,6 +188,38 @@ SIHL_OD_API int sihl_od_pos_loss_tiles(const int32_t *pos_chunks, const int32_t 
                            const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
                            const float *box_raw, const float *cls_logits, int num_classes,
                            double *sums, float *losses, uint32_t *done_counter, void *stream);
+
+/* ---- §8e: the one cross-GPU exchange, fused into the loss kernel ---------------
+ * Same as sihl_od_pos_loss_tiles with losses / done_counter given, plus the
+ * all-reduce (sum) of the 8 partial sums over the `world` GPUs of the node done
+ * by the kernel's last CTA over peer memory (NVLink P2P stores + release/acquire
+ * flags) before it finalizes: sums [8] then hold the global sums and losses the
+ * global-batch losses (identical bits on every rank: contributions are added in
+ * rank order) — no NCCL launch, no separate finalize launch.  peer_regions: DEVICE
+ * array of `world` device pointers, entry r = rank r's exchange region as seen
+ * from this process (own region at [rank]).  Every rank must launch the same
+ * sequence of calls on a region; a peer that never arrives ends the wait after
+ * 2 s with NaN sums (no hang).  world == 1 behaves like sihl_od_pos_loss_tiles. */
+SIHL_OD_API int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
+                           const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
+                           const float *offsets, const float *scales, int img_w, int img_h,
+                           const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                           const float *box_raw, const float *cls_logits, int num_classes,
+                           double *sums, float *losses, uint32_t *done_counter,
+                           void *const *peer_regions, int world, int rank, void *stream);
+
+/* Exchange regions (one per step in flight), allocated in blocks and shared between
+ * the per-GPU processes through CUDA IPC.  _create: cudaMalloc + zero a block of
+ * n_regions regions of sihl_od_exchange_region_bytes(world) each and export its
+ * handle (SIHL_OD_IPC_HANDLE_BYTES bytes, to be sent to the peers by any means,
+ * e.g. torch.distributed.all_gather); _open maps a peer's block into this process
+ * (peer access is enabled on first use); _close / _destroy undo them.  Not on the
+ * per-step path. */
+SIHL_OD_API size_t sihl_od_exchange_region_bytes(int world);
+SIHL_OD_API int sihl_od_exchange_create(int world, int n_regions, void **block, unsigned char *ipc_handle_out);
+SIHL_OD_API int sihl_od_exchange_open(const unsigned char *ipc_handle, void **peer_block);
+SIHL_OD_API int sihl_od_exchange_close(void *peer_block);
+SIHL_OD_API int sihl_od_exchange_destroy(void *block);
 
 /* ref :163-172, :180, :197, :208, :210 — losses fp32 [5] =
  * [location, box, class, iou, total]; early-out when sums[6] == 0. */

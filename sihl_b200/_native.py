@@ -28,6 +28,12 @@ _SIGNATURES = {
     "sihl_od_assign_resolve": (I, [P, P, P, P, I, I64, I, I, P, P, P, P, P, P, P, P, P, I, P, P, P]),
     "sihl_od_quad_matching": (I, [P, I64, P, P, I, I, I, P, P, P, P, P, P, P, P]),
     "sihl_od_pos_loss_tiles": (I, [P, P, P, I, I64, P, P, I, I, P, P, P, P, P, I, P, P, P, P]),
+    "sihl_od_pos_loss_tiles_exchange": (I, [P, P, P, I, I64, P, P, I, I, P, P, P, P, P, I, P, P, P, P, I, I, P]),
+    "sihl_od_exchange_region_bytes": (C.c_size_t, [I]),
+    "sihl_od_exchange_create": (I, [I, I, P, P]),
+    "sihl_od_exchange_open": (I, [P, P]),
+    "sihl_od_exchange_close": (I, [P]),
+    "sihl_od_exchange_destroy": (I, [P]),
     "sihl_od_pos_compact": (I, [P, P, I, I64, P, I64, P, P, P]),
     "sihl_od_dense_loss": (I, [P, P, P, I64, P, P]),
     "sihl_od_pos_loss": (I, [P, P, I64, I64, P, P, P, P, I, I, P, P, P, P, P, I, I, P, P]),

@@ -1,0 +1,67 @@
+// od_exchange.cu — peer-memory plumbing for the one cross-GPU exchange of the path: the 8 fp64
+// loss partial sums of a step.  Instead of an NCCL all-reduce node between the loss kernel and the finalize
+// kernel, the LAST CTA of k_pos_loss_tiles (od_loss.cu) pushes this GPU's sums into every peer's exchange
+// region with plain stores over NVLink (P2P), waits for the peers' pushes, adds the W contributions in rank
+// order (same bits on every rank) and finalizes the losses — compute and collective in one kernel.
+//
+// This file only allocates the regions and passes CUDA IPC handles around (one process per GPU):
+//   sihl_od_exchange_create  : cudaMalloc + zero a block of n_regions regions, export its IPC handle
+//   sihl_od_exchange_open    : map a peer's block (enables peer access lazily)
+//   sihl_od_exchange_close / _destroy
+// The handles travel between the processes through torch.distributed (sihl_b200/dist.py); nothing here is on
+// the per-step path.
+//
+// Region layout (8-byte words; W = world size; parity = step & 1 so a rank that is one step ahead never
+// overwrites what a slower rank still reads — a rank cannot be two steps ahead, it needs every peer's push):
+//   [0, 16 W)            sums   [parity][source rank][8]   double
+//   [16 W, 18 W)         flags  [parity][source rank]      u64: the step number whose sums are complete
+//   [18 W]               this GPU's own step counter       u64
+#include "od_common.cuh"
+
+using namespace sihl;
+
+extern "C" size_t sihl_od_exchange_region_bytes(int world)
+{
+    if (world < 1 || world > SIHL_OD_MAX_PEERS) return 0;
+    const size_t words = (size_t)18 * world + 1;
+    return (words * 8 + 255) / 256 * 256;
+}
+
+extern "C" int sihl_od_exchange_create(int world, int n_regions, void **block, unsigned char *ipc_handle_out)
+{
+    SIHL_CHECK_ARG(world >= 1 && world <= SIHL_OD_MAX_PEERS, "world=%d outside 1..%d", world, SIHL_OD_MAX_PEERS);
+    SIHL_CHECK_ARG(n_regions >= 1 && block && ipc_handle_out, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SIHL_OD_IPC_HANDLE_BYTES, "handle size");
+    const size_t bytes = sihl_od_exchange_region_bytes(world) * (size_t)n_regions;
+    void *ptr = nullptr;
+    int rc = cuda_status(cudaMalloc(&ptr, bytes), "cudaMalloc(exchange block)");
+    if (rc) return rc;
+    rc = cuda_status(cudaMemset(ptr, 0, bytes), "cudaMemset(exchange block)");
+    if (!rc) rc = cuda_status(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    cudaIpcMemHandle_t h;
+    if (!rc) rc = cuda_status(cudaIpcGetMemHandle(&h, ptr), "cudaIpcGetMemHandle");
+    if (rc) { cudaFree(ptr); return rc; }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *block = ptr;
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_exchange_open(const unsigned char *ipc_handle, void **peer_block)
+{
+    SIHL_CHECK_ARG(ipc_handle && peer_block, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    return cuda_status(cudaIpcOpenMemHandle(peer_block, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+extern "C" int sihl_od_exchange_close(void *peer_block)
+{
+    if (peer_block == nullptr) return SIHL_OD_OK;
+    return cuda_status(cudaIpcCloseMemHandle(peer_block), "cudaIpcCloseMemHandle");
+}
+
+extern "C" int sihl_od_exchange_destroy(void *block)
+{
+    if (block == nullptr) return SIHL_OD_OK;
+    return cuda_status(cudaFree(block), "cudaFree(exchange block)");
+}

@@ -127,7 +127,74 @@ struct PosTileParams {
     float *losses; unsigned *done_counter;       // optional fused finalize
 };
 
-__global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileParams p)
+// optional fused cross-GPU exchange of the sums (od_exchange.cu): world > 1, peer[r] = rank r's region
+struct ExchangeParams {
+    int world, rank;
+    unsigned long long *const *peer;             // device array [world]
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All-reduce (sum) of the 8 partial sums across the GPUs of the node, by the last CTA of the loss kernel:
+// thread q pushes this rank's sums into rank q's region (plain stores over NVLink, then a release store of the
+// step number), waits for rank q's push into the local region, and 8 threads add the W contributions in rank
+// order.  A peer that never shows up (a crashed rank) ends the wait after 2 s with NaN sums instead of a hang.
+__device__ __noinline__ void exchange_sums(unsigned long long *const *peer, int W, int rank, double *sums,
+                                           double *s_in /* shared [8] */)
+{
+    const int tid = threadIdx.x;
+    __shared__ unsigned long long s_step;
+    __shared__ int s_timeout;
+    unsigned long long *mine = peer[rank];
+    if (tid == 0) {
+        s_step = ++mine[18 * W];                                   // this GPU's step counter (only this CTA touches it)
+        s_timeout = 0;
+    }
+    if (tid < SIHL_OD_NUM_SUMS) s_in[tid] = reinterpret_cast<volatile double *>(sums)[tid];
+    __syncthreads();
+    const unsigned long long step = s_step;
+    const int parity = (int)(step & 1ull);
+    if (tid < W) {
+        unsigned long long *theirs = peer[tid];
+        double *dst = reinterpret_cast<double *>(theirs) + ((size_t)parity * W + rank) * SIHL_OD_NUM_SUMS;
+#pragma unroll
+        for (int i = 0; i < SIHL_OD_NUM_SUMS; ++i) dst[i] = s_in[i];
+        __threadfence_system();
+        st_release_sys(theirs + 16 * W + parity * W + rank, step);
+        const unsigned long long *flag = mine + 16 * W + parity * W + tid;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) != step) {
+            if (global_timer_ns() - t0 > 2000000000ull) { s_timeout = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (tid < SIHL_OD_NUM_SUMS) {
+        const volatile double *src = reinterpret_cast<volatile double *>(mine) + (size_t)parity * W * SIHL_OD_NUM_SUMS;
+        double total = 0.0;
+        for (int r = 0; r < W; ++r) total += src[r * SIHL_OD_NUM_SUMS + tid];
+        sums[tid] = s_timeout ? CUDART_NAN : total;
+    }
+    __syncthreads();
+}
+
+template <bool EXCHANGE>     // EXCHANGE: the last CTA all-reduces the sums over peer memory before it finalizes (multi-GPU)
+__global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileParams p, ExchangeParams x)
 {
     __shared__ double s_red[2 * 32];
     __shared__ bool s_last;
@@ -182,6 +249,12 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
             s_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
         }
         __syncthreads();
+        if (EXCHANGE) {
+            if (s_last) {                                         // block-uniform: the whole CTA takes part
+                __threadfence();
+                exchange_sums(x.peer, x.world, x.rank, p.sums, s_red);
+            }
+        }
         if (s_last && tid == 0) {
             __threadfence();
             finalize_losses(const_cast<const double *>(reinterpret_cast<volatile double *>(p.sums)), p.losses);
@@ -391,7 +464,23 @@ extern "C" int sihl_od_pos_loss_tiles(const int32_t *pos_chunks, const int32_t *
                                       const float *box_raw, const float *cls_logits, int num_classes, double *sums,
                                       float *losses, uint32_t *done_counter, void *stream)
 {
+    return sihl_od_pos_loss_tiles_exchange(pos_chunks, tile_pos_rows, tile_pos_aux, batch, num_anchors, offsets, scales, img_w,
+                                           img_h, gt_boxes, gt_classes, gt_offsets, box_raw, cls_logits, num_classes, sums,
+                                           losses, done_counter, nullptr, 1, 0, stream);
+}
+
+extern "C" int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
+                                               const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
+                                               const float *offsets, const float *scales, int img_w, int img_h,
+                                               const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                                               const float *box_raw, const float *cls_logits, int num_classes, double *sums,
+                                               float *losses, uint32_t *done_counter, void *const *peer_regions, int world,
+                                               int rank, void *stream)
+{
     (void)gt_offsets;
+    SIHL_CHECK_ARG(world >= 1 && world <= SIHL_OD_MAX_PEERS && rank >= 0 && rank < world, "world=%d rank=%d", world, rank);
+    SIHL_CHECK_ARG(world == 1 || (peer_regions != nullptr && losses != nullptr),
+                   "the fused exchange needs the peer regions and the fused finalize (losses, done_counter)");
     SIHL_CHECK_ARG(pos_chunks && tile_pos_rows && tile_pos_aux && sums, "NULL argument");
     SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
     SIHL_CHECK_ARG(box_raw == nullptr || (offsets && scales && img_w > 0 && img_h > 0),
@@ -410,11 +499,15 @@ extern "C" int sihl_od_pos_loss_tiles(const int32_t *pos_chunks, const int32_t *
     p.box_raw = box_raw; p.cls = cls_logits; p.num_classes = num_classes;
     p.cls_vec4 = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
     p.sums = sums; p.losses = losses; p.done_counter = done_counter;
+    ExchangeParams x;
+    x.world = world; x.rank = rank;
+    x.peer = reinterpret_cast<unsigned long long *const *>(peer_regions);
     // persistent grid: up to 12 CTAs of 128 threads per SM, never more than the chunk-list capacity
     int64_t blocks = n_slots * (kTile / 32);
     const int64_t cap = (int64_t)kNumSMs * 12;
     if (blocks > cap) blocks = cap;
-    k_pos_loss_tiles<<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p);
+    if (world > 1) k_pos_loss_tiles<true><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x);
+    else k_pos_loss_tiles<false><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x);
     SIHL_CHECK_LAUNCH("k_pos_loss_tiles");
     return SIHL_OD_OK;
 }

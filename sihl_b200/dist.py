@@ -50,3 +50,65 @@ def ddp_mean_of_local_losses(local_losses: torch.Tensor, group=None) -> torch.Te
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
         out /= dist.get_world_size(group)
     return out
+
+
+class PeerExchange:
+    """Exchange regions for the loss-sum all-reduce that ``k_pos_loss_tiles`` performs itself over peer memory
+    (``include/sihl_od.h``: sihl_od_pos_loss_tiles_exchange).  One block of ``n_regions`` regions per GPU — one
+    region per step in flight — allocated by the library, its CUDA-IPC handle all-gathered through
+    ``torch.distributed`` (plumbing only) and the peers' blocks mapped into this process.
+
+    ``peer_array(i)`` is the device array of ``world`` device pointers (entry r = rank r's region i) that the C
+    entry takes.  Collective: every rank of ``group`` must construct it at the same point of its program."""
+
+    def __init__(self, device, n_regions: int = 1, group=None):
+        import ctypes as C
+
+        from . import _native
+        assert dist.is_available() and dist.is_initialized(), "PeerExchange needs an initialised process group"
+        self.lib = _native.load()
+        self.device = torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_regions = int(n_regions)
+        self.region_bytes = int(self.lib.sihl_od_exchange_region_bytes(self.world))
+        assert self.region_bytes > 0, f"world size {self.world} not supported by the fused exchange"
+        self._own, self._opened = C.c_void_p(), {}
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.sihl_od_exchange_create(self.world, self.n_regions, C.byref(self._own), handle),
+                          "sihl_od_exchange_create")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            self.blocks = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.blocks.append(int(self._own.value))
+                    continue
+                raw = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
+                ptr = C.c_void_p()
+                _native.check(self.lib.sihl_od_exchange_open(raw, C.byref(ptr)), "sihl_od_exchange_open")
+                self._opened[r] = ptr
+                self.blocks.append(int(ptr.value))
+        dist.barrier(group=group)
+        # per region: device array of `world` pointers (entry r = rank r's region), what the kernel indexes
+        self._tables = torch.tensor([[b + i * self.region_bytes for b in self.blocks] for i in range(self.n_regions)],
+                                    dtype=torch.int64, device=self.device)
+
+    def peer_array(self, region: int) -> int:
+        """Device address of region ``region``'s pointer table."""
+        return self._tables[region].data_ptr()
+
+    def close(self, group=None) -> None:
+        """Unmap the peers' blocks, then (after a barrier: nobody still maps ours) free our own."""
+        if self._own.value is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for ptr in self._opened.values():
+                self.lib.sihl_od_exchange_close(ptr)
+            self._opened = {}
+            if dist.is_initialized():
+                dist.barrier(group=group)
+            self.lib.sihl_od_exchange_destroy(self._own)
+        self._own.value = None

@@ -83,6 +83,7 @@ class DetectionHeadPipeline:
         self.cand = ops.CandidateBuffers.allocate(B, int(cand_capacity or A), dev)
         self.side = torch.cuda.Stream(device=dev)
         self.lib = _native.load()
+        self._exchange = None
 
     def new_outputs(self) -> StepOutputs:
         dev, B, A, K = self.device, self.B, self.A, self.K
@@ -97,6 +98,11 @@ class DetectionHeadPipeline:
             boxes=torch.empty((B, K, 4), dtype=torch.float32, device=dev))
 
     # -- the two chains (enqueue only; no sync) --------------------------------------------
+    def attach_exchange(self, exchange, region: int) -> None:
+        """Multi-GPU: let the loss kernel all-reduce the 8 partial sums itself over peer memory
+        (``dist.PeerExchange``, one region per pipeline / step in flight) instead of an NCCL node + a finalize launch."""
+        self._exchange = (exchange.peer_array(region), exchange.world, exchange.rank)
+
     def train_chain(self, x: StepInputs, out: StepOutputs, finalize: bool = True) -> None:
         lib, st = self.lib, torch.cuda.current_stream(self.device).cuda_stream
         gt = x.gt
@@ -117,11 +123,12 @@ class DetectionHeadPipeline:
             self.C, p(self.pos_chunks), p(self.tile_pos_aux), st),
             "sihl_od_assign_resolve")
         # single GPU: the last CTA of the positive-loss kernel also finalizes the five losses
-        _native.check(lib.sihl_od_pos_loss_tiles(
+        peers, world, rank = self._exchange if (finalize and self._exchange is not None) else (None, 1, 0)
+        _native.check(lib.sihl_od_pos_loss_tiles_exchange(
             p(self.pos_chunks), p(self.tile_pos_rows), p(self.tile_pos_aux), self.B, self.A,
             p(self.offsets), p(self.scales), self.img_w, self.img_h, p(gt.boxes), p(gt.classes), p(gt.offsets),
             p(x.box_raw), p(x.cls_logits), self.C, p(out.sums), p(out.losses) if finalize else None,
-            p(self.done_counter) if finalize else None, st), "sihl_od_pos_loss_tiles")
+            p(self.done_counter) if finalize else None, peers, world, rank, st), "sihl_od_pos_loss_tiles_exchange")
 
     def finalize(self, out: StepOutputs) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -563,3 +563,52 @@ def test_quad_matching_corner_cases_and_full_size():
     for b in (0, 31, 63):
         ra, ro, ri, rr = tr.quad_canonical(*tr.quad_match_one(big, _t(per_image[b]).reshape(-1, 4), 9))
         assert torch.equal(a[b], ra) and torch.equal(o[b], ro) and torch.equal(i[b], ri) and torch.equal(r[b], rr)
+
+
+def test_fused_loss_sum_exchange_against_a_scripted_peer():
+    """The in-kernel all-reduce of the 8 loss sums (sihl_od_pos_loss_tiles_exchange, world = 2) on ONE GPU: the peer's
+    pushes are written into this rank's region from the host before each launch, so no kernel ever waits on another
+    kernel.  Checks the sums / losses of two consecutive steps (both parities), what this rank pushed to the peer, and
+    that a peer that never shows up ends in NaN after the bounded wait instead of hanging."""
+    from sihl_b200 import dist as sdist
+    from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs
+    W = H = 256
+    B, C, G, world = 2, 16, 12, 2
+    levels = synth.level_sizes(H, W)
+    pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, DEV)
+    gt = _gt_dev(synth.gt_batch_np(31, B, H, W, C, G, ragged=False))
+    maps = synth.dense_maps_np(32, B, pipe.A, C)
+    x = StepInputs(_t(maps.loc_logits), _t(maps.iou_preds), _t(maps.box_raw), _t(maps.cls_logits), gt)
+    plain = pipe.new_outputs()
+    pipe.train_chain(x, plain)
+    torch.cuda.synchronize()
+    local = plain.sums.clone()
+
+    words = 18 * world + 1
+    mine = torch.zeros(words, dtype=torch.float64, device=DEV)        # rank 0's region (this GPU)
+    theirs = torch.zeros(words, dtype=torch.float64, device=DEV)      # stands in for rank 1's region
+    table = torch.tensor([mine.data_ptr(), theirs.data_ptr()], dtype=torch.int64, device=DEV)
+    pipe._exchange = (table.data_ptr(), world, 0)
+    out = pipe.new_outputs()
+    for step in (1, 2, 3):
+        parity = step & 1
+        fake = torch.arange(8, dtype=torch.float64, device=DEV) * 0.5 + step
+        fake[7] = 0.0
+        mine[(parity * world + 1) * 8:(parity * world + 1) * 8 + 8] = fake          # the peer's push ...
+        mine.view(torch.int64)[16 * world + parity * world + 1] = step              # ... and its release flag
+        torch.cuda.synchronize()
+        pipe.train_chain(x, out)
+        torch.cuda.synchronize()
+        want = local + fake
+        torch.testing.assert_close(out.sums[:7], want[:7], rtol=1e-12, atol=0)
+        torch.testing.assert_close(out.losses.double(), sdist.losses_from_sums(want), rtol=1e-6, atol=0)
+        pushed = theirs[(parity * world + 0) * 8:(parity * world + 0) * 8 + 7]
+        torch.testing.assert_close(pushed, local[:7], rtol=1e-12, atol=0)           # what the peer would have received
+        assert int(theirs.view(torch.int64)[16 * world + parity * world + 0]) == step
+        assert int(mine.view(torch.int64)[18 * world]) == step                      # own step counter
+    import time
+    t0 = time.perf_counter()
+    pipe.train_chain(x, out)                                                        # step 4: the peer never arrives
+    torch.cuda.synchronize()
+    assert 1.5 < time.perf_counter() - t0 < 10.0
+    assert torch.isnan(out.losses).all()
