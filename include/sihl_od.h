@@ -308,6 +308,20 @@ SIHL_OD_API int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacit
                      int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
                      void *workspace, int reset_counts, void *stream);
 
+/* The same operation for LONG candidate lists (thousands per image): suppression never
+ * crosses classes, so every image's candidates are dealt to S = ceil(capacity / 2048)
+ * (2..32) sub-lists by class, each sub-list is handled by its own CTA (S SMs per image,
+ * sub-lists short enough for shared memory) and the image's K best are merged from the
+ * S x K survivors.  Same results as sihl_od_nms_topk; three launches instead of one, so
+ * the single-CTA entry stays the choice for the steady-state step with a few hundred
+ * candidates per image.  workspace: sihl_od_nms_split_workspace_bytes(batch, capacity, k).
+ * cand_count is consumed (zeroed when reset_counts != 0). */
+SIHL_OD_API size_t sihl_od_nms_split_workspace_bytes(int batch, int64_t cand_capacity, int k);
+SIHL_OD_API int sihl_od_nms_topk_split(int32_t *cand_count, int64_t cand_capacity, const uint64_t *cand_key,
+                     const float *cand_box, const int32_t *cand_cls, int batch, float iou_thr, int k,
+                     int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
+                     void *workspace, int reset_counts, void *stream);
+
 /* Stand-alone batched NMS with torchvision.ops.batched_nms's signature, over
  * `n_images` independent segments: boxes [N,4], scores [N], classes int64 [N],
  * seg_offsets int32 [n_images+1] (device).  keep int64 [N]: per segment, the

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "sihl_od_candidate_decode": (I, [P, P, P, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_nms_workspace_bytes": (C.c_size_t, [I, I64]),
     "sihl_od_nms_topk": (I, [P, I64, P, P, P, I, F, I, P, P, P, P, P, I, P]),
+    "sihl_od_nms_split_workspace_bytes": (C.c_size_t, [I, I64, I]),
+    "sihl_od_nms_topk_split": (I, [P, I64, P, P, P, I, F, I, P, P, P, P, P, I, P]),
     "sihl_od_batched_nms_workspace_bytes": (C.c_size_t, [I64]),
     "sihl_od_batched_nms": (I, [P, P, P, P, I, I64, F, P, P, P, P]),
 }

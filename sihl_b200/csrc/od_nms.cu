@@ -157,9 +157,12 @@ __device__ __forceinline__ unsigned chunk_greedy(float4 bi, float ai, bool dead,
 // One warp, one class segment [q0, q0 + m) in score order: chunks of 32 boxes; the kept boxes of a chunk then
 // suppress the later boxes of the segment (32 at a time).  m^2/2 pair tests like the serial formulation, but
 // m/32 dependent steps instead of m.
+template <bool SMEM>   // SMEM: the arrays live in shared memory (lets the compiler emit LDS/STS instead of generic accesses)
 __device__ __forceinline__ void warp_segment_nms(const float4 *box, const float *area, unsigned char *dead_flag, int q0, int m,
                                                  float thr, int lane)
 {
+    if (SMEM) { __builtin_assume(__isShared(box)); __builtin_assume(__isShared(area)); __builtin_assume(__isShared(dead_flag)); }
+    else { __builtin_assume(__isGlobal(box)); __builtin_assume(__isGlobal(area)); __builtin_assume(__isGlobal(dead_flag)); }
     for (int c0 = 0; c0 < m; c0 += 32) {
         __syncwarp();
         const int i = c0 + lane;
@@ -190,9 +193,13 @@ __device__ __forceinline__ void warp_segment_nms(const float4 *box, const float 
 // shared memory; every thread then tests its share of the later boxes against them.  2 barriers per 32 boxes.
 struct ChunkScratch { float4 box[32]; float area[32]; unsigned kept; int n_big; int big[32]; };
 
+template <bool SMEM>
 __device__ __forceinline__ void cta_segment_nms(const float4 *box, const float *area, unsigned char *dead_flag, int q0, int m,
                                                 float thr, ChunkScratch *sc)
 {
+    if (SMEM) { __builtin_assume(__isShared(box)); __builtin_assume(__isShared(area)); __builtin_assume(__isShared(dead_flag)); }
+    else { __builtin_assume(__isGlobal(box)); __builtin_assume(__isGlobal(area)); __builtin_assume(__isGlobal(dead_flag)); }
+    __builtin_assume(__isShared(sc));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int c0 = 0; c0 < m; c0 += 32) {
         __syncthreads();                                                  // flags of the previous pass are visible
@@ -236,7 +243,23 @@ struct NmsParams {
     int64_t *keep; int32_t *keep_count;                                                           // mode 1
     unsigned char *workspace; size_t ws_stride;   // mode 0: bytes per image; mode 1: unused (offset = 2*seg start)
     int reset_counts;          // mode 0: zero cand_count[img] once consumed (saves the next step's memset launch)
+    // mode 0, class-split launch (sihl_od_nms_topk_split): list i starts at list_offsets[i] inside the candidate
+    // arrays instead of i * cap, and the sort key of every emitted detection is written next to it
+    const int32_t *list_offsets;
+    unsigned long long *out_keys;
+    int smem_items;            // candidates per list that the launch's dynamic shared memory holds (<= kSmemItems)
 };
+
+__device__ __forceinline__ int64_t list_base(const NmsParams &p, int img)
+{
+    return p.list_offsets != nullptr ? (int64_t)__ldg(p.list_offsets + img) : (int64_t)img * p.cap;
+}
+__device__ __forceinline__ unsigned char *list_workspace(const NmsParams &p, int img, int src0)
+{
+    if (p.mode != 0) return p.workspace + (size_t)2 * src0 * kWsItemBytes;
+    if (p.list_offsets != nullptr) return p.workspace + (size_t)2 * __ldg(p.list_offsets + img) * kWsItemBytes;
+    return p.workspace + (size_t)img * p.ws_stride;
+}
 
 __device__ __forceinline__ void nms_big_body(const NmsParams &p)
 {
@@ -244,6 +267,7 @@ __device__ __forceinline__ void nms_big_body(const NmsParams &p)
     __shared__ int s_warp[33];
 
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t lb = p.mode == 0 ? list_base(p, img) : 0;
     int n, src0;
     if (p.mode == 0) {
         const int c = __ldg(p.cand_count + img);
@@ -259,15 +283,15 @@ __device__ __forceinline__ void nms_big_body(const NmsParams &p)
 
     if (n > 0) {
         unsigned char *base = s_dyn;
-        if (np > kSmemItems)
-            base = p.workspace + (p.mode == 0 ? (size_t)img * p.ws_stride : (size_t)2 * src0 * kWsItemBytes);
+        if (np > p.smem_items)
+            base = list_workspace(p, img, src0);
         const NmsArrays ar = carve(base, np);
 
         // 1. rank by (score desc, index asc)
         for (int i = tid; i < np; i += blockDim.x) {
             unsigned long long key = 0ull;
             if (i < n) {
-                if (p.mode == 0) key = __ldg(p.cand_key + (int64_t)img * p.cap + i);
+                if (p.mode == 0) key = __ldg(p.cand_key + lb + i);
                 else key = ((unsigned long long)f2ord_nms(__ldg(p.scores + src0 + i)) << 32) |
                            (unsigned long long)(0xffffffffu - (unsigned)i);
             }
@@ -282,7 +306,7 @@ __device__ __forceinline__ void nms_big_body(const NmsParams &p)
             unsigned long long key = ~0ull;
             if (r < n) {
                 const unsigned slot = ar.val[r];
-                const unsigned c = p.mode == 0 ? (unsigned)__ldg(p.cand_cls + (int64_t)img * p.cap + slot)
+                const unsigned c = p.mode == 0 ? (unsigned)__ldg(p.cand_cls + lb + slot)
                                                : (unsigned)__ldg(p.classes + src0 + slot);
                 key = ((unsigned long long)c << 32) | (unsigned long long)r;
             }
@@ -292,7 +316,7 @@ __device__ __forceinline__ void nms_big_body(const NmsParams &p)
         bitonic_kv<false>(ar.key, nullptr, np);
         for (int q = tid; q < n; q += blockDim.x) {
             const unsigned r = (unsigned)(ar.key[q] & 0xffffffffu), slot = ar.val[r];
-            const float4 bx = p.mode == 0 ? __ldg(p.cand_box + (int64_t)img * p.cap + slot) : __ldg(p.boxes + src0 + slot);
+            const float4 bx = p.mode == 0 ? __ldg(p.cand_box + lb + slot) : __ldg(p.boxes + src0 + slot);
             ar.box[q] = bx;
             ar.area[q] = (bx.z - bx.x) * (bx.w - bx.y);
             ar.slot[q] = slot;
@@ -347,9 +371,11 @@ __device__ __forceinline__ void nms_big_body(const NmsParams &p)
                 if (p.mode == 0) {
                     if (k < p.K) {
                         const int64_t o = (int64_t)img * p.K + k;
-                        p.out_scores[o] = __uint_as_float((unsigned)(__ldg(p.cand_key + (int64_t)img * p.cap + slot) >> 32));
+                        const unsigned long long ck = __ldg(p.cand_key + lb + slot);
+                        p.out_scores[o] = __uint_as_float((unsigned)(ck >> 32));
                         p.out_classes[o] = (int64_t)(ar.key[q] >> 32);
                         p.out_boxes[o] = ar.box[q];
+                        if (p.out_keys != nullptr) p.out_keys[o] = ck;
                     }
                 } else {
                     p.keep[src0 + k] = (int64_t)src0 + slot;
@@ -395,6 +421,7 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
     __shared__ int s_big;
 
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int64_t lb = p.mode == 0 ? list_base(p, img) : 0;
     const int item = tid >> 2, sub = tid & 3;
     SIHL_PHASE(0);
     int n, src0;
@@ -415,9 +442,9 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
         float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
         if (have) {
             if (p.mode == 0) {
-                key = __ldg(p.cand_key + (int64_t)img * p.cap + item);
-                cls = (unsigned)__ldg(p.cand_cls + (int64_t)img * p.cap + item);
-                bx = __ldg(p.cand_box + (int64_t)img * p.cap + item);
+                key = __ldg(p.cand_key + lb + item);
+                cls = (unsigned)__ldg(p.cand_cls + lb + item);
+                bx = __ldg(p.cand_box + lb + item);
             } else {
                 key = ((unsigned long long)f2ord_nms(__ldg(p.scores + src0 + item)) << 32) |
                       (unsigned long long)(0xffffffffu - (unsigned)item);
@@ -514,6 +541,7 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
                         p.out_scores[o] = __uint_as_float((unsigned)(s_key[slot] >> 32));
                         p.out_classes[o] = (int64_t)s_cls[slot];
                         p.out_boxes[o] = s_box[qq];
+                        if (p.out_keys != nullptr) p.out_keys[o] = s_key[slot];
                     }
                 } else {
                     p.keep[src0 + kk] = (int64_t)src0 + slot;
@@ -589,14 +617,15 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
     __builtin_assume(__isShared(h_start));
     int &s_distinct = h_start[0];                    // scratch until the scan overwrites h_start
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t lb = p.mode == 0 ? list_base(p, img) : 0;
     const MedArrays ar = carve_med(base, n_al);
 
     auto key_of = [&](int i) -> unsigned long long {
-        if (p.mode == 0) return __ldg(p.cand_key + (int64_t)img * p.cap + i);
+        if (p.mode == 0) return __ldg(p.cand_key + lb + i);
         return ((unsigned long long)f2ord_nms(__ldg(p.scores + src0 + i)) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
     };
     auto cls_of = [&](int i) -> unsigned {
-        return p.mode == 0 ? (unsigned)__ldg(p.cand_cls + (int64_t)img * p.cap + i) : (unsigned)__ldg(p.classes + src0 + i);
+        return p.mode == 0 ? (unsigned)__ldg(p.cand_cls + lb + i) : (unsigned)__ldg(p.classes + src0 + i);
     };
 
     SIHL_PHASE(0);
@@ -663,7 +692,7 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
         int rank = 0;
         for (int j = s0; j < e0; ++j) rank += ar.u_key[j] > key;
         const int q = s0 + rank;
-        const float4 bx = p.mode == 0 ? __ldg(p.cand_box + (int64_t)img * p.cap + slot) : __ldg(p.boxes + src0 + slot);
+        const float4 bx = p.mode == 0 ? __ldg(p.cand_box + lb + slot) : __ldg(p.boxes + src0 + slot);
         ar.f_key[q] = key;
         ar.f_slot[q] = slot;
         ar.f_box[q] = bx;
@@ -708,7 +737,7 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
     for (int h = warp; h < kHashSlots; h += nwarps) {             // long segments: one warp each, 32-box chunks
         const int m = h_cnt[h];
         if (m <= 64 || m > kWarpSegment) continue;
-        warp_segment_nms(ar.f_box, ar.f_area, ar.f_dead, h_start[h], m, p.iou_thr, lane);
+        warp_segment_nms<SMEM>(ar.f_box, ar.f_area, ar.f_dead, h_start[h], m, p.iou_thr, lane);
     }
     __syncthreads();
     const int n_big = chunk_scratch->n_big;                       // very long segments: the whole CTA, one after another
@@ -716,12 +745,12 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
         if (n_big <= 32) {
             for (int k = 0; k < n_big; ++k) {
                 const int h = chunk_scratch->big[k];               // (cta_segment_nms only touches box / area / kept)
-                cta_segment_nms(ar.f_box, ar.f_area, ar.f_dead, h_start[h], h_cnt[h], p.iou_thr, chunk_scratch);
+                cta_segment_nms<SMEM>(ar.f_box, ar.f_area, ar.f_dead, h_start[h], h_cnt[h], p.iou_thr, chunk_scratch);
             }
         } else {
             for (int h = 0; h < kHashSlots; ++h)
                 if (h_cnt[h] > kWarpSegment)
-                    cta_segment_nms(ar.f_box, ar.f_area, ar.f_dead, h_start[h], h_cnt[h], p.iou_thr, chunk_scratch);
+                    cta_segment_nms<SMEM>(ar.f_box, ar.f_area, ar.f_dead, h_start[h], h_cnt[h], p.iou_thr, chunk_scratch);
         }
     }
     // 6. survivors -> u_key/u_slot (ballot compaction), then ordered by (score desc, index asc) WITHOUT a sort:
@@ -741,6 +770,7 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
             p.out_scores[o] = __uint_as_float((unsigned)(ar.u_key[k_src] >> 32));
             p.out_classes[o] = (int64_t)h_cls[ar.b_id[slot]];
             p.out_boxes[o] = ar.f_box[q];
+            if (p.out_keys != nullptr) p.out_keys[o] = ar.u_key[k_src];
         } else {
             p.keep[src0 + rank] = (int64_t)src0 + slot;
         }
@@ -851,10 +881,10 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
     while (n_al < n) n_al <<= 1;
     int n_kept = 0;
     bool done;
-    if (n_al <= kSmemItems) {
+    if (n_al <= p.smem_items) {
         done = nms_medium_body<true>(p, n, src0, s_dyn_top, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &s_chunk, &n_kept);
     } else {
-        unsigned char *ws = p.workspace + (p.mode == 0 ? (size_t)blockIdx.x * p.ws_stride : (size_t)2 * src0 * kWsItemBytes);
+        unsigned char *ws = list_workspace(p, (int)blockIdx.x, src0);
         done = nms_medium_body<false>(p, n, src0, ws, n_al, s_warp_top, s_hcls, s_hcnt, s_hstart, &s_chunk, &n_kept);
     }
     if (done) {
@@ -880,6 +910,118 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
     nms_big_body(p);
 }
 
+// ---------------------------------------------------------------------------
+// Class-split NMS for long lists (mode 0).  Suppression never crosses classes, so an image's candidates can be
+// dealt to S independent sub-lists by class (hash % S) and every sub-list handled by its own CTA — S SMs per image
+// instead of one, and sub-lists short enough to stay in shared memory.  k_nms runs unchanged on the B*S sub-lists
+// (each yields its K best survivors, sorted, with their keys); k_nms_merge then picks the image's K best of the
+// S*K by rank = position in the own list + number of larger keys in every other list (binary search).
+// ---------------------------------------------------------------------------
+constexpr int kMaxSplit = 64;
+
+__device__ __forceinline__ int sub_list_of(unsigned cls, int S) { return (int)(((cls * 2654435761u) >> 16) % (unsigned)S); }
+
+struct SplitParams {
+    int32_t *cand_count; int64_t cap;
+    const unsigned long long *key; const float4 *box; const int32_t *cls;
+    int S; int32_t *sub_count; int32_t *sub_offset;          // [B*S]
+    unsigned long long *key2; float4 *box2; int32_t *cls2;     // [B*cap] re-bucketed copies
+    int reset_counts;
+};
+
+__global__ void __launch_bounds__(1024) k_nms_split_lists(SplitParams p)
+{
+    __shared__ int s_cnt[kMaxSplit], s_start[kMaxSplit], s_cur[kMaxSplit];
+    const int img = blockIdx.x, tid = threadIdx.x, S = p.S;
+    const int c = __ldg(p.cand_count + img);
+    const int n = (int)(c < p.cap ? c : p.cap);
+    const int64_t lb = (int64_t)img * p.cap;
+    if (tid < kMaxSplit) { s_cnt[tid] = 0; s_cur[tid] = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&s_cnt[sub_list_of((unsigned)__ldg(p.cls + lb + i), S)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int s = 0; s < S; ++s) { s_start[s] = run; run += s_cnt[s]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int cl = __ldg(p.cls + lb + i);
+        const int s = sub_list_of((unsigned)cl, S);
+        const int64_t dst = lb + s_start[s] + atomicAdd(&s_cur[s], 1);     // order inside a sub-list is irrelevant: keys carry it
+        p.key2[dst] = __ldg(p.key + lb + i);
+        p.box2[dst] = __ldg(p.box + lb + i);
+        p.cls2[dst] = cl;
+    }
+    if (tid < S) {
+        p.sub_count[img * S + tid] = s_cnt[tid];
+        p.sub_offset[img * S + tid] = (int32_t)(lb + s_start[tid]);
+    }
+    if (tid == 0 && p.reset_counts) p.cand_count[img] = 0;
+}
+
+struct MergeParams {
+    int S, K;
+    const int64_t *sub_num; const unsigned long long *sub_keys; const float *sub_scores; const int64_t *sub_classes;
+    const float4 *sub_boxes;                                   // [B*S] / [B*S, K]
+    int64_t *num_instances; float *out_scores; int64_t *out_classes; float4 *out_boxes;
+};
+
+// STAGED: the S*K keys of the image are copied to shared memory first (the binary searches are chains of dependent
+// loads: ~20 cycles each from shared memory, ~700 from L2).
+template <bool STAGED>
+__global__ void __launch_bounds__(512) k_nms_merge(MergeParams p)
+{
+    extern __shared__ __align__(16) unsigned char s_merge[];
+    __shared__ int s_num[kMaxSplit];
+    const int img = blockIdx.x, tid = threadIdx.x, S = p.S, K = p.K;
+    if (tid < S) s_num[tid] = (int)__ldg(p.sub_num + img * S + tid);
+    __syncthreads();
+    const unsigned long long *keys = p.sub_keys + (int64_t)img * S * K;
+    if (STAGED) {
+        unsigned long long *sk = reinterpret_cast<unsigned long long *>(s_merge);
+        for (int e = tid; e < S * K; e += blockDim.x) {
+            const int s = e / K, k = e - s * K;
+            if (k < s_num[s]) sk[e] = __ldg(keys + e);
+        }
+        __syncthreads();
+        keys = sk;
+    }
+    int total = 0;
+    for (int s = 0; s < S; ++s) total += s_num[s];
+    const int m = total < K ? total : K;
+    for (int e = tid; e < S * K; e += blockDim.x) {
+        const int s = e / K, k = e - s * K;
+        if (k >= s_num[s]) continue;
+        const unsigned long long key = keys[e];
+        int rank = k;                                          // the own list is sorted descending
+        for (int t = 0; t < S && rank < K; ++t) {
+            if (t == s) continue;
+            const unsigned long long *other = keys + t * K;
+            int lo = 0, hi = s_num[t];                         // number of keys of list t that are larger than key
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (other[mid] > key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < K) {
+            const int64_t src = ((int64_t)img * S + s) * K + k;
+            const int64_t o = (int64_t)img * K + rank;
+            p.out_scores[o] = __ldg(p.sub_scores + src);
+            p.out_classes[o] = __ldg(p.sub_classes + src);
+            p.out_boxes[o] = __ldg(p.sub_boxes + src);
+        }
+    }
+    if (tid == 0) p.num_instances[img] = m;
+    for (int k = m + tid; k < K; k += blockDim.x) {
+        const int64_t o = (int64_t)img * K + k;
+        p.out_scores[o] = 0.f;
+        p.out_classes[o] = 0;
+        p.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 static int pow2ceil(int64_t n)
 {
     int p = 2;
@@ -887,10 +1029,11 @@ static int pow2ceil(int64_t n)
     return p;
 }
 
-static int launch_nms(const NmsParams &p, int n_images, int64_t max_items, cudaStream_t st)
+static int launch_nms(NmsParams p, int n_images, int64_t max_items, cudaStream_t st, int smem_items = kSmemItems)
 {
     // dynamic shared memory only when a list can exceed the short-list path
-    const size_t smem = max_items > kSmallItems ? (size_t)kSmemItems * kSmemItemBytes : 0;
+    p.smem_items = smem_items;
+    const size_t smem = max_items > kSmallItems ? (size_t)smem_items * kSmemItemBytes : 0;
     static thread_local bool attr_set = false;
     if (smem && !attr_set) {
         int rc = cuda_status(cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -968,3 +1111,88 @@ extern "C" __attribute__((visibility("default"))) int sihl_od_debug_phases(long 
     return cudaMemcpyFromSymbol(out_host, sihl::g_phase_clock, sizeof(long long) * 16) == cudaSuccess ? 0 : 2;
 }
 #endif
+
+// ---- class-split variant (long lists) ------------------------------------------------------------------
+static int split_factor(int64_t cand_capacity)
+{
+    int64_t s = (cand_capacity + 2047) / 2048;                 // sub-lists of ~2k candidates at a full list
+    if (s < 2) s = 2;
+    if (s > 32) s = 32;
+    return (int)s;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t sihl_od_nms_split_workspace_bytes(int batch, int64_t cand_capacity, int k)
+{
+    if (batch <= 0 || cand_capacity <= 0 || k <= 0) return 0;
+    const size_t S = (size_t)split_factor(cand_capacity), B = (size_t)batch, cap = (size_t)cand_capacity, K = (size_t)k;
+    size_t bytes = 0;
+    bytes += align256(B * cap * 8) + align256(B * cap * 16) + align256(B * cap * 4);          // key2, box2, cls2
+    bytes += 2 * align256(B * S * 4);                                                         // sub_count, sub_offset
+    bytes += align256(B * S * 8) + align256(B * S * K * 8) + align256(B * S * K * 4) + align256(B * S * K * 8) +
+             align256(B * S * K * 16);                                                        // per-sub-list outputs
+    bytes += align256((size_t)(2 * B * cap + 2) * kWsItemBytes);                              // k_nms workspace for long sub-lists
+    return bytes;
+}
+
+extern "C" int sihl_od_nms_topk_split(int32_t *cand_count, int64_t cand_capacity, const uint64_t *cand_key,
+                                      const float *cand_box, const int32_t *cand_cls, int batch, float iou_thr, int k,
+                                      int64_t *num_instances, float *scores, int64_t *classes, float *boxes, void *workspace,
+                                      int reset_counts, void *stream)
+{
+    SIHL_CHECK_ARG(cand_count && cand_key && cand_box && cand_cls, "NULL input");
+    SIHL_CHECK_ARG(num_instances && scores && classes && boxes && workspace, "NULL output / workspace");
+    SIHL_CHECK_ARG(cand_capacity >= 1 && (int64_t)batch * cand_capacity < (1ll << 30) && k >= 1 && k <= 4096, "bad sizes");
+    if (batch <= 0) return SIHL_OD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = split_factor(cand_capacity);
+    const size_t B = (size_t)batch, cap = (size_t)cand_capacity, K = (size_t)k;
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    auto take = [&](size_t bytes) { unsigned char *ptr = w; w += align256(bytes); return ptr; };
+    SplitParams sp;
+    sp.cand_count = cand_count; sp.cap = cand_capacity;
+    sp.key = reinterpret_cast<const unsigned long long *>(cand_key); sp.box = reinterpret_cast<const float4 *>(cand_box);
+    sp.cls = cand_cls; sp.S = S; sp.reset_counts = reset_counts;
+    sp.key2 = reinterpret_cast<unsigned long long *>(take(B * cap * 8));
+    sp.box2 = reinterpret_cast<float4 *>(take(B * cap * 16));
+    sp.cls2 = reinterpret_cast<int32_t *>(take(B * cap * 4));
+    sp.sub_count = reinterpret_cast<int32_t *>(take(B * S * 4));
+    sp.sub_offset = reinterpret_cast<int32_t *>(take(B * S * 4));
+    int64_t *sub_num = reinterpret_cast<int64_t *>(take(B * S * 8));
+    unsigned long long *sub_keys = reinterpret_cast<unsigned long long *>(take(B * S * K * 8));
+    float *sub_scores = reinterpret_cast<float *>(take(B * S * K * 4));
+    int64_t *sub_classes = reinterpret_cast<int64_t *>(take(B * S * K * 8));
+    float4 *sub_boxes = reinterpret_cast<float4 *>(take(B * S * K * 16));
+    unsigned char *nms_ws = take((size_t)(2 * B * cap + 2) * kWsItemBytes);
+    k_nms_split_lists<<<batch, 1024, 0, st>>>(sp);
+    SIHL_CHECK_LAUNCH("k_nms_split_lists");
+    NmsParams p = {};
+    p.cand_count = sp.sub_count; p.cap = cand_capacity; p.list_offsets = sp.sub_offset;
+    p.cand_key = sp.key2; p.cand_box = sp.box2; p.cand_cls = sp.cls2;
+    p.mode = 0; p.iou_thr = iou_thr; p.K = k; p.reset_counts = 0;
+    p.num_instances = sub_num; p.out_scores = sub_scores; p.out_classes = sub_classes; p.out_boxes = sub_boxes;
+    p.out_keys = sub_keys; p.workspace = nms_ws; p.ws_stride = 0;
+    // sub-lists rarely exceed 2048 candidates: half the shared memory per CTA lets two of them share an SM
+    int rc = launch_nms(p, batch * S, cand_capacity, st, kSmemItems / 2);
+    if (rc) return rc;
+    MergeParams mp;
+    mp.S = S; mp.K = k; mp.sub_num = sub_num; mp.sub_keys = sub_keys; mp.sub_scores = sub_scores; mp.sub_classes = sub_classes;
+    mp.sub_boxes = sub_boxes; mp.num_instances = num_instances; mp.out_scores = scores; mp.out_classes = classes;
+    mp.out_boxes = reinterpret_cast<float4 *>(boxes);
+    const size_t stage = (size_t)S * K * 8;
+    if (stage <= 96 * 1024) {
+        static thread_local bool merge_attr = false;
+        if (!merge_attr) {
+            rc = cuda_status(cudaFuncSetAttribute(k_nms_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024),
+                             "cudaFuncSetAttribute(k_nms_merge)");
+            if (rc) return rc;
+            merge_attr = true;
+        }
+        k_nms_merge<true><<<batch, 512, stage, st>>>(mp);
+    } else {
+        k_nms_merge<false><<<batch, 512, 0, st>>>(mp);
+    }
+    SIHL_CHECK_LAUNCH("k_nms_merge");
+    return SIHL_OD_OK;
+}

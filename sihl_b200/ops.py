@@ -440,12 +440,29 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
     _native.check(rc, name)
 
 
+SPLIT_NMS_FROM = 4096      # list capacity beyond which the one-shot postprocess uses the class-split NMS
+
+
 def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Optional[tuple] = None,
-             reset_counts: bool = False):
+             reset_counts: bool = False, split: bool = False):
+    """Class-aware NMS + top-k over the candidate lists.  ``split``: the class-split multi-CTA variant for long lists
+    (same results; thousands of candidates per image)."""
     dev = cand.count.device
     if out is None:
         out = (torch.empty((batch,), dtype=torch.int64, device=dev), torch.empty((batch, k), dtype=torch.float32, device=dev),
                torch.empty((batch, k), dtype=torch.int64, device=dev), torch.empty((batch, k, 4), dtype=torch.float32, device=dev))
+    if split:
+        need = int(_lib().sihl_od_nms_split_workspace_bytes(int(batch), cand.capacity, int(k)))
+        ws = getattr(cand, "_split_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            cand._split_ws = ws
+        with torch.cuda.device(dev):
+            rc = _lib().sihl_od_nms_topk_split(_p(cand.count), cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(batch),
+                                               float(iou_thr), int(k), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(ws),
+                                               int(reset_counts), _stream(dev))
+        _native.check(rc, "sihl_od_nms_topk_split")
+        return out
     with torch.cuda.device(dev):
         rc = _lib().sihl_od_nms_topk(_p(cand.count), cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(batch),
                                      float(iou_thr), int(k), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
@@ -456,16 +473,22 @@ def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Op
 
 def dense_postprocess(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, levels, img_w: int, img_h: int,
                       score_thr: float = 0.05, iou_thr: float = 0.5, max_instances: int = 100,
-                      cand: Optional[CandidateBuffers] = None, mode: str = "dense"):
+                      cand: Optional[CandidateBuffers] = None, mode: str = "dense", split_nms: Optional[bool] = None):
     """Extension (no reference counterpart): dense decode of every location + class-aware NMS.
     Output format of ``ObjectDetection.forward`` (ref :122), zero padded past ``num_instances``.
-    ``mode``: see :func:`dense_decode` (identical results)."""
+    ``mode``: see :func:`dense_decode` (identical results).  ``split_nms``: class-split NMS (default: whenever the
+    lists can hold more than ``SPLIT_NMS_FROM`` candidates)."""
     B, A = loc_logits.shape
     offsets, scales, _ = anchor_tables(levels, img_w, img_h, loc_logits.device)
     if cand is None:
         cand = CandidateBuffers.allocate(B, A, loc_logits.device)
     dense_decode(loc_logits, cls_logits, box_raw, offsets, scales, img_w, img_h, score_thr, cand, mode=mode)
-    return nms_topk(cand, B, iou_thr, max_instances)
+    if split_nms is None:
+        # long lists on few images: one CTA per image would leave the GPU idle; with many images the single-CTA
+        # kernel already fills it (measured: profiles/r01_postprocess_sweep.json)
+        n_sub = min(32, max(2, -(-cand.capacity // 2048)))
+        split_nms = cand.capacity > SPLIT_NMS_FROM and B * n_sub <= 296
+    return nms_topk(cand, B, iou_thr, max_instances, split=split_nms)
 
 
 def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: float,

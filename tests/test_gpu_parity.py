@@ -309,13 +309,14 @@ def test_nms_idempotent_and_one_class():
 
 @pytest.mark.parametrize("geom,C,B,loc_mean,loc_std", [("test_128", 16, 5, -2.0, 2.0), ("cfg0_320", 10, 3, -2.0, 2.0),
                                                         ("cfg1_640", 80, 4, -5.0, 1.0), ("cfg1_640", 80, 2, -4.0, 2.0)])
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("mode", ops.DECODE_MODES)
-def test_dense_postprocess(geom, C, B, loc_mean, loc_std, mode):
+def test_dense_postprocess(geom, C, B, loc_mean, loc_std, mode, split):
     g, levels, W, H = _geom(geom)
     A = len(g["anchors"])
     maps = synth.dense_maps_np(4242, B, A, C, loc_mean, loc_std)
     loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(maps.cls_logits)
-    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, W, H, 0.05, 0.5, 100, mode=mode)
+    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, W, H, 0.05, 0.5, 100, mode=mode, split_nms=split)
     o_num, o_scores, o_cls, o_boxes, ncand = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw,
                                                                     g["offsets"], g["scales"], W, H, 0.05, 0.5, 100)
     np.testing.assert_array_equal(num.cpu().numpy(), o_num)
@@ -423,16 +424,18 @@ def test_crowd_config_nms_30k_candidates():
     np.testing.assert_array_equal(keep, orc.batched_nms(boxes, scores, classes, 0.5))
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("mode", ops.DECODE_MODES)
 @pytest.mark.parametrize("size,batch", [(640, 3), (1280, 2)])
-def test_inference_sweep_postprocess(size, batch, mode):
+def test_inference_sweep_postprocess(size, batch, mode, split):
     """configs[4]: decode + NMS at 640-1280 px with loc ~ N(-4, 2^2) (about 30 % of the locations pass 0.05)."""
     levels = synth.level_sizes(size, size)
     off, sc, an = orc.anchors(levels, size, size)
     A, C = len(an), 80
     maps = synth.dense_maps_np(900 + size, batch, A, C, loc_mean=-4.0, loc_std=2.0)
     loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(maps.cls_logits)
-    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, size, size, 0.05, 0.5, 100, mode=mode)
+    num, scores, classes, boxes = ops.dense_postprocess(loc, cls, box, levels, size, size, 0.05, 0.5, 100, mode=mode,
+                                                        split_nms=split)
     o_num, o_scores, o_cls, o_boxes, ncand = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw, off, sc,
                                                                     size, size, 0.05, 0.5, 100)
     assert ncand.min() > 0.2 * A
@@ -612,3 +615,26 @@ def test_fused_loss_sum_exchange_against_a_scripted_peer():
     torch.cuda.synchronize()
     assert 1.5 < time.perf_counter() - t0 < 10.0
     assert torch.isnan(out.losses).all()
+
+
+@pytest.mark.parametrize("C,K,loc_mean", [(80, 100, -4.0), (1, 100, -4.0), (3, 300, 0.0), (80, 1000, -7.0)])
+def test_class_split_nms_equals_single_cta_nms(C, K, loc_mean):
+    """sihl_od_nms_topk_split (candidates dealt to per-class-group sub-lists, one CTA each, merged) == sihl_od_nms_topk:
+    many classes, ONE class (everything lands in one sub-list, beyond shared memory), few classes with more outputs
+    than one sub-list yields, and almost no candidates (empty sub-lists, K larger than what survives)."""
+    size, B = 1024, 3
+    levels = synth.level_sizes(size, size)
+    off, sc, anchors = ops.anchor_tables(levels, size, size, DEV)
+    A = anchors.shape[0]
+    maps = synth.dense_maps_np(700 + C, B, A, C, loc_mean, 2.0)
+    loc, box, cls = _t(maps.loc_logits), _t(maps.box_raw), _t(maps.cls_logits)
+    outs = []
+    for split in (False, True):
+        cand = ops.CandidateBuffers.allocate(B, A, DEV)
+        ops.dense_decode(loc, cls, box, off, sc, size, size, 0.05, cand, mode="candidate_first")
+        n_cand = cand.count.clone()
+        outs.append(ops.nms_topk(cand, B, 0.5, K, reset_counts=True, split=split))
+        assert int(cand.count.abs().sum()) == 0                     # consumed and re-zeroed in both variants
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(n_cand.max()) > (4096 if loc_mean > -5 else 0)
