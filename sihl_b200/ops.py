@@ -459,7 +459,7 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
     _native.check(rc, name)
 
 
-SPLIT_NMS_FROM = 4096      # list capacity beyond which the one-shot postprocess uses the class-split NMS
+SPLIT_NMS_FROM = 16384     # list capacity (locations per image) from which the one-shot postprocess uses the class-split NMS
 
 
 def nms_topk(cand: CandidateBuffers, batch: int, iou_thr: float, k: int, out: Optional[tuple] = None,
@@ -503,10 +503,12 @@ def dense_postprocess(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, l
         cand = CandidateBuffers.allocate(B, A, loc_logits.device)
     dense_decode(loc_logits, cls_logits, box_raw, offsets, scales, img_w, img_h, score_thr, cand, mode=mode)
     if split_nms is None:
-        # long lists on few images: one CTA per image would leave the GPU idle; with many images the single-CTA
-        # kernel already fills it (measured: profiles/r01_postprocess_sweep.json)
+        # The list lengths are only known on the device, so the choice goes by what can happen: big images (>= 896^2)
+        # can yield many thousands of candidates, which one CTA per image would serialise on a few SMs; with many
+        # images the single-CTA kernel already fills the GPU, and for the few hundred candidates of a 640^2 image it is
+        # 3x cheaper than three launches (measured: profiles/r01_postprocess_sweep.json)
         n_sub = min(32, max(2, -(-cand.capacity // 2048)))
-        split_nms = cand.capacity > SPLIT_NMS_FROM and B * n_sub <= 296
+        split_nms = cand.capacity >= SPLIT_NMS_FROM and B * n_sub <= 296
     return nms_topk(cand, B, iou_thr, max_instances, split=split_nms)
 
 
