@@ -7,14 +7,20 @@ A *step* is one pass of the hot path over one batch of synthetic head outputs pe
 CIoU top-9 assignment + the four loss reductions (train chain) and dense decode + class-aware
 NMS (inference chain).  Workload ``cfg1`` = BASELINE.json configs[1]: 640x640, batch 64 per GPU,
 P3-P7 (A=8525), 80 classes, 100 gt / image, synthetic maps (SURVEY.md §8d distributions).
-Multi-GPU = the same batch per GPU (weak scaling, configs[2]: 512 images on 8 GPUs) with one
-all-reduce of the 8 fp64 loss sums per step (NCCL), overlapped with the next step.
+Multi-GPU = the same batch per GPU (weak scaling, configs[2]: 512 images on 8 GPUs); the one
+exchange, the 8 fp64 loss sums, is done by the loss kernel itself over NVLink peer memory
+(``--allreduce nccl``: an NCCL all-reduce node + a finalize launch instead).
 
-Prints ONE JSON line (rank 0).  ``value``: inputs resident in HBM, CUDA-graph replay, device
-timed.  ``e2e``: the same step through the public API with HOST (pinned) inputs, H2D and D2H
-inside the timed region.  ``roofline``: the dominant kernel (k_dense_decode) timed alone
-against MEASURED_PEAKS.json.  ``cpu_baseline``: the reference's operator sequence
-(oracle/torch_restatement.py, torch CPU, all host threads) on a bounded sample.
+Prints ONE JSON line (rank 0):
+  ``value``              inputs resident in HBM, CUDA-graph replay, device timed, dense class-map scan
+  ``other_decode_mode``  the same step with the candidate-first decode (same outputs), same run
+  ``e2e``                the step through the public API from pinned HOST buffers, results read back
+                         every step; class / box maps are read in place over PCIe (candidate-first)
+  ``e2e_full_upload``    the same with every input tensor uploaded
+  ``roofline``           the dominant kernel (k_dense_decode_tma) timed alone against MEASURED_PEAKS.json
+  ``roofline_step``      the whole step against SURVEY.md §8d's algorithmic bytes per image
+  ``cpu_baseline``       the reference's operator sequence (oracle/torch_restatement.py, torch CPU, all host
+                         threads) on a bounded sample; ``gpu_eager_reference``: the same on this GPU
 
 ``--impl reference``: only that CPU arm (rank 0), same metric/unit/config.
 """
