@@ -440,9 +440,10 @@ def run_ours(args, w, world, rank, local_rank):
     pipe.cand.count = counts_saved
     cand_mean = float(scratch[:iters].float().mean().item())
     k_ms = k0.elapsed_time(k1) / iters
-    # algorithmic bytes per launch (SURVEY.md §8d inference figure): every class logit, raw box and location
-    # logit read once (4*A*(C+5) per image) + 28 B (key 8, box 16, class 4) written per candidate
-    decode_bytes = B * 4 * A * (C + 5) + B * cand_mean * 28
+    # algorithmic bytes per launch: every class logit and location logit read once (4*A*(C+1) per image), the raw
+    # box (16 B) read and key 8 + box 16 + class 4 = 28 B written per candidate.  (SURVEY.md §8d counts 16*A for the
+    # raw boxes of every location; the kernel reads them for candidates only, so that figure would overstate it.)
+    decode_bytes = B * 4 * A * (C + 1) + B * cand_mean * (16 + 28)
     achieved = decode_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -455,11 +456,14 @@ def run_ours(args, w, world, rank, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_dense_decode", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": decode_bytes}
-    # whole step against the survey's per-image figure: train 20A+24G+(16+4C)P + infer 4A(C+5)+28K+8
-    step_bytes_per_image = 20 * A + 24 * G + (16 + 4 * C) * P_bar + 4 * A * (C + 5) + 28 * K + 8
+    # whole step: train 20A+24G+(16+4C)P + infer 4A(C+1)+16*cand+28K+8 bytes per image — SURVEY.md §8d's figure minus
+    # the raw boxes of the locations that are not candidates (never read); the survey's own figure is reported beside it
+    step_bytes_survey = 20 * A + 24 * G + (16 + 4 * C) * P_bar + 4 * A * (C + 5) + 28 * K + 8
+    step_bytes_per_image = step_bytes_survey - 16 * (A - cand_mean)
     step_gbs = step_bytes_per_image * B * args.steps / (ms * 1e-3) / 1e9          # per GPU
     roofline_step = {"bytes_per_image": step_bytes_per_image, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": step_gbs / peak, "per_gpu": True}
+                     "frac": step_gbs / peak, "per_gpu": True, "bytes_per_image_survey_8d": step_bytes_survey,
+                     "frac_survey_8d_bytes": step_bytes_survey * B * args.steps / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end: host (pinned) inputs -> H2D -> step -> D2H of losses + detections, every step
     e2e = e2e_full = None

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) k_dense_decode_v4(DenseDecodeParams p)
 // keeps in registers, and every byte is read from HBM exactly once.  Consumers: 4 lanes per
 // row, conflict-free LDS.128, first-argmax as above.
 // ---------------------------------------------------------------------------
-constexpr int kChunkRows = 64;
+constexpr int kChunkRows = 64;             // rows per ring stage == rows one pass of the 256-thread CTA covers (4 lanes per row)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
@@ -385,21 +385,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 constexpr int kStageCap = 256;
 
 struct StagedCand {
-    float4 raw;
     int row_lo, row_hi;      // 64-bit row index
     float x;
     int arg;
 };
 
-__device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const StagedCand *list, int count)
+// One warp turns up to 32 staged entries (one per lane) into candidates: no block-level synchronisation inside.  Entries
+// passed the conservative logit pre-filter only; the exact test sigmoid(x) > thr (ref :113) is made here.
+// `entry`: this lane's staged entry or nullptr; all 32 lanes of the warp must call.
+__device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const StagedCand *entry)
 {
     const int lane = threadIdx.x & 31;
-    for (int i0 = 0; i0 < count; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        const bool have = i < count;
-        StagedCand c = list[have ? i : 0];
-        const int64_t row = ((int64_t)c.row_hi << 32) | (unsigned)c.row_lo;
-        const int b = (int)(row / p.A), a = (int)(row - (int64_t)b * p.A);
+    const bool small = (int64_t)p.batch * p.A < (1ll << 31);
+    __syncwarp();
+    {
+        StagedCand c;
+        c.row_lo = c.row_hi = c.arg = 0; c.x = 0.f;
+        if (entry != nullptr) c = *entry;
+        const float s = entry != nullptr ? sigmoid_f(c.x) : 0.f;
+        const bool have = entry != nullptr && s > p.score_thr;
+        const int64_t row = have ? (((int64_t)c.row_hi << 32) | (unsigned)c.row_lo) : 0;
+        const int b = small ? (int)((unsigned)row / (unsigned)p.A) : (int)(row / p.A);
+        const int a = (int)(row - (int64_t)b * p.A);
+        // everything that does not depend on the output slot first: the raw box is only needed for candidates (2 % of
+        // the locations at cfg1; its line was prefetched into L2 when the candidate was staged), and the decode
+        // arithmetic runs while the slot atomic below is in flight — at the end of the kernel this chain is the tail
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), off = raw, sc = raw;
+        if (have) {
+            raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + row);
+            off = __ldg(p.offsets + a);
+            sc = __ldg(p.scales + a);
+        }
         // one returning atomic per (warp, image) instead of one per candidate: neighbours in the list come from
         // the same 64-row chunk, i.e. almost always the same image (same-address atomics serialise in L2)
         const unsigned act = __ballot_sync(kFullMask, have);
@@ -412,46 +428,46 @@ __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const S
             base = __shfl_sync(peers, base, leader);
             slot = base + __popc(peers & ((1u << lane) - 1u));
         }
-        if (!have || slot >= p.cap) continue;
-        const float s = sigmoid_f(c.x);
-        const float4 off = __ldg(p.offsets + a), sc = __ldg(p.scales + a);
-        const int64_t o = (int64_t)b * p.cap + slot;
-        p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
-        p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, c.raw.x) * p.img_w, decode_norm(off.y, sc.y, c.raw.y) * p.img_h,
-                                    decode_norm(off.z, sc.z, c.raw.z) * p.img_w, decode_norm(off.w, sc.w, c.raw.w) * p.img_h);
-        p.cand_cls[o] = c.arg;
+        const float4 box = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
+                                       decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
+        if (have && slot < p.cap) {
+            const int64_t o = (int64_t)b * p.cap + slot;
+            p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
+            p.cand_box[o] = box;
+            p.cand_cls[o] = c.arg;
+        }
     }
+    __syncwarp();
 }
 
 template <int VPL, bool EXACT>
 __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, int stages, int n_chunks)
 {
     extern __shared__ __align__(128) unsigned char s_ring[];
-    __shared__ StagedCand s_list[kStageCap];
-    __shared__ int s_count;
-    const int tid = threadIdx.x, gl = tid & 3, r = tid >> 2;
+    __shared__ StagedCand s_list[kStageCap];                      // one 32-entry segment per warp: no atomics to append
+    __shared__ int s_seg_count[8];
+    static_assert(kStageCap == 256, "8 warps x 32 staged candidates");
+    const int tid = threadIdx.x, gl = tid & 3, r = tid >> 2, lane = tid & 31, warp = tid >> 5;
+    int n_staged = 0;                                             // this warp's segment fill (warp-uniform)
     const int C4 = p.C >> 2;
     const int64_t rows = (int64_t)p.batch * p.A;
-    // per stage: 64 rows of class logits | 64 raw boxes | 64 location logits
-    const uint32_t cls_bytes = (uint32_t)kChunkRows * (uint32_t)p.C * 4u, box_bytes = kChunkRows * 16u, loc_bytes = kChunkRows * 4u;
-    const uint32_t stage_bytes = cls_bytes + box_bytes + loc_bytes;
+    // per stage: 64 rows of class logits — ONE bulk copy per stage.  The location logit of a row is a 4-byte
+    // coalesced load one chunk ahead (one lane per row), the raw box is read for candidates only (flush_staged):
+    // small bulk copies cost the TMA unit as much as big ones (measured with tools/micro/read_bw.cu: a ring of
+    // single 21 KB copies reaches the 6.3 TB/s read ceiling, the former 3-copy stage did not).
+    const uint32_t stage_bytes = (uint32_t)kChunkRows * (uint32_t)p.C * 4u;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + (size_t)stages * stage_bytes);
 
     const uint64_t policy = l2_evict_first_policy();
     auto issue = [&](int stage, int chunk) {                      // one elected thread
         const int64_t row0 = (int64_t)chunk * kChunkRows;
         const int64_t n = rows - row0 < kChunkRows ? rows - row0 : kChunkRows;
-        unsigned char *dst = s_ring + (size_t)stage * stage_bytes;
-        const uint32_t cb = (uint32_t)n * (uint32_t)p.C * 4u, bb = (uint32_t)n * 16u;
-        const bool full = n == kChunkRows;                        // partial tail: loc is read directly (16-B size rule)
-        mbar_expect_tx(bars + stage, cb + bb + (full ? loc_bytes : 0u));
-        bulk_g2s(dst, p.cls + row0 * p.C, cb, bars + stage, policy);
-        bulk_g2s(dst + cls_bytes, p.box_raw + row0 * 4, bb, bars + stage, policy);
-        if (full) bulk_g2s(dst + cls_bytes + box_bytes, p.loc + row0, loc_bytes, bars + stage, policy);
+        const uint32_t cb = (uint32_t)n * (uint32_t)p.C * 4u;
+        mbar_expect_tx(bars + stage, cb);
+        bulk_g2s(s_ring + (size_t)stage * stage_bytes, p.cls + row0 * p.C, cb, bars + stage, policy);
     };
 
     if (tid == 0) {
-        s_count = 0;
         for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -464,16 +480,21 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
 
     // sigmoid(x) > thr is monotone in x: compare logits against the smallest logit whose sigmoid passes
     const float x_thr = p.logit_thr;
+    auto load_loc = [&](int chunk) -> float {                     // lane gl == 0 of every row group
+        const int64_t row = (int64_t)chunk * kChunkRows + r;
+        return (gl == 0 && chunk < n_chunks && row < rows) ? __ldcs(p.loc + row) : -CUDART_INF_F;
+    };
+    float x_next = load_loc((int)blockIdx.x);
     int s = 0;                                                    // ring slot and its phase, carried (no k % stages,
     uint32_t phase = 0;                                           // k / stages: a runtime divisor costs ~35 instructions)
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const float x = x_next;
+        x_next = load_loc(c + (int)gridDim.x);                    // in flight while this chunk is consumed
         mbar_wait(bars + s, phase);
         const unsigned char *base = s_ring + (size_t)s * stage_bytes;
-#pragma unroll 1
-        for (int rr = r; rr < kChunkRows; rr += 64) {             // 256 threads cover 64 rows per pass
-        const int64_t row = (int64_t)c * kChunkRows + rr;
+        const int64_t row = (int64_t)c * kChunkRows + r;
         const bool ok = row < rows;
-        const float4 *src = reinterpret_cast<const float4 *>(base) + rr * C4;
+        const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
         // first arg-max of the row in two cheap steps: the row maximum (max tree + 2 shuffles), then the
         // lowest class index whose logit equals it (reverse predicated scan + 2 shuffles); half the
         // instructions of a running (value, index) comparison.  NaN logits never win (as before).
@@ -503,34 +524,44 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
         arg = min(arg, __shfl_xor_sync(kFullMask, arg, 1));
         arg = min(arg, __shfl_xor_sync(kFullMask, arg, 2));
         if (arg == 0x7fffffff) arg = 0;                           // all-NaN row
-        if (gl == 0 && ok) {
-            const bool full = rows - (int64_t)c * kChunkRows >= kChunkRows;
-            const float x = full ? reinterpret_cast<const float *>(base + cls_bytes + box_bytes)[rr] : __ldcs(p.loc + row);
-            if (x >= x_thr && sigmoid_f(x) > p.score_thr) {
-                const int i = atomicAdd(&s_count, 1);             // < kStageCap: flushed below before it can overflow
-                StagedCand sc;
-                sc.raw = reinterpret_cast<const float4 *>(base + cls_bytes)[rr];
-                sc.row_lo = (int)(row & 0xffffffff); sc.row_hi = (int)(row >> 32);
-                sc.x = x; sc.arg = arg;
-                s_list[i] = sc;
-            }
+        // Anything on a candidate's path delays the barrier below and with it the refill of this stage (a chunk has a
+        // candidate 3 times out of 4 at cfg1): only the logit pre-filter, a ballot and one shared-memory store stay in
+        // the loop (no atomic: the warp owns its segment and carries the fill count in a register); the sigmoid test,
+        // the slot atomic, the box decode and the stores happen in flush_staged.
+        const bool staged = gl == 0 && ok && x >= x_thr;
+        const unsigned sm = __ballot_sync(kFullMask, staged);
+        if (staged) {
+            StagedCand sc;
+            sc.row_lo = (int)(row & 0xffffffff); sc.row_hi = (int)(row >> 32);
+            sc.x = x; sc.arg = arg;
+            s_list[warp * 32 + n_staged + __popc(sm & ((1u << lane) - 1u))] = sc;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.box_raw + 4 * row));      // read at flush time
         }
-        }
+        n_staged += __popc(sm);
         __syncthreads();                                          // every lane is done with stage s
         if (tid == 0) {
             const int next = c + stages * gridDim.x;
             if (next < n_chunks) issue(s, next);
         }
-        if (s_count > kStageCap - kChunkRows) {                   // block-uniform: read after the barrier
-            flush_staged(p, s_list, s_count);
-            __syncthreads();
-            if (tid == 0) s_count = 0;
-            __syncthreads();
+        if (n_staged > 32 - 8) {                                  // warp-uniform: the segment could overflow next chunk
+            flush_staged(p, lane < n_staged ? s_list + warp * 32 + lane : nullptr);
+            n_staged = 0;
         }
         if (++s == stages) { s = 0; phase ^= 1u; }
     }
+    // What is left (a handful per warp at cfg1) is flushed by the CTA as ONE list: every CTA of the grid ends at the
+    // same time, and 8 slot atomics per CTA on the 64 per-image counters queue up at the L2 — one or two do not.
+    if (lane == 0) s_seg_count[warp] = n_staged;
     __syncthreads();
-    flush_staged(p, s_list, s_count);
+    int total = 0, mine_seg = -1, mine_idx = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int cnt = s_seg_count[w];
+        if (mine_seg < 0 && tid < total + cnt) { mine_seg = w; mine_idx = tid - total; }
+        total += cnt;
+    }
+    if ((tid & ~31) < total)                                       // warp-uniform: this warp has entries of the merged list
+        flush_staged(p, tid < total ? s_list + mine_seg * 32 + mine_idx : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -736,7 +767,7 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
     if (aligned && loc_aligned && c4 <= 32 && rows >= 4 * kChunkRows) {
         const int vpl = (c4 + 3) / 4;
         const bool exact = vpl * 4 == c4;
-        const size_t stage_bytes = (size_t)kChunkRows * num_classes * 4 + kChunkRows * 16 + kChunkRows * 4;
+        const size_t stage_bytes = (size_t)kChunkRows * num_classes * 4;
         // 2 stages x 2 CTAs per SM: measured on B200 the kernel is already at the HBM roof with ~87 KB in
         // flight per SM (3 and 4 stages give the same 32 us), and the smaller ring leaves ~120 KB of shared
         // memory per SM to the kernels of the other chain / the neighbouring step running concurrently
