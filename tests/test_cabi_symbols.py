@@ -64,3 +64,19 @@ def test_ops_reject_cpu_tensors():
         ops.topk_locations(torch.zeros(2, 300), 100)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         ops.dense_loss(torch.zeros(10), None, torch.zeros(10), torch.zeros(8, dtype=torch.float64))
+
+
+def test_exchange_and_split_helpers_without_a_gpu():
+    """Size queries and argument checks of the multi-GPU exchange / class-split NMS entries are host-only."""
+    lib = _native.load()
+    assert lib.sihl_od_exchange_region_bytes(0) == 0 and lib.sihl_od_exchange_region_bytes(17) == 0
+    assert lib.sihl_od_exchange_region_bytes(8) == 1280                # (18 * 8 + 1) words of 8 bytes, rounded to 256
+    assert lib.sihl_od_exchange_region_bytes(1) == 256
+    assert lib.sihl_od_nms_split_workspace_bytes(0, 100, 100) == 0
+    small, big = lib.sihl_od_nms_split_workspace_bytes(1, 8525, 100), lib.sihl_od_nms_split_workspace_bytes(16, 34100, 100)
+    assert 0 < small < big
+    rc = lib.sihl_od_pos_loss_tiles_exchange(None, None, None, 1, 100, None, None, 10, 10, None, None, None, None, None, 0,
+                                             None, None, None, None, 99, 0, None)
+    assert rc == 1 and b"world" in lib.sihl_od_last_error_string()
+    rc = lib.sihl_od_quad_matching(None, 10, None, None, 1, 5, 0, None, None, None, None, None, None, None, None)
+    assert rc == 1 and b"topk" in lib.sihl_od_last_error_string()
