@@ -472,7 +472,7 @@ def run_ours(args, w, world, rank, local_rank):
 
     cpu = None
     if not multi and not args.skip_cpu_baseline:
-        r = cpu_reference_images_per_sec(w, args.cpu_sample, 3, 1)
+        r = cpu_reference_images_per_sec(w, max(args.cpu_sample, min(B, 32)), 10, 1)     # ~10 s of host work at cfg1
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['sample_images']} images of {args.workload} x {r['steps']} passes (assign + losses + dense decode "
                          f"+ per-class NMS) with the reference's torch/torchvision operator sequence, {r['cores']} threads"}
