@@ -256,11 +256,21 @@ def run_ours(args, w, world, rank, local_rank):
     fused = multi and args.allreduce == "fused"
     exchanges = []
 
+    fallback_note = []
+
     def attach(pipes):
-        """fused exchange: one region per pipeline (= per step in flight); collective across the ranks"""
+        """fused exchange: one region per pipeline (= per step in flight); collective across the ranks.  If peer memory
+        cannot be set up (no CUDA IPC / P2P between the ranks) every rank learns it and all fall back to NCCL."""
+        nonlocal fused
         if fused:
             from sihl_b200.dist import PeerExchange
-            ex = PeerExchange(dev, n_regions=len(pipes))
+            try:
+                ex = PeerExchange(dev, n_regions=len(pipes))
+            except RuntimeError as exc:
+                fused = False
+                args.allreduce = "nccl"
+                fallback_note.append(str(exc))
+                return pipes
             exchanges.append(ex)
             for i, pp in enumerate(pipes):
                 pp.attach_exchange(ex, i)
@@ -494,7 +504,8 @@ def run_ours(args, w, world, rank, local_rank):
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
         "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi and not fused else 0)) * args.steps,
-        "allreduce": (args.allreduce if multi else None), "allreduce_check": allreduce_check, "roofline": roofline, "roofline_step": roofline_step,
+        "allreduce": (("fused" if fused else "nccl") if multi else None), "allreduce_check": allreduce_check,
+        "allreduce_fallback": (fallback_note[0] if fallback_note else None), "roofline": roofline, "roofline_step": roofline_step,
         "other_decode_mode": other, "cpu_baseline": cpu, "gpu_eager_reference": eager, "clocks": clocks,
         "losses_check": losses,
     }

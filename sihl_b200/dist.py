@@ -5,7 +5,7 @@ ranks (one process per GPU) and the only exchange is the 8 fp64 loss partial sum
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -71,29 +71,55 @@ class PeerExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_regions = int(n_regions)
         self.region_bytes = int(self.lib.sihl_od_exchange_region_bytes(self.world))
-        assert self.region_bytes > 0, f"world size {self.world} not supported by the fused exchange"
-        self._own, self._opened = C.c_void_p(), {}
+        self._own, self._opened, self.blocks = C.c_void_p(), {}, []
+
+        def agree(error: Optional[str], what: str) -> None:
+            """Every rank reaches every checkpoint; if any rank failed, ALL raise (nobody is left in a collective)."""
+            flag = torch.tensor([0 if error is None else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()) != 0:
+                self._release()
+                raise RuntimeError(f"PeerExchange: {what} failed on " + ("this rank: " + error if error else "another rank"))
+
         handle = (C.c_ubyte * 64)()
+        error = None
         with torch.cuda.device(self.device):
-            _native.check(self.lib.sihl_od_exchange_create(self.world, self.n_regions, C.byref(self._own), handle),
-                          "sihl_od_exchange_create")
+            try:
+                if self.region_bytes <= 0:
+                    raise RuntimeError(f"world size {self.world} not supported by the fused exchange")
+                _native.check(self.lib.sihl_od_exchange_create(self.world, self.n_regions, C.byref(self._own), handle),
+                              "sihl_od_exchange_create")
+            except Exception as exc:                      # noqa: BLE001 - reported to every rank below
+                error = str(exc)
+            agree(error, "allocating / exporting the exchange block")
             mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
             gathered = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(gathered, mine, group=group)
-            self.blocks = []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.blocks.append(int(self._own.value))
-                    continue
-                raw = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
-                ptr = C.c_void_p()
-                _native.check(self.lib.sihl_od_exchange_open(raw, C.byref(ptr)), "sihl_od_exchange_open")
-                self._opened[r] = ptr
-                self.blocks.append(int(ptr.value))
-        dist.barrier(group=group)
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.blocks.append(int(self._own.value))
+                        continue
+                    raw = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
+                    ptr = C.c_void_p()
+                    _native.check(self.lib.sihl_od_exchange_open(raw, C.byref(ptr)), "sihl_od_exchange_open")
+                    self._opened[r] = ptr
+                    self.blocks.append(int(ptr.value))
+            except Exception as exc:                      # noqa: BLE001
+                error = str(exc)
+            agree(error, "mapping the peers' exchange blocks (CUDA IPC / peer access)")
         # per region: device array of `world` pointers (entry r = rank r's region), what the kernel indexes
         self._tables = torch.tensor([[b + i * self.region_bytes for b in self.blocks] for i in range(self.n_regions)],
                                     dtype=torch.int64, device=self.device)
+
+    def _release(self) -> None:
+        with torch.cuda.device(self.device):
+            for ptr in self._opened.values():
+                self.lib.sihl_od_exchange_close(ptr)
+            self._opened = {}
+            if self._own.value is not None:
+                self.lib.sihl_od_exchange_destroy(self._own)
+                self._own.value = None
 
     def peer_array(self, region: int) -> int:
         """Device address of region ``region``'s pointer table."""
