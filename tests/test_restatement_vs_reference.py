@@ -93,3 +93,13 @@ def test_quad_match_one_is_the_reference_quad_bbox_matching(name):
     sizes = [tuple(int(v) for v in s) for s in gold["level_sizes"]]
     mine = quad_anchors(sizes, range(case["bottom"], case["top"] + 1), case["top"], case["width"], case["height"], "cpu")
     assert torch.equal(mine, anchors)
+
+
+def test_quads_to_boxes_equals_the_reference():
+    """sihl_b200.heads.quadrilateral_detection.quads_to_boxes == QuadrilateralDetection.quads_to_boxes (ref :318-324)."""
+    from sihl_b200.heads.quadrilateral_detection import quads_to_boxes
+    Q = ref_loader.QuadrilateralDetection()
+    g = torch.Generator().manual_seed(3)
+    quads = torch.rand((17, 4, 2), generator=g) * 300
+    assert torch.equal(quads_to_boxes(quads), Q.quads_to_boxes(quads))
+    assert quads_to_boxes(quads[:0]).shape == (0, 4)
