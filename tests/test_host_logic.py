@@ -86,3 +86,21 @@ def test_losses_from_sums_matches_oracle_finalize():
     sums[6] = 0.0
     got = sdist.losses_from_sums(sums).numpy()
     assert got[1] == got[2] == got[3] == 0 and got[4] == got[0]                               # ref :165-172 early-out
+
+
+def test_decode_mode_validation_needs_no_gpu():
+    """Bad decode modes are rejected on the host before anything touches CUDA."""
+    import pytest
+    import torch
+
+    from sihl_b200 import ops
+    from sihl_b200.pipeline import DetectionHeadPipeline
+    assert ops.DECODE_MODES == ("dense", "candidate_first")
+    z = torch.zeros(1, 4)
+    with pytest.raises(ValueError, match="mode="):
+        ops.dense_decode(z, torch.zeros(1, 4, 8), torch.zeros(1, 4, 4), z, z, 8, 8, 0.05, None, mode="sparse")
+    with pytest.raises(ValueError, match="decode_mode="):
+        DetectionHeadPipeline([(2, 2)], 16, 16, 1, 8, 4, "cpu", decode_mode="sparse")
+    # pinned host maps are only accepted by the gathering (candidate-first) decode: the dense scan is device-only
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.dense_decode(z, torch.zeros(1, 4, 8), torch.zeros(1, 4, 4), z, z, 8, 8, 0.05, None, mode="dense")
