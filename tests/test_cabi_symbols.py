@@ -80,3 +80,15 @@ def test_exchange_and_split_helpers_without_a_gpu():
     assert rc == 1 and b"world" in lib.sihl_od_last_error_string()
     rc = lib.sihl_od_quad_matching(None, 10, None, None, 1, 5, 0, None, None, None, None, None, None, None, None)
     assert rc == 1 and b"topk" in lib.sihl_od_last_error_string()
+
+
+def test_header_is_plain_c99():
+    """include/sihl_od.h is the boundary a non-C++ host would bind: it must compile as C."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        return
+    header = os.path.join(ROOT, "include", "sihl_od.h")
+    res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", header], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
