@@ -92,3 +92,13 @@ def test_header_is_plain_c99():
     header = os.path.join(ROOT, "include", "sihl_od.h")
     res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", header], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_integration_stub_matches_the_abi():
+    """The ctypes stub shown in INTEGRATION.md declares as many arguments as the library takes."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in ("sihl_od_assign_select", "sihl_od_assign_resolve"):
+        m = re.search(r"_lib\." + name + r"\.argtypes = \[(.*?)\]", text, re.S)
+        assert m, name
+        n = len([x for x in m.group(1).replace("\n", " ").split(",") if x.strip()])
+        assert n == len(_native._SIGNATURES[name][1]), (name, n)
