@@ -19,8 +19,9 @@ Prints ONE JSON line (rank 0):
   ``e2e_full_upload``    the same with every input tensor uploaded
   ``roofline``           the dominant kernel (k_dense_decode_tma) timed alone against MEASURED_PEAKS.json
   ``roofline_step``      the whole step against SURVEY.md §8d's algorithmic bytes per image
-  ``cpu_baseline``       the reference's operator sequence (oracle/torch_restatement.py, torch CPU, all host
-                         threads) on a bounded sample; ``gpu_eager_reference``: the same on this GPU
+  ``cpu_baseline``       the reference's OWN functions (oracle/ref_path.py over oracle/ref_loader.py: /root/reference or
+                         the staged copy oracle/_ref/sihl_src; "port" only if neither exists) on the host cores, all
+                         threads, bounded sample; ``gpu_eager_reference``: the same code as torch eager on this GPU
 
 ``--impl reference``: only that CPU arm (rank 0), same metric/unit/config.
 """
@@ -72,7 +73,6 @@ def parse_args():
     ap.add_argument("--skip-gpu-eager", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--e2e-lanes", type=int, default=2, help="end-to-end steps in flight (own stream + buffers each)")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="images per CPU-baseline pass")
     return ap.parse_args()
 
 
@@ -103,16 +103,43 @@ def config_dict(w, args, world, extra=None):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference_images_per_sec(w, sample, steps, warmup, seed=1234, budget_s=150.0):
-    """The reference's operator sequence on the host cores (torch CPU, all threads): assignment +
-    losses (ref object_detection.py:134-217) + dense decode + torchvision per-class NMS (extension)."""
+def reference_kind():
+    """Which code the baseline legs run: the reference's own functions ("reference" = /root/reference, "oracle/_ref" =
+    the byte-for-byte staged copy that travels to the GPU box) or, if neither exists, the operator-for-operator
+    restatement ("port")."""
+    from oracle import ref_loader
+    return ref_loader.kind() if ref_loader.available() else "port"
+
+
+def make_reference_pass(w, levels, boxes, classes, loc, iou, box, cls):
+    """One pass of the path by the baseline on the given (host or device) tensors -> callable."""
     import torch
+    H, W, C, K = w["height"], w["width"], w["classes"], w["k"]
+    if reference_kind() != "port":
+        from oracle import ref_path
+        path = ref_path.ReferencePath(levels, H, W, C, boxes, classes, loc, iou, box, cls, K)
+        return lambda: path.one_pass(SCORE_THR, IOU_THR)
     from oracle import torch_restatement as tr
+
+    def one_pass():
+        with torch.no_grad():
+            tr.train_losses(levels, W, H, boxes, classes, loc, iou, box, cls, TOPK)
+            tr.dense_postprocess(levels, W, H, loc, box, cls, SCORE_THR, IOU_THR, K)
+    return one_pass
+
+
+def cpu_reference_images_per_sec(w, sample, steps, warmup, seed=1234, budget_s=150.0):
+    """The reference's own implementation of the path on the host cores (torch CPU, all threads): its unmodified
+    ``ObjectDetection.training_step`` — anchors, the per-image ``bbox_matching`` loop, compaction, four losses (ref
+    object_detection.py:124-217) — on synthetic head outputs, + dense decode + ``torchvision.ops.batched_nms`` (the
+    NMS extension; the reference has no NMS).  ``sample`` images per pass, shrunk only if steps x sample would exceed
+    ``budget_s`` of host time."""
+    import torch
     from sihl_b200 import synth
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    H, W, C, G, K = w["height"], w["width"], w["classes"], w["gt"], w["k"]
+    H, W, C, G = w["height"], w["width"], w["classes"], w["gt"]
     levels = synth.level_sizes(H, W)
     A = synth.num_anchors(levels)
 
@@ -122,44 +149,45 @@ def cpu_reference_images_per_sec(w, sample, steps, warmup, seed=1234, budget_s=1
         boxes = [torch.from_numpy(b.copy()) for b, _ in gt.per_image()]
         classes = [torch.from_numpy(c.copy()) for _, c in gt.per_image()]
         t = torch.from_numpy
-        return boxes, classes, t(maps.loc_logits), t(maps.iou_preds), t(maps.box_raw), t(maps.cls_logits)
-
-    def one_pass(data):
-        boxes, classes, loc, iou, box, cls = data
-        with torch.no_grad():
-            tr.train_losses(levels, W, H, boxes, classes, loc, iou, box, cls, TOPK)
-            tr.dense_postprocess(levels, W, H, loc, box, cls, SCORE_THR, IOU_THR, K)
+        return make_reference_pass(w, levels, boxes, classes, t(maps.loc_logits), t(maps.iou_preds), t(maps.box_raw),
+                                   t(maps.cls_logits))
 
     probe = make(1)
-    one_pass(probe)
-    t0 = time.perf_counter(); one_pass(probe); t_img = time.perf_counter() - t0
+    probe()
+    t0 = time.perf_counter(); probe(); t_img = time.perf_counter() - t0
     sample = max(1, min(sample, w["batch"], int(budget_s / max((steps + warmup) * t_img, 1e-9))))
-    data = make(sample)
+    one_pass = make(sample)
     for _ in range(warmup):
-        one_pass(data)
+        one_pass()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one_pass(data)
+        one_pass()
     elapsed = time.perf_counter() - t0
-    return dict(value=sample * steps / elapsed, seconds=elapsed, sample_images=sample, cores=cores, steps=steps)
+    return dict(value=sample * steps / elapsed, seconds=elapsed, sample_images=sample, cores=cores, steps=steps,
+                kind=reference_kind())
+
+
+REFERENCE_WHAT = ("the reference's unmodified ObjectDetection.training_step (assign + losses, ref object_detection.py:124-217) "
+                  "on synthetic head outputs + dense decode + torchvision.ops.batched_nms")
 
 
 def run_reference_arm(args, w, world, rank):
     if rank != 0:
         return
     steps, warmup = max(args.steps, 1), max(args.warmup, 0)
-    r = cpu_reference_images_per_sec(w, args.cpu_sample, steps, warmup)
-    sample = (f"{r['sample_images']} images per step of {args.workload} (assign + losses + dense decode + per-class NMS), "
-              f"torch {r['cores']} threads, {steps} steps")
+    r = cpu_reference_images_per_sec(w, w["batch"], steps, warmup)
+    sample = (f"{r['sample_images']} of {w['batch']} images per step of {args.workload}: {REFERENCE_WHAT}; torch "
+              f"{r['cores']} threads, {steps} steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, args, world, {"sample_images_per_step": r["sample_images"]}),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": config_dict(w, args, world),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is pure Python and cannot travel to the GPU box; this arm runs oracle/torch_restatement.py — "
-                "the reference's own torch/torchvision operator sequence — on the host CPU",
+        "note": ("kind 'reference' / 'oracle/_ref': the reference's own Python functions, imported unmodified (from /root/reference, "
+                 "or from the byte-for-byte staged copy oracle/_ref/sihl_src made by oracle/stage_reference.py, which travels to the "
+                 "GPU box); kind 'port': oracle/torch_restatement.py, only when neither exists"),
     }
     print(json.dumps(line), flush=True)
 
@@ -482,10 +510,10 @@ def run_ours(args, w, world, rank, local_rank):
 
     cpu = None
     if not multi and not args.skip_cpu_baseline:
-        r = cpu_reference_images_per_sec(w, max(args.cpu_sample, min(B, 32)), 10, 1)     # ~10 s of host work at cfg1
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"{r['sample_images']} images of {args.workload} x {r['steps']} passes (assign + losses + dense decode "
-                         f"+ per-class NMS) with the reference's torch/torchvision operator sequence, {r['cores']} threads"}
+        r = cpu_reference_images_per_sec(w, B, 20, 1, budget_s=25.0)     # 10-25 s of host work
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{r['sample_images']} of {B} images of {args.workload} x {r['steps']} passes: {REFERENCE_WHAT}; "
+                         f"{r['cores']} threads"}
 
     # ---- the reference's operator sequence as torch eager on THIS GPU (the bar SURVEY.md §2b names)
     eager = None
@@ -513,25 +541,24 @@ def run_ours(args, w, world, rank, local_rank):
 
 
 def gpu_eager_reference(w, x, levels, dev, passes=2):
-    """oracle/torch_restatement.py (the reference's torch/torchvision operator sequence, per-image Python loop and
-    host syncs included) on the same GPU and the same resident inputs: the eager-PyTorch bar for this path."""
+    """The reference's own code (oracle/ref_path.py: its unmodified ``training_step`` with the per-image Python loop and
+    host syncs, + dense decode + torchvision.ops.batched_nms) as torch eager on the same GPU and the same resident
+    inputs: the eager-PyTorch bar for this path."""
     import torch
-    from oracle import torch_restatement as tr
     H, W, B, K, G = w["height"], w["width"], w["batch"], w["k"], w["gt"]
     boxes = [x.gt.boxes[b * G:(b + 1) * G] for b in range(B)]
     classes = [x.gt.classes[b * G:(b + 1) * G] for b in range(B)]
+    one_pass = make_reference_pass(w, levels, boxes, classes, x.loc_logits, x.iou_preds, x.box_raw, x.cls_logits)
     best = None
-    with torch.no_grad():
-        for _ in range(passes + 1):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            tr.train_losses(levels, W, H, boxes, classes, x.loc_logits, x.iou_preds, x.box_raw, x.cls_logits, TOPK)
-            tr.dense_postprocess(levels, W, H, x.loc_logits, x.box_raw, x.cls_logits, SCORE_THR, IOU_THR, K)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return {"value": B / best, "unit": UNIT, "ms_per_step": best * 1e3,
-            "kind": "torch eager on the same GPU: the reference's operator sequence (oracle/torch_restatement.py), best of %d" % passes}
+    for _ in range(passes + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one_pass()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": B / best, "unit": UNIT, "ms_per_step": best * 1e3, "impl_kind": reference_kind(),
+            "kind": "torch eager on the same GPU: %s, best of %d" % (REFERENCE_WHAT, passes)}
 
 
 def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathered_rows=0.0):

@@ -48,6 +48,14 @@ extern "C" {
 #define SIHL_OD_MAX_PEERS  16      /* GPUs of one node taking part in the fused loss-sum exchange */
 #define SIHL_OD_IPC_HANDLE_BYTES 64
 #define SIHL_OD_NUM_SUMS   8
+#define SIHL_OD_MAX_BATCH_BY_VALUE 512  /* images whose gt counts sihl_od_train_assign can take from the host by value */
+
+/* Element type of the head-output maps handed to the sihl_od_train_* and *_t entry points (the reference trains
+ * with precision="16-mixed", ref examples/object_detection.py:294, and upcasts inside its autocast-off blocks,
+ * ref object_detection.py:178,:195,:206): the kernels load this type and upcast in registers. */
+#define SIHL_OD_F32  0
+#define SIHL_OD_F16  1
+#define SIHL_OD_BF16 2
 
 /* Layout of the fp64 partial-sum vector every loss kernel accumulates into and
  * the one thing that crosses GPUs (one all-reduce of 8 doubles per step):
@@ -198,8 +206,12 @@ SIHL_OD_API int sihl_od_pos_loss_tiles(const int32_t *pos_chunks, const int32_t 
  * rank order) — no NCCL launch, no separate finalize launch.  peer_regions: DEVICE
  * array of `world` device pointers, entry r = rank r's exchange region as seen
  * from this process (own region at [rank]).  Every rank must launch the same
- * sequence of calls on a region; a peer that never arrives ends the wait after
- * 2 s with NaN sums (no hang).  world == 1 behaves like sihl_od_pos_loss_tiles. */
+ * sequence of calls on a region — a shard without images (batch == 0) included:
+ * it pushes zeros.  A peer that never arrives ends the wait after the region's
+ * timeout (sihl_od_exchange_set_timeout; default 120 s) with NaN sums (no hang)
+ * and the step number is latched in the region (sihl_od_exchange_status), so the
+ * host can tell a timeout from a NaN loss.  world == 1 behaves like
+ * sihl_od_pos_loss_tiles. */
 SIHL_OD_API int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
                            const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
                            const float *offsets, const float *scales, int img_w, int img_h,
@@ -220,6 +232,11 @@ SIHL_OD_API int sihl_od_exchange_create(int world, int n_regions, void **block, 
 SIHL_OD_API int sihl_od_exchange_open(const unsigned char *ipc_handle, void **peer_block);
 SIHL_OD_API int sihl_od_exchange_close(void *peer_block);
 SIHL_OD_API int sihl_od_exchange_destroy(void *block);
+/* Per region (own block only; synchronous copies, not on the per-step path): the bound of the in-kernel wait in ns
+ * (0 = default 120 s), and the sticky status: *timed_out_step = the first step whose wait ran out (0 = none),
+ * *steps_done (may be NULL) = exchanges performed on this region so far. */
+SIHL_OD_API int sihl_od_exchange_set_timeout(void *region, int world, uint64_t timeout_ns);
+SIHL_OD_API int sihl_od_exchange_status(const void *region, int world, uint64_t *timed_out_step, uint64_t *steps_done);
 
 /* ref :163-172, :180, :197, :208, :210 — losses fp32 [5] =
  * [location, box, class, iou, total]; early-out when sums[6] == 0. */
@@ -248,6 +265,76 @@ SIHL_OD_API int sihl_od_pos_loss_bwd(const int32_t *pos_index, const int32_t *n_
                          const double *sums, const float *grad_terms,
                          float *dbox, float *dcls, void *stream);
 
+/* ---- the training step of the drop-in head, three calls ------------------
+ * What ObjectDetection.training_step (ref :124-217) does around its MLPs, with no host
+ * synchronisation, no allocation and a fixed launch sequence (CUDA-graph capturable):
+ *
+ *   sihl_od_train_assign   before the MLPs   ref :134-148 (+ :182-184 positive compaction)
+ *   sihl_od_train_loss     after the MLPs    ref :157-217 (four losses + total, early-out on device)
+ *   sihl_od_train_loss_bwd backward          SURVEY.md §7.4
+ *
+ * The number of positives P is only known on the device (pos_total).  The gathered-row MLPs of
+ * the reference (box_head / cls_head on flat_feats[o2m_mask], ref :184-200) therefore run on a
+ * STATIC number of rows pos_capacity >= P — min(topk * sumG, B * A) is always enough — of which
+ * the kernels read / differentiate the first P only: pos_index[P..capacity) is filled with 0
+ * (a valid row to gather) and the gradients of those rows are written as zeros.
+ *
+ * sihl_od_train_assign: select + resolve + compaction (3 launches).
+ *   Ground truth: gt_boxes [gt_capacity,4] device; per-image counts EITHER as gt_counts_host
+ *   (HOST int32 [batch], batch <= SIHL_OD_MAX_BATCH_BY_VALUE: passed to the kernel by value,
+ *   which then also writes gt_offsets [batch+1] — no host->device copy, no sync) OR, with
+ *   gt_counts_host == NULL, as gt_offsets [batch+1] already on the device (then the true total
+ *   is read from gt_offsets[batch] on the device and gt_capacity only sizes the launch, so a
+ *   captured graph can be replayed on new ground truth).
+ *   Outputs: assignment int64 [B,A], rel_iou [B,A] (as sihl_od_assign_resolve, relative),
+ *   pos_index int32 [pos_capacity] (flat b*A+a ascending = row order of flat_feats[o2m_mask],
+ *   then zeros), pos_total int32 [1] (true P, may exceed pos_capacity: callers size it so that
+ *   it cannot), sums [8] zeroed.  workspace: sihl_od_train_workspace_bytes(). */
+SIHL_OD_API size_t sihl_od_train_workspace_bytes(int batch, int64_t num_anchors, int gt_capacity, int topk);
+
+SIHL_OD_API int sihl_od_train_assign(const float *anchors, const float *anchor_terms, int64_t num_anchors,
+                         const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
+                         const float *gt_boxes, const int32_t *gt_counts_host, int32_t *gt_offsets,
+                         int batch, int gt_capacity, int topk,
+                         int64_t *assignment, float *rel_iou,
+                         int32_t *pos_index, int64_t pos_capacity, int32_t *pos_total,
+                         double *sums, void *workspace, size_t workspace_bytes, void *stream);
+
+/* sihl_od_train_loss: ONE launch for the four loss sums (dense BCE / MSE over [B*A], weighted
+ * CIoU loss / cross-entropy over the first P compact rows) and — if losses != NULL — the five
+ * losses [location, box, class, iou, total] written by the last CTA (ref :163-172 early-out
+ * included).  losses == NULL leaves sums for an all-reduce + sihl_od_loss_finalize.
+ * Maps of element type map_dtype: loc_logits [B*A], iou_preds [B*A], box_rows [pos_capacity,4],
+ * cls_rows [pos_capacity,C].  For half types the location term reproduces the reference, which
+ * evaluates log_sigmoid on the HALF logits (ref :160-161 has no .to(float32)): the per-element
+ * log-sigmoid is rounded to the map type before it enters the fp32 sum.
+ * A gt class outside [0, num_classes) makes the class loss NaN (torch raises a device assert).
+ * sums must be the vector sihl_od_train_assign zeroed for this step (sums[7] is used as the
+ * completion counter of the launch). */
+SIHL_OD_API int sihl_od_train_loss(const void *loc_logits, const void *iou_preds, const void *box_rows, const void *cls_rows,
+                       int map_dtype, int batch, int64_t num_anchors, int num_classes,
+                       const float *rel_iou, const int64_t *assignment,
+                       const int32_t *pos_index, int64_t pos_capacity, const int32_t *pos_total,
+                       const float *offsets, const float *scales, int img_w, int img_h,
+                       const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                       double *sums, float *losses, void *stream);
+
+/* sihl_od_train_loss_bwd: ONE launch for all four gradients, written in map_dtype.
+ * grad_losses: device fp32 [5] = upstream gradient of [location, box, class, iou, total]
+ * (NULL: d total = 1); the effective weights are g_i + g_total * {1,10,1,1}[i] (ref :210),
+ * times grad_scale (1, or the world size when the sums were all-reduced and DDP will average
+ * the gradients).  dloc / diou [B*A]; dbox_rows [pos_capacity,4] / dcls_rows [pos_capacity,C]:
+ * rows >= P are zeroed.  Any output may be NULL.  With no positives (sums[6] == 0) everything
+ * but dloc is zero (the reference's early-out returns before those heads run). */
+SIHL_OD_API int sihl_od_train_loss_bwd(const void *loc_logits, const void *iou_preds, const void *box_rows, const void *cls_rows,
+                           int map_dtype, int batch, int64_t num_anchors, int num_classes,
+                           const float *rel_iou, const int64_t *assignment,
+                           const int32_t *pos_index, int64_t pos_capacity, const int32_t *pos_total,
+                           const float *offsets, const float *scales, int img_w, int img_h,
+                           const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                           const double *sums, const float *grad_losses, float grad_scale,
+                           void *dloc, void *diou, void *dbox_rows, void *dcls_rows, void *stream);
+
 /* ---- a11: forward tail ------------------------------------------------------
  * ref :108-109: per image the K largest location logits, sorted descending
  * (ties: lowest index).  idx int64 [B,K], top_logits fp32 [B,K]. */
@@ -263,6 +350,18 @@ SIHL_OD_API int sihl_od_decode_rows(const float *top_logits, const int64_t *idx,
                         const float *offsets, const float *scales, int img_w, int img_h,
                         int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
                         void *stream);
+
+/* The same two entry points for head outputs of element type map_dtype (SIHL_OD_F32 / _F16 / _BF16), loaded as
+ * they are and upcast in registers.  top_logits stay fp32 (half values are exact in fp32).  For half maps
+ * scores = sigmoid() and exp(raw box) are rounded to the map type before use, which is what the reference's
+ * `.sigmoid()` / `.exp()` return under autocast (ref :113,:121), so num_instances and boxes follow it. */
+SIHL_OD_API int sihl_od_topk_t(const void *loc_logits, int map_dtype, int batch, int64_t num_anchors, int k,
+                   int64_t *idx, float *top_logits, void *stream);
+SIHL_OD_API int sihl_od_decode_rows_t(const float *top_logits, const int64_t *idx, int batch, int k,
+                          const void *cls_rows, int num_classes, const void *box_rows, int map_dtype,
+                          const float *offsets, const float *scales, int img_w, int img_h,
+                          int64_t *num_instances, float *scores, int64_t *classes, float *boxes,
+                          void *stream);
 
 /* ---- a15 (extension, not in the reference): dense decode + class-aware NMS --
  * Dense decode of every location: class = first argmax over C logits, score =
@@ -286,6 +385,14 @@ SIHL_OD_API int sihl_od_dense_decode(const float *loc_logits, const float *cls_l
  * 4*A + n_cand*(4C+16) bytes read per image instead of 4*A*(C+5).  Preferred
  * while fewer than about half of the locations pass the threshold. */
 SIHL_OD_API int sihl_od_candidate_decode(const float *loc_logits, const float *cls_logits, const float *box_raw,
+                         int batch, int64_t num_anchors, int num_classes,
+                         const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
+                         int32_t *cand_count, int64_t cand_capacity,
+                         uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                         void *stream);
+
+/* sihl_od_candidate_decode for maps of element type map_dtype (all three maps share it). */
+SIHL_OD_API int sihl_od_candidate_decode_t(const void *loc_logits, const void *cls_logits, const void *box_raw, int map_dtype,
                          int batch, int64_t num_anchors, int num_classes,
                          const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
                          int32_t *cand_count, int64_t cand_capacity,

@@ -32,37 +32,12 @@ from sihl_b200 import synth  # noqa: E402
 from oracle.golden_cases import (ASSIGN_CASES, FORWARD_CASES, GEOMETRIES, GOLDEN_DIR, NMS_CASES, QUAD_CASES,  # noqa: E402
                                  TRAIN_CASES, case_gt, forward_maps, geom_levels, nms_inputs, quad_gt, train_maps)
 
-class _Table(nn.Module):
-    """Stands in for an MLP head: row id rides in channel 0 of the features."""
-
-    def __init__(self, table: torch.Tensor):
-        super().__init__()
-        self.table = nn.Parameter(table)
-
-    def forward(self, feats):
-        return self.table[feats[..., 0].round().long()]
-
-
 def reference_head(levels, g, num_classes, batch, maps: synth.DenseMaps, max_instances=100):
-    RefOD = ref_loader.ObjectDetection()
-    top, bottom = g["top"], g["bottom"]
-    head = RefOD(in_channels=[3] + [4] * top, num_classes=num_classes, bottom_level=bottom, top_level=top,
-                 num_channels=4, num_layers=0, max_instances=max_instances)
-    head.laterals = nn.ModuleList([nn.Identity() for _ in levels])
-    A = synth.num_anchors(levels)
-    t = lambda x, c: torch.from_numpy(x).reshape(batch * A, c).clone()
-    head.loc_head = _Table(t(maps.loc_logits, 1))
-    head.iou_head = _Table(t(maps.iou_preds, 1))
-    head.box_head = _Table(t(maps.box_raw, 4))
-    head.cls_head = _Table(t(maps.cls_logits, num_classes))
-    inputs = [torch.zeros(batch, 3, g["height"], g["width"])] + [torch.zeros(batch, 1, 1, 1) for _ in range(1, bottom)]
-    start = 0
-    for (h, w) in levels:
-        ids = torch.arange(start, start + h * w, dtype=torch.float32).view(1, 1, h, w)
-        ids = ids + (torch.arange(batch, dtype=torch.float32) * A).view(batch, 1, 1, 1)
-        inputs.append(torch.cat([ids, torch.zeros(batch, 3, h, w)], dim=1))
-        start += h * w
-    return head, inputs
+    """The unmodified reference head over table look-ups (oracle/ref_path.py)."""
+    from oracle import ref_path
+    t = torch.from_numpy
+    return ref_path.reference_head(levels, g["height"], g["width"], g["bottom"], g["top"], num_classes, batch,
+                                   t(maps.loc_logits), t(maps.iou_preds), t(maps.box_raw), t(maps.cls_logits), max_instances)
 
 
 def save(name, **arrays):

@@ -34,14 +34,23 @@ _SIGNATURES = {
     "sihl_od_exchange_open": (I, [P, P]),
     "sihl_od_exchange_close": (I, [P]),
     "sihl_od_exchange_destroy": (I, [P]),
+    "sihl_od_exchange_set_timeout": (I, [P, I, C.c_uint64]),
+    "sihl_od_exchange_status": (I, [P, I, P, P]),
     "sihl_od_pos_compact": (I, [P, P, I, I64, P, I64, P, P, P]),
     "sihl_od_dense_loss": (I, [P, P, P, I64, P, P]),
     "sihl_od_pos_loss": (I, [P, P, I64, I64, P, P, P, P, I, I, P, P, P, P, P, I, I, P, P]),
     "sihl_od_loss_finalize": (I, [P, P, P]),
     "sihl_od_dense_loss_bwd": (I, [P, P, P, I64, P, P, P, P, P]),
     "sihl_od_pos_loss_bwd": (I, [P, P, I64, I64, P, P, P, P, I, I, P, P, P, P, P, I, I, P, P, P, P, P]),
+    "sihl_od_train_workspace_bytes": (C.c_size_t, [I, I64, I, I]),
+    "sihl_od_train_assign": (I, [P, P, I64, P, I, I, I, P, P, P, I, I, I, P, P, P, I64, P, P, P, C.c_size_t, P]),
+    "sihl_od_train_loss": (I, [P, P, P, P, I, I, I64, I, P, P, P, I64, P, P, P, I, I, P, P, P, P, P, P]),
+    "sihl_od_train_loss_bwd": (I, [P, P, P, P, I, I, I64, I, P, P, P, I64, P, P, P, I, I, P, P, P, P, P, F, P, P, P, P, P]),
     "sihl_od_topk": (I, [P, I, I64, I, P, P, P]),
     "sihl_od_decode_rows": (I, [P, P, I, I, P, I, P, P, P, I, I, P, P, P, P, P]),
+    "sihl_od_topk_t": (I, [P, I, I, I64, I, P, P, P]),
+    "sihl_od_decode_rows_t": (I, [P, P, I, I, P, I, P, I, P, P, I, I, P, P, P, P, P]),
+    "sihl_od_candidate_decode_t": (I, [P, P, P, I, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_dense_decode": (I, [P, P, P, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_candidate_decode": (I, [P, P, P, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_nms_workspace_bytes": (C.c_size_t, [I, I64]),
@@ -79,6 +88,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                     raise RuntimeError(
                         "libsihl_b200.so is missing and could not be built; the detection-head path has no "
                         f"CPU or PyTorch fallback ({exc})") from exc
+                if not _build.is_fresh():
+                    # a library exists but was built from OTHER sources than the ones in the tree: binding today's
+                    # ctypes signatures to yesterday's ABI would be undefined behaviour on the GPU, not an error
+                    raise RuntimeError(
+                        "libsihl_b200.so is stale (its build stamp does not match csrc/ + include/) and the rebuild "
+                        f"failed: {exc}") from exc
                 path = _build.LIB_PATH
         if not os.path.exists(path):
             raise RuntimeError(f"{path} not found; run `python -m sihl_b200.build` (no fallback path exists)")

@@ -22,7 +22,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsihl_b200.so")
 STAMP_PATH = os.path.join(LIB_DIR, "libsihl_b200.stamp")
-SOURCES = ["od_api.cu", "od_anchors.cu", "od_assign.cu", "od_quad.cu", "od_loss.cu", "od_exchange.cu", "od_infer.cu", "od_nms.cu"]
+SOURCES = ["od_api.cu", "od_anchors.cu", "od_assign.cu", "od_quad.cu", "od_loss.cu", "od_train.cu", "od_exchange.cu", "od_infer.cu", "od_nms.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -60,6 +60,11 @@ def _fresh(fp: str) -> bool:
             return os.path.exists(LIB_PATH) and fh.read().strip() == fp
     except OSError:
         return False
+
+
+def is_fresh() -> bool:
+    """True when the library on disk was built from exactly the sources + flags now in the tree."""
+    return _fresh(_fingerprint())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -83,17 +83,38 @@ __device__ __forceinline__ int select_compress(unsigned long long *bk, int cnt, 
     return cnt < topk ? cnt : topk;
 }
 
+// How the kernel learns the ground-truth layout (sihl_od_train_assign):
+//   kGtHost    total_gt is exact (legacy entry point), nothing else to do;
+//   kGtByValue the per-image prefix sums arrive BY VALUE in the kernel parameters and block 0 writes them to
+//              gt_offsets for the kernels that follow — ragged python lists reach the device without a copy or a sync;
+//   kGtDevice  gt_offsets is already on the device: the true total is gt_offsets[batch], total_gt sizes the launch
+//              (a captured graph can be replayed on new ground truth).
+enum { kGtHost = 0, kGtByValue = 1, kGtDevice = 2 };
+template <int MODE> struct GtLayoutArg { };                          // empty for kGtHost
+template <> struct GtLayoutArg<kGtByValue> { int32_t *gt_offsets; int batch; int prefix[SIHL_OD_MAX_BATCH_BY_VALUE + 1]; };
+template <> struct GtLayoutArg<kGtDevice> { const int32_t *gt_total; };
+
 // anchor_terms (optional): per anchor (area, cx, cy, atan(w/h)) as sihl_od_anchor_terms writes them —
 // the same fp32 operations box_terms() performs, hoisted out of the pair loop and cached with the tables.
+template <int MODE>
 __global__ void __launch_bounds__(kSelWarps * 32, kSelMinBlocks)
 k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4 *__restrict__ anchor_terms,
                 const float4 *__restrict__ gt_boxes, int total_gt, int32_t *__restrict__ sel_anchor,
-                float *__restrict__ sel_val, float *__restrict__ best_iou, double *__restrict__ sums)
+                float *__restrict__ sel_val, float *__restrict__ best_iou, double *__restrict__ sums,
+                const __grid_constant__ GtLayoutArg<MODE> layout)
 {
     __shared__ unsigned long long s_key[kSelWarps][kBufCap];
     __shared__ int4 s_tab[kSelWarps][SIHL_OD_MAX_LEVELS];
 
     if (sums != nullptr && blockIdx.x == 0 && threadIdx.x < SIHL_OD_NUM_SUMS) sums[threadIdx.x] = 0.0;
+    if constexpr (MODE == kGtByValue) {
+        if (blockIdx.x == 0)
+            for (int i = threadIdx.x; i <= layout.batch; i += blockDim.x) layout.gt_offsets[i] = layout.prefix[i];
+    }
+    if constexpr (MODE == kGtDevice) {
+        const int t = __ldg(layout.gt_total);
+        total_gt = t < total_gt ? t : total_gt;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * kSelWarps + warp;
@@ -479,7 +500,7 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
 __global__ void __launch_bounds__(256)
 k_pos_compact(const int32_t *__restrict__ tile_pos_count, const int32_t *__restrict__ tile_pos_rows, int n_tiles,
               int n_slots, int32_t *__restrict__ pos_index, int64_t capacity, int32_t *__restrict__ pos_total,
-              int32_t *__restrict__ pos_image_offsets)
+              int32_t *__restrict__ pos_image_offsets, int pad_tail)
 {
     __shared__ int s_red[32];
     const int slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -505,6 +526,9 @@ k_pos_compact(const int32_t *__restrict__ tile_pos_count, const int32_t *__restr
     const int n = __ldg(tile_pos_count + slot);
     for (int r = tid; r < n; r += blockDim.x)
         if ((int64_t)before + r < capacity) pos_index[before + r] = __ldg(tile_pos_rows + (int64_t)slot * kTile + r);
+    if (pad_tail)           // rows [total, capacity) are gathered by the static-size MLP batch: any valid row will do
+        for (int64_t r = (int64_t)total + (int64_t)slot * blockDim.x + tid; r < capacity; r += (int64_t)n_slots * blockDim.x)
+            pos_index[r] = 0;
 }
 
 }  // namespace sihl
@@ -521,19 +545,15 @@ extern "C" int sihl_od_anchor_terms(const float *anchors, int64_t num_anchors, f
     return SIHL_OD_OK;
 }
 
-extern "C" int sihl_od_assign_select(const float *anchors, const float *anchor_terms, int64_t num_anchors,
-                                     const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
-                                     const float *gt_boxes, const int32_t *gt_offsets, int batch, int total_gt,
-                                     int topk, int32_t *sel_anchor, float *sel_val, float *best_iou, double *sums,
-                                     void *stream)
+static int fill_select_params(SelectParams *out, int64_t num_anchors, const int32_t *level_hw_host, int n_levels,
+                              int img_w, int img_h, int total_gt, int topk)
 {
-    (void)gt_offsets; (void)batch;
+    SelectParams &p = *out;
     SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
     SIHL_CHECK_ARG(total_gt >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
     SIHL_CHECK_ARG(total_gt == 0 || num_anchors >= topk,
                    "selected index k out of range: %lld anchors < topk=%d (torch.topk raises in the reference)",
                    (long long)num_anchors, topk);
-    SelectParams p;
     p.use_levels = level_hw_host != nullptr;
     for (int l = 0; l < SIHL_OD_MAX_LEVELS; ++l) { p.inv_sx[l] = p.inv_sy[l] = 0.f; p.cell_w[l] = p.cell_h[l] = 1.f; }
     if (p.use_levels) {
@@ -554,12 +574,114 @@ extern "C" int sihl_od_assign_select(const float *anchors, const float *anchor_t
         p.lv.base[SIHL_OD_MAX_LEVELS] = 0;
     }
     p.num_anchors = (int)num_anchors; p.topk = topk;
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_assign_select(const float *anchors, const float *anchor_terms, int64_t num_anchors,
+                                     const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
+                                     const float *gt_boxes, const int32_t *gt_offsets, int batch, int total_gt,
+                                     int topk, int32_t *sel_anchor, float *sel_val, float *best_iou, double *sums,
+                                     void *stream)
+{
+    (void)gt_offsets; (void)batch;
+    SelectParams p;
+    int rc = fill_select_params(&p, num_anchors, level_hw_host, n_levels, img_w, img_h, total_gt, topk);
+    if (rc) return rc;
     if (total_gt == 0 && sums == nullptr) return SIHL_OD_OK;
     const int blocks = total_gt > 0 ? (total_gt + kSelWarps - 1) / kSelWarps : 1;
-    k_assign_select<<<blocks, kSelWarps * 32, 0, (cudaStream_t)stream>>>(
+    k_assign_select<kGtHost><<<blocks, kSelWarps * 32, 0, (cudaStream_t)stream>>>(
         p, reinterpret_cast<const float4 *>(anchors), reinterpret_cast<const float4 *>(anchor_terms),
-        reinterpret_cast<const float4 *>(gt_boxes), total_gt, sel_anchor, sel_val, best_iou, sums);
+        reinterpret_cast<const float4 *>(gt_boxes), total_gt, sel_anchor, sel_val, best_iou, sums, GtLayoutArg<kGtHost>{});
     SIHL_CHECK_LAUNCH("k_assign_select");
+    return SIHL_OD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// The drop-in head's "before the MLPs" call: select -> resolve -> compaction, all scratch from one workspace.
+// ---------------------------------------------------------------------------
+namespace {
+struct TrainWorkspace {
+    int32_t *sel_anchor; float *sel_val; float *best_iou; int32_t *tile_pos_count; int32_t *tile_pos_rows;
+    size_t bytes;
+};
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+TrainWorkspace carve_train_workspace(void *base, int batch, int64_t num_anchors, int gt_capacity, int topk)
+{
+    const size_t n_tiles = (size_t)((num_anchors + kTile - 1) / kTile);
+    const size_t gk = (size_t)(gt_capacity > 0 ? gt_capacity : 0) * (size_t)topk;
+    unsigned char *b = reinterpret_cast<unsigned char *>(base);
+    size_t o = 0;
+    TrainWorkspace w;
+    w.sel_anchor = reinterpret_cast<int32_t *>(b + o); o += align_up(gk * 4);
+    w.sel_val = reinterpret_cast<float *>(b + o); o += align_up(gk * 4);
+    w.best_iou = reinterpret_cast<float *>(b + o); o += align_up((size_t)(gt_capacity > 0 ? gt_capacity : 0) * 4);
+    w.tile_pos_count = reinterpret_cast<int32_t *>(b + o); o += align_up((size_t)batch * n_tiles * 4);
+    w.tile_pos_rows = reinterpret_cast<int32_t *>(b + o); o += align_up((size_t)batch * n_tiles * kTile * 4);
+    w.bytes = o;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t sihl_od_train_workspace_bytes(int batch, int64_t num_anchors, int gt_capacity, int topk)
+{
+    if (batch < 0 || num_anchors < 0 || topk < 1) return 0;
+    return carve_train_workspace(nullptr, batch, num_anchors, gt_capacity, topk).bytes;
+}
+
+extern "C" int sihl_od_train_assign(const float *anchors, const float *anchor_terms, int64_t num_anchors,
+                                    const int32_t *level_hw_host, int n_levels, int img_w, int img_h,
+                                    const float *gt_boxes, const int32_t *gt_counts_host, int32_t *gt_offsets,
+                                    int batch, int gt_capacity, int topk, int64_t *assignment, float *rel_iou,
+                                    int32_t *pos_index, int64_t pos_capacity, int32_t *pos_total, double *sums,
+                                    void *workspace, size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    SIHL_CHECK_ARG(anchors && gt_offsets && assignment && rel_iou && pos_index && pos_total && sums, "NULL argument");
+    SIHL_CHECK_ARG(batch >= 1 && batch <= 65535 && gt_capacity >= 0 && pos_capacity >= 1, "bad sizes");
+    SIHL_CHECK_ARG(gt_capacity == 0 || gt_boxes != nullptr, "gt_boxes is NULL");
+    SIHL_CHECK_ARG(workspace != nullptr && workspace_bytes >= sihl_od_train_workspace_bytes(batch, num_anchors, gt_capacity, topk),
+                   "workspace too small: %zu < %zu bytes", workspace_bytes,
+                   sihl_od_train_workspace_bytes(batch, num_anchors, gt_capacity, topk));
+    SIHL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    int total_gt = gt_capacity;
+    GtLayoutArg<kGtByValue> table;
+    if (gt_counts_host != nullptr) {
+        SIHL_CHECK_ARG(batch <= SIHL_OD_MAX_BATCH_BY_VALUE, "batch=%d > %d: pass gt_offsets on the device instead of host counts",
+                       batch, SIHL_OD_MAX_BATCH_BY_VALUE);
+        table.gt_offsets = gt_offsets; table.batch = batch; table.prefix[0] = 0;
+        for (int b = 0; b < batch; ++b) {
+            SIHL_CHECK_ARG(gt_counts_host[b] >= 0, "negative gt count for image %d", b);
+            table.prefix[b + 1] = table.prefix[b] + gt_counts_host[b];
+        }
+        total_gt = table.prefix[batch];
+        SIHL_CHECK_ARG(total_gt <= gt_capacity, "gt counts add up to %d > gt_capacity=%d", total_gt, gt_capacity);
+    }
+    SelectParams sp;
+    int rc = fill_select_params(&sp, num_anchors, level_hw_host, n_levels, img_w, img_h, total_gt, topk);
+    if (rc) return rc;
+    const TrainWorkspace w = carve_train_workspace(workspace, batch, num_anchors, gt_capacity, topk);
+    const int blocks = total_gt > 0 ? (total_gt + kSelWarps - 1) / kSelWarps : 1;
+    const float4 *an = reinterpret_cast<const float4 *>(anchors), *at = reinterpret_cast<const float4 *>(anchor_terms);
+    const float4 *gb = reinterpret_cast<const float4 *>(gt_boxes);
+    if (gt_counts_host != nullptr) {
+        k_assign_select<kGtByValue><<<blocks, kSelWarps * 32, 0, st>>>(sp, an, at, gb, total_gt, w.sel_anchor, w.sel_val,
+                                                                        w.best_iou, sums, table);
+    } else {
+        GtLayoutArg<kGtDevice> dv;
+        dv.gt_total = gt_offsets + batch;
+        k_assign_select<kGtDevice><<<blocks, kSelWarps * 32, 0, st>>>(sp, an, at, gb, total_gt, w.sel_anchor, w.sel_val,
+                                                                       w.best_iou, sums, dv);
+    }
+    SIHL_CHECK_LAUNCH("k_assign_select");
+    rc = sihl_od_assign_resolve(w.sel_anchor, w.sel_val, w.best_iou, gt_offsets, batch, num_anchors, topk, 1, nullptr, nullptr,
+                                assignment, rel_iou, nullptr, w.tile_pos_count, w.tile_pos_rows, nullptr, nullptr, 0, nullptr,
+                                nullptr, stream);
+    if (rc) return rc;
+    const int n_tiles = (int)((num_anchors + kTile - 1) / kTile);
+    const int n_slots = batch * n_tiles;
+    k_pos_compact<<<n_slots, 256, 0, st>>>(w.tile_pos_count, w.tile_pos_rows, n_tiles, n_slots, pos_index, pos_capacity,
+                                           pos_total, nullptr, 1);
+    SIHL_CHECK_LAUNCH("k_pos_compact");
     return SIHL_OD_OK;
 }
 
@@ -613,7 +735,7 @@ extern "C" int sihl_od_pos_compact(const int32_t *tile_pos_count, const int32_t 
     const int n_slots = batch * n_tiles;
     if (n_slots == 0) return SIHL_OD_OK;
     k_pos_compact<<<n_slots, 256, 0, (cudaStream_t)stream>>>(tile_pos_count, tile_pos_rows, n_tiles, n_slots, pos_index,
-                                                              capacity, pos_total, pos_image_offsets);
+                                                              capacity, pos_total, pos_image_offsets, 0);
     SIHL_CHECK_LAUNCH("k_pos_compact");
     return SIHL_OD_OK;
 }

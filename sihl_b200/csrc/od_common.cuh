@@ -8,6 +8,8 @@
 // only where torch's own kernels have them, written explicitly (__fmaf_rn).
 #pragma once
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -46,6 +48,67 @@ struct LevelTable {                   // passed by value as a kernel parameter
 };
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// Head-output maps may arrive in half precision (the reference trains with precision="16-mixed",
+// ref examples/object_detection.py:294, and upcasts inside its autocast-off blocks, ref :178,:195,:206):
+// kernels templated on the map type load T and upcast in registers — no fp32 copy of the map is ever made.
+// The dtype codes are SIHL_OD_F32 / _F16 / _BF16 of include/sihl_od.h.
+template <typename T> __device__ __forceinline__ float ldf(const T *p);
+template <> __device__ __forceinline__ float ldf<float>(const float *p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half *p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(__ldg(p)); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// v rounded to T and back (what an ATen op "run in the input dtype" returns for a half input)
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// four consecutive elements (a raw box) as float4
+template <typename T> __device__ __forceinline__ float4 ldf4(const T *p);
+template <> __device__ __forceinline__ float4 ldf4<float>(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+template <> __device__ __forceinline__ float4 ldf4<__half>(const __half *p)
+{
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 ldf4<__nv_bfloat16>(const __nv_bfloat16 *p)
+{
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void stf4(T *p, float4 v);
+template <> __device__ __forceinline__ void stf4<float>(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+template <> __device__ __forceinline__ void stf4<__half>(__half *p, float4 v)
+{
+    uint2 u;
+    *reinterpret_cast<__half2 *>(&u.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2 *>(&u.y) = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = u;
+}
+template <> __device__ __forceinline__ void stf4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v)
+{
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162 *>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162 *>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = u;
+}
+
+// Run `stmt` with the alias T bound to the C++ type of dtype code `code`; returns SIHL_OD_EINVAL on a bad code.
+#define SIHL_DISPATCH_DTYPE(code, ...)                                                           \
+    do {                                                                                         \
+        if ((code) == SIHL_OD_F32) { using T = float; __VA_ARGS__; }                             \
+        else if ((code) == SIHL_OD_F16) { using T = __half; __VA_ARGS__; }                       \
+        else if ((code) == SIHL_OD_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }               \
+        else { ::sihl::set_error("map dtype code %d is not one of f32/f16/bf16", (int)(code)); return SIHL_OD_EINVAL; } \
+    } while (0)
 
 __device__ __forceinline__ Box4 to_box(float4 b) { return Box4{b.x, b.y, b.z, b.w}; }
 

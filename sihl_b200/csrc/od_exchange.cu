@@ -16,6 +16,8 @@
 //   [0, 16 W)            sums   [parity][source rank][8]   double
 //   [16 W, 18 W)         flags  [parity][source rank]      u64: the step number whose sums are complete
 //   [18 W]               this GPU's own step counter       u64
+//   [18 W + 1]           wait limit in ns (0 = 120 s default)   u64   sihl_od_exchange_set_timeout
+//   [18 W + 2]           sticky error: first step whose wait timed out (0 = none)   sihl_od_exchange_status
 #include "od_common.cuh"
 
 using namespace sihl;
@@ -23,7 +25,7 @@ using namespace sihl;
 extern "C" size_t sihl_od_exchange_region_bytes(int world)
 {
     if (world < 1 || world > SIHL_OD_MAX_PEERS) return 0;
-    const size_t words = (size_t)18 * world + 1;
+    const size_t words = (size_t)18 * world + 3;
     return (words * 8 + 255) / 256 * 256;
 }
 
@@ -64,4 +66,23 @@ extern "C" int sihl_od_exchange_destroy(void *block)
 {
     if (block == nullptr) return SIHL_OD_OK;
     return cuda_status(cudaFree(block), "cudaFree(exchange block)");
+}
+
+extern "C" int sihl_od_exchange_set_timeout(void *region, int world, uint64_t timeout_ns)
+{
+    SIHL_CHECK_ARG(region && world >= 1 && world <= SIHL_OD_MAX_PEERS, "bad arguments");
+    return cuda_status(cudaMemcpy(reinterpret_cast<unsigned long long *>(region) + 18 * world + 1, &timeout_ns, sizeof(timeout_ns),
+                                  cudaMemcpyHostToDevice), "cudaMemcpy(exchange timeout)");
+}
+
+extern "C" int sihl_od_exchange_status(const void *region, int world, uint64_t *timed_out_step, uint64_t *steps_done)
+{
+    SIHL_CHECK_ARG(region && world >= 1 && world <= SIHL_OD_MAX_PEERS && timed_out_step, "bad arguments");
+    unsigned long long w[3] = {0, 0, 0};
+    int rc = cuda_status(cudaMemcpy(w, reinterpret_cast<const unsigned long long *>(region) + 18 * world, sizeof(w),
+                                    cudaMemcpyDeviceToHost), "cudaMemcpy(exchange status)");
+    if (rc) return rc;
+    *timed_out_step = w[2];
+    if (steps_done) *steps_done = w[0];
+    return SIHL_OD_OK;
 }

@@ -35,8 +35,9 @@ __device__ __forceinline__ float ord2f(unsigned k)
 constexpr int kTopkThreads = 1024;
 constexpr int kTopkMaxK = 1024;
 
+template <typename T>     // element type of the location map (upcast on load; half values are exact in fp32)
 __global__ void __launch_bounds__(kTopkThreads)
-k_topk(const float *__restrict__ loc, int A, int K, int KP /* pow2 >= K */, int64_t *__restrict__ idx_out,
+k_topk(const T *__restrict__ loc, int A, int K, int KP /* pow2 >= K */, int64_t *__restrict__ idx_out,
        float *__restrict__ val_out)
 {
     __shared__ unsigned s_hist[256];
@@ -46,7 +47,7 @@ k_topk(const float *__restrict__ loc, int A, int K, int KP /* pow2 >= K */, int6
     __shared__ int s_ngt;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const float *row = loc + (int64_t)blockIdx.x * A;
+    const T *row = loc + (int64_t)blockIdx.x * A;
 
     unsigned prefix = 0, mask = 0, remaining = (unsigned)K;
     for (int pass = 0; pass < 4; ++pass) {
@@ -56,7 +57,7 @@ k_topk(const float *__restrict__ loc, int A, int K, int KP /* pow2 >= K */, int6
         for (int i0 = 0; i0 < A; i0 += blockDim.x) {
             const int i = i0 + tid;
             const bool ok = i < A;
-            const unsigned u = ok ? f2ord(__ldg(row + i)) : 0u;
+            const unsigned u = ok ? f2ord(ldf(row + i)) : 0u;
             const bool in = ok && ((u & mask) == prefix);
             const unsigned digit = (u >> shift) & 255u;
             // warp-aggregated histogram update (logits cluster in a few exponent buckets)
@@ -105,7 +106,7 @@ k_topk(const float *__restrict__ loc, int A, int K, int KP /* pow2 >= K */, int6
     int eq_seen = 0;                             // block-uniform running count of equal elements
     for (int i0 = 0; i0 < A; i0 += blockDim.x) {
         const int i = i0 + tid;
-        const unsigned u = (i < A) ? f2ord(__ldg(row + i)) : 0u;
+        const unsigned u = (i < A) ? f2ord(ldf(row + i)) : 0u;
         const bool gt = (i < A) && u > kth, eq = (i < A) && u == kth;
         const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
         if (gt) s_sel[atomicAdd(&s_ngt, 1)] = key;           // fewer than K of these by construction
@@ -185,10 +186,32 @@ __device__ __forceinline__ int row_argmax8(const float *__restrict__ z, int C, i
     return arg;
 }
 
-// ref :113-121 on the K gathered rows of one image per CTA.
+// The same first arg-max on a row of element type T (half maps: 2-byte loads, upcast in registers).
+template <typename T>
+__device__ __forceinline__ int row_argmax8_t(const T *__restrict__ z, int C, int gl)
+{
+    float best = -CUDART_INF_F;
+    int arg = 0x7fffffff;
+    for (int c = gl; c < C; c += 8) {
+        const float x = ldf(z + c);
+        if (x > best || arg == 0x7fffffff) { best = x; arg = c; }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(kFullMask, best, o);
+        const int oa = __shfl_xor_sync(kFullMask, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    return arg;
+}
+
+// ref :113-121 on the K gathered rows of one image per CTA.  For half maps the reference's `.sigmoid()` and `.exp()`
+// run in the map dtype (evaluated in fp32, rounded to half): round_to<T> reproduces that, so scores, the
+// `scores > 0.5` count and the decoded boxes follow the reference under autocast too.
+template <typename T>
 __global__ void __launch_bounds__(256)
 k_decode_rows(const float *__restrict__ top_logits, const int64_t *__restrict__ idx, int K,
-              const float *__restrict__ cls_rows, int C, const float *__restrict__ box_rows,
+              const T *__restrict__ cls_rows, int C, const T *__restrict__ box_rows,
               const float4 *__restrict__ offsets, const float4 *__restrict__ scales, float img_w, float img_h,
               int64_t *__restrict__ num_instances, float *__restrict__ scores, int64_t *__restrict__ classes,
               float *__restrict__ boxes)
@@ -200,14 +223,14 @@ k_decode_rows(const float *__restrict__ top_logits, const int64_t *__restrict__ 
     int local = 0;
     for (int k = tid; k < K; k += blockDim.x) {
         const int64_t r = (int64_t)b * K + k;
-        const float s = sigmoid_f(__ldg(top_logits + r));                  // ref :113
+        const float s = round_to<T>(sigmoid_f(__ldg(top_logits + r)));     // ref :113
         scores[r] = s;
         local += (s > 0.5f) ? 1 : 0;                                       // ref :114
         const int a = (int)__ldg(idx + r);
-        const float4 raw = ldg4(box_rows + 4 * r), off = __ldg(offsets + a), sc = __ldg(scales + a);
+        const float4 raw = ldf4(box_rows + 4 * r), off = __ldg(offsets + a), sc = __ldg(scales + a);
         *reinterpret_cast<float4 *>(boxes + 4 * r) =                       // ref :121
-            make_float4(decode_norm(off.x, sc.x, raw.x) * img_w, decode_norm(off.y, sc.y, raw.y) * img_h,
-                        decode_norm(off.z, sc.z, raw.z) * img_w, decode_norm(off.w, sc.w, raw.w) * img_h);
+            make_float4((off.x + sc.x * round_to<T>(expf(raw.x))) * img_w, (off.y + sc.y * round_to<T>(expf(raw.y))) * img_h,
+                        (off.z + sc.z * round_to<T>(expf(raw.z))) * img_w, (off.w + sc.w * round_to<T>(expf(raw.w))) * img_h);
     }
     local = warp_sum(local);
     if ((tid & 31) == 0 && local) atomicAdd(&s_count, local);
@@ -215,7 +238,7 @@ k_decode_rows(const float *__restrict__ top_logits, const int64_t *__restrict__ 
     for (int k0 = 0; k0 < K; k0 += ngrp) {
         const int k = k0 + grp;
         const int64_t r = (int64_t)b * K + (k < K ? k : K - 1);
-        const int arg = row_argmax8<0>(cls_rows + r * C, C, gl);           // ref :117
+        const int arg = row_argmax8_t<T>(cls_rows + r * C, C, gl);         // ref :117
         if (k < K && gl == 0) classes[r] = arg;
     }
     __syncthreads();
@@ -579,9 +602,11 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
 // (3 shuffles) then lowest index equal to it (3 shuffles), like the TMA consumer.
 // VEC = 4: 16-byte loads (C % 4 == 0, aligned); VEC = 1: any C.
 // ---------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, typename T = float>     // T: element type of the three maps (VEC == 4 needs T == float)
 __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
 {
+    const T *t_loc = reinterpret_cast<const T *>(p.loc), *t_cls = reinterpret_cast<const T *>(p.cls);
+    const T *t_box = reinterpret_cast<const T *>(p.box_raw);
     const int lane = threadIdx.x & 31, gq = lane >> 3, gl = lane & 7;
     const int64_t rows = (int64_t)p.batch * p.A;
     const int64_t n_blocks = (rows + 31) >> 5;
@@ -591,10 +616,10 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
     for (int64_t blk = warp0; blk < n_blocks; blk += n_warps) {
         const int64_t row = (blk << 5) + lane;
         const bool in = row < rows;
-        const float x = in ? __ldcs(p.loc + row) : -CUDART_INF_F;
+        const float x = in ? ldf(t_loc + row) : -CUDART_INF_F;
         float s = 0.f;
         bool cand = false;
-        if (in && x >= p.logit_thr) { s = sigmoid_f(x); cand = s > p.score_thr; }
+        if (in && x >= p.logit_thr) { s = round_to<T>(sigmoid_f(x)); cand = s > p.score_thr; }
         const unsigned m = __ballot_sync(kFullMask, cand);
         if (m == 0u) continue;
         const int b = !in ? 0 : (rows < (1ll << 31) ? (int)((unsigned)row / (unsigned)p.A) : (int)(row / p.A));
@@ -641,9 +666,9 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
                     }
                 }
             } else {
-                const float *srow = p.cls + crow * p.C;
+                const T *srow = t_cls + crow * p.C;
                 for (int c = gl; c < (have ? p.C : 0); c += 8) {
-                    const float e = __ldcs(srow + c);
+                    const float e = ldf(srow + c);
                     if (e > best) { best = e; arg = c; }
                 }
             }
@@ -660,12 +685,12 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             const int ca = __shfl_sync(kFullMask, a, src), cb = __shfl_sync(kFullMask, b, src);
             const int cslot = __shfl_sync(kFullMask, slot, src);
             if (have && gl == 0 && cslot < p.cap) {
-                const float4 raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + crow);
+                const float4 raw = ldf4(t_box + 4 * crow);
                 const float4 off = __ldg(p.offsets + ca), sc = __ldg(p.scales + ca);
                 const int64_t o = (int64_t)cb * p.cap + cslot;
                 p.cand_key[o] = ((unsigned long long)__float_as_uint(cs) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ca);
-                p.cand_box[o] = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
-                                            decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
+                p.cand_box[o] = make_float4((off.x + sc.x * round_to<T>(expf(raw.x))) * p.img_w, (off.y + sc.y * round_to<T>(expf(raw.y))) * p.img_h,
+                                            (off.z + sc.z * round_to<T>(expf(raw.z))) * p.img_w, (off.w + sc.w * round_to<T>(expf(raw.w))) * p.img_h);
                 p.cand_cls[o] = arg;
             }
         }
@@ -684,6 +709,12 @@ using namespace sihl;
 extern "C" int sihl_od_topk(const float *loc_logits, int batch, int64_t num_anchors, int k, int64_t *idx,
                             float *top_logits, void *stream)
 {
+    return sihl_od_topk_t(loc_logits, SIHL_OD_F32, batch, num_anchors, k, idx, top_logits, stream);
+}
+
+extern "C" int sihl_od_topk_t(const void *loc_logits, int map_dtype, int batch, int64_t num_anchors, int k, int64_t *idx,
+                              float *top_logits, void *stream)
+{
     SIHL_CHECK_ARG(loc_logits && idx && top_logits, "NULL argument");
     SIHL_CHECK_ARG(k >= 1 && k <= kTopkMaxK, "k=%d outside 1..%d", k, kTopkMaxK);
     SIHL_CHECK_ARG(num_anchors >= k && num_anchors < (1ll << 30),
@@ -692,7 +723,8 @@ extern "C" int sihl_od_topk(const float *loc_logits, int batch, int64_t num_anch
     if (batch <= 0) return SIHL_OD_OK;
     int kp = 1;
     while (kp < k) kp <<= 1;
-    k_topk<<<batch, kTopkThreads, 0, (cudaStream_t)stream>>>(loc_logits, (int)num_anchors, k, kp, idx, top_logits);
+    SIHL_DISPATCH_DTYPE(map_dtype, (k_topk<T><<<batch, kTopkThreads, 0, (cudaStream_t)stream>>>(
+                                       reinterpret_cast<const T *>(loc_logits), (int)num_anchors, k, kp, idx, top_logits)));
     SIHL_CHECK_LAUNCH("k_topk");
     return SIHL_OD_OK;
 }
@@ -702,13 +734,24 @@ extern "C" int sihl_od_decode_rows(const float *top_logits, const int64_t *idx, 
                                    const float *offsets, const float *scales, int img_w, int img_h,
                                    int64_t *num_instances, float *scores, int64_t *classes, float *boxes, void *stream)
 {
+    return sihl_od_decode_rows_t(top_logits, idx, batch, k, cls_rows, num_classes, box_rows, SIHL_OD_F32, offsets, scales, img_w,
+                                 img_h, num_instances, scores, classes, boxes, stream);
+}
+
+extern "C" int sihl_od_decode_rows_t(const float *top_logits, const int64_t *idx, int batch, int k,
+                                     const void *cls_rows, int num_classes, const void *box_rows, int map_dtype,
+                                     const float *offsets, const float *scales, int img_w, int img_h,
+                                     int64_t *num_instances, float *scores, int64_t *classes, float *boxes, void *stream)
+{
     SIHL_CHECK_ARG(top_logits && idx && cls_rows && box_rows && offsets && scales, "NULL input");
     SIHL_CHECK_ARG(num_instances && scores && classes && boxes, "NULL output");
     SIHL_CHECK_ARG(k >= 1 && num_classes >= 1 && img_w > 0 && img_h > 0, "bad sizes");
     if (batch <= 0) return SIHL_OD_OK;
-    k_decode_rows<<<batch, 256, 0, (cudaStream_t)stream>>>(
-        top_logits, idx, k, cls_rows, num_classes, box_rows, reinterpret_cast<const float4 *>(offsets),
-        reinterpret_cast<const float4 *>(scales), (float)img_w, (float)img_h, num_instances, scores, classes, boxes);
+    SIHL_CHECK_ARG((reinterpret_cast<uintptr_t>(box_rows) & 15u) == 0, "box_rows must be 16-byte aligned");
+    SIHL_DISPATCH_DTYPE(map_dtype, (k_decode_rows<T><<<batch, 256, 0, (cudaStream_t)stream>>>(
+        top_logits, idx, k, reinterpret_cast<const T *>(cls_rows), num_classes, reinterpret_cast<const T *>(box_rows),
+        reinterpret_cast<const float4 *>(offsets), reinterpret_cast<const float4 *>(scales), (float)img_w, (float)img_h,
+        num_instances, scores, classes, boxes)));
     SIHL_CHECK_LAUNCH("k_decode_rows");
     return SIHL_OD_OK;
 }
@@ -850,7 +893,20 @@ extern "C" int sihl_od_candidate_decode(const float *loc_logits, const float *cl
                                         uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
                                         void *stream)
 {
+    return sihl_od_candidate_decode_t(loc_logits, cls_logits, box_raw, SIHL_OD_F32, batch, num_anchors, num_classes, offsets,
+                                      scales, img_w, img_h, score_thr, cand_count, cand_capacity, cand_key, cand_box, cand_cls,
+                                      zero_counts, stream);
+}
+
+extern "C" int sihl_od_candidate_decode_t(const void *loc_logits_v, const void *cls_logits_v, const void *box_raw_v, int map_dtype,
+                                          int batch, int64_t num_anchors, int num_classes, const float *offsets,
+                                          const float *scales, int img_w, int img_h, float score_thr, int32_t *cand_count,
+                                          int64_t cand_capacity, uint64_t *cand_key, float *cand_box, int32_t *cand_cls,
+                                          int zero_counts, void *stream)
+{
     cudaStream_t st = (cudaStream_t)stream;
+    const float *loc_logits = reinterpret_cast<const float *>(loc_logits_v), *cls_logits = reinterpret_cast<const float *>(cls_logits_v);
+    const float *box_raw = reinterpret_cast<const float *>(box_raw_v);
     DenseDecodeParams p;
     int nothing = 0;
     int rc0 = decode_prologue(loc_logits, cls_logits, box_raw, batch, num_anchors, num_classes, offsets, scales, img_w, img_h,
@@ -863,8 +919,15 @@ extern "C" int sihl_od_candidate_decode(const float *loc_logits, const float *cl
     if (blocks > cap) blocks = cap;
     const bool vec = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
     SIHL_CHECK_ARG((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0, "box_raw must be 16-byte aligned");
-    if (vec) k_candidate_decode<4><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else k_candidate_decode<1><<<(unsigned)blocks, 256, 0, st>>>(p);
+    if (map_dtype == SIHL_OD_F32) {
+        if (vec) k_candidate_decode<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+        else k_candidate_decode<1><<<(unsigned)blocks, 256, 0, st>>>(p);
+    } else {
+        // half maps: the score is sigmoid() ROUNDED to the map type (what the reference's `.sigmoid()` returns under
+        // autocast), which can cross the threshold from below: widen the conservative logit pre-filter accordingly
+        if (p.logit_thr > -HUGE_VALF && p.logit_thr < HUGE_VALF) p.logit_thr -= 0.05f * (1.f + fabsf(p.logit_thr));
+        SIHL_DISPATCH_DTYPE(map_dtype, (k_candidate_decode<1, T><<<(unsigned)blocks, 256, 0, st>>>(p)));
+    }
     SIHL_CHECK_LAUNCH("k_candidate_decode");
     return SIHL_OD_OK;
 }

@@ -91,8 +91,11 @@ __global__ void __launch_bounds__(kLossThreads) k_pos_loss(PosParams p)
             const int b = (int)(flat / A);
             const int g = __ldg(p.gt_offsets + b) + (int)__ldg(p.assignment + flat);
             const int64_t row = p.dense_rows ? flat : (ok ? r : 0);
-            const float ce = ce_row_group8(p.cls + row * p.num_classes, p.num_classes, (int)__ldg(p.gt_classes + g), gl);
-            if (ok && gl == 0) acc_cls += __ldg(p.rel + flat) * ce;   // ref :208
+            // a label outside [0, C) would read foreign memory (torch raises a device assert there): NaN loss instead
+            const int64_t tgt64 = __ldg(p.gt_classes + g);
+            const bool tgt_ok = tgt64 >= 0 && tgt64 < p.num_classes;
+            const float ce = ce_row_group8(p.cls + row * p.num_classes, p.num_classes, tgt_ok ? (int)tgt64 : 0, gl);
+            if (ok && gl == 0) acc_cls += __ldg(p.rel + flat) * (tgt_ok ? ce : CUDART_NAN_F);   // ref :208
         }
     }
     double v[2] = {acc_box, acc_cls};
@@ -153,7 +156,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // All-reduce (sum) of the 8 partial sums across the GPUs of the node, by the last CTA of the loss kernel:
 // thread q pushes this rank's sums into rank q's region (plain stores over NVLink, then a release store of the
 // step number), waits for rank q's push into the local region, and 8 threads add the W contributions in rank
-// order.  A peer that never shows up (a crashed rank) ends the wait after 2 s with NaN sums instead of a hang.
+// order.  A peer that never shows up (a crashed rank) ends the wait after the region's timeout (word 18W+1 in ns,
+// sihl_od_exchange_set_timeout; 0 = the 120 s default — long enough for a rank stalled by a dataloader, a checkpoint
+// or first-step lazy initialisation) with NaN sums instead of a hang, AND records the step in the region's sticky
+// error word (18W+2), which the host reads with sihl_od_exchange_status: a late peer is reported, not only NaN-ed.
 __device__ __noinline__ void exchange_sums(unsigned long long *const *peer, int W, int rank, double *sums,
                                            double *s_in /* shared [8] */)
 {
@@ -178,8 +184,14 @@ __device__ __noinline__ void exchange_sums(unsigned long long *const *peer, int 
         st_release_sys(theirs + 16 * W + parity * W + rank, step);
         const unsigned long long *flag = mine + 16 * W + parity * W + tid;
         const unsigned long long t0 = global_timer_ns();
+        unsigned long long limit = *reinterpret_cast<volatile unsigned long long *>(mine + 18 * W + 1);
+        if (limit == 0ull) limit = 120000000000ull;
         while (ld_acquire_sys(flag) != step) {
-            if (global_timer_ns() - t0 > 2000000000ull) { s_timeout = 1; break; }
+            if (global_timer_ns() - t0 > limit) {
+                s_timeout = 1;
+                atomicCAS(mine + 18 * W + 2, 0ull, step);            // sticky: the first step that timed out
+                break;
+            }
             __nanosleep(64);
         }
     }
@@ -202,8 +214,9 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
     SIHL_PT(0);
     // the first descriptor is fetched together with the list length (stale entries are harmless: they are
     // only used when blockIdx.x < n_chunks)
-    int desc = __ldg(p.pos_chunks + blockIdx.x);
-    const int n_chunks = (int)p.sums[7];
+    // pos_chunks == NULL: a shard without a single image still takes part in the exchange (it pushes its zero sums)
+    int desc = p.pos_chunks != nullptr ? __ldg(p.pos_chunks + blockIdx.x) : 0;
+    const int n_chunks = p.pos_chunks != nullptr ? (int)p.sums[7] : 0;
     const int lpr = p.cls_vec4 ? 4 : 8;                           // lanes per positive row
     const int gl = tid & (lpr - 1), grp = tid / lpr, ngrp = kPosTileThreads / lpr;
     const int A = p.num_anchors;
@@ -220,13 +233,15 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
                 const bool ok = r < n;
                 const int64_t flat = __ldg(rows + (ok ? r : 0));
                 const int2 ga = __ldg(aux + (ok ? r : 0));
-                const int tgt = (int)__ldg(p.gt_classes + ga.x);
+                const int64_t tgt64 = __ldg(p.gt_classes + ga.x);
+                const bool tgt_ok = tgt64 >= 0 && tgt64 < p.num_classes;   // out-of-range label: NaN loss, no foreign read
+                const int tgt = tgt_ok ? (int)tgt64 : 0;
                 float m, se;
                 if (p.cls_vec4) row_softmax_stats4v<true>(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
                 else row_softmax_stats8<true>(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
                 if (ok && gl == 0) {
                     const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + tgt);
-                    acc_cls += __int_as_float(ga.y) * ce;         // ref :208
+                    acc_cls += __int_as_float(ga.y) * (tgt_ok ? ce : CUDART_NAN_F);         // ref :208
                 }
             }
         }
@@ -339,8 +354,9 @@ __global__ void __launch_bounds__(kLossThreads) k_pos_loss_bwd(PosParams p)
             float m, s;
             row_softmax_stats8(z, C, gl, &m, &s);
             if (ok) {
-                const int target = (int)__ldg(p.gt_classes + g);
-                const float k = g_cls * __ldg(p.rel + flat) * inv_w;  // ref :208
+                const int64_t tgt64 = __ldg(p.gt_classes + g);
+                const int target = (tgt64 >= 0 && tgt64 < C) ? (int)tgt64 : -1;
+                const float k = target >= 0 ? g_cls * __ldg(p.rel + flat) * inv_w : CUDART_NAN_F;  // ref :208
                 const float inv_s = 1.f / s;
                 float *out = p.dcls + row * C;
                 for (int c = gl; c < C; c += 8)
@@ -481,17 +497,20 @@ extern "C" int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const 
     SIHL_CHECK_ARG(world >= 1 && world <= SIHL_OD_MAX_PEERS && rank >= 0 && rank < world, "world=%d rank=%d", world, rank);
     SIHL_CHECK_ARG(world == 1 || (peer_regions != nullptr && losses != nullptr),
                    "the fused exchange needs the peer regions and the fused finalize (losses, done_counter)");
-    SIHL_CHECK_ARG(pos_chunks && tile_pos_rows && tile_pos_aux && sums, "NULL argument");
     SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
+    const bool empty_shard = (int64_t)batch * ((num_anchors + kTile - 1) / kTile) == 0;
+    SIHL_CHECK_ARG(sums && (empty_shard || (pos_chunks && tile_pos_rows && tile_pos_aux)), "NULL argument");
     SIHL_CHECK_ARG(box_raw == nullptr || (offsets && scales && img_w > 0 && img_h > 0),
                    "box loss needs offsets, scales and the image size");
     SIHL_CHECK_ARG(cls_logits == nullptr || num_classes > 0, "class loss needs num_classes");
     SIHL_CHECK_ARG((losses == nullptr) == (done_counter == nullptr), "losses and done_counter go together");
     const int n_tiles = (int)((num_anchors + kTile - 1) / kTile);
     const int64_t n_slots = (int64_t)batch * n_tiles;
-    if (n_slots == 0) return SIHL_OD_OK;
+    // an empty shard has nothing to add, but with peers it must still push its (zero) sums and step number:
+    // returning here would leave every other rank waiting for it until the timeout
+    if (n_slots == 0 && world == 1) return SIHL_OD_OK;
     PosTileParams p;
-    p.pos_chunks = pos_chunks; p.tile_pos_rows = tile_pos_rows; p.tile_pos_aux = reinterpret_cast<const int2 *>(tile_pos_aux);
+    p.pos_chunks = n_slots == 0 ? nullptr : pos_chunks; p.tile_pos_rows = tile_pos_rows; p.tile_pos_aux = reinterpret_cast<const int2 *>(tile_pos_aux);
     p.n_tiles = n_tiles; p.num_anchors = (int)num_anchors;
     p.offsets = reinterpret_cast<const float4 *>(offsets); p.scales = reinterpret_cast<const float4 *>(scales);
     p.img_w = (float)img_w; p.img_h = (float)img_h;
@@ -506,6 +525,7 @@ extern "C" int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const 
     int64_t blocks = n_slots * (kTile / 32);
     const int64_t cap = (int64_t)kNumSMs * 12;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     if (world > 1) k_pos_loss_tiles<true><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x);
     else k_pos_loss_tiles<false><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x);
     SIHL_CHECK_LAUNCH("k_pos_loss_tiles");

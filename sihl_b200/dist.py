@@ -52,6 +52,11 @@ def ddp_mean_of_local_losses(local_losses: torch.Tensor, group=None) -> torch.Te
     return out
 
 
+def _check(status: int, what: str) -> None:
+    from . import _native
+    _native.check(status, what)
+
+
 class PeerExchange:
     """Exchange regions for the loss-sum all-reduce that ``k_pos_loss_tiles`` performs itself over peer memory
     (``include/sihl_od.h``: sihl_od_pos_loss_tiles_exchange).  One block of ``n_regions`` regions per GPU — one
@@ -120,6 +125,29 @@ class PeerExchange:
             if self._own.value is not None:
                 self.lib.sihl_od_exchange_destroy(self._own)
                 self._own.value = None
+
+    def set_timeout(self, seconds: float) -> None:
+        """Bound of the in-kernel wait for the peers' sums (default 120 s).  A rank that is merely slow — dataloader
+        stall, checkpoint, first-step lazy initialisation — must not be mistaken for a dead one."""
+        with torch.cuda.device(self.device):
+            for i in range(self.n_regions):
+                _check(self.lib.sihl_od_exchange_set_timeout(self.blocks[self.rank] + i * self.region_bytes, self.world,
+                                                              int(seconds * 1e9)), "sihl_od_exchange_set_timeout")
+
+    def check(self) -> None:
+        """Raise if any exchange on this rank ever gave up waiting for a peer (the kernel then wrote NaN sums for that
+        step and latched the step number).  Synchronises the device; call it where a host sync is acceptable
+        (end of an epoch, before a checkpoint)."""
+        import ctypes as C
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for i in range(self.n_regions):
+                bad, done = C.c_uint64(0), C.c_uint64(0)
+                _check(self.lib.sihl_od_exchange_status(self.blocks[self.rank] + i * self.region_bytes, self.world,
+                                                         C.byref(bad), C.byref(done)), "sihl_od_exchange_status")
+                if bad.value:
+                    raise RuntimeError(f"fused loss-sum exchange: rank {self.rank} timed out waiting for a peer at step "
+                                       f"{bad.value} of region {i} ({done.value} exchanges done); that step's losses are NaN")
 
     def peer_array(self, region: int) -> int:
         """Device address of region ``region``'s pointer table."""

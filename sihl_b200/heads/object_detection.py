@@ -36,48 +36,49 @@ from .. import ops
 _TOTAL_WEIGHTS = (1.0, 10.0, 1.0, 1.0)          # loss = loc + 10*box + class + iou, ref :210
 
 
-class _DetectionLoss(torch.autograd.Function):
-    """[location, box, class, iou, total] losses of ref :157-210 from the head outputs.
-
-    forward: k_dense_loss + k_pos_loss + k_loss_finalize; backward: k_dense_loss_bwd +
-    k_pos_loss_bwd.  ``assignment`` / ``rel_iou`` carry no gradient (they are
-    functions of the anchors and the ground truth only)."""
+class _TrainLoss(torch.autograd.Function):
+    """[location, box, class, iou, total] losses of ref :157-217 from the head outputs: one kernel launch forward
+    (``sihl_od_train_loss``), one backward (``sihl_od_train_loss_bwd``), on fp32 / fp16 / bf16 maps as
+    they come out of the MLPs (no fp32 copies).  The number of positives stays on the device: ``box_rows`` /
+    ``cls_rows`` hold ``st.capacity`` rows of which the kernels use the first P.  ``assignment`` / ``rel_iou`` carry
+    no gradient (functions of the anchors and the ground truth only)."""
 
     @staticmethod
-    def forward(ctx, loc_logits, iou_preds, box_raw, cls_logits, state):
-        s = state
-        sums = ops.new_sums(loc_logits.device)
-        loc32 = loc_logits.detach().float().contiguous()
-        iou32 = None if iou_preds is None else iou_preds.detach().float().contiguous()
-        ops.dense_loss(loc32, iou32, s["rel_iou"], sums)
-        box32 = cls32 = None
-        if s["P"] > 0:
-            box32 = box_raw.detach().float().contiguous()
-            cls32 = cls_logits.detach().float().contiguous()
-            ops.pos_loss(s["pos_index"], None, s["P"], s["A"], s["rel_iou"], s["assignment"], s["offsets"], s["scales"],
-                         s["img_w"], s["img_h"], s["gt"], box32, cls32, False, sums)
-        if s.get("reduce_sums") is not None:
-            s["reduce_sums"](sums)                      # global-batch normalisers across ranks (dist.py)
-        ctx.state, ctx.sums = s, sums
-        ctx.saved = (loc32, iou32, box32, cls32)
-        ctx.in_dtypes = tuple(None if t is None else t.dtype for t in (loc_logits, iou_preds, box_raw, cls_logits))
-        return ops.loss_finalize(sums)
+    def forward(ctx, loc_logits, iou_preds, box_rows, cls_rows, st, reduce_sums):
+        if reduce_sums is None:
+            losses, maps = ops.train_loss(st, loc_logits, iou_preds, box_rows, cls_rows, finalize=True)
+        else:                                   # global-batch normalisers: sums cross the ranks before the division
+            _, maps = ops.train_loss(st, loc_logits, iou_preds, box_rows, cls_rows, finalize=False)
+            reduce_sums(st.sums)
+            losses = ops.loss_finalize(st.sums)
+        ctx.st, ctx.maps = st, maps
+        return losses
 
     @staticmethod
     def backward(ctx, grad_out):
-        s, sums = ctx.state, ctx.sums
-        loc32, iou32, box32, cls32 = ctx.saved
-        w = torch.tensor(_TOTAL_WEIGHTS, dtype=torch.float32, device=grad_out.device)
-        grad_terms = (grad_out[:4].float() + grad_out[4].float() * w).contiguous()
-        dloc, diou = ops.dense_loss_bwd(loc32, iou32, s["rel_iou"], sums, grad_terms,
-                                        want_dloc=ctx.needs_input_grad[0], want_diou=ctx.needs_input_grad[1])
-        dbox = dcls = None
-        if s["P"] > 0 and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
-            dbox, dcls = ops.pos_loss_bwd(s["pos_index"], None, s["P"], s["A"], s["rel_iou"], s["assignment"], s["offsets"],
-                                          s["scales"], s["img_w"], s["img_h"], s["gt"], box32, cls32, False, sums, grad_terms)
-        cast = lambda g, dt: None if g is None or dt is None else g.to(dt)
-        return (cast(dloc, ctx.in_dtypes[0]), cast(diou, ctx.in_dtypes[1]), cast(dbox, ctx.in_dtypes[2]),
-                cast(dcls, ctx.in_dtypes[3]), None)
+        grads = ops.train_loss_bwd(ctx.st, ctx.maps, grad_out.float().contiguous() if grad_out.dtype != torch.float32
+                                   or not grad_out.is_contiguous() else grad_out, ctx.needs_input_grad[:4])
+        return grads[0], grads[1], grads[2], grads[3], None, None
+
+
+def _cat_gt(boxes: List[Tensor], classes: Optional[List[Tensor]], device):
+    """ref :127-128 — per-image lists (possibly empty, possibly ``tv_tensors`` subclasses) -> one [sumG,4] fp32 and one
+    [sumG] int64 tensor on ``device`` + the host list of counts (from shapes: no sync)."""
+    counts = [int(b.shape[0]) for b in boxes]
+    plain = [b if type(b) is Tensor else b.as_subclass(Tensor) for b in boxes]
+    plain = [b if b.dim() == 2 else b.reshape(-1, 4) for b in plain]
+    cat = torch.cat(plain) if plain else torch.empty((0, 4))
+    if cat.dtype != torch.float32 or cat.device != device:
+        cat = cat.to(device=device, dtype=torch.float32)
+    cls = None
+    if classes is not None:
+        plain_c = [c if type(c) is Tensor else c.as_subclass(Tensor) for c in classes]
+        cls = torch.cat([c.reshape(-1) for c in plain_c]) if plain_c else torch.empty((0,), dtype=torch.int64)
+        if cls.dtype != torch.int64 or cls.device != device:
+            cls = cls.to(device=device, dtype=torch.int64)
+        if cls.numel() != cat.shape[0]:
+            raise ValueError("classes and boxes disagree on the number of objects")
+    return cat.contiguous(), cls, counts
 
 
 class ObjectDetection(nn.Module):
@@ -127,7 +128,10 @@ class ObjectDetection(nn.Module):
             "boxes": ("batch_size", max_instances, 4),
         }
         # "local": normalise by this process's batch (what the reference does, also under DDP);
-        # "global": all-reduce the 8 partial sums first (equals one process over the global batch).
+        # "global": all-reduce the 8 partial sums first: the losses equal one process over the global batch, the
+        #   early-out of ref :165-172 is decided on the GLOBAL number of positives (every rank runs every head, so DDP
+        #   sees gradients for every parameter on every rank), and the backward is scaled by the world size so that
+        #   DDP's gradient *average* over the ranks equals the gradient of the global-batch loss.
         self.loss_reduction = "local"
         self.process_group = None
 
@@ -144,7 +148,7 @@ class ObjectDetection(nn.Module):
         device = inputs[0].device
         height, width = inputs[0].shape[2:]
         offsets, scales, _ = ops.anchor_tables(self._level_sizes(inputs), int(width), int(height), device)
-        return offsets, scales
+        return offsets.clone(), scales.clone()      # the cached tables stay private: callers may edit what they get
 
     def get_saliency(self, inputs: List[Tensor]) -> Tensor:
         """ref :70-81 (visualisation only; learned part, stays PyTorch)."""
@@ -161,32 +165,57 @@ class ObjectDetection(nn.Module):
 
     # ------------------------------------------------------------------ inference
     def forward(self, inputs: List[Tensor]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-        """ref :99-122 -> (num_instances i64 [B], scores [B,K], classes i64 [B,K], boxes [B,K,4] px)."""
+        """ref :99-122 -> (num_instances i64 [B], scores [B,K], classes i64 [B,K], boxes [B,K,4] px).
+
+        The MLP outputs go to the kernels in the dtype they have (fp32, or fp16 / bf16 under autocast: upcast in
+        registers, no fp32 copies); ``scores`` come back in the dtype of the location logits like the reference's
+        ``loc_logits.sigmoid()``.  Traceable: under ``torch.compile`` the same kernels run as ``sihl_b200::*`` custom ops
+        (``sihl_b200/torch_ops.py``) with fake implementations."""
         (batch_size, _, height, width), device = inputs[0].shape, inputs[0].device
         flat_feats = self._flat_feats(inputs)
-        offsets, scales, _ = ops.anchor_tables(self._level_sizes(inputs), int(width), int(height), device)
+        levels = self._level_sizes(inputs)
         loc_logits = self.loc_head(flat_feats).squeeze(2)                                   # ref :108
-        top_logits, loc_idxs = ops.topk_locations(loc_logits.detach().float(), self.max_instances)   # ref :109
+        compiling = torch.compiler.is_compiling()
+        if compiling:
+            from .. import torch_ops
+            level_hw = torch_ops.flat_levels(levels)
+            top_logits, loc_idxs = torch_ops.topk_locations(loc_logits.detach(), self.max_instances)
+        else:
+            top_logits, loc_idxs = ops.topk_locations(loc_logits.detach(), self.max_instances)   # ref :109
         rows = torch.arange(batch_size, device=device).view(batch_size, 1)
         top_feats = flat_feats[rows, loc_idxs]                                              # ref :112
         class_logits = self.cls_head(top_feats)                                             # ref :116
         box_raw = self.box_head(top_feats)                                                  # ref :121
-        return ops.decode_rows(top_logits, loc_idxs, class_logits.detach().float(), box_raw.detach().float(),
-                               offsets, scales, int(width), int(height))
+        if compiling:
+            num, scores, classes, boxes = torch_ops.decode_rows(top_logits, loc_idxs, class_logits.detach(), box_raw.detach(),
+                                                                level_hw, int(width), int(height))
+        else:
+            offsets, scales, _ = ops.anchor_tables(levels, int(width), int(height), device)
+            num, scores, classes, boxes = ops.decode_rows(top_logits, loc_idxs, class_logits.detach(), box_raw.detach(),
+                                                          offsets, scales, int(width), int(height))
+        if loc_logits.dtype != torch.float32:
+            scores = scores.to(loc_logits.dtype)
+        return num, scores, classes, boxes
 
     @torch.no_grad()
-    def postprocess(self, inputs: List[Tensor], score_threshold: float = 0.05, iou_threshold: float = 0.5
-                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    def postprocess(self, inputs: List[Tensor], score_threshold: float = 0.05, iou_threshold: float = 0.5,
+                    mode: Optional[str] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         """North-star extension (the reference has no NMS): every location is decoded with the
         score/class semantics of ``forward`` (score = sigmoid(location logit), class = argmax),
-        thresholded, and de-duplicated by class-aware NMS; same output format as ``forward``."""
+        thresholded, and de-duplicated by class-aware NMS; same output format as ``forward``.
+
+        ``mode``: ``"dense"`` streams the whole class map (TMA ring), ``"candidate_first"`` reads the class row and raw
+        box of the locations that pass the threshold only — identical results; default: ``"dense"`` for fp32 maps,
+        ``"candidate_first"`` for half maps (autocast), which are then read as they are (no fp32 copies)."""
         (_, _, height, width) = inputs[0].shape
         flat_feats = self._flat_feats(inputs)
-        loc_logits = self.loc_head(flat_feats).squeeze(2).float()
-        cls_logits = self.cls_head(flat_feats).float()
-        box_raw = self.box_head(flat_feats).float()
+        loc_logits = self.loc_head(flat_feats).squeeze(2)
+        cls_logits = self.cls_head(flat_feats)
+        box_raw = self.box_head(flat_feats)
+        if mode is None:
+            mode = "dense" if loc_logits.dtype == torch.float32 else "candidate_first"
         return ops.dense_postprocess(loc_logits, cls_logits, box_raw, self._level_sizes(inputs), int(width), int(height),
-                                     score_threshold, iou_threshold, self.max_instances)
+                                     score_threshold, iou_threshold, self.max_instances, mode=mode)
 
     # ------------------------------------------------------------------ training
     def _reduce_sums(self) -> Optional[callable]:
@@ -195,6 +224,10 @@ class ObjectDetection(nn.Module):
         from .. import dist
         return partial(dist.all_reduce_sums, group=self.process_group)
 
+    def _world_size(self) -> int:
+        import torch.distributed as tdist
+        return tdist.get_world_size(self.process_group) if (tdist.is_available() and tdist.is_initialized()) else 1
+
     def training_step(
         self,
         inputs: List[Tensor],
@@ -202,7 +235,14 @@ class ObjectDetection(nn.Module):
         boxes: List[Tensor],
         is_validating: bool = False,
     ) -> Tuple[Tensor, Dict[str, float]]:
-        """ref :124-217 -> (loss, {"location_loss", "box_loss", "class_loss", "iou_loss"})."""
+        """ref :124-217 -> (loss, {"location_loss", "box_loss", "class_loss", "iou_loss"}).
+
+        Three C calls and no host synchronisation (the reference syncs ~7x per image): ``sihl_od_train_assign`` before
+        the MLPs, ``sihl_od_train_loss`` after them, ``sihl_od_train_loss_bwd`` in backward.  The number of positives P
+        stays on the device, so ``box_head`` / ``cls_head`` run on a static ``min(9 * sumG, B * A)`` rows
+        (``flat_feats[o2m_mask]`` followed by repeats of row 0 whose gradient is zero) and the early-out of ref :165-172
+        is taken inside the kernels: with no positive in the batch the loss is the location loss alone and the other
+        three heads receive zero gradients (the reference leaves them without any)."""
         assert len(inputs) > self.top_level, "too few input levels"
         device = inputs[0].device
         batch_size, _, full_height, full_width = inputs[0].shape
@@ -210,31 +250,49 @@ class ObjectDetection(nn.Module):
         width, height = int(full_width), int(full_height)
 
         # anchors + assignment: functions of shapes and gt only (ref :139-148) -> before the MLPs
-        offsets, scales, anchors = ops.anchor_tables(levels, width, height, device)
-        num_anchors = anchors.shape[0]
-        gt = ops.GtBatch.from_lists(boxes, classes, device)
-        assert gt.batch_size == batch_size, (gt.batch_size, batch_size)
-        sel = ops.assign_select(anchors, levels, width, height, gt, self.topk,
-                                terms=ops.anchor_terms(levels, width, height, device))
-        res = ops.assign_resolve(sel, gt, num_anchors, self.topk, True, want_positives=True)
-        pos_index, pos_total, _ = ops.pos_compact(res["tile_pos_count"], res["tile_pos_rows"], batch_size, num_anchors)
-        # the one host sync of the step: P sizes the gathered rows (the reference syncs ~7x per image)
-        num_pos = int(pos_total.item())
-        pos_index = pos_index[:num_pos]
+        gt_boxes, gt_classes, counts = _cat_gt(boxes, classes, device)
+        assert len(counts) == batch_size, (len(counts), batch_size)
+        if torch.compiler.is_compiling():
+            return self._training_step_traced(inputs, levels, width, height, gt_boxes, gt_classes, counts)
+        st = ops.train_assign(levels, width, height, gt_boxes, gt_classes, counts, batch_size, self.topk)
+        reduce_sums = self._reduce_sums()
+        if reduce_sums is not None:
+            st.grad_scale = float(self._world_size())      # DDP averages the gradients of W ranks (see loss_reduction)
 
         flat_feats = self._flat_feats(inputs)                                               # ref :151-154
         loc_logits = self.loc_head(flat_feats).squeeze(2)                                   # ref :157
-        state = dict(rel_iou=res["iou"], assignment=res["assignment"], pos_index=pos_index, P=num_pos, A=num_anchors,
-                     offsets=offsets, scales=scales, img_w=width, img_h=height, gt=gt, reduce_sums=self._reduce_sums())
-        if num_pos == 0:                                                                    # ref :165-172
-            out = _DetectionLoss.apply(loc_logits, None, None, None, state)
-        else:
-            iou_preds = self.iou_head(flat_feats).squeeze(2)                                # ref :175
-            o2m_feats = flat_feats.reshape(batch_size * num_anchors, -1)[pos_index.long()]  # ref :184
-            box_raw = self.box_head(o2m_feats)                                              # ref :189
-            class_logits = self.cls_head(o2m_feats)                                         # ref :200
-            out = _DetectionLoss.apply(loc_logits, iou_preds, box_raw, class_logits, state)
-        self.last_assignment, self.last_rel_iou = res["assignment"], res["iou"]
+        iou_preds = self.iou_head(flat_feats).squeeze(2)                                    # ref :175
+        o2m_feats = flat_feats.reshape(batch_size * st.A, -1).index_select(0, st.pos_index)  # ref :184 (+ padding rows)
+        box_raw = self.box_head(o2m_feats)                                                  # ref :189
+        class_logits = self.cls_head(o2m_feats)                                             # ref :200
+        out = _TrainLoss.apply(loc_logits, iou_preds, box_raw, class_logits, st, reduce_sums)
+        self.last_assignment, self.last_rel_iou, self.last_train_state = st.assignment, st.rel_iou, st
+        metrics = {"location_loss": out[0], "box_loss": out[1], "class_loss": out[2], "iou_loss": out[3]}
+        return out[4], metrics
+
+    def _training_step_traced(self, inputs, levels, width, height, gt_boxes, gt_classes, counts):
+        """The same step through the ``sihl_b200::*`` custom ops (fake implementations + registered autograd): what
+        ``torch.compile`` / ``torch.export`` trace.  ``loss_reduction="global"`` is an eager-only feature."""
+        from .. import torch_ops
+        assert self.loss_reduction == "local", "loss_reduction='global' is not traceable; call the eager module"
+        batch_size, device = len(counts), gt_boxes.device
+        level_hw = torch_ops.flat_levels(levels)
+        num_anchors = sum(h * w for h, w in levels)
+        prefix = [0]
+        for c in counts:
+            prefix.append(prefix[-1] + c)
+        gt_offsets = torch.tensor(prefix, dtype=torch.int32, device=device)
+        capacity = max(1, min(self.topk * prefix[-1], batch_size * num_anchors))
+        assignment, rel_iou, pos_index, meta = torch_ops.train_assign(gt_boxes, gt_offsets, level_hw, width, height,
+                                                                      self.topk, capacity)
+        flat_feats = self._flat_feats(inputs)
+        loc_logits = self.loc_head(flat_feats).squeeze(2)
+        iou_preds = self.iou_head(flat_feats).squeeze(2)
+        o2m_feats = flat_feats.reshape(batch_size * num_anchors, -1).index_select(0, pos_index)
+        box_raw = self.box_head(o2m_feats)
+        class_logits = self.cls_head(o2m_feats)
+        out, _ = torch_ops.train_loss(loc_logits, iou_preds, box_raw, class_logits, assignment, rel_iou, pos_index, meta,
+                                      gt_boxes, gt_classes, level_hw, width, height)
         metrics = {"location_loss": out[0], "box_loss": out[1], "class_loss": out[2], "iou_loss": out[3]}
         return out[4], metrics
 

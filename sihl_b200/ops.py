@@ -22,6 +22,7 @@ from . import _native
 
 NUM_SUMS = 8
 MAX_TOPK = 16
+DTYPE_CODES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}       # SIHL_OD_F32 / _F16 / _BF16 (sihl_od.h)
 
 
 def _lib():
@@ -67,6 +68,15 @@ def _req(t: Tensor, dtype, name: str, ndim: Optional[int] = None, pinned_ok: boo
     if ndim is not None and t.dim() != ndim:
         raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
     return t if t.is_contiguous() else t.contiguous()
+
+
+def _req_map(t: Tensor, name: str, ndim: Optional[int] = None, pinned_ok: bool = False) -> Tuple[Tensor, int]:
+    """A head-output map in any of the three supported element types -> (contiguous tensor, SIHL_OD_* dtype code);
+    anything else (fp64, ...) is converted to fp32."""
+    if isinstance(t, Tensor) and t.dtype not in DTYPE_CODES:
+        t = t.float()
+    t = _req(t, t.dtype if isinstance(t, Tensor) else torch.float32, name, ndim, pinned_ok)
+    return t, DTYPE_CODES[t.dtype]
 
 
 def _levels_array(levels: Sequence[Tuple[int, int]]) -> np.ndarray:
@@ -380,17 +390,181 @@ def pos_loss_bwd(pos_index, n_pos_dev, capacity, num_anchors, rel_iou, assignmen
     return dbox, dcls
 
 
+# --------------------------------------------------------------------------- the drop-in head's training step (N2)
+MAX_BATCH_BY_VALUE = 512                                                    # SIHL_OD_MAX_BATCH_BY_VALUE
+_geom_cache: Dict[tuple, tuple] = {}
+_ws_bytes_cache: Dict[tuple, int] = {}
+
+
+def _geometry(levels, img_w: int, img_h: int, device):
+    """Cached per (levels, image, device): anchor tables + terms + the host level array the C entry takes."""
+    key = (tuple(map(tuple, levels)), int(img_w), int(img_h), device.type, device.index)
+    g = _geom_cache.get(key)
+    if g is None:
+        offsets, scales, anchors = anchor_tables(levels, img_w, img_h, device)
+        hw = _levels_array(levels)
+        g = (offsets, scales, anchors, _anchor_cache[key][3], hw, hw.ctypes.data, len(hw), int(anchors.shape[0]))
+        _geom_cache[key] = g
+    return g
+
+
+class TrainAssignment:
+    """What ``sihl_od_train_assign`` leaves on the device for one training step (no host sync happened):
+    ``assignment`` i64 [B,A], ``rel_iou`` f32 [B,A], ``pos_index`` i32 [capacity] (first P = ``pos_total`` entries
+    real, the rest 0), plus the raw pointers ``sihl_od_train_loss`` / ``_bwd`` need."""
+    __slots__ = ("assignment", "rel_iou", "pos_index", "capacity", "meta", "B", "A", "img_w", "img_h", "offsets", "scales",
+                 "gt_boxes", "gt_classes", "device", "_p_sums", "_p_gt_offsets", "_p_pos_total", "grad_scale")
+
+    @staticmethod
+    def from_tensors(assignment: Tensor, rel_iou: Tensor, pos_index: Tensor, meta: Tensor, offsets: Tensor, scales: Tensor,
+                     gt_boxes: Tensor, gt_classes: Optional[Tensor], img_w: int, img_h: int,
+                     grad_scale: float = 1.0) -> "TrainAssignment":
+        """Rebuild the state from the tensors ``train_assign`` returned (the torch.library ops pass tensors only)."""
+        st = TrainAssignment()
+        st.assignment, st.rel_iou, st.pos_index, st.meta = assignment, rel_iou, pos_index, meta
+        st.B, st.A = int(rel_iou.shape[0]), int(rel_iou.shape[1])
+        st.capacity, st.device, st.img_w, st.img_h = int(pos_index.numel()), rel_iou.device, int(img_w), int(img_h)
+        st.offsets, st.scales, st.gt_boxes, st.gt_classes, st.grad_scale = offsets, scales, gt_boxes, gt_classes, grad_scale
+        base = meta.data_ptr()
+        st._p_sums, st._p_gt_offsets, st._p_pos_total = base, base + 64, base + 64 + 4 * (st.B + 1)
+        return st
+
+    @property
+    def sums(self) -> Tensor:
+        """fp64 [8] view of the step's partial sums (what crosses GPUs in ``loss_reduction="global"``)."""
+        return self.meta[:16].view(torch.float64)
+
+    @property
+    def gt_offsets(self) -> Tensor:
+        return self.meta[16:16 + self.B + 1]
+
+    @property
+    def pos_total(self) -> Tensor:
+        return self.meta[16 + self.B + 1:16 + self.B + 2]
+
+
+def train_assign(levels: Sequence[Tuple[int, int]], img_w: int, img_h: int, gt_boxes: Tensor, gt_classes: Optional[Tensor],
+                 gt_counts: Optional[Sequence[int]], batch: int, topk: int = 9, gt_offsets: Optional[Tensor] = None,
+                 pos_capacity: Optional[int] = None) -> TrainAssignment:
+    """ref :134-148 + the positive compaction of :182-184 for the whole batch: ONE C call (select, resolve, compact),
+    no host synchronisation.  ``gt_boxes`` fp32 [sumG,4] on the device; the per-image counts either as a host list
+    ``gt_counts`` (they come from tensor shapes; passed to the kernel by value) or as ``gt_offsets`` int32 [B+1] on
+    the device (then ``gt_boxes.shape[0]`` is only a capacity and the call is replayable from a CUDA graph on new
+    ground truth)."""
+    gt_boxes = _req(gt_boxes, torch.float32, "gt_boxes", 2)
+    dev = gt_boxes.device
+    offsets, scales, anchors, terms, hw, hw_ptr, n_levels, A = _geometry(levels, img_w, img_h, dev)
+    B, G = int(batch), int(gt_boxes.shape[0])
+    cap = int(pos_capacity) if pos_capacity is not None else max(1, min(int(topk) * G, B * A))
+    key = (B, A, G, int(topk))
+    ws_bytes = _ws_bytes_cache.get(key)
+    if ws_bytes is None:
+        ws_bytes = _ws_bytes_cache[key] = int(_lib().sihl_od_train_workspace_bytes(B, A, G, int(topk)))
+    st = TrainAssignment()
+    st.B, st.A, st.capacity, st.device, st.img_w, st.img_h = B, A, cap, dev, int(img_w), int(img_h)
+    st.offsets, st.scales, st.gt_boxes, st.gt_classes, st.grad_scale = offsets, scales, gt_boxes, gt_classes, 1.0
+    with _on(dev):
+        st.assignment = torch.empty((B, A), dtype=torch.int64, device=dev)
+        st.rel_iou = torch.empty((B, A), dtype=torch.float32, device=dev)
+        st.pos_index = torch.empty((cap,), dtype=torch.int32, device=dev)
+        # sums f64[8] | gt_offsets i32[B+1] | pos_total i32[1] in one small buffer (allocations are 512-byte aligned)
+        st.meta = torch.empty((16 + B + 2,), dtype=torch.int32, device=dev)
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+        base = st.meta.data_ptr()
+        st._p_sums, st._p_gt_offsets, st._p_pos_total = base, base + 64, base + 64 + 4 * (B + 1)
+        counts_ptr = None
+        if gt_offsets is not None:
+            st.meta[16:16 + B + 1].copy_(_req(gt_offsets, torch.int32, "gt_offsets", 1))
+        else:
+            if len(gt_counts) != B:
+                raise ValueError(f"{len(gt_counts)} gt counts for a batch of {B}")
+            if B > MAX_BATCH_BY_VALUE:                      # too many images for the kernel-parameter table: upload
+                off = np.zeros(B + 1, dtype=np.int32)
+                off[1:] = np.cumsum(gt_counts)
+                st.meta[16:16 + B + 1].copy_(torch.from_numpy(off))
+            else:
+                counts = np.asarray(gt_counts, dtype=np.int32)
+                counts_ptr = counts.ctypes.data
+        rc = _lib().sihl_od_train_assign(
+            anchors.data_ptr(), terms.data_ptr(), A, hw_ptr, n_levels, int(img_w), int(img_h), gt_boxes.data_ptr() if G else None,
+            counts_ptr, st._p_gt_offsets, B, G, int(topk), st.assignment.data_ptr(), st.rel_iou.data_ptr(),
+            st.pos_index.data_ptr(), cap, st._p_pos_total, st._p_sums, ws.data_ptr(), ws.numel(), _stream(dev))
+    _native.check(rc, "sihl_od_train_assign")
+    return st
+
+
+def _train_maps(st: TrainAssignment, loc_logits, iou_preds, box_rows, cls_rows):
+    """Common dtype + contiguity of the four head outputs; mixed dtypes are upcast to fp32 (never seen under autocast:
+    all four MLPs end in a Linear)."""
+    maps = [loc_logits, iou_preds, box_rows, cls_rows]
+    dt = loc_logits.dtype
+    if dt not in DTYPE_CODES or any(m is not None and m.dtype != dt for m in maps):
+        dt = torch.float32
+        maps = [None if m is None else m.float() for m in maps]
+    maps = [None if m is None else (m if m.is_contiguous() else m.contiguous()) for m in maps]
+    if not maps[0].is_cuda:
+        raise RuntimeError("sihl_b200 kernels run on CUDA tensors only; there is no CPU path")
+    if maps[0].numel() != st.B * st.A or (maps[1] is not None and maps[1].numel() != st.B * st.A):
+        raise ValueError("loc_logits / iou_preds must hold B*A elements")
+    C = 0
+    if maps[3] is not None:
+        C = int(maps[3].shape[-1])
+        if maps[3].numel() != st.capacity * C:
+            raise ValueError(f"cls_rows must be [{st.capacity}, C], got {tuple(maps[3].shape)}")
+    if maps[2] is not None and maps[2].numel() != st.capacity * 4:
+        raise ValueError(f"box_rows must be [{st.capacity}, 4], got {tuple(maps[2].shape)}")
+    return maps, DTYPE_CODES[dt], C
+
+
+def _train_common_args(st: TrainAssignment, maps, code: int, C: int):
+    return (_p(maps[0]), _p(maps[1]), _p(maps[2]), _p(maps[3]), code, st.B, st.A, C, st.rel_iou.data_ptr(),
+            st.assignment.data_ptr(), st.pos_index.data_ptr(), st.capacity, st._p_pos_total, st.offsets.data_ptr(),
+            st.scales.data_ptr(), st.img_w, st.img_h, _p(st.gt_boxes) if st.gt_boxes.numel() else None,
+            _p(st.gt_classes) if (st.gt_classes is not None and st.gt_classes.numel()) else None, st._p_gt_offsets)
+
+
+def train_loss(st: TrainAssignment, loc_logits: Tensor, iou_preds: Optional[Tensor], box_rows: Optional[Tensor],
+               cls_rows: Optional[Tensor], finalize: bool = True):
+    """ref :157-217 in one launch.  Returns ``(losses fp32 [5] or None, maps)`` — ``maps`` are the (contiguous, common
+    dtype) tensors the kernel read, to be saved for :func:`train_loss_bwd`."""
+    maps, code, C = _train_maps(st, loc_logits, iou_preds, box_rows, cls_rows)
+    if cls_rows is not None and st.gt_classes is None:
+        raise ValueError("the class loss needs gt classes")
+    dev = st.device
+    with _on(dev):
+        losses = torch.empty((5,), dtype=torch.float32, device=dev) if finalize else None
+        rc = _lib().sihl_od_train_loss(*_train_common_args(st, maps, code, C), st._p_sums, _p(losses), _stream(dev))
+    _native.check(rc, "sihl_od_train_loss")
+    return losses, maps
+
+
+def train_loss_bwd(st: TrainAssignment, maps, grad_losses: Optional[Tensor], want=(True, True, True, True)):
+    """SURVEY.md §7.4 in one launch; gradients come back in the dtype of ``maps``."""
+    code = DTYPE_CODES[maps[0].dtype]
+    C = 0 if maps[3] is None else int(maps[3].shape[-1])
+    dev = st.device
+    with _on(dev):
+        grads = [torch.empty_like(m) if (m is not None and w) else None for m, w in zip(maps, want)]
+        if grad_losses is not None:
+            grad_losses = _req(grad_losses, torch.float32, "grad_losses", 1)
+        rc = _lib().sihl_od_train_loss_bwd(*_train_common_args(st, maps, code, C), st._p_sums, _p(grad_losses),
+                                           float(st.grad_scale), _p(grads[0]), _p(grads[1]), _p(grads[2]), _p(grads[3]),
+                                           _stream(dev))
+    _native.check(rc, "sihl_od_train_loss_bwd")
+    return grads
+
+
 # --------------------------------------------------------------------------- a11
 def topk_locations(loc_logits: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """ref :109 — ``loc_logits.topk(k, dim=1)``: ``(values [B,k] f32, indices [B,k] i64)``,
     sorted descending, exact ties broken towards the lowest index."""
-    loc = _req(loc_logits, torch.float32, "loc_logits", 2)
+    loc, code = _req_map(loc_logits, "loc_logits", 2)
     B, A = loc.shape
     idx = torch.empty((B, k), dtype=torch.int64, device=loc.device)
-    top = torch.empty((B, k), dtype=torch.float32, device=loc.device)
+    top = torch.empty((B, k), dtype=torch.float32, device=loc.device)       # half values are exact in fp32
     with _on(loc.device):
-        rc = _lib().sihl_od_topk(_p(loc), B, A, int(k), _p(idx), _p(top), _stream(loc.device))
-    _native.check(rc, "sihl_od_topk")
+        rc = _lib().sihl_od_topk_t(_p(loc), code, B, A, int(k), _p(idx), _p(top), _stream(loc.device))
+    _native.check(rc, "sihl_od_topk_t")
     return top, idx
 
 
@@ -400,17 +574,20 @@ def decode_rows(top_logits: Tensor, idx: Tensor, cls_rows: Tensor, box_rows: Ten
     top = _req(top_logits, torch.float32, "top_logits", 2)
     B, K = top.shape
     dev = top.device
-    cls_rows = _req(cls_rows, torch.float32, "cls_rows", 3)
+    if cls_rows.dtype != box_rows.dtype or cls_rows.dtype not in DTYPE_CODES:
+        cls_rows, box_rows = cls_rows.float(), box_rows.float()
+    cls_rows, code = _req_map(cls_rows, "cls_rows", 3)
+    box_rows, _ = _req_map(box_rows, "box_rows", 3)
     num = torch.empty((B,), dtype=torch.int64, device=dev)
     scores = torch.empty((B, K), dtype=torch.float32, device=dev)
     classes = torch.empty((B, K), dtype=torch.int64, device=dev)
     boxes = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
     with _on(dev):
-        rc = _lib().sihl_od_decode_rows(_p(top), _p(_req(idx, torch.int64, "idx", 2)), B, K, _p(cls_rows),
-                                        int(cls_rows.shape[-1]), _p(_req(box_rows, torch.float32, "box_rows", 3)),
-                                        _p(offsets), _p(scales), int(img_w), int(img_h), _p(num), _p(scores),
-                                        _p(classes), _p(boxes), _stream(dev))
-    _native.check(rc, "sihl_od_decode_rows")
+        rc = _lib().sihl_od_decode_rows_t(_p(top), _p(_req(idx, torch.int64, "idx", 2)), B, K, _p(cls_rows),
+                                          int(cls_rows.shape[-1]), _p(box_rows), code,
+                                          _p(offsets), _p(scales), int(img_w), int(img_h), _p(num), _p(scores),
+                                          _p(classes), _p(boxes), _stream(dev))
+    _native.check(rc, "sihl_od_decode_rows_t")
     return num, scores, classes, boxes
 
 
@@ -447,9 +624,23 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
     if mode not in DECODE_MODES:
         raise ValueError(f"mode={mode!r}: expected one of {DECODE_MODES}")
     host_ok = mode == "candidate_first"        # gathers rows: the class / box maps may stay in pinned host memory
-    loc = _req(loc_logits, torch.float32, "loc_logits", 2)
-    cls = _req(cls_logits, torch.float32, "cls_logits", 3, pinned_ok=host_ok)
-    box = _req(box_raw, torch.float32, "box_raw", 3, pinned_ok=host_ok)
+    if mode == "candidate_first" and loc_logits.dtype in (torch.float16, torch.bfloat16) \
+            and cls_logits.dtype == loc_logits.dtype and box_raw.dtype == loc_logits.dtype:
+        # half maps straight from the MLPs (autocast): loaded as they are, upcast in registers
+        loc, code = _req_map(loc_logits, "loc_logits", 2)
+        cls, _ = _req_map(cls_logits, "cls_logits", 3, pinned_ok=True)
+        box, _ = _req_map(box_raw, "box_raw", 3, pinned_ok=True)
+        B, A = loc.shape
+        with _on(loc.device):
+            rc = _lib().sihl_od_candidate_decode_t(_p(loc), _p(cls), _p(box), code, B, A, int(cls.shape[-1]), _p(offsets),
+                                                   _p(scales), int(img_w), int(img_h), float(score_thr), _p(cand.count),
+                                                   cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts),
+                                                   _stream(loc.device))
+        _native.check(rc, "sihl_od_candidate_decode_t")
+        return
+    loc = _req(loc_logits.float() if loc_logits.dtype != torch.float32 else loc_logits, torch.float32, "loc_logits", 2)
+    cls = _req(cls_logits.float() if cls_logits.dtype != torch.float32 else cls_logits, torch.float32, "cls_logits", 3, pinned_ok=host_ok)
+    box = _req(box_raw.float() if box_raw.dtype != torch.float32 else box_raw, torch.float32, "box_raw", 3, pinned_ok=host_ok)
     B, A = loc.shape
     name = "sihl_od_dense_decode" if mode == "dense" else "sihl_od_candidate_decode"
     with _on(loc.device):

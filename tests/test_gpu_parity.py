@@ -17,7 +17,7 @@ import torch
 from oracle import golden_cases as gc
 from oracle import od_oracle as orc
 from oracle import torch_restatement as tr
-from sihl_b200 import ops, synth
+from sihl_b200 import _native, ops, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -587,7 +587,8 @@ def test_fused_loss_sum_exchange_against_a_scripted_peer():
     torch.cuda.synchronize()
     local = plain.sums.clone()
 
-    words = 18 * world + 1
+    words = 18 * world + 3
+    assert words * 8 <= _native.load().sihl_od_exchange_region_bytes(world)
     mine = torch.zeros(words, dtype=torch.float64, device=DEV)        # rank 0's region (this GPU)
     theirs = torch.zeros(words, dtype=torch.float64, device=DEV)      # stands in for rank 1's region
     table = torch.tensor([mine.data_ptr(), theirs.data_ptr()], dtype=torch.int64, device=DEV)
@@ -609,12 +610,20 @@ def test_fused_loss_sum_exchange_against_a_scripted_peer():
         torch.testing.assert_close(pushed, local[:7], rtol=1e-12, atol=0)           # what the peer would have received
         assert int(theirs.view(torch.int64)[16 * world + parity * world + 0]) == step
         assert int(mine.view(torch.int64)[18 * world]) == step                      # own step counter
+    import ctypes as C
     import time
+    lib = _native.load()
+    bad, done = C.c_uint64(7), C.c_uint64(0)
+    _native.check(lib.sihl_od_exchange_status(mine.data_ptr(), world, C.byref(bad), C.byref(done)), "status")
+    assert bad.value == 0 and done.value == 3                                       # nothing timed out so far
+    _native.check(lib.sihl_od_exchange_set_timeout(mine.data_ptr(), world, int(2e9)), "set_timeout")   # default: 120 s
     t0 = time.perf_counter()
     pipe.train_chain(x, out)                                                        # step 4: the peer never arrives
     torch.cuda.synchronize()
     assert 1.5 < time.perf_counter() - t0 < 10.0
     assert torch.isnan(out.losses).all()
+    _native.check(lib.sihl_od_exchange_status(mine.data_ptr(), world, C.byref(bad), C.byref(done)), "status")
+    assert bad.value == 4 and done.value == 4                                       # the host can see WHICH step gave up
 
 
 @pytest.mark.parametrize("C,K,loc_mean", [(80, 100, -4.0), (1, 100, -4.0), (3, 300, 0.0), (80, 1000, -7.0)])

@@ -1,5 +1,5 @@
 // Developer microbenchmark (not part of the product): what read bandwidth can a streaming kernel reach on this GPU?
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o read_bw read_bw.cu && ./read_bw
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/read_bw read_bw.cu && /tmp/read_bw   (binary outside the tree)
 // (1) plain LDG.128 grid-stride reduction, (2) the cp.async.bulk ring of k_dense_decode_tma with an empty consumer,
 // (3) the same ring with one LDS.128 pass + max tree over the stage (the decode kernel's consumer without the argmax).
 #include <cstdio>
