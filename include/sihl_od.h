@@ -235,6 +235,10 @@ SIHL_OD_API int sihl_od_exchange_destroy(void *block);
 /* Per region (own block only; synchronous copies, not on the per-step path): the bound of the in-kernel wait in ns
  * (0 = default 120 s), and the sticky status: *timed_out_step = the first step whose wait ran out (0 = none),
  * *steps_done (may be NULL) = exchanges performed on this region so far. */
+/* Device-side barrier over the node's GPUs on a region of its own (never one the fused exchange uses): enqueues one
+ * tiny kernel that returns once every rank has enqueued — and the GPU reached — the same call.  Aligns the start of a
+ * timed region across GPUs without a host barrier.  peer_regions as for sihl_od_pos_loss_tiles_exchange. */
+SIHL_OD_API int sihl_od_exchange_barrier(void *const *peer_regions, int world, int rank, void *stream);
 SIHL_OD_API int sihl_od_exchange_set_timeout(void *region, int world, uint64_t timeout_ns);
 SIHL_OD_API int sihl_od_exchange_status(const void *region, int world, uint64_t *timed_out_step, uint64_t *steps_done);
 

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "sihl_od_exchange_open": (I, [P, P]),
     "sihl_od_exchange_close": (I, [P]),
     "sihl_od_exchange_destroy": (I, [P]),
+    "sihl_od_exchange_barrier": (I, [P, I, I, P]),
     "sihl_od_exchange_set_timeout": (I, [P, I, C.c_uint64]),
     "sihl_od_exchange_status": (I, [P, I, P, P]),
     "sihl_od_pos_compact": (I, [P, P, I, I64, P, I64, P, P, P]),

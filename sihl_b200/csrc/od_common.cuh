@@ -101,6 +101,56 @@ template <> __device__ __forceinline__ void stf4<__nv_bfloat16>(__nv_bfloat16 *p
     *reinterpret_cast<uint2 *>(p) = u;
 }
 
+// 16 bytes of a row (4 floats / 8 halfs) as floats; p must be 16-byte aligned.
+template <typename T> struct Vec16 { static constexpr int N = 16 / (int)sizeof(T); };
+template <typename T> __device__ __forceinline__ void ld_vec16(const T *p, float (&out)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void ld_vec16<float>(const float *p, float (&out)[4])
+{
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+    out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+}
+template <> __device__ __forceinline__ void ld_vec16<__half>(const __half *p, float (&out)[8])
+{
+    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+        out[2 * i] = f.x; out[2 * i + 1] = f.y;
+    }
+}
+template <> __device__ __forceinline__ void ld_vec16<__nv_bfloat16>(const __nv_bfloat16 *p, float (&out)[8])
+{
+    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
+        out[2 * i] = f.x; out[2 * i + 1] = f.y;
+    }
+}
+template <typename T> __device__ __forceinline__ void st_vec16(T *p, const float (&v)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void st_vec16<float>(float *p, const float (&v)[4])
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st_vec16<__half>(__half *p, const float (&v)[8])
+{
+    uint4 u;
+    unsigned *w = reinterpret_cast<unsigned *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<__half2 *>(&w[i]) = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+template <> __device__ __forceinline__ void st_vec16<__nv_bfloat16>(__nv_bfloat16 *p, const float (&v)[8])
+{
+    uint4 u;
+    unsigned *w = reinterpret_cast<unsigned *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<__nv_bfloat162 *>(&w[i]) = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+
 // Run `stmt` with the alias T bound to the C++ type of dtype code `code`; returns SIHL_OD_EINVAL on a bad code.
 #define SIHL_DISPATCH_DTYPE(code, ...)                                                           \
     do {                                                                                         \

@@ -68,6 +68,48 @@ extern "C" int sihl_od_exchange_destroy(void *block)
     return cuda_status(cudaFree(block), "cudaFree(exchange block)");
 }
 
+// Device-side barrier over the node's GPUs on one exchange region (one CTA, thread q talks to rank q): every rank
+// publishes its next step number into every peer's flag word with a release store and waits, with acquire loads, until
+// every peer's flag has arrived.  Enqueued in front of a timed region it makes all GPUs start within an NVLink
+// round trip of each other WITHOUT a host barrier (whose rank skew would land inside the region); same region layout,
+// timeout and sticky error word as the fused loss-sum exchange (od_loss.cu), so a region must be used for one or the
+// other, never both.
+__global__ void __launch_bounds__(32) k_exchange_barrier(unsigned long long *const *peer, int W, int rank)
+{
+    __shared__ unsigned long long s_step;
+    const int tid = threadIdx.x;
+    unsigned long long *mine = peer[rank];
+    if (tid == 0) s_step = ++mine[18 * W];
+    __syncwarp();
+    const unsigned long long step = s_step;
+    const int parity = (int)(step & 1ull);
+    if (tid < W) {
+        unsigned long long *theirs = peer[tid];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs + 16 * W + parity * W + rank), "l"(step) : "memory");
+        const unsigned long long *flag = mine + 16 * W + parity * W + tid;
+        unsigned long long t0, now, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned long long limit = *reinterpret_cast<volatile unsigned long long *>(mine + 18 * W + 1);
+        if (limit == 0ull) limit = 120000000000ull;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v == step) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > limit) { atomicCAS(mine + 18 * W + 2, 0ull, step); break; }
+            __nanosleep(64);
+        }
+    }
+}
+
+extern "C" int sihl_od_exchange_barrier(void *const *peer_regions, int world, int rank, void *stream)
+{
+    SIHL_CHECK_ARG(peer_regions && world >= 1 && world <= SIHL_OD_MAX_PEERS && rank >= 0 && rank < world, "bad arguments");
+    if (world == 1) return SIHL_OD_OK;
+    k_exchange_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *const *>(peer_regions), world, rank);
+    SIHL_CHECK_LAUNCH("k_exchange_barrier");
+    return SIHL_OD_OK;
+}
+
 extern "C" int sihl_od_exchange_set_timeout(void *region, int world, uint64_t timeout_ns)
 {
     SIHL_CHECK_ARG(region && world >= 1 && world <= SIHL_OD_MAX_PEERS, "bad arguments");

@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(256) k_dense_decode_v4(DenseDecodeParams p)
 // keeps in registers, and every byte is read from HBM exactly once.  Consumers: 4 lanes per
 // row, conflict-free LDS.128, first-argmax as above.
 // ---------------------------------------------------------------------------
-constexpr int kChunkRows = 64;             // rows per ring stage == rows one pass of the 256-thread CTA covers (4 lanes per row)
+constexpr int kChunkRows = 64;             // rows per ring stage of the default variant == rows one pass of a 256-thread CTA covers
+                                           // (4 lanes per row); small scans use 32-row stages on 128-thread CTAs (see the entry point)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
@@ -463,13 +464,14 @@ __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const S
     __syncwarp();
 }
 
-template <int VPL, bool EXACT>
-__global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, int stages, int n_chunks)
+template <int VPL, bool EXACT, int ROWS = kChunkRows>     // ROWS per stage; the CTA has 4 * ROWS threads (4 lanes per row)
+__global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams p, int stages, int n_chunks)
 {
+    constexpr int kWarps = 4 * ROWS / 32;
     extern __shared__ __align__(128) unsigned char s_ring[];
-    __shared__ StagedCand s_list[kStageCap];                      // one 32-entry segment per warp: no atomics to append
-    __shared__ int s_seg_count[8];
-    static_assert(kStageCap == 256, "8 warps x 32 staged candidates");
+    __shared__ StagedCand s_list[kWarps * 32];                    // one 32-entry segment per warp: no atomics to append
+    __shared__ int s_seg_count[kWarps];
+    static_assert(kStageCap == 256 && kWarps <= 8, "at most 8 warps x 32 staged candidates");
     const int tid = threadIdx.x, gl = tid & 3, r = tid >> 2, lane = tid & 31, warp = tid >> 5;
     int n_staged = 0;                                             // this warp's segment fill (warp-uniform)
     const int C4 = p.C >> 2;
@@ -478,13 +480,13 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
     // coalesced load one chunk ahead (one lane per row), the raw box is read for candidates only (flush_staged):
     // small bulk copies cost the TMA unit as much as big ones (measured with tools/micro/read_bw.cu: a ring of
     // single 21 KB copies reaches the 6.3 TB/s read ceiling, the former 3-copy stage did not).
-    const uint32_t stage_bytes = (uint32_t)kChunkRows * (uint32_t)p.C * 4u;
+    const uint32_t stage_bytes = (uint32_t)ROWS * (uint32_t)p.C * 4u;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + (size_t)stages * stage_bytes);
 
     const uint64_t policy = l2_evict_first_policy();
     auto issue = [&](int stage, int chunk) {                      // one elected thread
-        const int64_t row0 = (int64_t)chunk * kChunkRows;
-        const int64_t n = rows - row0 < kChunkRows ? rows - row0 : kChunkRows;
+        const int64_t row0 = (int64_t)chunk * ROWS;
+        const int64_t n = rows - row0 < ROWS ? rows - row0 : ROWS;
         const uint32_t cb = (uint32_t)n * (uint32_t)p.C * 4u;
         mbar_expect_tx(bars + stage, cb);
         bulk_g2s(s_ring + (size_t)stage * stage_bytes, p.cls + row0 * p.C, cb, bars + stage, policy);
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
     // sigmoid(x) > thr is monotone in x: compare logits against the smallest logit whose sigmoid passes
     const float x_thr = p.logit_thr;
     auto load_loc = [&](int chunk) -> float {                     // lane gl == 0 of every row group
-        const int64_t row = (int64_t)chunk * kChunkRows + r;
+        const int64_t row = (int64_t)chunk * ROWS + r;
         return (gl == 0 && chunk < n_chunks && row < rows) ? __ldcs(p.loc + row) : -CUDART_INF_F;
     };
     float x_next = load_loc((int)blockIdx.x);
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
         x_next = load_loc(c + (int)gridDim.x);                    // in flight while this chunk is consumed
         mbar_wait(bars + s, phase);
         const unsigned char *base = s_ring + (size_t)s * stage_bytes;
-        const int64_t row = (int64_t)c * kChunkRows + r;
+        const int64_t row = (int64_t)c * ROWS + r;
         const bool ok = row < rows;
         const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
         // first arg-max of the row in two cheap steps: the row maximum (max tree + 2 shuffles), then the
@@ -578,7 +580,7 @@ __global__ void __launch_bounds__(256) k_dense_decode_tma(DenseDecodeParams p, i
     __syncthreads();
     int total = 0, mine_seg = -1, mine_idx = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kWarps; ++w) {
         const int cnt = s_seg_count[w];
         if (mine_seg < 0 && tid < total + cnt) { mine_seg = w; mine_idx = tid - total; }
         total += cnt;
@@ -810,25 +812,41 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
     if (aligned && loc_aligned && c4 <= 32 && rows >= 4 * kChunkRows) {
         const int vpl = (c4 + 3) / 4;
         const bool exact = vpl * 4 == c4;
-        const size_t stage_bytes = (size_t)kChunkRows * num_classes * 4;
-        // 2 stages x 2 CTAs per SM: measured on B200 the kernel is already at the HBM roof with ~87 KB in
-        // flight per SM (3 and 4 stages give the same 32 us), and the smaller ring leaves ~120 KB of shared
-        // memory per SM to the kernels of the other chain / the neighbouring step running concurrently
-        int stages = 2;
-        int ctas_per_sm = 2;
-        if (const char *e = getenv("SIHL_DECODE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 10 && (size_t)v * stage_bytes < 200 * 1024) stages = v; }
-        if (const char *e = getenv("SIHL_DECODE_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 4) ctas_per_sm = v; }
+        // 2 stages x 2 CTAs per SM of 64-row stages: measured on B200 the kernel is already at the HBM roof with ~87 KB
+        // in flight per SM (3 and 4 stages give the same 32 us), and the smaller ring leaves ~120 KB of shared
+        // memory per SM to the kernels of the other chain / the neighbouring step running concurrently.
+        // SMALL scans (fewer than ~16 such stages per CTA: the 1024^2 / batch 8 crowd config has 9) are dominated by
+        // ring start-up, the last partial round and the end-of-kernel flush: they take 32-row stages on 128-thread
+        // CTAs, 4 per SM with 4 stages each — twice as many, half as long work items (5 % instead of 10 % imbalance),
+        // twice the bytes in flight from the first microsecond.
+        int rows_per_stage = kChunkRows, stages = 2, ctas_per_sm = 2;
+        if ((rows + kChunkRows - 1) / kChunkRows < (int64_t)16 * kNumSMs * 2) { rows_per_stage = 32; stages = 4; ctas_per_sm = 4; }
+        if (const char *e = getenv("SIHL_DECODE_ROWS")) { const int v = atoi(e); if (v == 32 || v == 64) rows_per_stage = v; }
+        const size_t stage_bytes = (size_t)rows_per_stage * num_classes * 4;
+        if (const char *e = getenv("SIHL_DECODE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 16 && (size_t)v * stage_bytes < 200 * 1024) stages = v; }
+        if (const char *e = getenv("SIHL_DECODE_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 8) ctas_per_sm = v; }
+        while ((size_t)stages * stage_bytes * ctas_per_sm > 200 * 1024 && stages > 2) --stages;
         const size_t smem = stages * stage_bytes + stages * sizeof(uint64_t);
-        const int n_chunks = (int)((rows + kChunkRows - 1) / kChunkRows);
+        const int n_chunks = (int)((rows + rows_per_stage - 1) / rows_per_stage);
         int blocks = kNumSMs * ctas_per_sm;
         if (blocks > n_chunks) blocks = n_chunks;
-#define SIHL_DT(VPL)                                                                                              \
+#define SIHL_DT_LAUNCH(KERN, THREADS)                                                                             \
     do {                                                                                                          \
-        auto kern = exact ? k_dense_decode_tma<VPL, true> : k_dense_decode_tma<VPL, false>;                       \
+        auto kern = KERN;                                                                                         \
         int rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),  \
                              "cudaFuncSetAttribute(k_dense_decode_tma)");                                         \
         if (rc) return rc;                                                                                        \
-        kern<<<blocks, 256, smem, st>>>(p, stages, n_chunks);                                                     \
+        kern<<<blocks, THREADS, smem, st>>>(p, stages, n_chunks);                                                 \
+    } while (0)
+#define SIHL_DT(VPL)                                                                                              \
+    do {                                                                                                          \
+        if (rows_per_stage == 64) {                                                                               \
+            if (exact) SIHL_DT_LAUNCH((k_dense_decode_tma<VPL, true, 64>), 256);                                  \
+            else SIHL_DT_LAUNCH((k_dense_decode_tma<VPL, false, 64>), 256);                                       \
+        } else {                                                                                                  \
+            if (exact) SIHL_DT_LAUNCH((k_dense_decode_tma<VPL, true, 32>), 128);                                  \
+            else SIHL_DT_LAUNCH((k_dense_decode_tma<VPL, false, 32>), 128);                                       \
+        }                                                                                                         \
     } while (0)
         switch (vpl) {
             case 1: SIHL_DT(1); break;
@@ -841,6 +859,7 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
             default: SIHL_DT(8); break;
         }
 #undef SIHL_DT
+#undef SIHL_DT_LAUNCH
     } else if (aligned && c4 <= 32 * 8) {
         // 4 lanes per row up to C = 128, a full warp per row beyond; grid = 4 resident CTAs per SM
         const int lpr = c4 <= 32 ? 4 : 32;

@@ -4,17 +4,23 @@
 // (score desc, index asc); a kept box suppresses every later box of the same class with
 // inter / (area_i + area_j - inter) > thr.
 //
-// One CTA per image (segment), everything for that image on chip when it fits:
-//   1. bitonic sort of (score-key | ~index, slot) descending         -> rank r (output order)
-//   2. bitonic sort of (class << 32 | r) ascending                   -> class segments, score
-//      order preserved inside each (the rank makes the second sort stable)
-//   3. greedy suppression inside each class segment only: one warp per segment, the kept box
-//      is broadcast and 32 later boxes are tested per step (dead flags in shared memory);
-//      segments longer than kBigSegment are swept by the whole CTA instead
-//   4. ordered compaction of the survivors by rank r               -> keep list / top-K rows
-// Lists longer than kSmemItems spill the same arrays to a global workspace (same code,
-// generic pointers).  Work is O(sum_c n_c^2 / 32) warp steps instead of the O(N^2) pair
-// tests of the all-pairs bitmask formulation.
+// k_nms: one CTA per image (segment), sort-free, the list length (known only on the device) picks the body:
+//   * n <= 256 (nms_small_body): 4 lanes per candidate; ONE counting pass over the list gives every candidate its
+//     rank (score desc, index asc), its class-major position and its class segment; suppression bitmasks per
+//     candidate against the earlier boxes of its class (all pairs in parallel), greedy chain on bits.
+//   * top-K entry with n > 256 and K <= 128 (lazy prefix): greedy NMS is prefix-closed — whether a box is kept
+//     depends only on higher-ranked boxes — so the K best survivors are found among the ~200 highest-ranked
+//     candidates whenever at least K of them survive: a 4-pass radix select picks that prefix (all ties with it),
+//     the short-list body runs on it, and only if fewer than K survive does the full list get processed.
+//   * longer lists (nms_medium_body): class buckets through a shared-memory hash table (count -> scan -> scatter),
+//     rank by counting inside the class, 64-bit suppression masks for classes <= 64 boxes, 32-box chunks (all
+//     pairs of a chunk in parallel by shuffles, then the chunk's kept boxes against the rest) by one warp per
+//     class up to 2048 boxes and by the whole CTA beyond, top-K by radix select of the K-th score; arrays in
+//     shared memory up to 4096 candidates, in the global workspace beyond.
+//   * more than 512 distinct classes (nms_big_body): the two-bitonic-sort fallback — sort by rank, sort by
+//     (class, rank), per-segment suppression, ordered compaction.
+// sihl_od_nms_topk_split deals an image's candidates to several CTAs by class; stand-alone batched NMS of
+// 8192..90000 boxes takes the multi-CTA bitmask path of od_nms_wide.cu (whole GPU) instead of one CTA.
 #include "od_common.cuh"
 
 namespace sihl {
@@ -407,7 +413,10 @@ __device__ __forceinline__ void nms_big_body(const NmsParams &p)
 // IoU > thr (all pairs in parallel, no serial dependence), resolved by one lane per segment with
 // pure bit operations — the greedy chain costs a few cycles per box instead of a shared-memory
 // round trip per kept box.  Segments longer than 32 fall back to the broadcast loop of k_nms.
-__device__ __forceinline__ void nms_small_body(const NmsParams &p)
+// `sel` (optional, shared memory): the body runs on the n_sel candidates lb + sel[0..n_sel) instead of the whole list
+// (lazy top-K prefix).  Returns the number of survivors; with finalize == false the per-image epilogue
+// (num_instances, zero padding, counter reset) is left to the caller.
+__device__ __forceinline__ int nms_small_body(const NmsParams &p, const int *sel = nullptr, int n_sel = 0, bool finalize = true)
 {
     __shared__ unsigned long long s_key[kSmallItems];
     __shared__ unsigned s_cls[kSmallItems];        // by slot
@@ -433,6 +442,7 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
         src0 = __ldg(p.seg_offsets + img);
         n = __ldg(p.seg_offsets + img + 1) - src0;
     }
+    if (sel != nullptr) n = n_sel;
     SIHL_PHASE(1);
     int n_kept = 0;
     if (n > 0) {
@@ -442,9 +452,10 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
         float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
         if (have) {
             if (p.mode == 0) {
-                key = __ldg(p.cand_key + lb + item);
-                cls = (unsigned)__ldg(p.cand_cls + lb + item);
-                bx = __ldg(p.cand_box + lb + item);
+                const int src = sel != nullptr ? sel[item] : item;
+                key = __ldg(p.cand_key + lb + src);
+                cls = (unsigned)__ldg(p.cand_cls + lb + src);
+                bx = __ldg(p.cand_box + lb + src);
             } else {
                 key = ((unsigned long long)f2ord_nms(__ldg(p.scores + src0 + item)) << 32) |
                       (unsigned long long)(0xffffffffu - (unsigned)item);
@@ -549,6 +560,7 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
             });
     }
     SIHL_PHASE(6);
+    if (!finalize) return n_kept;
     if (p.mode == 0) {
         const int m = n_kept < p.K ? n_kept : p.K;
         if (tid == 0) {
@@ -565,6 +577,79 @@ __device__ __forceinline__ void nms_small_body(const NmsParams &p)
         p.keep_count[img] = n_kept;
     }
     SIHL_PHASE(7);
+    return n_kept;
+}
+
+// Lazy prefix for the top-K entry (mode 0): pick the ~kLazyTarget highest-ranked candidates of a long list — every
+// candidate whose score is >= the kLazyTarget-th largest score, i.e. a prefix of the visit order closed under
+// ties — into s_sel.  4-pass MSB radix select on the score word of the key (scores are sigmoid outputs > 0: their
+// bit patterns order like the values).  Returns the prefix length, or 0 if it would not fit (a tie wider than the
+// short-list body) and the caller should process the full list.
+constexpr int kLazyTarget = 200;
+constexpr int kLazyMaxK = 128;
+__device__ __forceinline__ int lazy_prefix_select(const NmsParams &p, int64_t lb, int n, int *s_sel, unsigned *s_hist,
+                                                  unsigned *s_pick, int *s_count)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    unsigned prefix = 0u, mask = 0u, remaining = (unsigned)kLazyTarget;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + tid;
+            const bool ok = i < n;
+            const unsigned u = ok ? (unsigned)(__ldg(p.cand_key + lb + i) >> 32) : 0u;
+            const bool in = ok && ((u & mask) == prefix);
+            const unsigned digit = (u >> shift) & 255u;
+            const unsigned act = __ballot_sync(kFullMask, in);
+            if (in) {                                       // warp-aggregated histogram update (scores cluster)
+                const unsigned peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {                                     // lane handles 8 digits, descending
+            unsigned c[8], tot = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = s_hist[255 - (lane * 8 + j)]; tot += c[j]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += y;
+            }
+            unsigned before = incl - tot;
+            if (before < remaining && remaining <= incl) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (before < remaining && remaining <= before + c[j]) {
+                        s_pick[0] = 255u - (unsigned)(lane * 8 + j);
+                        s_pick[1] = remaining - before;
+                    }
+                    before += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= s_pick[0] << shift;
+        mask |= 255u << shift;
+        remaining = s_pick[1];
+        __syncthreads();
+    }
+    // everything with score word >= prefix: kLazyTarget - remaining strictly above + the whole tie group
+    if (tid == 0) *s_count = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        if (i < n && (unsigned)(__ldg(p.cand_key + lb + i) >> 32) >= prefix) {
+            const int pos = atomicAdd(s_count, 1);
+            if (pos < kSmallItems) s_sel[pos] = i;
+        }
+    }
+    __syncthreads();
+    const int c = *s_count;
+    return c <= kSmallItems ? c : 0;
 }
 
 // Medium and long lists (n > kSmallItems).  No global sort: candidates are bucketed by class through a small
@@ -877,6 +962,25 @@ __global__ void __launch_bounds__(kNmsThreads) k_nms(NmsParams p)
         n = __ldg(p.seg_offsets + blockIdx.x + 1) - src0;
     }
     if (n <= kSmallItems) { nms_small_body(p); return; }
+    if (p.mode == 0 && p.K <= kLazyMaxK) {
+        // top-K of a long list: try the highest-ranked ~200 candidates first (exact: see the file header)
+        __shared__ int s_sel[kSmallItems];
+        __shared__ unsigned s_pick[2];
+        __shared__ int s_count;
+        const int64_t lb = list_base(p, (int)blockIdx.x);
+        const int m = lazy_prefix_select(p, lb, n, s_sel, reinterpret_cast<unsigned *>(s_hcnt), s_pick, &s_count);
+        if (m > 0) {
+            const int kept = nms_small_body(p, s_sel, m, false);
+            if (kept >= p.K) {                             // the K best survivors are all inside the prefix: done
+                if (threadIdx.x == 0) {
+                    p.num_instances[blockIdx.x] = p.K;
+                    if (p.reset_counts) const_cast<int32_t *>(p.cand_count)[blockIdx.x] = 0;
+                }
+                return;
+            }
+            __syncthreads();                               // fewer than K survived: the full list decides
+        }
+    }
     int n_al = 2;
     while (n_al < n) n_al <<= 1;
     int n_kept = 0;
@@ -1082,8 +1186,17 @@ extern "C" int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacity
     return launch_nms(p, batch, cand_capacity, (cudaStream_t)stream);
 }
 
+namespace sihl {                 // od_nms_wide.cu: the multi-CTA bitmask path for one long list
+size_t wide_nms_workspace_bytes(int64_t n);
+bool wide_nms_applies(int64_t n);
+int launch_wide_batched_nms(const float *boxes, const float *scores, const int64_t *classes, const int32_t *seg_offsets,
+                            int n_images, int64_t n, float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace,
+                            cudaStream_t st);
+}
+
 extern "C" size_t sihl_od_batched_nms_workspace_bytes(int64_t n)
 {
+    if (wide_nms_applies(n)) return wide_nms_workspace_bytes(n);
     if (n <= kSmemItems) return 0;
     return (size_t)(2 * n + 2) * kWsItemBytes;
 }
@@ -1098,6 +1211,9 @@ extern "C" int sihl_od_batched_nms(const float *boxes, const float *scores, cons
     SIHL_CHECK_ARG(workspace != nullptr || sihl_od_batched_nms_workspace_bytes(n) == 0, "workspace needed for n=%lld",
                    (long long)n);
     if (n_images == 0) return SIHL_OD_OK;
+    if (wide_nms_applies(n))        // 8192..90000 boxes: bitmask-parallel suppression over all SMs (od_nms_wide.cu)
+        return launch_wide_batched_nms(boxes, scores, classes, seg_offsets, n_images, n, iou_thr, keep, keep_count, workspace,
+                                       (cudaStream_t)stream);
     NmsParams p = {};
     p.boxes = reinterpret_cast<const float4 *>(boxes); p.scores = scores; p.classes = classes; p.seg_offsets = seg_offsets;
     p.mode = 1; p.iou_thr = iou_thr; p.keep = keep; p.keep_count = keep_count;

@@ -27,6 +27,7 @@ struct TrainLossParams {
     const float4 *gt_boxes; const int64_t *gt_classes; const int32_t *gt_offsets;
     double *sums; float *losses;
     int dense_blocks, pos_blocks;
+    int cls_vec;               // class rows are read / written 16 bytes at a time (C * sizeof(T) % 16 == 0, aligned bases)
     // backward
     const float *grad_losses; float grad_scale;
     void *dloc; void *diou; void *dbox; void *dcls;
@@ -128,12 +129,30 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss(TrainLossParams p)
                 const int b = (int)(flat / A);
                 const int tgt = pos_target(p, flat, b);
                 const T *z = cls_rows + rr * C;
-                float m = -CUDART_INF_F;
-                for (int c = gl; c < C; c += 8) m = fmaxf(m, ldf(z + c));
+                float m = -CUDART_INF_F, s = 0.f;
+                if (p.cls_vec) {                                      // 16-byte loads: 8 lanes x 128 contiguous bytes
+                    constexpr int N = Vec16<T>::N;
+                    const int CV = C / N;
+                    for (int v = gl; v < CV; v += 8) {
+                        float x[N];
+                        ld_vec16(z + v * N, x);
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
-                float s = 0.f;
-                for (int c = gl; c < C; c += 8) s += expf(ldf(z + c) - m);
+                        for (int e = 0; e < N; ++e) m = fmaxf(m, x[e]);
+                    }
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+                    for (int v = gl; v < CV; v += 8) {                // second pass: L1 hits
+                        float x[N];
+                        ld_vec16(z + v * N, x);
+#pragma unroll
+                        for (int e = 0; e < N; ++e) s += expf(x[e] - m);
+                    }
+                } else {
+                    for (int c = gl; c < C; c += 8) m = fmaxf(m, ldf(z + c));
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+                    for (int c = gl; c < C; c += 8) s += expf(ldf(z + c) - m);
+                }
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
                 if (ok && gl == 0) {
@@ -217,8 +236,17 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss_bwd(TrainLossParam
             const int64_t r = it * ngrp + grp;
             if (r >= p.pos_capacity) continue;                        // group-uniform (8 lanes share r)
             T *out = dcls + r * C;
+            constexpr int N = Vec16<T>::N;
+            const int CV = C / N;
             if (r >= n) {                                             // padding row: zero gradient
-                for (int c = gl; c < C; c += 8) out[c] = from_f<T>(0.f);
+                if (p.cls_vec) {
+                    float zero[N];
+#pragma unroll
+                    for (int e = 0; e < N; ++e) zero[e] = 0.f;
+                    for (int v = gl; v < CV; v += 8) st_vec16(out + v * N, zero);
+                } else {
+                    for (int c = gl; c < C; c += 8) out[c] = from_f<T>(0.f);
+                }
                 continue;
             }
             const int64_t flat = __ldg(p.pos_index + r);
@@ -227,18 +255,44 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss_bwd(TrainLossParam
             const T *z = cls_rows + r * C;
             // the 8 lanes of a group may diverge from the other groups of the warp: group-local shuffles
             const unsigned gmask = 0xffu << ((tid & 31) & ~7);
-            float m = -CUDART_INF_F;
-            for (int c = gl; c < C; c += 8) m = fmaxf(m, ldf(z + c));
+            float m = -CUDART_INF_F, s = 0.f;
+            if (p.cls_vec) {
+                for (int v = gl; v < CV; v += 8) {
+                    float x[N];
+                    ld_vec16(z + v * N, x);
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
-            float s = 0.f;
-            for (int c = gl; c < C; c += 8) s += expf(ldf(z + c) - m);
+                    for (int e = 0; e < N; ++e) m = fmaxf(m, x[e]);
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
+                for (int v = gl; v < CV; v += 8) {
+                    float x[N];
+                    ld_vec16(z + v * N, x);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) s += expf(x[e] - m);
+                }
+            } else {
+                for (int c = gl; c < C; c += 8) m = fmaxf(m, ldf(z + c));
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
+                for (int c = gl; c < C; c += 8) s += expf(ldf(z + c) - m);
+            }
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
             const float k = tgt >= 0 ? g_cls * __ldg(p.rel + flat) * inv_w : CUDART_NAN_F;   // ref :208
             const float inv_s = 1.f / s;
-            for (int c = gl; c < C; c += 8)
-                out[c] = from_f<T>(k * (expf(ldf(z + c) - m) * inv_s - (c == tgt ? 1.f : 0.f)));
+            if (p.cls_vec) {
+                for (int v = gl; v < CV; v += 8) {
+                    float x[N];
+                    ld_vec16(z + v * N, x);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) x[e] = k * (expf(x[e] - m) * inv_s - ((v * N + e) == tgt ? 1.f : 0.f));
+                    st_vec16(out + v * N, x);
+                }
+            } else {
+                for (int c = gl; c < C; c += 8)
+                    out[c] = from_f<T>(k * (expf(ldf(z + c) - m) * inv_s - (c == tgt ? 1.f : 0.f)));
+            }
         }
     }
 }
@@ -276,7 +330,17 @@ static int fill_train(TrainLossParams *out, const void *loc_logits, const void *
     int64_t pb = (p.pos_capacity * 8 + kTrainThreads - 1) / kTrainThreads;
     if (pb > (int64_t)kNumSMs * 8) pb = (int64_t)kNumSMs * 8;
     p.dense_blocks = (int)db; p.pos_blocks = rows ? (int)(pb < 1 ? 1 : pb) : 0;
+    p.cls_vec = 0;                                  // set per dtype by the callers (needs sizeof(T))
     return SIHL_OD_OK;
+}
+
+static int class_rows_vectorisable(int map_dtype, int num_classes, const void *a, const void *b)
+{
+    const int esz = map_dtype == SIHL_OD_F32 ? 4 : 2;
+    if (num_classes <= 0 || ((size_t)num_classes * esz) % 16 != 0) return 0;
+    if (a != nullptr && (reinterpret_cast<uintptr_t>(a) & 15u) != 0) return 0;
+    if (b != nullptr && (reinterpret_cast<uintptr_t>(b) & 15u) != 0) return 0;
+    return 1;
 }
 
 }  // namespace sihl
@@ -296,6 +360,7 @@ extern "C" int sihl_od_train_loss(const void *loc_logits, const void *iou_preds,
     if (rc) return rc;
     SIHL_CHECK_ARG(loc_logits != nullptr && sums != nullptr, "loc_logits / sums is NULL");
     p.sums = sums; p.losses = losses;
+    p.cls_vec = class_rows_vectorisable(map_dtype, num_classes, cls_rows, nullptr);
     const int blocks = p.dense_blocks + p.pos_blocks;
     if (blocks == 0) return SIHL_OD_OK;
     SIHL_DISPATCH_DTYPE(map_dtype, (k_train_loss<T><<<blocks, kTrainThreads, 0, (cudaStream_t)stream>>>(p)));
@@ -323,6 +388,7 @@ extern "C" int sihl_od_train_loss_bwd(const void *loc_logits, const void *iou_pr
     SIHL_CHECK_ARG(dbox_rows == nullptr || (reinterpret_cast<uintptr_t>(dbox_rows) & 15u) == 0, "dbox_rows must be 16-byte aligned");
     p.sums = const_cast<double *>(sums); p.grad_losses = grad_losses; p.grad_scale = grad_scale;
     p.dloc = dloc; p.diou = diou; p.dbox = dbox_rows; p.dcls = dcls_rows;
+    p.cls_vec = class_rows_vectorisable(map_dtype, num_classes, cls_rows, dcls_rows);
     if (dloc == nullptr && diou == nullptr) p.dense_blocks = 0;
     if (dbox_rows == nullptr && dcls_rows == nullptr) p.pos_blocks = 0;
     const int blocks = p.dense_blocks + p.pos_blocks;

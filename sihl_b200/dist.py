@@ -126,6 +126,14 @@ class PeerExchange:
                 self.lib.sihl_od_exchange_destroy(self._own)
                 self._own.value = None
 
+    def device_barrier(self, region: int, stream=None) -> None:
+        """Enqueue a device-side barrier over the ranks on ``region`` (a region no pipeline is attached to): the stream
+        continues once every rank's GPU has reached the same point.  No host synchronisation."""
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        with torch.cuda.device(self.device):
+            _check(self.lib.sihl_od_exchange_barrier(self.peer_array(region), self.world, self.rank, st),
+                   "sihl_od_exchange_barrier")
+
     def set_timeout(self, seconds: float) -> None:
         """Bound of the in-kernel wait for the peers' sums (default 120 s).  A rank that is merely slow — dataloader
         stall, checkpoint, first-step lazy initialisation — must not be mistaken for a dead one."""

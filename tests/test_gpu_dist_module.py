@@ -87,7 +87,11 @@ def test_global_loss_reduction_two_ranks_equal_one_process():
         assert got[r]["loss"].item() == got[0]["loss"].item()                       # identical bits on every rank
         for k, v in want_metrics.items():
             assert got[r]["metrics"][k].item() == pytest.approx(v.item(), rel=1e-4, abs=1e-7), (r, k)
+        # scale per sub-module (laterals, loc_head, ...): a lone bias gradient such as sum_i d iou_i is a near-cancelling
+        # sum of ~1e3 terms, so its own magnitude is no yardstick for GEMM-order noise
+        scale = {}
         for n, g in want_grads.items():
-            scale = max(g.abs().max().item(), 1e-30)
-            err = (got[r]["grads"][n] - g).abs().max().item() / scale
+            scale[n.split(".")[0]] = max(scale.get(n.split(".")[0], 1e-30), g.abs().max().item())
+        for n, g in want_grads.items():
+            err = (got[r]["grads"][n] - g).abs().max().item() / scale[n.split(".")[0]]
             assert err < 2e-3, f"rank {r} {n}: {err}"

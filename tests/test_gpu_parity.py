@@ -647,3 +647,63 @@ def test_class_split_nms_equals_single_cta_nms(C, K, loc_mean):
     for a, b in zip(*outs):
         assert torch.equal(a, b)
     assert int(n_cand.max()) > (4096 if loc_mean > -5 else 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# long lists on the whole GPU (od_nms_wide.cu) and the lazy top-K prefix of k_nms
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,n_cls", [(30000, 1), (30000, 80), (8192, 3), (20000, 5000)])
+def test_wide_batched_nms_one_long_list(n, n_cls):
+    """8192..90000 boxes take the multi-CTA bitmask path: keep lists equal to the C oracle (torchvision's per-class
+    semantics, (score desc, index asc) order) — incl. 30 000 boxes of ONE class, the case one CTA handled worst."""
+    boxes, scores, classes = synth.nms_candidates_np(4242 + n_cls, n, 1024, n_cls)
+    keep = ops.batched_nms(_t(boxes), _t(scores), _t(classes), 0.5).cpu().numpy()
+    np.testing.assert_array_equal(keep, orc.batched_nms(boxes, scores, classes, 0.5))
+    import torchvision
+    tv = torchvision.ops.batched_nms(_t(boxes), _t(scores), _t(classes), 0.5).cpu().numpy()
+    assert set(keep.tolist()) == set(tv.tolist())                                  # the library this path extends
+
+
+def test_wide_batched_nms_segments_ties_and_threshold_edge():
+    """Several segments in one wide call (a 256-item tile straddles segment borders), tied scores (index order decides),
+    duplicate boxes (IoU == 1) and a threshold that equals an IoU exactly (strict '>')."""
+    sizes = [3000, 0, 7000, 1, 2500]
+    parts = [synth.nms_candidates_np(77 + i, n, 800, 7) for i, n in enumerate(sizes)]
+    boxes = np.concatenate([p[0] for p in parts]); scores = np.concatenate([p[1] for p in parts])
+    classes = np.concatenate([p[2] for p in parts])
+    scores[::3] = np.round(scores[::3], 2)                                          # many exact score ties
+    boxes[100:200] = boxes[0:100]; classes[100:200] = classes[0:100]                # duplicates of earlier boxes
+    boxes[5000] = [0, 0, 10, 10]; boxes[5001] = [0, 0, 10, 5]; classes[5000] = classes[5001] = 3   # IoU = 0.5 exactly
+    scores[5000], scores[5001] = 0.99, 0.98
+    seg = np.zeros(len(sizes) + 1, np.int32); seg[1:] = np.cumsum(sizes)
+    assert seg[-1] >= 8192
+    keep, count = ops.batched_nms(_t(boxes), _t(scores), _t(classes), 0.5, seg_offsets=_t(seg))
+    keep, count = keep.cpu().numpy(), count.cpu().numpy()
+    for i, n in enumerate(sizes):
+        s, e = seg[i], seg[i + 1]
+        want = orc.batched_nms(boxes[s:e], scores[s:e], classes[s:e], 0.5) + s
+        assert count[i] == len(want), i
+        np.testing.assert_array_equal(keep[s:s + count[i]], want)
+    kept = set(keep[seg[2]:seg[2] + count[2]].tolist())
+    assert 5000 in kept and 5001 in kept                                            # IoU == thr does not suppress
+
+
+@pytest.mark.parametrize("C,loc_mean,K,what", [(80, 0.0, 100, "prefix holds K survivors"), (1, 3.0, 100, "one class: prefix exhausted, full list decides"),
+                                              (80, 0.0, 128, "largest K of the lazy path"), (3, 1.0, 20, "few classes")])
+def test_lazy_topk_prefix_equals_full_nms(C, loc_mean, K, what):
+    """k_nms, top-K entry, long lists: the ~200 highest-ranked candidates decide when K of them survive; otherwise the
+    full list is processed.  Both outcomes must equal the oracle's full NMS."""
+    size, B = 640, 3
+    levels = synth.level_sizes(size, size)
+    A = synth.num_anchors(levels)
+    maps = synth.dense_maps_np(91, B, A, C, loc_mean=loc_mean, loc_std=2.0)
+    maps.loc_logits[:, ::5] = np.round(maps.loc_logits[:, ::5], 1)                  # tied scores inside the prefix
+    num, scores, classes, boxes = ops.dense_postprocess(_t(maps.loc_logits), _t(maps.cls_logits), _t(maps.box_raw), levels,
+                                                        size, size, 0.05, 0.5, K, mode="candidate_first", split_nms=False)
+    o_off, o_sc, _ = orc.anchors(levels, size, size)
+    w_num, w_scores, w_cls, w_boxes, _ = orc.dense_postprocess(maps.loc_logits, maps.cls_logits, maps.box_raw, o_off, o_sc,
+                                                               size, size, 0.05, 0.5, K)
+    np.testing.assert_array_equal(num.cpu().numpy(), w_num)
+    np.testing.assert_array_equal(classes.cpu().numpy(), w_cls)
+    np.testing.assert_allclose(scores.cpu().numpy(), w_scores, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(boxes.cpu().numpy(), w_boxes, rtol=1e-5, atol=1e-4)
