@@ -71,6 +71,10 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-gpu-eager", action="store_true")
+    ap.add_argument("--regions", type=int, default=5,
+                    help="timed regions of --steps steps each; the line reports the median region (SURVEY.md §8d), min/max "
+                         "and per-rank times beside it")
+    ap.add_argument("--skip-train-tail", action="store_true", help="do not time the drop-in head's training tail with backward")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--e2e-lanes", type=int, default=2, help="end-to-end steps in flight (own stream + buffers each)")
     return ap.parse_args()
@@ -243,6 +247,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_rank_to_gpu_numa(local_rank, world):
+    """Multi-GPU end-to-end runs feed every GPU from pinned host memory: give each rank its own slice of the CPUs that
+    are local to its GPU (NVML CPU affinity), BEFORE any pinned buffer is allocated, so that the rank's host thread and
+    (first-touch) its pinned pages sit on the GPU's NUMA node and the ranks do not share cores.  Returns what was done."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = [c for c in range(n_cpu) if (int(words[c // 64]) >> (c % 64)) & 1]
+        allowed = sorted(set(local) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        # ranks whose GPUs share this CPU set split it evenly (local ranks are 0..world-1 on one node)
+        sharing = []
+        for r in range(world):
+            wr = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), (n_cpu + 63) // 64)
+            if list(wr) == list(words):
+                sharing.append(r)
+        per = max(1, len(allowed) // max(1, len(sharing)))
+        k = sharing.index(local_rank) if local_rank in sharing else 0
+        mine = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        return {"gpu_local_cpus": len(local), "ranks_sharing_them": len(sharing), "bound_to": [mine[0], mine[-1]], "n_bound": len(mine)}
+    except Exception as exc:                                  # noqa: BLE001 - affinity is an optimisation, never fatal
+        return {"error": str(exc)[:120]}
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, w, world, rank, local_rank):
     import torch
@@ -252,6 +285,7 @@ def run_ours(args, w, world, rank, local_rank):
     from sihl_b200.pipeline import LAUNCHES_PER_STEP, DetectionHeadPipeline, StepInputs
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    affinity = bind_rank_to_gpu_numa(local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     H, W, B, C, G, K = w["height"], w["width"], w["batch"], w["classes"], w["gt"], w["k"]
@@ -295,7 +329,7 @@ def run_ours(args, w, world, rank, local_rank):
         if fused:
             from sihl_b200.dist import PeerExchange
             try:
-                ex = PeerExchange(dev, n_regions=len(pipes))
+                ex = PeerExchange(dev, n_regions=len(pipes) + 1)      # + one region for the device-side start barrier
             except RuntimeError as exc:
                 fused = False
                 args.allreduce = "nccl"
@@ -304,6 +338,7 @@ def run_ours(args, w, world, rank, local_rank):
             exchanges.append(ex)
             for i, pp in enumerate(pipes):
                 pp.attach_exchange(ex, i)
+                pp.start_barrier = (ex, len(pipes))
         return pipes
 
     def barrier():
@@ -311,16 +346,17 @@ def run_ours(args, w, world, rank, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(mode, steps, warmup):
-        """Build the lanes for one decode mode, replay `warmup` + `steps` steps, return (ms, pipes, outs, graphs)."""
+    def timed_steps(mode, steps, warmup, n_regions):
+        """Build the lanes for one decode mode, replay `warmup` steps and `n_regions` regions of `steps` steps, return
+        (median region ms, pipes, outs, graphs, timing)."""
         pipes = attach([DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
                         for _ in range(n_lanes)])
         # every (lane, input set) pair owns its outputs: steps in flight on different lanes never share a buffer
         outs = [[pipes[ln].new_outputs() for _ in range(n_sets)] for ln in range(n_lanes)]
         torch.cuda.synchronize()
-        return _timed_steps(pipes, outs, steps, warmup)
+        return _timed_steps(pipes, outs, steps, warmup, n_regions)
 
-    def _timed_steps(pipes, outs, n_steps, n_warmup):
+    def _timed_steps(pipes, outs, n_steps, n_warmup, n_regions):
         def full_step(ln, i):
             """One step incl. the cross-GPU exchange: 8 fp64 sums all-reduced between the loss kernels and finalize."""
             out = outs[ln][i]
@@ -375,25 +411,45 @@ def run_ours(args, w, world, rank, local_rank):
         for s in range(n_warmup):
             run_step(s)
         drain()
-        barrier()
-        if sampler: sampler.mark()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(main)
-        fork()
-        for s in range(n_steps):
-            run_step(s)
-        drain()
-        e1.record(main)
-        barrier()
-        if sampler: sampler.mark()
-        ms = e0.elapsed_time(e1)
+        # R timed regions of exactly n_steps steps each.  Every region: host barrier + synchronize on both sides (the
+        # contract), and — with the fused exchange — a DEVICE-side barrier enqueued in front of the start event, so that
+        # all GPUs enter the region within an NVLink round trip of each other and the host barrier's rank skew stays
+        # outside it.  Reported: the median region of the max-over-ranks times, min / max, and every rank's median.
+        start_barrier = getattr(pipes[0], "start_barrier", None) if fused else None
+        per_region, step_no = [], n_warmup
+        for _ in range(max(1, n_regions)):
+            barrier()
+            if sampler: sampler.mark()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if start_barrier is not None:
+                start_barrier[0].device_barrier(start_barrier[1], main)
+            e0.record(main)
+            fork()
+            for s in range(step_no, step_no + n_steps):
+                run_step(s)
+            step_no += n_steps
+            drain()
+            e1.record(main)
+            barrier()
+            if sampler: sampler.mark()
+            per_region.append(e0.elapsed_time(e1))
+        mine = torch.tensor(per_region, dtype=torch.float64, device=dev)
         if multi:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, pipes, outs, graphs
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            allr = torch.stack(allr)                        # [rank, region]
+        else:
+            allr = mine.view(1, -1)
+        region_max = allr.max(dim=0).values                 # max over ranks, per region
+        ms = float(region_max.median().item())
+        timing = {"regions": len(per_region), "steps_per_region": n_steps, "ms_per_step_median": ms / n_steps,
+                  "ms_per_step_min": float(region_max.min().item()) / n_steps,
+                  "ms_per_step_max": float(region_max.max().item()) / n_steps,
+                  "per_rank_ms_per_step_median": [float(v) / n_steps for v in allr.median(dim=1).values.tolist()],
+                  "start": "device-side barrier over NVLink peer memory" if start_barrier is not None else "host barrier"}
+        return ms, pipes, outs, graphs, timing
 
-    ms, pipes, outs, graphs = timed_steps(args.decode_mode, args.steps, max(args.warmup, 3))
+    ms, pipes, outs, graphs, timing = timed_steps(args.decode_mode, args.steps, max(args.warmup, 3), args.regions)
     pipe = pipes[0]
     value = B * world * args.steps / (ms * 1e-3)
     outs0 = outs[0]
@@ -422,7 +478,7 @@ def run_ours(args, w, world, rank, local_rank):
     if not args.skip_candidate_first:
         other_mode = "candidate_first" if args.decode_mode == "dense" else "dense"
         o_steps = max(3, min(args.steps, 1000))
-        o_ms, o_pipes, o_outs, _ = timed_steps(other_mode, o_steps, max(min(args.warmup, 100), 3))
+        o_ms, o_pipes, o_outs, _, _ = timed_steps(other_mode, o_steps, max(min(args.warmup, 100), 3), min(args.regions, 3))
         same = all(torch.equal(a, b) for a, b in zip(
             (outs0[0].num_instances, outs0[0].scores, outs0[0].classes, outs0[0].boxes, outs0[0].assignment),
             (o_outs[0][0].num_instances, o_outs[0][0].scores, o_outs[0][0].classes, o_outs[0][0].boxes, o_outs[0][0].assignment)))
@@ -436,10 +492,11 @@ def run_ours(args, w, world, rank, local_rank):
         n_e2e = max(1, args.e2e_lanes)
         mk = lambda mode: attach([_P(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
                                   for _ in range(n_e2e)])
-        full, _ = run_e2e(args, mk(args.decode_mode), sets[0], world, multi, dev, smp)
+        e2e_sets = sets[:min(len(sets), 3)]                     # rotating pinned host sets (3 x 188 MB at cfg1)
+        full, _ = run_e2e(args, mk(args.decode_mode), e2e_sets, world, multi, dev, smp)
         ref = (outs0[0].num_instances, outs0[0].scores, outs0[0].classes, outs0[0].boxes, outs0[0].assignment,
                outs0[0].rel_iou)
-        sparse, cf_out = run_e2e(args, mk("candidate_first"), sets[0], world, multi, dev, smp, host_maps=True,
+        sparse, cf_out = run_e2e(args, mk("candidate_first"), e2e_sets, world, multi, dev, smp, host_maps=True,
                                  gathered_rows=rows)
         got = (cf_out.num_instances, cf_out.scores, cf_out.classes, cf_out.boxes, cf_out.assignment, cf_out.rel_iou)
         sparse["outputs_equal_to_resident_run"] = bool(all(torch.equal(a, b) for a, b in zip(ref, got)))
@@ -451,6 +508,7 @@ def run_ours(args, w, world, rank, local_rank):
         if not args.skip_e2e:
             both_e2e(None, 0.0)
         for ex in exchanges:
+            ex.check()                                   # raises if any in-kernel wait for a peer ever timed out
             ex.close()
         return
 
@@ -517,12 +575,18 @@ def run_ours(args, w, world, rank, local_rank):
                "sample": f"{r['sample_images']} of {B} images of {args.workload} x {r['steps']} passes: {REFERENCE_WHAT}; "
                          f"{r['cores']} threads"}
 
+    # ---- the drop-in head's training tail WITH gradients (what ObjectDetection.training_step runs around its MLPs)
+    train_tail = None
+    if not multi and not args.skip_train_tail:
+        train_tail = train_tail_with_backward(w, sets[0], levels, dev)
+
     # ---- the reference's operator sequence as torch eager on THIS GPU (the bar SURVEY.md §2b names)
     eager = None
     if not multi and not args.skip_gpu_eager:
         eager = gpu_eager_reference(w, sets[0], levels, dev)
 
     for ex in exchanges:
+        ex.check()
         ex.close()
     clocks = sampler.stop() if sampler else None
     line = {
@@ -533,6 +597,7 @@ def run_ours(args, w, world, rank, local_rank):
                                                 "steps_in_flight": n_lanes, "decode_mode": args.decode_mode,
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
+        "timing": timing, "train_with_backward": train_tail, "cpu_affinity": affinity,
         "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi and not fused else 0)) * args.steps,
         "allreduce": (("fused" if fused else "nccl") if multi else None), "allreduce_check": allreduce_check,
         "allreduce_fallback": (fallback_note[0] if fallback_note else None), "roofline": roofline, "roofline_step": roofline_step,
@@ -540,6 +605,64 @@ def run_ours(args, w, world, rank, local_rank):
         "losses_check": losses,
     }
     print(json.dumps(line), flush=True)
+
+
+def train_tail_with_backward(w, x, levels, dev, reps=300):
+    """The training tail of the drop-in head with gradients, as ``ObjectDetection.training_step`` + ``backward`` run it
+    around the MLPs: ``sihl_od_train_assign`` (select, resolve, compaction) -> ``sihl_od_train_loss`` (one launch) ->
+    ``sihl_od_train_loss_bwd`` (one launch): 3 C calls, 5 launches, no host synchronisation.  The MLP outputs are
+    synthetic leaf tensors (rows gathered once, outside the timed region).  ``graph``: the step captured once into a CUDA
+    graph and replayed, device-timed; ``eager``: host-launched every step, wall clock."""
+    import torch
+    from sihl_b200 import ops
+    from sihl_b200.heads.object_detection import _TrainLoss
+    H, W, B, C, G = w["height"], w["width"], w["batch"], w["classes"], w["gt"]
+    counts = list(x.gt.counts)
+    st0 = ops.train_assign(levels, W, H, x.gt.boxes, x.gt.classes, counts, B, TOPK)
+    bx0 = x.box_raw.view(-1, 4).index_select(0, st0.pos_index).contiguous()
+    cl0 = x.cls_logits.view(-1, C).index_select(0, st0.pos_index).contiguous()
+
+    def step(gt_offsets=None):
+        st = ops.train_assign(levels, W, H, x.gt.boxes, x.gt.classes, None if gt_offsets is not None else counts, B, TOPK,
+                              gt_offsets=gt_offsets)
+        leaves = [t.detach().requires_grad_(True) for t in (x.loc_logits, x.iou_preds, bx0, cl0)]
+        out = _TrainLoss.apply(*leaves, st, None)
+        out[4].backward()
+        return out, [t.grad for t in leaves]
+
+    out, grads = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    eager_ms = (time.perf_counter() - t0) / reps * 1e3
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(x.gt.offsets)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out, g_grads = step(x.gt.offsets)
+    for _ in range(20):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    graph_ms = e0.elapsed_time(e1) / reps
+    same = bool(torch.equal(g_out, out) and all(torch.equal(a, b) for a, b in zip(g_grads, grads)))
+    return {"what": "assign + positive compaction + 4 losses + backward (drop-in head's own path; MLP outputs are leaf tensors)",
+            "ms_per_step": graph_ms, "value": B / (graph_ms * 1e-3), "unit": UNIT, "mode": "CUDA graph replay, device timed",
+            "eager_ms_per_step": eager_ms, "eager_value": B / (eager_ms * 1e-3), "graph_equals_eager": same,
+            "gpu_launches_per_step": 5, "c_calls_per_step": 3, "host_syncs_per_step": 0,
+            "positives": int(st0.pos_total.item()), "row_capacity": st0.capacity, "losses": out.detach().cpu().tolist()}
 
 
 def gpu_eager_reference(w, x, levels, dev, passes=2):
@@ -563,17 +686,18 @@ def gpu_eager_reference(w, x, levels, dev, passes=2):
             "kind": "torch eager on the same GPU: %s, best of %d" % (REFERENCE_WHAT, passes)}
 
 
-def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathered_rows=0.0):
+def run_e2e(args, pipes, xs, world, multi, dev, sampler, host_maps=False, gathered_rows=0.0):
     """End to end through the public API (DetectionHeadPipeline.step) from pinned HOST inputs, every step: inputs
     cross PCIe inside the timed region, losses + detections are read back to the host.  One lane per pipeline in
     `pipes` (own stream, device input slot, outputs, host result buffers): step i runs on lane i % len(pipes), so
-    the PCIe traffic of one step overlaps the kernels of its neighbours.
+    the PCIe traffic of one step overlaps the kernels of its neighbours.  The host inputs ROTATE over the sets `xs`
+    (step i reads set i % len(xs)), so no step re-reads what the previous one left in a cache.
 
     host_maps=False: all seven input tensors are uploaded (copy stream), any decode mode.
     host_maps=True (pipelines in candidate-first mode): only the location / IoU maps and the gt are uploaded; the class
     and box maps stay in pinned host memory and the kernels read the rows they need (positives, candidates) in place
     over PCIe.  `gathered_rows` = positives + candidates per step, to count those bytes.
-    Returns (result dict, outputs of lane 0)."""
+    Returns (result dict, outputs of lane 0 for set 0)."""
     import torch
     import torch.distributed as dist
 
@@ -581,9 +705,10 @@ def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathere
     from sihl_b200.pipeline import StepInputs
 
     n = max(args.e2e_steps, 2)
-    L = len(pipes)
-    host = [t.cpu().pin_memory() for t in (x.loc_logits, x.iou_preds, x.box_raw, x.cls_logits, x.gt.boxes, x.gt.classes,
-                                            x.gt.offsets)]
+    L, S = len(pipes), len(xs)
+    fields = lambda x: (x.loc_logits, x.iou_preds, x.box_raw, x.cls_logits, x.gt.boxes, x.gt.classes, x.gt.offsets)
+    hosts = [[t.cpu().pin_memory() for t in fields(x)] for x in xs]
+    host = hosts[0]
     copied = [i for i in range(len(host)) if not (host_maps and i in (2, 3))]
     h2d = sum(host[i].numel() * host[i].element_size() for i in copied)
     if host_maps:
@@ -592,22 +717,22 @@ def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathere
     main = torch.cuda.current_stream(dev)
     lanes = []
     for pipe in pipes:
-        d = [torch.empty_like(t, device=dev) if i in copied else t for i, t in enumerate(host)]
+        d = [torch.empty_like(t, device=dev) if i in copied else None for i, t in enumerate(host)]
         out = pipe.new_outputs()
         results = (out.losses, out.num_instances, out.scores, out.classes, out.boxes)
-        lanes.append(dict(pipe=pipe, out=out, results=results, stream=torch.cuda.Stream(device=dev),
-                          slot=StepInputs(d[0], d[1], d[2], d[3], ops.GtBatch(d[4], d[5], d[6], list(x.gt.counts))),
+        # one StepInputs per host set: the uploaded tensors are shared, host-resident maps point at that set's buffers
+        slots = [StepInputs(d[0], d[1], d[2] if d[2] is not None else hosts[k][2], d[3] if d[3] is not None else hosts[k][3],
+                            ops.GtBatch(d[4], d[5], d[6], list(xs[k].gt.counts))) for k in range(S)]
+        lanes.append(dict(pipe=pipe, out=out, results=results, stream=torch.cuda.Stream(device=dev), slots=slots, dev=d,
                           res_host=[torch.empty_like(t, device="cpu").pin_memory() for t in results],
                           ready=torch.cuda.Event(), done=torch.cuda.Event()))
     d2h = sum(t.numel() * t.element_size() for t in lanes[0]["res_host"])
 
-    def upload(ln):
-        s = ln["slot"]
-        dst = (s.loc_logits, s.iou_preds, s.box_raw, s.cls_logits, s.gt.boxes, s.gt.classes, s.gt.offsets)
+    def upload(ln, k):
         with torch.cuda.stream(copy):
             copy.wait_event(ln["done"])                 # the step that last read this slot has finished
             for i in copied:
-                dst[i].copy_(host[i], non_blocking=True)
+                ln["dev"][i].copy_(hosts[k][i], non_blocking=True)
             ln["ready"].record(copy)
 
     def one(i, total):
@@ -616,22 +741,23 @@ def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathere
         with torch.cuda.stream(st):
             st.wait_event(ln["ready"])
             separate = multi and pipe._exchange is None      # no fused exchange attached: NCCL all-reduce + finalize
-            pipe.step(ln["slot"], out, finalize=not separate)
+            pipe.step(ln["slots"][i % S], out, finalize=not separate)
             if separate:
                 dist.all_reduce(out.sums, op=dist.ReduceOp.SUM)
                 pipe.finalize(out)
             ln["done"].record(st)
             if i + L < total:
-                upload(ln)                               # refill this lane's slot for step i+L while its neighbours compute
+                upload(ln, (i + L) % S)                  # refill this lane's slot for step i+L while its neighbours compute
             for h, d in zip(ln["res_host"], ln["results"]):
                 h.copy_(d, non_blocking=True)
 
     for ln in lanes:
         ln["done"].record(main)
     torch.cuda.synchronize()
-    # warm-up (L steps) then timed n steps; the uploads of the first L timed steps are inside the region
+    # warm-up (L steps), timed n steps, then ONE untimed step of set 0 on lane 0 (the outputs the caller compares);
+    # the uploads of the first L steps of a phase are inside its region
     ms = 0.0
-    for phase, count in (("warm", L), ("timed", n)):
+    for phase, count in (("warm", L), ("timed", n), ("check", 1)):
         if multi:
             dist.barrier()
         torch.cuda.synchronize()
@@ -639,17 +765,18 @@ def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathere
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
         copy.wait_event(e0)
-        for ln in lanes:
+        for j, ln in enumerate(lanes):
             ln["stream"].wait_event(e0)
-            upload(ln)
+            upload(ln, j % S)
         for i in range(count):
             one(i, count)
         for ln in lanes:
             main.wait_stream(ln["stream"])
         e1.record(main)
         torch.cuda.synchronize()
-        if phase == "timed" and sampler: sampler.mark()
-        ms = e0.elapsed_time(e1)
+        if phase == "timed":
+            if sampler: sampler.mark()
+            ms = e0.elapsed_time(e1)
     if multi:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -659,7 +786,7 @@ def run_e2e(args, pipes, x, world, multi, dev, sampler, host_maps=False, gathere
             if host_maps else "pinned host inputs, all maps uploaded on a copy stream; PCIe-bound")
     res = {"value": pipes[0].B * world * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "steps": n, "ms_per_step": ms / n, "decode_mode": pipes[0].decode_mode, "host_maps": bool(host_maps),
-           "steps_in_flight": L, "note": note}
+           "steps_in_flight": L, "host_input_sets": S, "note": note}
     return res, lanes[0]["out"]
 
 

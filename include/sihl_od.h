@@ -447,6 +447,24 @@ SIHL_OD_API int sihl_od_batched_nms(const float *boxes, const float *scores, con
                         float iou_thr, int64_t *keep, int32_t *keep_count,
                         void *workspace, void *stream);
 
+/* ---- N3: detection <-> ground-truth matching for the validation mAP ----------
+ * What torchmetrics' MeanAveragePrecision (ref object_detection.py:219-237, :245; COCOeval.evaluateImg of its
+ * faster_coco_eval backend) does per image on the CPU at epoch end, done on the GPU right after forward():
+ * detections [B,K] (boxes xyxy px, scores, classes int64 — all K rows of forward()'s output, as the reference passes
+ * them) are ranked by (score desc, input order) and greedily matched per category to the CSR ground truth at
+ * n_thresholds IoU thresholds and n_areas area ranges [lo, hi] (px^2; a gt outside the range is "ignored" and only
+ * matched while no regular gt fits; an unmatched detection outside the range is ignored).  Box IoU in fp64.
+ * HOST arrays: iou_thresholds_host [n_thresholds], area_ranges_host [n_areas][2].
+ * Outputs: det_order int32 [B,K] (rank -> detection), dt_match int32 [B,n_areas,n_thresholds,K] by rank (global gt
+ * index or -1), dt_ignore uint8 (same shape), gt_ignore uint8 [n_areas, total_gt].
+ * workspace: sihl_od_map_workspace_bytes().  torchmetrics / faster_coco_eval are absent here: parity UNPINNED. */
+SIHL_OD_API size_t sihl_od_map_workspace_bytes(int total_gt, int n_thresholds, int n_areas);
+SIHL_OD_API int sihl_od_map_match(const float *det_boxes, const float *det_scores, const int64_t *det_classes, int batch, int k,
+                      const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets, int total_gt,
+                      const double *iou_thresholds_host, int n_thresholds, const double *area_ranges_host, int n_areas,
+                      int32_t *det_order, int32_t *dt_match, uint8_t *dt_ignore, uint8_t *gt_ignore,
+                      void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

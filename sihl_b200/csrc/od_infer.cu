@@ -10,6 +10,7 @@
 //                     _tma  C % 4 == 0, C <= 128: TMA bulk copies into a shared-memory ring
 //                     _v4   C % 4 == 0, larger C: 16-byte loads, 4 or 32 lanes per row
 //                     plain any C: 4-byte loads, 8 lanes per row
+#include <cstdio>
 #include <cstdlib>
 
 #include "od_common.cuh"
@@ -817,10 +818,12 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
         // memory per SM to the kernels of the other chain / the neighbouring step running concurrently.
         // SMALL scans (fewer than ~16 such stages per CTA: the 1024^2 / batch 8 crowd config has 9) are dominated by
         // ring start-up, the last partial round and the end-of-kernel flush: they take 32-row stages on 128-thread
-        // CTAs, 4 per SM with 4 stages each — twice as many, half as long work items (5 % instead of 10 % imbalance),
-        // twice the bytes in flight from the first microsecond.
+        // CTAs, 3 per SM with 2 stages each — half as long work items (5 % instead of 10 % imbalance in the last round)
+        // and 1.5x the CTAs.  Measured at crowd (tools/decode_sweep.py, profiles/r02_decode_sweep_crowd.json): 18.5 us
+        // with the cfg1 ring, 14.1 us with this one (14.0-14.5 us for every 32-row ring with >= 3 CTAs per SM; this is
+        // the one with the smallest shared-memory footprint, 60 KB per SM).
         int rows_per_stage = kChunkRows, stages = 2, ctas_per_sm = 2;
-        if ((rows + kChunkRows - 1) / kChunkRows < (int64_t)16 * kNumSMs * 2) { rows_per_stage = 32; stages = 4; ctas_per_sm = 4; }
+        if ((rows + kChunkRows - 1) / kChunkRows < (int64_t)16 * kNumSMs * 2) { rows_per_stage = 32; stages = 2; ctas_per_sm = 3; }
         if (const char *e = getenv("SIHL_DECODE_ROWS")) { const int v = atoi(e); if (v == 32 || v == 64) rows_per_stage = v; }
         const size_t stage_bytes = (size_t)rows_per_stage * num_classes * 4;
         if (const char *e = getenv("SIHL_DECODE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 16 && (size_t)v * stage_bytes < 200 * 1024) stages = v; }
@@ -830,6 +833,9 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
         const int n_chunks = (int)((rows + rows_per_stage - 1) / rows_per_stage);
         int blocks = kNumSMs * ctas_per_sm;
         if (blocks > n_chunks) blocks = n_chunks;
+        if (getenv("SIHL_DECODE_DEBUG"))
+            fprintf(stderr, "k_dense_decode_tma: rows/stage %d, stages %d, CTAs/SM %d, grid %d, smem %zu B, chunks %d\n",
+                    rows_per_stage, stages, ctas_per_sm, blocks, smem, n_chunks);
 #define SIHL_DT_LAUNCH(KERN, THREADS)                                                                             \
     do {                                                                                                          \
         auto kern = KERN;                                                                                         \

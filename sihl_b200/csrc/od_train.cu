@@ -117,9 +117,10 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss(TrainLossParams p)
                 acc_box += __ldg(p.rel + flat) * l;                   // ref :197
             }
         }
-        if (cls_rows != nullptr) {                                    // 8 lanes per positive row
-            const int gl = tid & 7;
-            const int64_t ngrp = nthreads >> 3, grp = first >> 3;
+        if (cls_rows != nullptr) {                                    // 4 lanes (16-byte loads) or 8 lanes per positive row
+            const int lsh = p.cls_vec ? 2 : 3, lpr = 1 << lsh;
+            const int gl = tid & (lpr - 1);
+            const int64_t ngrp = nthreads >> lsh, grp = first >> lsh;
             const int64_t rounds = (n + ngrp - 1) / ngrp;
             for (int64_t it = 0; it < rounds; ++it) {
                 const int64_t r = it * ngrp + grp;
@@ -130,31 +131,33 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss(TrainLossParams p)
                 const int tgt = pos_target(p, flat, b);
                 const T *z = cls_rows + rr * C;
                 float m = -CUDART_INF_F, s = 0.f;
-                if (p.cls_vec) {                                      // 16-byte loads: 8 lanes x 128 contiguous bytes
+                if (p.cls_vec) {                                      // 16-byte loads: 4 lanes x 64 contiguous bytes per step
                     constexpr int N = Vec16<T>::N;
                     const int CV = C / N;
-                    for (int v = gl; v < CV; v += 8) {
+                    for (int v = gl; v < CV; v += 4) {
                         float x[N];
                         ld_vec16(z + v * N, x);
 #pragma unroll
                         for (int e = 0; e < N; ++e) m = fmaxf(m, x[e]);
                     }
-#pragma unroll
-                    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
-                    for (int v = gl; v < CV; v += 8) {                // second pass: L1 hits
+                    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
+                    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+                    for (int v = gl; v < CV; v += 4) {                // second pass: L1 hits
                         float x[N];
                         ld_vec16(z + v * N, x);
 #pragma unroll
                         for (int e = 0; e < N; ++e) s += expf(x[e] - m);
                     }
+                    s += __shfl_xor_sync(kFullMask, s, 2);
+                    s += __shfl_xor_sync(kFullMask, s, 1);
                 } else {
                     for (int c = gl; c < C; c += 8) m = fmaxf(m, ldf(z + c));
 #pragma unroll
                     for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
                     for (int c = gl; c < C; c += 8) s += expf(ldf(z + c) - m);
-                }
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+                    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+                }
                 if (ok && gl == 0) {
                     const float ce = tgt >= 0 ? (logf(s) + m) - ldf(z + tgt) : CUDART_NAN_F;   // ref :205-207
                     acc_cls += __ldg(p.rel + flat) * ce;              // ref :208
@@ -229,12 +232,13 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss_bwd(TrainLossParam
         }
     }
     if (dcls != nullptr) {
-        const int gl = tid & 7;
-        const int64_t ngrp = nthreads >> 3, grp = first >> 3;
+        const int lsh = p.cls_vec ? 2 : 3, lpr = 1 << lsh;             // 4 lanes (16-byte accesses) or 8 lanes per row
+        const int gl = tid & (lpr - 1);
+        const int64_t ngrp = nthreads >> lsh, grp = first >> lsh;
         const int64_t rounds = (p.pos_capacity + ngrp - 1) / ngrp;
         for (int64_t it = 0; it < rounds; ++it) {
             const int64_t r = it * ngrp + grp;
-            if (r >= p.pos_capacity) continue;                        // group-uniform (8 lanes share r)
+            if (r >= p.pos_capacity) continue;                        // group-uniform (the lanes of a group share r)
             T *out = dcls + r * C;
             constexpr int N = Vec16<T>::N;
             const int CV = C / N;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss_bwd(TrainLossParam
                     float zero[N];
 #pragma unroll
                     for (int e = 0; e < N; ++e) zero[e] = 0.f;
-                    for (int v = gl; v < CV; v += 8) st_vec16(out + v * N, zero);
+                    for (int v = gl; v < CV; v += 4) st_vec16(out + v * N, zero);
                 } else {
                     for (int c = gl; c < C; c += 8) out[c] = from_f<T>(0.f);
                 }
@@ -253,36 +257,38 @@ __global__ void __launch_bounds__(kTrainThreads) k_train_loss_bwd(TrainLossParam
             const int b = (int)(flat / A);
             const int tgt = pos_target(p, flat, b);
             const T *z = cls_rows + r * C;
-            // the 8 lanes of a group may diverge from the other groups of the warp: group-local shuffles
-            const unsigned gmask = 0xffu << ((tid & 31) & ~7);
+            // the lanes of a group may diverge from the other groups of the warp: group-local shuffles
+            const unsigned gmask = (lpr == 4 ? 0xfu : 0xffu) << ((tid & 31) & ~(lpr - 1));
             float m = -CUDART_INF_F, s = 0.f;
             if (p.cls_vec) {
-                for (int v = gl; v < CV; v += 8) {
+                for (int v = gl; v < CV; v += 4) {
                     float x[N];
                     ld_vec16(z + v * N, x);
 #pragma unroll
                     for (int e = 0; e < N; ++e) m = fmaxf(m, x[e]);
                 }
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
-                for (int v = gl; v < CV; v += 8) {
+                m = fmaxf(m, __shfl_xor_sync(gmask, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(gmask, m, 1));
+                for (int v = gl; v < CV; v += 4) {
                     float x[N];
                     ld_vec16(z + v * N, x);
 #pragma unroll
                     for (int e = 0; e < N; ++e) s += expf(x[e] - m);
                 }
+                s += __shfl_xor_sync(gmask, s, 2);
+                s += __shfl_xor_sync(gmask, s, 1);
             } else {
                 for (int c = gl; c < C; c += 8) m = fmaxf(m, ldf(z + c));
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
                 for (int c = gl; c < C; c += 8) s += expf(ldf(z + c) - m);
-            }
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
+                for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
+            }
             const float k = tgt >= 0 ? g_cls * __ldg(p.rel + flat) * inv_w : CUDART_NAN_F;   // ref :208
             const float inv_s = 1.f / s;
             if (p.cls_vec) {
-                for (int v = gl; v < CV; v += 8) {
+                for (int v = gl; v < CV; v += 4) {
                     float x[N];
                     ld_vec16(z + v * N, x);
 #pragma unroll
@@ -323,12 +329,14 @@ static int fill_train(TrainLossParams *out, const void *loc_logits, const void *
     p.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); p.gt_classes = gt_classes; p.gt_offsets = gt_offsets;
     p.sums = nullptr; p.losses = nullptr; p.grad_losses = nullptr; p.grad_scale = 1.f;
     p.dloc = p.diou = p.dbox = p.dcls = nullptr;
-    // dense role: 4 elements per thread and pass, at most 4 CTAs per SM; positive role: one row per thread for the
-    // box term, 8 lanes per row for the class term -> capacity/32 CTAs, capped at 8 per SM
+    // Few, fat CTAs: every CTA ends with up to 5 fp64 atomics on ONE 64-byte line plus the completion ticket, and
+    // same-line atomics serialise in one L2 slice (measured: 1776 CTAs spent 9 of 23 us there).  Dense role: 2 CTAs
+    // per SM (4 elements per thread and pass); positive role: one row per thread for the box term, 4 or 8 lanes per
+    // row for the class term, at most 6 CTAs per SM (one round over 9 x 6400 rows at cfg1).
     int64_t db = (p.n_dense + (int64_t)kTrainThreads * 4 - 1) / ((int64_t)kTrainThreads * 4);
-    if (db > (int64_t)kNumSMs * 4) db = (int64_t)kNumSMs * 4;
-    int64_t pb = (p.pos_capacity * 8 + kTrainThreads - 1) / kTrainThreads;
-    if (pb > (int64_t)kNumSMs * 8) pb = (int64_t)kNumSMs * 8;
+    if (db > (int64_t)kNumSMs * 2) db = (int64_t)kNumSMs * 2;
+    int64_t pb = (p.pos_capacity * 4 + kTrainThreads - 1) / kTrainThreads;
+    if (pb > (int64_t)kNumSMs * 6) pb = (int64_t)kNumSMs * 6;
     p.dense_blocks = (int)db; p.pos_blocks = rows ? (int)(pb < 1 ? 1 : pb) : 0;
     p.cls_vec = 0;                                  // set per dtype by the callers (needs sizeof(T))
     return SIHL_OD_OK;

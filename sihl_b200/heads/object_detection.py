@@ -300,24 +300,33 @@ class ObjectDetection(nn.Module):
 
     # ------------------------------------------------------------------ validation
     def on_validation_start(self) -> None:
-        """ref :219-225.  torchmetrics is optional here: without it the mAP is skipped and the
-        loss is averaged by a two-scalar running mean."""
-        try:
-            from torchmetrics import MeanMetric
-            from torchmetrics.detection.mean_ap import MeanAveragePrecision
-            self.loss_computer = MeanMetric(nan_strategy="ignore")
-            thresholds = [1, min(self.max_instances, 10), self.max_instances]
-            self.map_computer = MeanAveragePrecision(max_detection_thresholds=thresholds, backend="faster_coco_eval")
-        except Exception:
-            self.loss_computer = _RunningMean()
-            if hasattr(self, "map_computer"):
-                del self.map_computer
+        """ref :219-225.  ``self.map_backend``: "auto" (default) uses torchmetrics' MeanAveragePrecision exactly like the
+        reference when torchmetrics is importable and the GPU matcher ``sihl_b200.metrics.DetectionMAP`` (SURVEY.md §8f
+        N3: COCO matching per batch on the GPU, same metric keys) otherwise; "gpu" always uses the GPU matcher."""
+        thresholds = [1, min(self.max_instances, 10), self.max_instances]
+        use_tm = getattr(self, "map_backend", "auto") != "gpu"
+        if use_tm:
+            try:
+                from torchmetrics import MeanMetric
+                from torchmetrics.detection.mean_ap import MeanAveragePrecision
+                self.loss_computer = MeanMetric(nan_strategy="ignore")
+                self.map_computer = MeanAveragePrecision(max_detection_thresholds=thresholds, backend="faster_coco_eval")
+                return
+            except Exception:
+                pass
+        from ..metrics import DetectionMAP
+        self.loss_computer = _RunningMean()
+        self.map_computer = DetectionMAP(max_detection_thresholds=thresholds)
 
     def validation_step(self, inputs: List[Tensor], classes: List[Tensor], boxes: List[Tensor]
                         ) -> Tuple[Tensor, Dict[str, float]]:
         """ref :227-240."""
+        from ..metrics import DetectionMAP
         num_instances, scores, pred_classes, pred_boxes = self.forward(inputs)
-        if hasattr(self, "map_computer"):
+        if isinstance(getattr(self, "map_computer", None), DetectionMAP):
+            gt_boxes, gt_classes, counts = _cat_gt(boxes, classes, scores.device)
+            self.map_computer.update_batch(scores, pred_classes, pred_boxes, gt_boxes, gt_classes, counts)   # one kernel, no sync
+        elif hasattr(self, "map_computer"):
             self.map_computer.to(scores.device).update(
                 [{"scores": s, "labels": c, "boxes": b} for s, c, b in zip(scores, pred_classes, pred_boxes)],
                 [{"labels": c, "boxes": b} for c, b in zip(classes, boxes)],

@@ -730,3 +730,38 @@ def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: floa
     if single:
         return keep[: int(count.item())]
     return keep[:N], count
+
+
+# --------------------------------------------------------------------------- N3: matching for the validation mAP
+COCO_IOU_THRESHOLDS = tuple(0.5 + 0.05 * i for i in range(10))
+COCO_AREA_RANGES = ((0.0, 1e5 ** 2), (0.0, 32.0 ** 2), (32.0 ** 2, 96.0 ** 2), (96.0 ** 2, 1e5 ** 2))    # all, small, medium, large
+
+
+def map_match(det_boxes: Tensor, det_scores: Tensor, det_classes: Tensor, gt_boxes: Tensor, gt_classes: Tensor,
+              gt_offsets: Tensor, iou_thresholds: Sequence[float] = COCO_IOU_THRESHOLDS,
+              area_ranges: Sequence[Tuple[float, float]] = COCO_AREA_RANGES) -> Dict[str, Tensor]:
+    """COCOeval.evaluateImg for a whole batch on the GPU (ref object_detection.py:230-237 feeds this to torchmetrics,
+    which matches on the CPU at epoch end).  ``det_*`` [B,K,...] as ``forward`` returns them, ground truth in CSR form.
+    Returns dict(det_order i32 [B,K], dt_match i32 [B,NA,T,K], dt_ignore u8 [B,NA,T,K], gt_ignore u8 [NA,sumG])."""
+    det_boxes = _req(det_boxes, torch.float32, "det_boxes", 3)
+    det_scores = _req(det_scores.float() if det_scores.dtype != torch.float32 else det_scores, torch.float32, "det_scores", 2)
+    det_classes = _req(det_classes, torch.int64, "det_classes", 2)
+    dev = det_boxes.device
+    B, K = det_scores.shape
+    G = int(gt_boxes.shape[0])
+    thr = np.ascontiguousarray(np.asarray(iou_thresholds, dtype=np.float64))
+    areas = np.ascontiguousarray(np.asarray(area_ranges, dtype=np.float64).reshape(-1, 2))
+    T, NA = len(thr), len(areas)
+    with _on(dev):
+        order = torch.empty((B, K), dtype=torch.int32, device=dev)
+        dtm = torch.empty((B, NA, T, K), dtype=torch.int32, device=dev)
+        dti = torch.empty((B, NA, T, K), dtype=torch.uint8, device=dev)
+        gti = torch.empty((NA, max(G, 1)), dtype=torch.uint8, device=dev)
+        ws = torch.empty((int(_lib().sihl_od_map_workspace_bytes(G, T, NA)),), dtype=torch.uint8, device=dev)
+        rc = _lib().sihl_od_map_match(
+            _p(det_boxes), _p(det_scores), _p(det_classes), B, K,
+            _p(_req(gt_boxes, torch.float32, "gt_boxes", 2)) if G else None, _p(_req(gt_classes, torch.int64, "gt_classes", 1)) if G else None,
+            _p(_req(gt_offsets, torch.int32, "gt_offsets", 1)), G, thr.ctypes.data, T, areas.ctypes.data, NA,
+            _p(order), _p(dtm), _p(dti), _p(gti), _p(ws), _stream(dev))
+    _native.check(rc, "sihl_od_map_match")
+    return dict(det_order=order, dt_match=dtm, dt_ignore=dti, gt_ignore=gti[:, :G])

@@ -186,3 +186,17 @@ def test_pipeline_buffers_are_not_overrun(guarded, mode):
         pipe.step(x, out)
     assert torch.isfinite(out.losses).all()
     guarded.check()
+
+
+def test_map_match_stays_inside_its_buffers(guarded):
+    rng = np.random.RandomState(3)
+    B, K, G = 4, 33, 9
+    xy = rng.uniform(0, 300, (B, K, 2)).astype(np.float32)
+    det = np.concatenate([xy, xy + rng.uniform(5, 120, (B, K, 2)).astype(np.float32)], -1)
+    gxy = rng.uniform(0, 300, (3 * G, 2)).astype(np.float32)
+    gtb = np.concatenate([gxy, gxy + rng.uniform(5, 120, (3 * G, 2)).astype(np.float32)], -1)
+    off = np.array([0, G, G, 2 * G, 3 * G], np.int32)                  # image 1 has no ground truth
+    res = ops.map_match(_t(det), _t(rng.uniform(0, 1, (B, K)).astype(np.float32)), _t(rng.randint(0, 3, (B, K)).astype(np.int64)),
+                        _t(gtb), _t(rng.randint(0, 3, 3 * G).astype(np.int64)), _t(off))
+    assert res["dt_match"].shape == (B, 4, 10, K)
+    guarded.check()
