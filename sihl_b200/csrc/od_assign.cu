@@ -191,11 +191,11 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
         for (int t0 = 0; t0 < p.num_anchors; t0 += 32) consider(t0 + lane < p.num_anchors, t0 + lane);
     } else {
         // Candidate windows, one pyramid level per lane.  A positive CIoU needs BOTH
-        //  (i)  overlap (CIoU <= IoU): cells from floor(x1/sx) to floor(x2/sx), widened by one, and
+        //  (i)  overlap (CIoU <= IoU): cells from floor((x1 - slack)/sx) to floor((x2 + slack)/sx), and
         //  (ii) rho^2 / c^2 < IoU (CIoU <= IoU - rho^2/c^2) with IoU <= min(area)/max(area) and, for
         //       overlapping boxes, c^2 <= (Wg+sx)^2 + (Hg+sy)^2: the cell centre lies within
         //       R = sqrt(IoU_max * c_max^2) of the gt centre in x and in y.
-        // Both are supersets evaluated with slack (2 % + 0.01 px on R, one cell on the overlap window); the
+        // Both are supersets evaluated with slack (2 % + 0.01 px on R, 0.02 px on the overlap window); the
         // decision itself is always the exact CIoU arithmetic on the real anchor table above.
         int4 *tab = s_tab[warp];
         int n_l = 0;
@@ -204,8 +204,15 @@ k_assign_select(SelectParams p, const float4 *__restrict__ anchors, const float4
             const int lw = p.lv.w[l], lh = p.lv.h[l];
             const float isx = p.inv_sx[l], isy = p.inv_sy[l], sx = p.cell_w[l], sy = p.cell_h[l];
             const float fw = (float)(lw - 1), fh = (float)(lh - 1);
-            float jlo = floorf(gt.x1 * isx) - 1.f, jhi = floorf(gt.x2 * isx) + 1.f;
-            float ilo = floorf(gt.y1 * isy) - 1.f, ihi = floorf(gt.y2 * isy) + 1.f;
+            // (i) overlap window: cell j spans [j sx, (j+1) sx) up to the ~1e-4 px by which the real anchor table is off
+            // the ideal lattice (linspace rounding); a cell whose span ends more than `slack` before
+            // the gt starts (or starts more than `slack` after it ends) cannot intersect it.  slack = 0.02 px + 1e-5
+            // of the coordinate is ~100x the lattice error and ~1000x the rounding of the products below — and costs
+            // a fraction of a cell, where a whole extra cell per side (the first version) tripled the candidates of
+            // a small gt on its best level (6 x 6 instead of 3 x 3 cells for a gt of two cells).
+            const float ex = 0.02f + 1e-5f * fmaxf(fabsf(gt.x1), fabsf(gt.x2)), ey = 0.02f + 1e-5f * fmaxf(fabsf(gt.y1), fabsf(gt.y2));
+            float jlo = floorf((gt.x1 - ex) * isx), jhi = floorf((gt.x2 + ex) * isx);
+            float ilo = floorf((gt.y1 - ey) * isy), ihi = floorf((gt.y2 + ey) * isy);
             if (gt.area > 0.f) {
                 const float cell = sx * sy;
                 const float iou_max = __fdividef(fminf(cell, gt.area), fmaxf(cell, gt.area));
