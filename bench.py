@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--regions", type=int, default=5,
                     help="timed regions of --steps steps each; the line reports the median region (SURVEY.md §8d), min/max "
                          "and per-rank times beside it")
+    ap.add_argument("--skip-half-maps", action="store_true", help="do not also time the step on bf16 head outputs")
     ap.add_argument("--skip-train-tail", action="store_true", help="do not time the drop-in head's training tail with backward")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--e2e-lanes", type=int, default=2, help="end-to-end steps in flight (own stream + buffers each)")
@@ -346,7 +347,7 @@ def run_ours(args, w, world, rank, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(mode, steps, warmup, n_regions):
+    def timed_steps(mode, steps, warmup, n_regions, in_sets=None):
         """Build the lanes for one decode mode, replay `warmup` steps and `n_regions` regions of `steps` steps, return
         (median region ms, pipes, outs, graphs, timing)."""
         pipes = attach([DetectionHeadPipeline(levels, W, H, B, C, B * G, dev, TOPK, K, SCORE_THR, IOU_THR, decode_mode=mode)
@@ -354,9 +355,9 @@ def run_ours(args, w, world, rank, local_rank):
         # every (lane, input set) pair owns its outputs: steps in flight on different lanes never share a buffer
         outs = [[pipes[ln].new_outputs() for _ in range(n_sets)] for ln in range(n_lanes)]
         torch.cuda.synchronize()
-        return _timed_steps(pipes, outs, steps, warmup, n_regions)
+        return _timed_steps(pipes, outs, steps, warmup, n_regions, in_sets if in_sets is not None else sets)
 
-    def _timed_steps(pipes, outs, n_steps, n_warmup, n_regions):
+    def _timed_steps(pipes, outs, n_steps, n_warmup, n_regions, sets):
         def full_step(ln, i):
             """One step incl. the cross-GPU exchange: 8 fp64 sums all-reduced between the loss kernels and finalize."""
             out = outs[ln][i]
@@ -588,6 +589,22 @@ def run_ours(args, w, world, rank, local_rank):
                "sample": f"{r['sample_images']} of {B} images of {args.workload} x {r['steps']} passes: {REFERENCE_WHAT}; "
                          f"{r['cores']} threads"}
 
+    # ---- the same step on bf16 head outputs (what the MLPs emit under precision="16-mixed"): maps read as they are
+    half_maps = None
+    if not multi and not args.skip_half_maps:
+        hsets = [StepInputs(x.loc_logits.bfloat16(), x.iou_preds.bfloat16(), x.box_raw.bfloat16(), x.cls_logits.bfloat16(), x.gt)
+                 for x in sets]
+        half_maps = {"map_dtype": "bf16", "note": "extra line, never the headline: identical kernels templated on the map type, "
+                                                   "half the bytes in the dense scan; losses / detections follow the reference's "
+                                                   "half-precision operator semantics (tests/test_gpu_half_maps.py)"}
+        for mode in ("dense", "candidate_first"):
+            h_steps = max(3, min(args.steps, 1000))
+            h_ms, h_pipes, h_outs, _, _ = timed_steps(mode, h_steps, max(min(args.warmup, 100), 3), min(args.regions, 3), hsets)
+            half_maps[mode] = {"value": B * h_steps / (h_ms * 1e-3), "unit": UNIT, "ms_per_step": h_ms / h_steps,
+                               "losses": h_outs[0][0].losses.cpu().tolist()}
+            del h_pipes, h_outs
+        del hsets
+
     # ---- the drop-in head's training tail WITH gradients (what ObjectDetection.training_step runs around its MLPs)
     train_tail = None
     if not multi and not args.skip_train_tail:
@@ -610,7 +627,7 @@ def run_ours(args, w, world, rank, local_rank):
                                                 "steps_in_flight": n_lanes, "decode_mode": args.decode_mode,
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
-        "timing": timing, "train_with_backward": train_tail, "cpu_affinity": affinity,
+        "timing": timing, "train_with_backward": train_tail, "half_maps": half_maps, "cpu_affinity": affinity,
         "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi and not fused else 0)) * args.steps,
         "allreduce": (("fused" if fused else "nccl") if multi else None), "allreduce_check": allreduce_check,
         "allreduce_fallback": (fallback_note[0] if fallback_note else None), "roofline": roofline, "roofline_step": roofline_step,

@@ -137,6 +137,17 @@ SIHL_OD_API int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *s
                            const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
                            int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream);
 
+/* The same entry for head-output maps of element type map_dtype (loc_logits, iou_preds and the two prefetch maps share
+ * it): loaded as they are, upcast in registers.  For half types the BCE term follows the reference, which evaluates
+ * log_sigmoid on the half logits (ref :160-161): it is rounded to the map type before entering the fp32 sum. */
+SIHL_OD_API int sihl_od_assign_resolve_t(const int32_t *sel_anchor, const float *sel_val, const float *best_iou,
+                           const int32_t *gt_offsets, int batch, int64_t num_anchors, int topk, int relative,
+                           const void *loc_logits, const void *iou_preds, int map_dtype,
+                           int64_t *assignment, float *out_iou, double *sums,
+                           int32_t *tile_pos_count, int32_t *tile_pos_rows,
+                           const void *prefetch_box_raw, const void *prefetch_cls_logits, int num_classes,
+                           int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream);
+
 /* ---- N1: the un-clamped assignment of QuadrilateralDetection ---
  * ref: src/sihl/heads/quadrilateral_detection.py:266-294 (bbox_matching) and the
  * per-image loop :165-172, for a whole batch in two launches.  Arbitrary anchors
@@ -217,6 +228,15 @@ SIHL_OD_API int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const
                            const float *offsets, const float *scales, int img_w, int img_h,
                            const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
                            const float *box_raw, const float *cls_logits, int num_classes,
+                           double *sums, float *losses, uint32_t *done_counter,
+                           void *const *peer_regions, int world, int rank, void *stream);
+
+/* ... and for dense maps of element type map_dtype (box_raw [B*A,4], cls_logits [B*A,C]). */
+SIHL_OD_API int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
+                           const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
+                           const float *offsets, const float *scales, int img_w, int img_h,
+                           const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                           const void *box_raw, const void *cls_logits, int map_dtype, int num_classes,
                            double *sums, float *losses, uint32_t *done_counter,
                            void *const *peer_regions, int world, int rank, void *stream);
 
@@ -376,6 +396,16 @@ SIHL_OD_API int sihl_od_decode_rows_t(const float *top_logits, const int64_t *id
  * cand_key: uint64 [B,cap] sort key (score desc, location asc); cand_box
  * [B,cap,4]; cand_cls int32 [B,cap]. */
 SIHL_OD_API int sihl_od_dense_decode(const float *loc_logits, const float *cls_logits, const float *box_raw,
+                         int batch, int64_t num_anchors, int num_classes,
+                         const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
+                         int32_t *cand_count, int64_t cand_capacity,
+                         uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
+                         void *stream);
+
+/* sihl_od_dense_decode for maps of element type map_dtype (all three maps share it).  Half maps stream HALF the bytes
+ * through the same TMA ring; scores and decoded boxes follow the reference's half semantics (sigmoid / exp rounded to
+ * the map type, see sihl_od_decode_rows_t), so the candidate lists equal those of sihl_od_candidate_decode_t. */
+SIHL_OD_API int sihl_od_dense_decode_t(const void *loc_logits, const void *cls_logits, const void *box_raw, int map_dtype,
                          int batch, int64_t num_anchors, int num_classes,
                          const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
                          int32_t *cand_count, int64_t cand_capacity,

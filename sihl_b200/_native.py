@@ -26,6 +26,9 @@ _SIGNATURES = {
     "sihl_od_assign_select": (I, [P, P, I64, P, I, I, I, P, P, I, I, I, P, P, P, P, P]),
     "sihl_od_resolve_tiles": (I, [I64, P, P]),
     "sihl_od_assign_resolve": (I, [P, P, P, P, I, I64, I, I, P, P, P, P, P, P, P, P, P, I, P, P, P]),
+    "sihl_od_assign_resolve_t": (I, [P, P, P, P, I, I64, I, I, P, P, I, P, P, P, P, P, P, P, I, P, P, P]),
+    "sihl_od_pos_loss_tiles_exchange_t": (I, [P, P, P, I, I64, P, P, I, I, P, P, P, P, P, I, I, P, P, P, P, I, I, P]),
+    "sihl_od_dense_decode_t": (I, [P, P, P, I, I, I64, I, P, P, I, I, F, P, I64, P, P, P, I, P]),
     "sihl_od_quad_matching": (I, [P, I64, P, P, I, I, I, P, P, P, P, P, P, P, P]),
     "sihl_od_pos_loss_tiles": (I, [P, P, P, I, I64, P, P, I, I, P, P, P, P, P, I, P, P, P, P]),
     "sihl_od_pos_loss_tiles_exchange": (I, [P, P, P, I, I64, P, P, I, I, P, P, P, P, P, I, P, P, P, P, I, I, P]),

@@ -298,17 +298,29 @@ constexpr int kResWarps = kResThreads / 32;
 struct ResolveParams {
     const int32_t *sel_anchor; const float *sel_val; const float *best_iou; const int32_t *gt_offsets;
     int num_anchors, topk, relative;
-    const float *loc; const float *iou_pred;
+    const void *loc; const void *iou_pred;     // element type T of the kernel template (SIHL_OD_F32 / _F16 / _BF16)
     int64_t *assignment; float *out_iou; double *sums;
     int32_t *tile_pos_count; int32_t *tile_pos_rows;
-    const float *prefetch_box; const float *prefetch_cls; int num_classes;   // L2 hints for k_pos_loss_tiles
+    const void *prefetch_box; const void *prefetch_cls; int num_classes;     // L2 hints for k_pos_loss_tiles (same T)
     float inv_topk;            // 1 / topk: e / topk == (int)((e + 0.5f) * inv_topk) for e < 2^21 (checked for topk <= 64)
     int32_t *pos_chunks;       // work list for k_pos_loss_tiles: (slot << 10 | first_row / 32 << 6 | rows - 1)
     int2 *tile_pos_aux;        // per listed positive: (global gt index, rel bits) — saves that kernel two dependent hops
 };
 
+// BCE term of the fused pass for a map of type T.  fp32: the fast form above.  Half types: what the reference computes
+// on half logits (ref :160-161 has no .to(float32)): (1 - t) x - log_sigmoid(x) with log_sigmoid rounded to the map type.
+template <typename T> __device__ __forceinline__ float bce_fused(float x, float t)
+{
+    const float ax = fabsf(x);
+    const float ls = fminf(0.f, x) - log1pf(expf(-ax));
+    return (1.f - t) * x - round_to<T>(ls);
+}
+template <> __device__ __forceinline__ float bce_fused<float>(float x, float t) { return bce_logits_fast(x, t); }
+
+template <typename T>
 __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
 {
+    const T *t_loc = reinterpret_cast<const T *>(p.loc), *t_iou = reinterpret_cast<const T *>(p.iou_pred);
     __shared__ unsigned s_v[kTile], s_g[kTile];
     __shared__ float s_rel[kTile];
     __shared__ unsigned short s_pos[kTile];
@@ -328,8 +340,8 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
     for (int c = 0; c < kChunks; ++c) {
         const int la = c * kResThreads + tid;
         const int64_t flat = (int64_t)b * A + a0 + (la < na ? la : 0);
-        x_loc[c] = p.loc != nullptr ? __ldcs(p.loc + flat) : 0.f;
-        x_iou[c] = p.iou_pred != nullptr ? __ldcs(p.iou_pred + flat) : 0.f;
+        x_loc[c] = t_loc != nullptr ? ldf(t_loc + flat) : 0.f;
+        x_iou[c] = t_iou != nullptr ? ldf(t_iou + flat) : 0.f;
     }
 
     for (int i = tid; i < kTile; i += kResThreads) { s_v[i] = 0u; s_g[i] = 0xffffffffu; }
@@ -414,17 +426,18 @@ __global__ void __launch_bounds__(kResThreads) k_assign_resolve(ResolveParams p)
             p.out_iou[flat] = rel;
             s_rel[la] = rel;
             if (pos) {                                    // the positive-row kernel gathers these next: warm L2 now
-                if (p.prefetch_box != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.prefetch_box + 4 * flat));
+                if (p.prefetch_box != nullptr)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const T *>(p.prefetch_box) + 4 * flat));
                 if (p.prefetch_cls != nullptr) {
-                    const char *row = reinterpret_cast<const char *>(p.prefetch_cls + flat * p.num_classes);
-                    const int bytes = p.num_classes * 4;
+                    const char *row = reinterpret_cast<const char *>(reinterpret_cast<const T *>(p.prefetch_cls) + flat * p.num_classes);
+                    const int bytes = p.num_classes * (int)sizeof(T);
                     for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(row + bytes - 4));
                 }
             }
             if (p.loc != nullptr) {
                 const float t = (rel == 1.0f) ? 1.f : 0.f;                       // ref :159
-                acc_bce += bce_logits_fast(x_loc[c], t);
+                acc_bce += bce_fused<T>(x_loc[c], t);
                 acc_one += t;
                 if (p.iou_pred != nullptr) {
                     const float d = x_iou[c] - rel;                              // ref :177-179
@@ -706,6 +719,18 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
                                       const float *prefetch_box_raw, const float *prefetch_cls_logits, int num_classes,
                                       int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream)
 {
+    return sihl_od_assign_resolve_t(sel_anchor, sel_val, best_iou, gt_offsets, batch, num_anchors, topk, relative, loc_logits,
+                                    iou_preds, SIHL_OD_F32, assignment, out_iou, sums, tile_pos_count, tile_pos_rows,
+                                    prefetch_box_raw, prefetch_cls_logits, num_classes, pos_chunks, tile_pos_aux, stream);
+}
+
+extern "C" int sihl_od_assign_resolve_t(const int32_t *sel_anchor, const float *sel_val, const float *best_iou,
+                                        const int32_t *gt_offsets, int batch, int64_t num_anchors, int topk, int relative,
+                                        const void *loc_logits, const void *iou_preds, int map_dtype, int64_t *assignment,
+                                        float *out_iou, double *sums, int32_t *tile_pos_count, int32_t *tile_pos_rows,
+                                        const void *prefetch_box_raw, const void *prefetch_cls_logits, int num_classes,
+                                        int32_t *pos_chunks, int32_t *tile_pos_aux, void *stream)
+{
     SIHL_CHECK_ARG(topk >= 1 && topk <= SIHL_OD_MAX_TOPK, "topk=%d outside 1..%d", topk, SIHL_OD_MAX_TOPK);
     SIHL_CHECK_ARG(batch >= 0 && num_anchors >= 0 && num_anchors < (1ll << 30), "bad sizes");
     SIHL_CHECK_ARG(assignment && out_iou && gt_offsets, "assignment / out_iou / gt_offsets must not be NULL");
@@ -727,7 +752,7 @@ extern "C" int sihl_od_assign_resolve(const int32_t *sel_anchor, const float *se
     p.tile_pos_aux = reinterpret_cast<int2 *>(tile_pos_aux);
     const dim3 grid((unsigned)((num_anchors + kTile - 1) / kTile), (unsigned)batch);
     SIHL_CHECK_ARG(batch <= 65535, "batch=%d > 65535", batch);
-    k_assign_resolve<<<grid, kResThreads, 0, (cudaStream_t)stream>>>(p);
+    SIHL_DISPATCH_DTYPE(map_dtype, (k_assign_resolve<T><<<grid, kResThreads, 0, (cudaStream_t)stream>>>(p)));
     SIHL_CHECK_LAUNCH("k_assign_resolve");
     return SIHL_OD_OK;
 }

@@ -11,6 +11,7 @@
 //                     _v4   C % 4 == 0, larger C: 16-byte loads, 4 or 32 lanes per row
 //                     plain any C: 4-byte loads, 8 lanes per row
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 
 #include "od_common.cuh"
@@ -418,6 +419,7 @@ struct StagedCand {
 // One warp turns up to 32 staged entries (one per lane) into candidates: no block-level synchronisation inside.  Entries
 // passed the conservative logit pre-filter only; the exact test sigmoid(x) > thr (ref :113) is made here.
 // `entry`: this lane's staged entry or nullptr; all 32 lanes of the warp must call.
+template <typename T = float>
 __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const StagedCand *entry)
 {
     const int lane = threadIdx.x & 31;
@@ -427,7 +429,7 @@ __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const S
         StagedCand c;
         c.row_lo = c.row_hi = c.arg = 0; c.x = 0.f;
         if (entry != nullptr) c = *entry;
-        const float s = entry != nullptr ? sigmoid_f(c.x) : 0.f;
+        const float s = entry != nullptr ? round_to<T>(sigmoid_f(c.x)) : 0.f;
         const bool have = entry != nullptr && s > p.score_thr;
         const int64_t row = have ? (((int64_t)c.row_hi << 32) | (unsigned)c.row_lo) : 0;
         const int b = small ? (int)((unsigned)row / (unsigned)p.A) : (int)(row / p.A);
@@ -437,7 +439,8 @@ __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const S
         // arithmetic runs while the slot atomic below is in flight — at the end of the kernel this chain is the tail
         float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), off = raw, sc = raw;
         if (have) {
-            raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + row);
+            if constexpr (sizeof(T) == 4) raw = __ldcs(reinterpret_cast<const float4 *>(p.box_raw) + row);
+            else raw = ldf4(reinterpret_cast<const T *>(p.box_raw) + 4 * row);
             off = __ldg(p.offsets + a);
             sc = __ldg(p.scales + a);
         }
@@ -453,8 +456,8 @@ __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const S
             base = __shfl_sync(peers, base, leader);
             slot = base + __popc(peers & ((1u << lane) - 1u));
         }
-        const float4 box = make_float4(decode_norm(off.x, sc.x, raw.x) * p.img_w, decode_norm(off.y, sc.y, raw.y) * p.img_h,
-                                       decode_norm(off.z, sc.z, raw.z) * p.img_w, decode_norm(off.w, sc.w, raw.w) * p.img_h);
+        const float4 box = make_float4((off.x + sc.x * round_to<T>(expf(raw.x))) * p.img_w, (off.y + sc.y * round_to<T>(expf(raw.y))) * p.img_h,
+                                       (off.z + sc.z * round_to<T>(expf(raw.z))) * p.img_w, (off.w + sc.w * round_to<T>(expf(raw.w))) * p.img_h);
         if (have && slot < p.cap) {
             const int64_t o = (int64_t)b * p.cap + slot;
             p.cand_key[o] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
@@ -465,9 +468,12 @@ __device__ __forceinline__ void flush_staged(const DenseDecodeParams &p, const S
     __syncwarp();
 }
 
-template <int VPL, bool EXACT, int ROWS = kChunkRows>     // ROWS per stage; the CTA has 4 * ROWS threads (4 lanes per row)
+// T: element type of the three maps.  Half maps put ROWS x C x 2 bytes into a stage (half the HBM traffic); a lane then
+// owns 16-byte vectors of EIGHT logits (VPL counts those).
+template <int VPL, bool EXACT, int ROWS = kChunkRows, typename T = float>     // ROWS per stage; the CTA has 4 * ROWS threads
 __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams p, int stages, int n_chunks)
 {
+    constexpr int kPerVec = 16 / (int)sizeof(T);
     constexpr int kWarps = 4 * ROWS / 32;
     extern __shared__ __align__(128) unsigned char s_ring[];
     __shared__ StagedCand s_list[kWarps * 32];                    // one 32-entry segment per warp: no atomics to append
@@ -475,22 +481,22 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
     static_assert(kStageCap == 256 && kWarps <= 8, "at most 8 warps x 32 staged candidates");
     const int tid = threadIdx.x, gl = tid & 3, r = tid >> 2, lane = tid & 31, warp = tid >> 5;
     int n_staged = 0;                                             // this warp's segment fill (warp-uniform)
-    const int C4 = p.C >> 2;
+    const int C4 = p.C / kPerVec;                                  // 16-byte vectors per row
     const int64_t rows = (int64_t)p.batch * p.A;
     // per stage: 64 rows of class logits — ONE bulk copy per stage.  The location logit of a row is a 4-byte
     // coalesced load one chunk ahead (one lane per row), the raw box is read for candidates only (flush_staged):
     // small bulk copies cost the TMA unit as much as big ones (measured with tools/micro/read_bw.cu: a ring of
     // single 21 KB copies reaches the 6.3 TB/s read ceiling, the former 3-copy stage did not).
-    const uint32_t stage_bytes = (uint32_t)ROWS * (uint32_t)p.C * 4u;
+    const uint32_t stage_bytes = (uint32_t)ROWS * (uint32_t)p.C * (uint32_t)sizeof(T);
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + (size_t)stages * stage_bytes);
 
     const uint64_t policy = l2_evict_first_policy();
     auto issue = [&](int stage, int chunk) {                      // one elected thread
         const int64_t row0 = (int64_t)chunk * ROWS;
         const int64_t n = rows - row0 < ROWS ? rows - row0 : ROWS;
-        const uint32_t cb = (uint32_t)n * (uint32_t)p.C * 4u;
+        const uint32_t cb = (uint32_t)n * (uint32_t)p.C * (uint32_t)sizeof(T);
         mbar_expect_tx(bars + stage, cb);
-        bulk_g2s(s_ring + (size_t)stage * stage_bytes, p.cls + row0 * p.C, cb, bars + stage, policy);
+        bulk_g2s(s_ring + (size_t)stage * stage_bytes, reinterpret_cast<const T *>(p.cls) + row0 * p.C, cb, bars + stage, policy);
     };
 
     if (tid == 0) {
@@ -508,7 +514,9 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
     const float x_thr = p.logit_thr;
     auto load_loc = [&](int chunk) -> float {                     // lane gl == 0 of every row group
         const int64_t row = (int64_t)chunk * ROWS + r;
-        return (gl == 0 && chunk < n_chunks && row < rows) ? __ldcs(p.loc + row) : -CUDART_INF_F;
+        if (!(gl == 0 && chunk < n_chunks && row < rows)) return -CUDART_INF_F;
+        if constexpr (sizeof(T) == 4) return __ldcs(p.loc + row);
+        else return ldf(reinterpret_cast<const T *>(p.loc) + row);
     };
     float x_next = load_loc((int)blockIdx.x);
     int s = 0;                                                    // ring slot and its phase, carried (no k % stages,
@@ -520,31 +528,63 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
         const unsigned char *base = s_ring + (size_t)s * stage_bytes;
         const int64_t row = (int64_t)c * ROWS + r;
         const bool ok = row < rows;
-        const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
         // first arg-max of the row in two cheap steps: the row maximum (max tree + 2 shuffles), then the
         // lowest class index whose logit equals it (reverse predicated scan + 2 shuffles); half the
         // instructions of a running (value, index) comparison.  NaN logits never win (as before).
-        float4 q[VPL];
         float m = -CUDART_INF_F;
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int v = gl + 4 * i;
-            if (EXACT || v < C4) {
-                q[i] = src[v];
-                m = fmaxf(m, fmaxf(fmaxf(q[i].x, q[i].y), fmaxf(q[i].z, q[i].w)));
-            }
-        }
-        m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
         int arg = 0x7fffffff;
+        if constexpr (sizeof(T) == 4) {
+            const float4 *src = reinterpret_cast<const float4 *>(base) + r * C4;
+            float4 q[VPL];
 #pragma unroll
-        for (int i = VPL - 1; i >= 0; --i) {
-            const int v = gl + 4 * i;
-            if (EXACT || v < C4) {
-                if (q[i].w == m) arg = 4 * v + 3;
-                if (q[i].z == m) arg = 4 * v + 2;
-                if (q[i].y == m) arg = 4 * v + 1;
-                if (q[i].x == m) arg = 4 * v;
+            for (int i = 0; i < VPL; ++i) {
+                const int v = gl + 4 * i;
+                if (EXACT || v < C4) {
+                    q[i] = src[v];
+                    m = fmaxf(m, fmaxf(fmaxf(q[i].x, q[i].y), fmaxf(q[i].z, q[i].w)));
+                }
+            }
+            m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
+#pragma unroll
+            for (int i = VPL - 1; i >= 0; --i) {
+                const int v = gl + 4 * i;
+                if (EXACT || v < C4) {
+                    if (q[i].w == m) arg = 4 * v + 3;
+                    if (q[i].z == m) arg = 4 * v + 2;
+                    if (q[i].y == m) arg = 4 * v + 1;
+                    if (q[i].x == m) arg = 4 * v;
+                }
+            }
+        } else {
+            const uint4 *src = reinterpret_cast<const uint4 *>(base) + r * C4;
+            float q[VPL][8];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int v = gl + 4 * i;
+                if (EXACT || v < C4) {
+                    const uint4 u = src[v];
+                    const unsigned w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 f;
+                        if constexpr (std::is_same<T, __half>::value) f = __half22float2(*reinterpret_cast<const __half2 *>(&w4[e]));
+                        else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
+                        q[i][2 * e] = f.x; q[i][2 * e + 1] = f.y;
+                        m = fmaxf(m, fmaxf(f.x, f.y));
+                    }
+                }
+            }
+            m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
+#pragma unroll
+            for (int i = VPL - 1; i >= 0; --i) {
+                const int v = gl + 4 * i;
+                if (EXACT || v < C4) {
+#pragma unroll
+                    for (int e = 7; e >= 0; --e)
+                        if (q[i][e] == m) arg = 8 * v + e;
+                }
             }
         }
         arg = min(arg, __shfl_xor_sync(kFullMask, arg, 1));
@@ -561,7 +601,7 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
             sc.row_lo = (int)(row & 0xffffffff); sc.row_hi = (int)(row >> 32);
             sc.x = x; sc.arg = arg;
             s_list[warp * 32 + n_staged + __popc(sm & ((1u << lane) - 1u))] = sc;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.box_raw + 4 * row));      // read at flush time
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const T *>(p.box_raw) + 4 * row));      // read at flush time
         }
         n_staged += __popc(sm);
         __syncthreads();                                          // every lane is done with stage s
@@ -570,7 +610,7 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
             if (next < n_chunks) issue(s, next);
         }
         if (n_staged > 32 - 8) {                                  // warp-uniform: the segment could overflow next chunk
-            flush_staged(p, lane < n_staged ? s_list + warp * 32 + lane : nullptr);
+            flush_staged<T>(p, lane < n_staged ? s_list + warp * 32 + lane : nullptr);
             n_staged = 0;
         }
         if (++s == stages) { s = 0; phase ^= 1u; }
@@ -587,7 +627,7 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
         total += cnt;
     }
     if ((tid & ~31) < total)                                       // warp-uniform: this warp has entries of the merged list
-        flush_staged(p, tid < total ? s_list + mine_seg * 32 + mine_idx : nullptr);
+        flush_staged<T>(p, tid < total ? s_list + mine_seg * 32 + mine_idx : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -799,12 +839,83 @@ extern "C" int sihl_od_dense_decode(const float *loc_logits, const float *cls_lo
                                     uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
                                     void *stream)
 {
+    return sihl_od_dense_decode_t(loc_logits, cls_logits, box_raw, SIHL_OD_F32, batch, num_anchors, num_classes, offsets, scales,
+                                  img_w, img_h, score_thr, cand_count, cand_capacity, cand_key, cand_box, cand_cls, zero_counts,
+                                  stream);
+}
+
+// Half maps: the TMA ring with 2-byte elements (C % 8 == 0, C <= 256, 16-byte aligned maps).
+template <typename T>
+static int launch_decode_tma_half(const DenseDecodeParams &p, int64_t rows, int num_classes, cudaStream_t st)
+{
+    const int cv = num_classes / 8;
+    const int vpl = (cv + 3) / 4;
+    const bool exact = vpl * 4 == cv;
+    int rows_per_stage = kChunkRows, stages = 2, ctas_per_sm = 2;
+    if ((rows + kChunkRows - 1) / kChunkRows < (int64_t)16 * kNumSMs * 2) { rows_per_stage = 32; stages = 2; ctas_per_sm = 3; }
+    else { stages = 4; }                                   // half-size stages: twice as many keep the same bytes in flight
+    const size_t stage_bytes = (size_t)rows_per_stage * num_classes * sizeof(T);
+    const size_t smem = stages * stage_bytes + stages * sizeof(uint64_t);
+    const int n_chunks = (int)((rows + rows_per_stage - 1) / rows_per_stage);
+    int blocks = kNumSMs * ctas_per_sm;
+    if (blocks > n_chunks) blocks = n_chunks;
+#define SIHL_DH_LAUNCH(KERN, THREADS)                                                                             \
+    do {                                                                                                          \
+        auto kern = KERN;                                                                                         \
+        int rc = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),  \
+                             "cudaFuncSetAttribute(k_dense_decode_tma)");                                         \
+        if (rc) return rc;                                                                                        \
+        kern<<<blocks, THREADS, smem, st>>>(p, stages, n_chunks);                                                 \
+    } while (0)
+#define SIHL_DH(VPL)                                                                                              \
+    do {                                                                                                          \
+        if (rows_per_stage == 64) {                                                                               \
+            if (exact) SIHL_DH_LAUNCH((k_dense_decode_tma<VPL, true, 64, T>), 256);                               \
+            else SIHL_DH_LAUNCH((k_dense_decode_tma<VPL, false, 64, T>), 256);                                    \
+        } else {                                                                                                  \
+            if (exact) SIHL_DH_LAUNCH((k_dense_decode_tma<VPL, true, 32, T>), 128);                               \
+            else SIHL_DH_LAUNCH((k_dense_decode_tma<VPL, false, 32, T>), 128);                                    \
+        }                                                                                                         \
+    } while (0)
+    switch (vpl) {
+        case 1: SIHL_DH(1); break;
+        case 2: SIHL_DH(2); break;
+        case 3: SIHL_DH(3); break;
+        case 4: SIHL_DH(4); break;
+        default: SIHL_DH(8); break;
+    }
+#undef SIHL_DH
+#undef SIHL_DH_LAUNCH
+    SIHL_CHECK_LAUNCH("k_dense_decode_tma (half maps)");
+    return SIHL_OD_OK;
+}
+
+extern "C" int sihl_od_dense_decode_t(const void *loc_logits_v, const void *cls_logits_v, const void *box_raw_v, int map_dtype,
+                                      int batch, int64_t num_anchors, int num_classes, const float *offsets,
+                                      const float *scales, int img_w, int img_h, float score_thr, int32_t *cand_count,
+                                      int64_t cand_capacity, uint64_t *cand_key, float *cand_box, int32_t *cand_cls,
+                                      int zero_counts, void *stream)
+{
     cudaStream_t st = (cudaStream_t)stream;
+    const float *loc_logits = reinterpret_cast<const float *>(loc_logits_v), *cls_logits = reinterpret_cast<const float *>(cls_logits_v);
+    const float *box_raw = reinterpret_cast<const float *>(box_raw_v);
     DenseDecodeParams p;
     int nothing = 0;
     int rc0 = decode_prologue(loc_logits, cls_logits, box_raw, batch, num_anchors, num_classes, offsets, scales, img_w, img_h,
                               score_thr, cand_count, cand_capacity, cand_key, cand_box, cand_cls, zero_counts, st, &p, &nothing);
     if (rc0 || nothing) return rc0;
+    if (map_dtype != SIHL_OD_F32) {
+        SIHL_CHECK_ARG(map_dtype == SIHL_OD_F16 || map_dtype == SIHL_OD_BF16, "map dtype code %d", map_dtype);
+        const bool ok = num_classes % 8 == 0 && num_classes <= 256 && (int64_t)batch * num_anchors >= 4 * kChunkRows &&
+                        ((reinterpret_cast<uintptr_t>(cls_logits_v) | reinterpret_cast<uintptr_t>(box_raw_v)) & 15u) == 0;
+        SIHL_CHECK_ARG(ok, "the dense scan of half maps needs C %% 8 == 0, C <= 256, >= 256 rows and 16-byte aligned maps "
+                           "(C=%d): use sihl_od_candidate_decode_t", num_classes);
+        // scores are sigmoid() rounded to the map type and may cross the threshold from below: widen the pre-filter
+        if (p.logit_thr > -HUGE_VALF && p.logit_thr < HUGE_VALF) p.logit_thr -= 0.05f * (1.f + fabsf(p.logit_thr));
+        const int64_t rows_h = (int64_t)batch * num_anchors;
+        if (map_dtype == SIHL_OD_F16) return launch_decode_tma_half<__half>(p, rows_h, num_classes, st);
+        return launch_decode_tma_half<__nv_bfloat16>(p, rows_h, num_classes, st);
+    }
     const int64_t rows = (int64_t)batch * num_anchors;
     const bool aligned = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0);

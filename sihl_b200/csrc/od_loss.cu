@@ -125,8 +125,8 @@ struct PosTileParams {
     const int32_t *pos_chunks; const int32_t *tile_pos_rows; const int2 *tile_pos_aux; int n_tiles; int num_anchors;
     const float4 *offsets; const float4 *scales; float img_w, img_h;
     const float4 *gt_boxes; const int64_t *gt_classes; const int32_t *gt_offsets;
-    const float *box_raw; const float *cls; int num_classes; int cls_vec4;
-    double *sums;
+    const void *box_raw; const void *cls; int num_classes; int cls_vec4;   // element type T of the kernel template;
+    double *sums;                                                         // cls_vec4: rows are read 16 bytes at a time
     float *losses; unsigned *done_counter;       // optional fused finalize
 };
 
@@ -180,7 +180,11 @@ __device__ __noinline__ void exchange_sums(unsigned long long *const *peer, int 
         double *dst = reinterpret_cast<double *>(theirs) + ((size_t)parity * W + rank) * SIHL_OD_NUM_SUMS;
 #pragma unroll
         for (int i = 0; i < SIHL_OD_NUM_SUMS; ++i) dst[i] = s_in[i];
+#ifdef SIHL_EXCHANGE_FENCE
         __threadfence_system();
+#endif
+        // the release store orders THIS thread's eight stores above before the flag at system scope: no separate
+        // (and, over NVLink, microsecond-expensive) __threadfence_system() is needed
         st_release_sys(theirs + 16 * W + parity * W + rank, step);
         const unsigned long long *flag = mine + 16 * W + parity * W + tid;
         const unsigned long long t0 = global_timer_ns();
@@ -205,9 +209,39 @@ __device__ __noinline__ void exchange_sums(unsigned long long *const *peer, int 
     __syncthreads();
 }
 
-template <bool EXCHANGE>     // EXCHANGE: the last CTA all-reduces the sums over peer memory before it finalizes (multi-GPU)
+// Row statistics of a class-logit row of type T by 4 lanes with 16-byte loads (C * sizeof(T) % 16 == 0, aligned rows).
+template <typename T>
+__device__ __forceinline__ void row_softmax_stats4t(const T *__restrict__ z, int C, int gl, float *m_out, float *s_out)
+{
+    constexpr int N = Vec16<T>::N;
+    const int CV = C / N;
+    float m = -CUDART_INF_F;
+    for (int v = gl; v < CV; v += 4) {
+        float q[N];
+        ld_vec16(z + v * N, q);
+#pragma unroll
+        for (int e = 0; e < N; ++e) m = fmaxf(m, q[e]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+    float s = 0.f;
+    for (int v = gl; v < CV; v += 4) {
+        float q[N];
+        ld_vec16(z + v * N, q);
+#pragma unroll
+        for (int e = 0; e < N; ++e) s += __expf(q[e] - m);
+    }
+    s += __shfl_xor_sync(kFullMask, s, 2);
+    s += __shfl_xor_sync(kFullMask, s, 1);
+    *m_out = m;
+    *s_out = s;
+}
+
+// EXCHANGE: the last CTA all-reduces the sums over peer memory before it finalizes (multi-GPU); T: map element type
+template <bool EXCHANGE, typename T = float>
 __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileParams p, ExchangeParams x)
 {
+    const T *t_cls = reinterpret_cast<const T *>(p.cls), *t_box = reinterpret_cast<const T *>(p.box_raw);
     __shared__ double s_red[2 * 32];
     __shared__ bool s_last;
     const int tid = threadIdx.x;
@@ -237,10 +271,27 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
                 const bool tgt_ok = tgt64 >= 0 && tgt64 < p.num_classes;   // out-of-range label: NaN loss, no foreign read
                 const int tgt = tgt_ok ? (int)tgt64 : 0;
                 float m, se;
-                if (p.cls_vec4) row_softmax_stats4v<true>(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
-                else row_softmax_stats8<true>(p.cls + flat * p.num_classes, p.num_classes, gl, &m, &se);
+                if constexpr (sizeof(T) == 4) {
+                    const float *zf = reinterpret_cast<const float *>(p.cls) + flat * p.num_classes;
+                    if (p.cls_vec4) row_softmax_stats4v<true>(zf, p.num_classes, gl, &m, &se);
+                    else row_softmax_stats8<true>(zf, p.num_classes, gl, &m, &se);
+                } else {
+                    const T *zt = t_cls + flat * p.num_classes;
+                    if (p.cls_vec4) {
+                        row_softmax_stats4t<T>(zt, p.num_classes, gl, &m, &se);
+                    } else {                                       // 8 lanes, element loads
+                        m = -CUDART_INF_F;
+                        for (int c = gl; c < p.num_classes; c += 8) m = fmaxf(m, ldf(zt + c));
+#pragma unroll
+                        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+                        se = 0.f;
+                        for (int c = gl; c < p.num_classes; c += 8) se += __expf(ldf(zt + c) - m);
+#pragma unroll
+                        for (int o = 4; o > 0; o >>= 1) se += __shfl_xor_sync(kFullMask, se, o);
+                    }
+                }
                 if (ok && gl == 0) {
-                    const float ce = (logf(se) + m) - __ldg(p.cls + flat * p.num_classes + tgt);
+                    const float ce = (logf(se) + m) - ldf(t_cls + flat * p.num_classes + tgt);
                     acc_cls += __int_as_float(ga.y) * (tgt_ok ? ce : CUDART_NAN_F);         // ref :208
                 }
             }
@@ -249,7 +300,7 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
             const int64_t flat = __ldg(rows + tid);
             const int2 ga = __ldg(aux + tid);
             const int a = (int)(flat - (int64_t)b * A);
-            acc_box += __int_as_float(ga.y) * pos_box_loss(ldg4(p.box_raw + 4 * flat), __ldg(p.offsets + a), __ldg(p.scales + a),
+            acc_box += __int_as_float(ga.y) * pos_box_loss(ldf4(t_box + 4 * flat), __ldg(p.offsets + a), __ldg(p.scales + a),
                                                            __ldg(p.gt_boxes + ga.x), p.img_w, p.img_h);      // ref :197
         }
     }
@@ -493,6 +544,19 @@ extern "C" int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const 
                                                float *losses, uint32_t *done_counter, void *const *peer_regions, int world,
                                                int rank, void *stream)
 {
+    return sihl_od_pos_loss_tiles_exchange_t(pos_chunks, tile_pos_rows, tile_pos_aux, batch, num_anchors, offsets, scales, img_w,
+                                             img_h, gt_boxes, gt_classes, gt_offsets, box_raw, cls_logits, SIHL_OD_F32,
+                                             num_classes, sums, losses, done_counter, peer_regions, world, rank, stream);
+}
+
+extern "C" int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
+                                                 const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
+                                                 const float *offsets, const float *scales, int img_w, int img_h,
+                                                 const float *gt_boxes, const int64_t *gt_classes, const int32_t *gt_offsets,
+                                                 const void *box_raw, const void *cls_logits, int map_dtype, int num_classes,
+                                                 double *sums, float *losses, uint32_t *done_counter,
+                                                 void *const *peer_regions, int world, int rank, void *stream)
+{
     (void)gt_offsets;
     SIHL_CHECK_ARG(world >= 1 && world <= SIHL_OD_MAX_PEERS && rank >= 0 && rank < world, "world=%d rank=%d", world, rank);
     SIHL_CHECK_ARG(world == 1 || (peer_regions != nullptr && losses != nullptr),
@@ -516,7 +580,9 @@ extern "C" int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const 
     p.img_w = (float)img_w; p.img_h = (float)img_h;
     p.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); p.gt_classes = gt_classes; p.gt_offsets = gt_offsets;
     p.box_raw = box_raw; p.cls = cls_logits; p.num_classes = num_classes;
-    p.cls_vec4 = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
+    const int esz = map_dtype == SIHL_OD_F32 ? 4 : 2;
+    p.cls_vec4 = (((size_t)num_classes * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
+    SIHL_CHECK_ARG(box_raw == nullptr || (reinterpret_cast<uintptr_t>(box_raw) & (4 * esz - 1)) == 0, "box_raw rows must be aligned");
     p.sums = sums; p.losses = losses; p.done_counter = done_counter;
     ExchangeParams x;
     x.world = world; x.rank = rank;
@@ -526,8 +592,8 @@ extern "C" int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const 
     const int64_t cap = (int64_t)kNumSMs * 12;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (world > 1) k_pos_loss_tiles<true><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x);
-    else k_pos_loss_tiles<false><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x);
+    if (world > 1) SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<true, T><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
+    else SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<false, T><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
     SIHL_CHECK_LAUNCH("k_pos_loss_tiles");
     return SIHL_OD_OK;
 }

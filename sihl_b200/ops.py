@@ -624,19 +624,21 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
     if mode not in DECODE_MODES:
         raise ValueError(f"mode={mode!r}: expected one of {DECODE_MODES}")
     host_ok = mode == "candidate_first"        # gathers rows: the class / box maps may stay in pinned host memory
-    if mode == "candidate_first" and loc_logits.dtype in (torch.float16, torch.bfloat16) \
-            and cls_logits.dtype == loc_logits.dtype and box_raw.dtype == loc_logits.dtype:
-        # half maps straight from the MLPs (autocast): loaded as they are, upcast in registers
+    if loc_logits.dtype in (torch.float16, torch.bfloat16) and cls_logits.dtype == loc_logits.dtype \
+            and box_raw.dtype == loc_logits.dtype and (mode == "candidate_first" or half_dense_scan_ok(cls_logits)):
+        # half maps straight from the MLPs (autocast): loaded as they are, upcast in registers — half the bytes of the
+        # dense scan (same TMA ring), or the candidates' rows only
         loc, code = _req_map(loc_logits, "loc_logits", 2)
-        cls, _ = _req_map(cls_logits, "cls_logits", 3, pinned_ok=True)
-        box, _ = _req_map(box_raw, "box_raw", 3, pinned_ok=True)
+        cls, _ = _req_map(cls_logits, "cls_logits", 3, pinned_ok=host_ok)
+        box, _ = _req_map(box_raw, "box_raw", 3, pinned_ok=host_ok)
         B, A = loc.shape
+        name = "sihl_od_dense_decode_t" if mode == "dense" else "sihl_od_candidate_decode_t"
         with _on(loc.device):
-            rc = _lib().sihl_od_candidate_decode_t(_p(loc), _p(cls), _p(box), code, B, A, int(cls.shape[-1]), _p(offsets),
-                                                   _p(scales), int(img_w), int(img_h), float(score_thr), _p(cand.count),
-                                                   cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts),
-                                                   _stream(loc.device))
-        _native.check(rc, "sihl_od_candidate_decode_t")
+            rc = getattr(_lib(), name)(_p(loc), _p(cls), _p(box), code, B, A, int(cls.shape[-1]), _p(offsets),
+                                       _p(scales), int(img_w), int(img_h), float(score_thr), _p(cand.count),
+                                       cand.capacity, _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts),
+                                       _stream(loc.device))
+        _native.check(rc, name)
         return
     loc = _req(loc_logits.float() if loc_logits.dtype != torch.float32 else loc_logits, torch.float32, "loc_logits", 2)
     cls = _req(cls_logits.float() if cls_logits.dtype != torch.float32 else cls_logits, torch.float32, "cls_logits", 3, pinned_ok=host_ok)
@@ -648,6 +650,13 @@ def dense_decode(loc_logits: Tensor, cls_logits: Tensor, box_raw: Tensor, offset
                                    int(img_w), int(img_h), float(score_thr), _p(cand.count), cand.capacity,
                                    _p(cand.key), _p(cand.box), _p(cand.cls), int(zero_counts), _stream(loc.device))
     _native.check(rc, name)
+
+
+def half_dense_scan_ok(cls_logits: Tensor) -> bool:
+    """Whether ``sihl_od_dense_decode_t`` takes these half class maps (C % 8 == 0, C <= 256, enough rows); otherwise
+    the caller converts to fp32 or uses the candidate-first decode."""
+    C = int(cls_logits.shape[-1])
+    return C % 8 == 0 and C <= 256 and cls_logits.numel() // C >= 256
 
 
 SPLIT_NMS_FROM = 16384     # list capacity (locations per image) from which the one-shot postprocess uses the class-split NMS

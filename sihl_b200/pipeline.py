@@ -30,10 +30,10 @@ class StepInputs:
     """Inputs of one step (one batch shard), device resident — except that ``box_raw`` / ``cls_logits`` may be pinned
     host tensors when the pipeline runs ``decode_mode="candidate_first"``: both chains only gather rows of them
     (positives, candidates), which the kernels then read in place over PCIe instead of uploading the whole maps."""
-    loc_logits: Tensor     # [B, A] f32
-    iou_preds: Tensor      # [B, A] f32
-    box_raw: Tensor        # [B, A, 4] f32
-    cls_logits: Tensor     # [B, A, C] f32
+    loc_logits: Tensor     # [B, A]      fp32, or fp16 / bf16 (all four maps alike: loaded as they are, upcast in registers)
+    iou_preds: Tensor      # [B, A]
+    box_raw: Tensor        # [B, A, 4]
+    cls_logits: Tensor     # [B, A, C]
     gt: ops.GtBatch
 
     def nbytes(self) -> int:
@@ -112,23 +112,27 @@ class DetectionHeadPipeline:
         # the L2 prefetch hints of k_assign_resolve only make sense for device memory
         maps_on_device = x.cls_logits.is_cuda and x.box_raw.is_cuda
         assert maps_on_device or (x.cls_logits.is_pinned() and x.box_raw.is_pinned()), "host maps must be pinned"
+        dt = x.loc_logits.dtype
+        assert dt in ops.DTYPE_CODES and all(t.dtype == dt for t in (x.iou_preds, x.box_raw, x.cls_logits)), \
+            "the four head-output maps must share one of fp32 / fp16 / bf16"
+        code = ops.DTYPE_CODES[dt]
         _native.check(lib.sihl_od_assign_select(
             p(self.anchors), p(self.terms), self.A, self._hw.ctypes.data, len(self._hw), self.img_w, self.img_h, p(gt.boxes),
             p(gt.offsets), self.B, gt.total, self.topk, p(self.sel_anchor), p(self.sel_val), p(self.best_iou),
             p(out.sums), st), "sihl_od_assign_select")
-        _native.check(lib.sihl_od_assign_resolve(
+        _native.check(lib.sihl_od_assign_resolve_t(
             p(self.sel_anchor), p(self.sel_val), p(self.best_iou), p(gt.offsets), self.B, self.A, self.topk, 1,
-            p(x.loc_logits), p(x.iou_preds), p(out.assignment), p(out.rel_iou), p(out.sums), p(self.tile_pos_count),
+            p(x.loc_logits), p(x.iou_preds), code, p(out.assignment), p(out.rel_iou), p(out.sums), p(self.tile_pos_count),
             p(self.tile_pos_rows), p(x.box_raw) if maps_on_device else None, p(x.cls_logits) if maps_on_device else None,
             self.C, p(self.pos_chunks), p(self.tile_pos_aux), st),
-            "sihl_od_assign_resolve")
+            "sihl_od_assign_resolve_t")
         # single GPU: the last CTA of the positive-loss kernel also finalizes the five losses
         peers, world, rank = self._exchange if (finalize and self._exchange is not None) else (None, 1, 0)
-        _native.check(lib.sihl_od_pos_loss_tiles_exchange(
+        _native.check(lib.sihl_od_pos_loss_tiles_exchange_t(
             p(self.pos_chunks), p(self.tile_pos_rows), p(self.tile_pos_aux), self.B, self.A,
             p(self.offsets), p(self.scales), self.img_w, self.img_h, p(gt.boxes), p(gt.classes), p(gt.offsets),
-            p(x.box_raw), p(x.cls_logits), self.C, p(out.sums), p(out.losses) if finalize else None,
-            p(self.done_counter) if finalize else None, peers, world, rank, st), "sihl_od_pos_loss_tiles_exchange")
+            p(x.box_raw), p(x.cls_logits), code, self.C, p(out.sums), p(out.losses) if finalize else None,
+            p(self.done_counter) if finalize else None, peers, world, rank, st), "sihl_od_pos_loss_tiles_exchange_t")
 
     def finalize(self, out: StepOutputs) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -4,7 +4,7 @@
 # Every command runs plainly first (exit code checked) and only then under ncu; numbers printed under ncu are not used.
 tag=${1:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 12 --warmup 3 --regions 1 --no-graph --lanes 1 --skip-e2e --skip-cpu-baseline --skip-gpu-eager --skip-candidate-first --skip-train-tail"
+CMD="python bench.py --steps 12 --warmup 3 --regions 1 --no-graph --lanes 1 --skip-e2e --skip-cpu-baseline --skip-gpu-eager --skip-candidate-first --skip-train-tail --skip-half-maps"
 $CMD > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 # 1. every launch of our kernels with its device time (cold cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 200 --csv --log-file gpurun_out/${tag}_launches.csv \
