@@ -9,6 +9,8 @@
 //
 // Sums are accumulated per thread in fp32 over a handful of elements, then in fp64
 // through warp shuffles, one shared-memory hop and one atomicAdd per CTA and term.
+#include <cstdlib>
+
 #include "od_common.cuh"
 #include "od_pos.cuh"
 
@@ -589,7 +591,13 @@ extern "C" int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, cons
     x.peer = reinterpret_cast<unsigned long long *const *>(peer_regions);
     // persistent grid: up to 12 CTAs of 128 threads per SM, never more than the chunk-list capacity
     int64_t blocks = n_slots * (kTile / 32);
-    const int64_t cap = (int64_t)kNumSMs * 12;
+    // 6 persistent CTAs per SM (2-3 chunks each at cfg1), not the 12 the launch bounds allow: every CTA ends with two
+    // fp64 atomics on one 64-byte line + the completion ticket, and ~1800 of those serialise in one L2 slice.  Measured
+    // in the cfg1 pipeline (same box A/B): 12 -> 41.6 / 28.2 us per step (dense / candidate-first), 6 -> 40.8 / 25.6,
+    // 4 -> 40.6 / 26.0.
+    int per_sm = 6;
+    if (const char *e = getenv("SIHL_POS_TILE_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 12) per_sm = v; }   // developer A/B
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (world > 1) SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<true, T><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));

@@ -82,6 +82,43 @@ def test_exchange_and_split_helpers_without_a_gpu():
     assert rc == 1 and b"topk" in lib.sihl_od_last_error_string()
 
 
+def test_round2_entry_points_check_their_arguments_on_the_host():
+    """Workspace queries and argument errors of the training-step, dtype-generic, wide-NMS and mAP entries need no GPU."""
+    import ctypes as C
+    lib = _native.load()
+    # training step: workspace grows with the batch / gt capacity; too many images for the by-value gt layout; bad workspace
+    a = lib.sihl_od_train_workspace_bytes(2, 2134, 27, 9)
+    b = lib.sihl_od_train_workspace_bytes(64, 8525, 6400, 9)
+    assert 0 < a < b and lib.sihl_od_train_workspace_bytes(2, 2134, 27, 0) == 0
+    dummy = C.c_void_p(16)
+    counts = (C.c_int32 * 600)(*([1] * 600))
+    big = lib.sihl_od_train_workspace_bytes(600, 8525, 600, 9)
+    rc = lib.sihl_od_train_assign(dummy, None, 8525, None, 0, 640, 640, dummy, counts, dummy, 600, 600, 9, dummy, dummy, dummy, 10,
+                                  dummy, dummy, dummy, big, None)
+    assert rc == 1 and b"gt_offsets on the device" in lib.sihl_od_last_error_string()
+    rc = lib.sihl_od_train_assign(dummy, None, 8525, None, 0, 640, 640, dummy, None, dummy, 64, 6400, 9, dummy, dummy, dummy, 10,
+                                  dummy, dummy, dummy, 16, None)
+    assert rc == 1 and b"workspace too small" in lib.sihl_od_last_error_string()
+    # map dtype codes: 0 / 1 / 2 only
+    rc = lib.sihl_od_train_loss(dummy, None, None, None, 7, 1, 100, 0, dummy, dummy, None, 0, None, None, None, 0, 0, None, None,
+                                dummy, dummy, None, None)
+    assert rc == 1 and b"dtype" in lib.sihl_od_last_error_string()
+    # the dense scan of half maps states its shape requirements (callers fall back to the candidate-first decode)
+    rc = lib.sihl_od_dense_decode_t(dummy, dummy, dummy, 2, 1, 2134, 10, dummy, dummy, 320, 320, 0.05, dummy, 2134, dummy, dummy,
+                                    dummy, 0, None)
+    assert rc == 1 and b"C % 8" in lib.sihl_od_last_error_string()
+    # stand-alone NMS: the whole-GPU path (and its mask workspace) from 8192 boxes, up to 90000
+    small, wide, huge = (lib.sihl_od_batched_nms_workspace_bytes(n) for n in (8000, 30000, 100000))
+    assert small == (2 * 8000 + 2) * 48 and wide > 30000 * 30000 // 8 and huge == (2 * 100000 + 2) * 48
+    # N3: at most 1024 detections per image, 16 thresholds, 8 area ranges
+    assert lib.sihl_od_map_workspace_bytes(100, 10, 4) == 100 * 10 * 4 * 4
+    thr = (C.c_double * 10)(*[0.5 + 0.05 * i for i in range(10)])
+    rc = lib.sihl_od_map_match(dummy, dummy, dummy, 1, 5000, None, None, dummy, 0, thr, 10, thr, 4, dummy, dummy, dummy, None,
+                               dummy, None)
+    assert rc == 1 and b"detections per image" in lib.sihl_od_last_error_string()
+    assert lib.sihl_od_exchange_region_bytes(8) == 1280 and lib.sihl_od_exchange_barrier(None, 2, 0, None) == 1
+
+
 def test_header_is_plain_c99():
     """include/sihl_od.h is the boundary a non-C++ host would bind: it must compile as C."""
     import shutil

@@ -150,3 +150,28 @@ def test_get_saliency_and_offsets():
     off, sc = model.get_offsets_and_scales(inputs)
     t_off, t_sc = tr.offsets_and_scales(model._level_sizes(inputs), DEV)
     assert torch.equal(off, t_off) and torch.equal(sc, t_sc)
+
+
+def test_training_assign_with_more_images_than_fit_the_kernel_parameters():
+    """Above SIHL_OD_MAX_BATCH_BY_VALUE (512) images the per-image gt counts cannot ride in the kernel parameters: the
+    offsets are uploaded instead.  Same assignment as two half-size calls; the device-offsets form (CUDA-graph replayable)
+    gives the same result as the host-counts form."""
+    from sihl_b200 import ops
+    size, B, C = 64, 600, 3
+    levels = synth.level_sizes(size, size, 3, 5)
+    counts = [(i * 7) % 4 for i in range(B)]                      # 0..3 gts per image, some images empty
+    gt = synth.gt_batch_np(11, B, size, size, C, 3, counts=counts)
+    gb, gc_ = torch.from_numpy(gt.boxes).to(DEV), torch.from_numpy(gt.classes).to(DEV)
+    st = ops.train_assign(levels, size, size, gb, gc_, counts, B, 9)                         # B > 512: upload path
+    half = B // 2
+    cut = int(gt.offsets[half])
+    a = ops.train_assign(levels, size, size, gb[:cut], gc_[:cut], counts[:half], half, 9)    # by-value path
+    b = ops.train_assign(levels, size, size, gb[cut:], gc_[cut:], counts[half:], half, 9)
+    assert torch.equal(st.assignment, torch.cat([a.assignment, b.assignment]))
+    assert torch.equal(st.rel_iou, torch.cat([a.rel_iou, b.rel_iou]))
+    assert int(st.pos_total) == int(a.pos_total) + int(b.pos_total) > 0
+    dev_form = ops.train_assign(levels, size, size, gb[:cut], gc_[:cut], None, half, 9,
+                                gt_offsets=torch.from_numpy(gt.offsets[:half + 1].copy()).to(DEV))
+    assert torch.equal(dev_form.assignment, a.assignment) and torch.equal(dev_form.pos_index, a.pos_index)
+    P = int(a.pos_total)
+    assert (a.pos_index[P:] == 0).all() and (a.pos_index[1:P] > a.pos_index[:P - 1]).all()   # ascending rows, zero padding

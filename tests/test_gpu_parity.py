@@ -698,6 +698,8 @@ def test_lazy_topk_prefix_equals_full_nms(C, loc_mean, K, what):
     A = synth.num_anchors(levels)
     maps = synth.dense_maps_np(91, B, A, C, loc_mean=loc_mean, loc_std=2.0)
     maps.loc_logits[:, ::5] = np.round(maps.loc_logits[:, ::5], 1)                  # tied scores inside the prefix
+    if what == "few classes":
+        maps.loc_logits[1, :] = 1.5                                                 # one image where EVERY score ties: the prefix cannot be cut, the full list runs
     num, scores, classes, boxes = ops.dense_postprocess(_t(maps.loc_logits), _t(maps.cls_logits), _t(maps.box_raw), levels,
                                                         size, size, 0.05, 0.5, K, mode="candidate_first", split_nms=False)
     o_off, o_sc, _ = orc.anchors(levels, size, size)
