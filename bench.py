@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--serial", action="store_true", help="run both chains on one stream")
-    ap.add_argument("--lanes", type=int, default=0, help="steps in flight (independent scratch + stream each); 0 = 4")
+    ap.add_argument("--lanes", type=int, default=0, help="steps in flight (independent scratch + stream each); 0 = 4 on one GPU, 6 on several")
     ap.add_argument("--decode-mode", default="dense", choices=["dense", "candidate_first"],
                     help="inference chain of the timed step: dense class-map scan (TMA ring, the roofline kernel) or the "
                          "candidate-first gather (same outputs, ~30x fewer bytes at 2 %% candidates)")
@@ -291,7 +291,9 @@ def run_ours(args, w, world, rank, local_rank):
     dev = torch.device("cuda", local_rank)
     H, W, B, C, G, K = w["height"], w["width"], w["batch"], w["classes"], w["gt"], w["k"]
     levels = synth.level_sizes(H, W)
-    n_lanes = args.lanes if args.lanes > 0 else 4
+    # steps in flight: 4 on one GPU; 6 when the loss kernel waits for its peers' sums (measured at 2 GPUs, same box:
+    # 4 lanes 39.4 us, 6 lanes 39.0 us, 8 lanes 40.4 us per step; one GPU: 38.60 vs 38.57 us)
+    n_lanes = args.lanes if args.lanes > 0 else (4 if world == 1 else 6)
     A = synth.num_anchors(levels)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + 1000 * rank)
@@ -308,7 +310,9 @@ def run_ours(args, w, world, rank, local_rank):
     multi = world > 1
     use_graph = not args.no_graph
     main = torch.cuda.current_stream(dev)
-    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+    _lp = os.environ.get("SIHL_LANE_PRIORITY")            # developer A/B: CUDA priority of the lanes' (train-chain) streams
+    lane_streams = [torch.cuda.Stream(device=dev) if _lp is None else torch.cuda.Stream(device=dev, priority=int(_lp))
+                    for _ in range(n_lanes)]
 
     # multi-GPU: one NCCL communicator per lane (collectives of different lanes may be in flight at once)
     groups = [dist.new_group(ranks=list(range(world)), backend="nccl") for _ in range(n_lanes)] if multi else None

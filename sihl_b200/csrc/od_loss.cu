@@ -241,7 +241,7 @@ __device__ __forceinline__ void row_softmax_stats4t(const T *__restrict__ z, int
 
 // EXCHANGE: the last CTA all-reduces the sums over peer memory before it finalizes (multi-GPU); T: map element type
 template <bool EXCHANGE, typename T = float>
-__global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileParams p, ExchangeParams x)
+__global__ void __launch_bounds__(kPosTileThreads, 8) k_pos_loss_tiles(PosTileParams p, ExchangeParams x)
 {
     const T *t_cls = reinterpret_cast<const T *>(p.cls), *t_box = reinterpret_cast<const T *>(p.box_raw);
     __shared__ double s_red[2 * 32];
@@ -253,10 +253,58 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
     // pos_chunks == NULL: a shard without a single image still takes part in the exchange (it pushes its zero sums)
     int desc = p.pos_chunks != nullptr ? __ldg(p.pos_chunks + blockIdx.x) : 0;
     const int n_chunks = p.pos_chunks != nullptr ? (int)p.sums[7] : 0;
-    const int lpr = p.cls_vec4 ? 4 : 8;                           // lanes per positive row
-    const int gl = tid & (lpr - 1), grp = tid / lpr, ngrp = kPosTileThreads / lpr;
     const int A = p.num_anchors;
     float acc_box = 0.f, acc_cls = 0.f;
+    if (p.cls == nullptr || p.cls_vec4) {
+        // WARP per chunk (the common case: class rows readable 16 bytes at a time).  Lane = row for everything that is
+        // per row — list entry, gt / class target, the whole CIoU term (all 32 lanes busy, where a CTA per chunk kept
+        // 96 of 128 threads idle through the ~300-instruction box loss) and the final cross-entropy — and 4 lanes per
+        // row, 8 rows per pass, for the class-row statistics.  One dependent chain per chunk (descriptor -> list
+        // entries -> targets + rows), four chunks in flight per CTA.
+        const int lane = tid & 31, warp = tid >> 5;
+        constexpr int kWarps = kPosTileThreads / 32;
+        const int gl4 = lane & 3, grp8 = lane >> 2;
+        for (int w = (int)blockIdx.x * kWarps + warp; w < n_chunks; w += (int)gridDim.x * kWarps) {
+            const int d = (w == (int)blockIdx.x && warp == 0) ? desc : __ldg(p.pos_chunks + w);
+            const int slot = d >> 10, r_begin = ((d >> 6) & 15) * 32, n = (d & 63) + 1;
+            const int b = slot / p.n_tiles;
+            const bool mine = lane < n;
+            const int32_t flat = __ldg(p.tile_pos_rows + (int64_t)slot * kTile + r_begin + (mine ? lane : 0));
+            const int2 ga = __ldg(p.tile_pos_aux + (int64_t)slot * kTile + r_begin + (mine ? lane : 0));
+            const float wgt = __int_as_float(ga.y);
+            if (p.box_raw != nullptr && mine) {
+                const int a = flat - b * A;
+                acc_box += wgt * pos_box_loss(ldf4(t_box + 4 * (int64_t)flat), __ldg(p.offsets + a), __ldg(p.scales + a),
+                                              __ldg(p.gt_boxes + ga.x), p.img_w, p.img_h);                  // ref :197
+            }
+            if (p.cls != nullptr) {
+                const int64_t tgt64 = __ldg(p.gt_classes + ga.x);
+                const bool tgt_ok = tgt64 >= 0 && tgt64 < p.num_classes;   // out-of-range label: NaN loss, no foreign read
+                float my_m = 0.f, my_se = 1.f;
+#pragma unroll
+                for (int pass = 0; pass < 4; ++pass) {
+                    if (pass * 8 >= n) break;                              // warp-uniform
+                    const int r = pass * 8 + grp8;
+                    const int32_t rflat = __shfl_sync(kFullMask, flat, r < n ? r : 0);
+                    float m, se;
+                    if constexpr (sizeof(T) == 4)
+                        row_softmax_stats4v<true>(reinterpret_cast<const float *>(p.cls) + (int64_t)rflat * p.num_classes,
+                                                  p.num_classes, gl4, &m, &se);
+                    else
+                        row_softmax_stats4t<T>(t_cls + (int64_t)rflat * p.num_classes, p.num_classes, gl4, &m, &se);
+                    // hand the statistics of row r to lane r (its group sits at lanes 4 * (r & 7) .. + 3 of this pass)
+                    const float m_r = __shfl_sync(kFullMask, m, 4 * (lane & 7)), se_r = __shfl_sync(kFullMask, se, 4 * (lane & 7));
+                    if ((lane >> 3) == pass) { my_m = m_r; my_se = se_r; }
+                }
+                if (mine) {
+                    const float ce = (logf(my_se) + my_m) - ldf(t_cls + (int64_t)flat * p.num_classes + (tgt_ok ? (int)tgt64 : 0));
+                    acc_cls += wgt * (tgt_ok ? ce : CUDART_NAN_F);                                          // ref :208
+                }
+            }
+        }
+    } else {
+    const int lpr = 8;                                            // lanes per positive row (element loads, any C)
+    const int gl = tid & (lpr - 1), grp = tid / lpr, ngrp = kPosTileThreads / lpr;
     for (int w = blockIdx.x; w < n_chunks; w += gridDim.x) {
         if (w != (int)blockIdx.x) desc = __ldg(p.pos_chunks + w);
         const int slot = desc >> 10, r_begin = ((desc >> 6) & 15) * 32, n = (desc & 63) + 1;
@@ -305,6 +353,7 @@ __global__ void __launch_bounds__(kPosTileThreads, 12) k_pos_loss_tiles(PosTileP
             acc_box += __int_as_float(ga.y) * pos_box_loss(ldf4(t_box + 4 * flat), __ldg(p.offsets + a), __ldg(p.scales + a),
                                                            __ldg(p.gt_boxes + ga.x), p.img_w, p.img_h);      // ref :197
         }
+    }
     }
     SIHL_PT(1);
     double v[2] = {acc_box, acc_cls};

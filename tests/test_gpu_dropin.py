@@ -196,3 +196,27 @@ def test_empty_batch_early_out_matches_the_reference_head():
     assert torch.isinf(r_loss) and torch.isinf(o_loss)
     for k in ("box_loss", "class_loss", "iou_loss"):
         assert float(o_metrics[k]) == float(r_metrics[k]) == 0.0
+
+
+def test_config0_a_few_optimizer_steps_follow_the_reference_trajectory():
+    """What the Lightning loop does without Lightning (it is not installed): four SGD steps on both models from the same
+    initialisation and the same batches (ref lightning_module.py:68-119 -> optimizer step).  The losses must stay
+    together step after step — gradients flow through the replacement exactly as through the reference head."""
+    ref, ours = _build()
+    ref.train(), ours.train()
+    opt_r = torch.optim.SGD(ref.parameters(), lr=2e-3, momentum=0.9)
+    opt_o = torch.optim.SGD(ours.parameters(), lr=2e-3, momentum=0.9)
+    trace = []
+    for step in range(4):
+        x, target = _batch(seed=20 + step)
+        losses = []
+        for model, opt in ((ref, opt_r), (ours, opt_o)):
+            opt.zero_grad(set_to_none=True)
+            loss, _ = model.heads[0].training_step(model.extract_features(x), **target)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)      # ref examples/object_detection.py:293 (grad-clip 0.1)
+            opt.step()
+            losses.append(loss.item())
+        trace.append(losses)
+        assert losses[1] == pytest.approx(losses[0], rel=5e-4), (step, trace)
+    assert trace[-1][0] != trace[0][0]                                    # the models did move
