@@ -75,7 +75,10 @@ res["both_serial"] = timeit(capture(lambda i: (pipe.infer_chain(sets[i], outs[i]
 res["select"] = timeit(capture(k_select))
 res["select+resolve"] = timeit(capture(lambda i: (k_select(i), k_resolve(i))))
 res["select+resolve+pos"] = timeit(capture(lambda i: (k_select(i), k_resolve(i), k_pos(i))))
-res["decode"] = timeit(capture(k_decode))
+# decode alone: re-zero the counters every launch (left to accumulate, the lists would fill with DUPLICATES of the same
+# locations, which k_nms' rank-by-counting does not accept: every location may be listed once per image)
+res["decode"] = timeit(capture(lambda i: (pipe.cand.count.zero_(), k_decode(i))))
+pipe.cand.count.zero_()
 res["decode+nms"] = timeit(capture(lambda i: (k_decode(i), k_nms(i))))
 for k, v in res.items():
     print(f"{k:22s} {v:8.2f} us")
