@@ -294,12 +294,16 @@ def run_ours(args, w, world, rank, local_rank):
     # steps in flight: 4 on one GPU; 6 when the loss kernel waits for its peers' sums (measured at 2 GPUs, same box:
     # 4 lanes 39.4 us, 6 lanes 39.0 us, 8 lanes 40.4 us per step; one GPU: 38.60 vs 38.57 us)
     n_lanes = args.lanes if args.lanes > 0 else (4 if world == 1 else 6)
+    if args.lanes <= 0 and w["batch"] * synth.num_anchors(levels) < 250_000:
+        n_lanes = 8          # small steps (crowd: 8 images) are latency-bound kernel by kernel: 4 lanes 18.7 us, 8 lanes 17.5 us
     A = synth.num_anchors(levels)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + 1000 * rank)
     # rotating input sets: together at least 3x the 126 MB L2, so that every step streams from HBM (3 sets of 188 MB at
     # cfg1; the small workloads need more sets)
     n_sets = min(16, max(3, -(-(400 << 20) // (B * A * (C + 5) * 4))))
+    if os.environ.get("SIHL_BENCH_SETS"):                  # developer A/B: more rotating sets than needed
+        n_sets = max(n_sets, int(os.environ["SIHL_BENCH_SETS"]))
     sets = []
     for _ in range(n_sets):
         boxes, classes, offsets = synth.gt_batch_torch(gen, B, H, W, C, G, dev)

@@ -440,7 +440,10 @@ SIHL_OD_API int sihl_od_candidate_decode_t(const void *loc_logits, const void *c
  * K kept detections per image, zero padded, in the reference forward()'s output
  * format.  workspace: sihl_od_nms_workspace_bytes(batch, cand_capacity).
  * reset_counts != 0: cand_count[b] is zeroed once consumed, so the next
- * sihl_od_dense_decode needs no zeroing launch. */
+ * sihl_od_dense_decode needs no zeroing launch.
+ * Precondition: the sort keys of a list are DISTINCT (every location listed at most once per image — what the decode
+ * kernels write when cand_count started at zero).  Ranks are computed by counting; a list into which the same
+ * candidates were appended twice (decode called again without zeroing the counters) is not a valid input. */
 SIHL_OD_API size_t sihl_od_nms_workspace_bytes(int batch, int64_t cand_capacity);
 
 SIHL_OD_API int sihl_od_nms_topk(const int32_t *cand_count, int64_t cand_capacity,

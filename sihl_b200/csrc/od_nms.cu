@@ -474,7 +474,9 @@ __device__ __forceinline__ int nms_small_body(const NmsParams &p, const int *sel
             for (int j = sub; j < n; j += 4) {
                 const unsigned long long kj = s_key[j];
                 const unsigned cj = s_cls[j];
-                const bool better = kj > key, same = cj == cls;
+                // keys are distinct in every valid list; the (==, lower slot) arm only keeps the ranks a permutation —
+                // and every index derived from them in bounds — should a caller hand in a list with repeated entries
+                const bool better = kj > key || (kj == key && j < item), same = cj == cls;
                 r += better;
                 seg0 += cj < cls;
                 k += same && better;
@@ -775,7 +777,14 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
         const int h = ar.b_id[slot];
         const int s0 = h_start[h], e0 = s0 + h_cnt[h];
         int rank = 0;
-        for (int j = s0; j < e0; ++j) rank += ar.u_key[j] > key;
+        if (p.mode == 0) {                                   // candidate lists: (==, earlier position), see nms_small_body
+            for (int j = s0; j < e0; ++j) {
+                const unsigned long long kj = ar.u_key[j];
+                rank += kj > key || (kj == key && j < pp);
+            }
+        } else {                                             // batched_nms: the keys carry the box index, always distinct
+            for (int j = s0; j < e0; ++j) rank += ar.u_key[j] > key;
+        }
         const int q = s0 + rank;
         const float4 bx = p.mode == 0 ? __ldg(p.cand_box + lb + slot) : __ldg(p.boxes + src0 + slot);
         ar.f_key[q] = key;
@@ -934,7 +943,11 @@ __device__ __forceinline__ bool nms_medium_body(const NmsParams &p, int n, int s
         for (int r = tid; r < n_pass; r += blockDim.x) {
             const unsigned long long key = pass_key[r];
             int rank = 0;
-            for (int j = 0; j < n_pass; ++j) rank += pass_key[j] > key;
+            if (p.mode == 0) {
+                for (int j = 0; j < n_pass; ++j) rank += pass_key[j] > key || (pass_key[j] == key && j < r);
+            } else {
+                for (int j = 0; j < n_pass; ++j) rank += pass_key[j] > key;
+            }
             if (rank < want) emit((int)pass_src[r], rank);
         }
     }

@@ -200,3 +200,22 @@ def test_map_match_stays_inside_its_buffers(guarded):
                         _t(gtb), _t(rng.randint(0, 3, 3 * G).astype(np.int64)), _t(off))
     assert res["dt_match"].shape == (B, 4, 10, K)
     guarded.check()
+
+
+@pytest.mark.parametrize("loc_mean,what", [(-5.0, "short lists"), (-2.0, "lists beyond 256: lazy prefix, then the full-list body")])
+def test_nms_survives_lists_with_repeated_entries(guarded, loc_mean, what):
+    """Not a valid input (sihl_od.h: keys must be distinct) but a plausible mistake — the decode called twice without
+    zeroing the counters appends every candidate twice.  The ranks stay a permutation, so nothing is read or written
+    out of bounds and the call completes; (an earlier version took stale shared-memory indices and faulted)."""
+    size, B, C, K = 640, 2, 80, 100
+    levels = synth.level_sizes(size, size)
+    A = synth.num_anchors(levels)
+    loc, _, box, cls = _maps(21, B, A, C, loc_mean, 1.0)
+    off, sc, _ = ops.anchor_tables(levels, size, size, DEV)
+    cand = ops.CandidateBuffers.allocate(B, A, DEV)
+    for _ in range(3):
+        ops.dense_decode(loc, cls, box, off, sc, size, size, 0.05, cand, zero_counts=False)
+    num, scores, classes, boxes = ops.nms_topk(cand, B, 0.5, K, reset_counts=True)
+    torch.cuda.synchronize()
+    assert int(num.max()) <= K and int(cand.count.sum()) == 0 and torch.isfinite(boxes).all()
+    guarded.check()
