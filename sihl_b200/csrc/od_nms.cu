@@ -465,6 +465,15 @@ __device__ __forceinline__ int nms_small_body(const NmsParams &p, const int *sel
             if (sub == 0) { s_key[item] = key; s_cls[item] = cls; }
         }
         if (tid == 0) s_big = 0;
+        // Keys are distinct in every valid list, which makes the ranks below a permutation of 0..n-1.  Should a caller
+        // hand in a list with repeated entries (decode run twice without zeroing the counters), ranks collide and some
+        // slots of the rank-indexed tables are never written: give them in-bounds defaults, so that such a list yields
+        // a meaningless but memory-safe result instead of stale shared-memory indices (measured: a tie-break inside
+        // the counting loop would do the same for 2 % of the candidate-first step; these five stores are free).
+        if (sub == 0 && item < kSmallItems) {
+            s_q_of_r[item] = 0; s_slot_of_r[item] = 0; s_seg0_of_q[item] = 0; s_len_of_q[item] = 1; s_mask[item] = 0u;
+            s_keep[item] = 0u; s_dead[item] = 0; s_box[item] = make_float4(0.f, 0.f, 0.f, 0.f); s_area[item] = 0.f;
+        }
         __syncthreads();
         SIHL_PHASE(2);
         // one pass: r = #better keys; seg0 = #smaller classes; k = #better keys of the same class; len = #same class
@@ -474,9 +483,7 @@ __device__ __forceinline__ int nms_small_body(const NmsParams &p, const int *sel
             for (int j = sub; j < n; j += 4) {
                 const unsigned long long kj = s_key[j];
                 const unsigned cj = s_cls[j];
-                // keys are distinct in every valid list; the (==, lower slot) arm only keeps the ranks a permutation —
-                // and every index derived from them in bounds — should a caller hand in a list with repeated entries
-                const bool better = kj > key || (kj == key && j < item), same = cj == cls;
+                const bool better = kj > key, same = cj == cls;
                 r += better;
                 seg0 += cj < cls;
                 k += same && better;
