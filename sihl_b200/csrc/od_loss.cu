@@ -127,6 +127,7 @@ struct PosTileParams {
     const int32_t *pos_chunks; const int32_t *tile_pos_rows; const int2 *tile_pos_aux; int n_tiles; int num_anchors;
     const float4 *offsets; const float4 *scales; float img_w, img_h;
     const float4 *gt_boxes; const int64_t *gt_classes; const int32_t *gt_offsets;
+    int host_rows;                                                        // the maps live in pinned host memory
     const void *box_raw; const void *cls; int num_classes; int cls_vec4;   // element type T of the kernel template;
     double *sums;                                                         // cls_vec4: rows are read 16 bytes at a time
     float *losses; unsigned *done_counter;       // optional fused finalize
@@ -239,6 +240,36 @@ __device__ __forceinline__ void row_softmax_stats4t(const T *__restrict__ z, int
     *s_out = s;
 }
 
+// The same with 8 lanes per row: every load instruction covers 128 contiguous bytes of a row.  For maps in device memory
+// this is no better than 4 lanes; for maps left in PINNED HOST memory (read in place over PCIe) the request size is what
+// counts: the link runs out of read tags long before it runs out of bandwidth, and 128-byte reads need half as many.
+template <typename T>
+__device__ __forceinline__ void row_softmax_stats8t(const T *__restrict__ z, int C, int gl, float *m_out, float *s_out)
+{
+    constexpr int N = Vec16<T>::N;
+    const int CV = C / N;
+    float m = -CUDART_INF_F;
+    for (int v = gl; v < CV; v += 8) {
+        float q[N];
+        ld_vec16(z + v * N, q);
+#pragma unroll
+        for (int e = 0; e < N; ++e) m = fmaxf(m, q[e]);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+    float s = 0.f;
+    for (int v = gl; v < CV; v += 8) {
+        float q[N];
+        ld_vec16(z + v * N, q);
+#pragma unroll
+        for (int e = 0; e < N; ++e) s += __expf(q[e] - m);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    *m_out = m;
+    *s_out = s;
+}
+
 // EXCHANGE: the last CTA all-reduces the sums over peer memory before it finalizes (multi-GPU); T: map element type
 template <bool EXCHANGE, typename T = float>
 __global__ void __launch_bounds__(kPosTileThreads, 8) k_pos_loss_tiles(PosTileParams p, ExchangeParams x)
@@ -281,6 +312,19 @@ __global__ void __launch_bounds__(kPosTileThreads, 8) k_pos_loss_tiles(PosTilePa
                 const int64_t tgt64 = __ldg(p.gt_classes + ga.x);
                 const bool tgt_ok = tgt64 >= 0 && tgt64 < p.num_classes;   // out-of-range label: NaN loss, no foreign read
                 float my_m = 0.f, my_se = 1.f;
+                if (p.host_rows) {                                         // 8 lanes per row, 4 rows per pass (see row_softmax_stats8t)
+                    const int gl8 = lane & 7, grp4 = lane >> 3;
+#pragma unroll
+                    for (int pass = 0; pass < 8; ++pass) {
+                        if (pass * 4 >= n) break;                          // warp-uniform
+                        const int r = pass * 4 + grp4;
+                        const int32_t rflat = __shfl_sync(kFullMask, flat, r < n ? r : 0);
+                        float m, se;
+                        row_softmax_stats8t<T>(t_cls + (int64_t)rflat * p.num_classes, p.num_classes, gl8, &m, &se);
+                        const float m_r = __shfl_sync(kFullMask, m, 8 * (lane & 3)), se_r = __shfl_sync(kFullMask, se, 8 * (lane & 3));
+                        if ((lane >> 2) == pass) { my_m = m_r; my_se = se_r; }
+                    }
+                } else
 #pragma unroll
                 for (int pass = 0; pass < 4; ++pass) {
                     if (pass * 8 >= n) break;                              // warp-uniform
@@ -635,6 +679,13 @@ extern "C" int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, cons
     p.cls_vec4 = (((size_t)num_classes * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
     SIHL_CHECK_ARG(box_raw == nullptr || (reinterpret_cast<uintptr_t>(box_raw) & (4 * esz - 1)) == 0, "box_raw rows must be aligned");
     p.sums = sums; p.losses = losses; p.done_counter = done_counter;
+    p.host_rows = 0;
+    if (cls_logits != nullptr && p.cls_vec4) {                    // pinned host maps (zero-copy): wider row reads
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, cls_logits) == cudaSuccess) p.host_rows = attr.type == cudaMemoryTypeHost;
+        else (void)cudaGetLastError();
+        if (const char *e = getenv("SIHL_HOST_ROWS")) p.host_rows = p.host_rows && atoi(e) != 0;             // developer A/B
+    }
     ExchangeParams x;
     x.world = world; x.rank = rank;
     x.peer = reinterpret_cast<unsigned long long *const *>(peer_regions);
