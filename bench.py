@@ -547,7 +547,7 @@ def run_ours(args, w, world, rank, local_rank):
         torch.cuda.synchronize()
         settle.append(w0.elapsed_time(w1) / warm)
         # at least ~40 ms of back-to-back launches: a 57 MB scan settles only after ~15 ms (crowd: 18 us -> 14 us)
-        if sum(settle) * warm >= 40.0 and abs(settle[-1] - settle[-2]) <= 0.03 * settle[-1]:
+        if len(settle) >= 2 and sum(settle) * warm >= 40.0 and abs(settle[-1] - settle[-2]) <= 0.03 * settle[-1]:
             break
     if sampler: sampler.mark()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
