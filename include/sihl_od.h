@@ -498,6 +498,21 @@ SIHL_OD_API int sihl_od_map_match(const float *det_boxes, const float *det_score
                       int32_t *det_order, int32_t *dt_match, uint8_t *dt_ignore, uint8_t *gt_ignore,
                       void *workspace, void *stream);
 
+/* ---- N4: the per-location MLP towers in front of the hot path ----------------
+ * ref object_detection.py:51-61 builds loc / cls / box / iou heads as torchvision ops.MLP(256 -> [256]*num_layers
+ * + [out], norm_layer=LayerNorm, activation_layer=SiLU) and applies them to every location (:116, :121, :175).
+ * One call = one layer over M locations, bf16 operands on the 5th-generation tensor cores (tcgen05.mma, fp32
+ * accumulators in TMEM, operands staged by TMA), the whole Linear -> LayerNorm -> SiLU chain in one kernel:
+ *   sihl_od_mlp_hidden: y = SiLU(LayerNorm(x W^T + bias; eps) * gamma + beta)   x [M,256], W [256,256], y [M,256] bf16
+ *   sihl_od_mlp_out:    y = x W^T + bias       W [n_pad,256] bf16 (rows >= out_cols zero), y [M,out_cols] fp32
+ * channels must be 256 (the reference's num_channels default); n_pad in {16,32,64,96,128,256}; bias/gamma/beta are
+ * fp32 device arrays of length 256 (hidden) or n_pad (out).  x, W, y: device pointers, 16-byte aligned, row-major,
+ * contiguous.  Inference only (no gradient is produced): training keeps torch's MLP. */
+SIHL_OD_API int sihl_od_mlp_hidden(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
+                       const float *gamma, const float *beta, float eps, void *y_bf16, void *stream);
+SIHL_OD_API int sihl_od_mlp_out(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
+                    int n_pad, int out_cols, float *y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -774,3 +774,54 @@ def map_match(det_boxes: Tensor, det_scores: Tensor, det_classes: Tensor, gt_box
             _p(order), _p(dtm), _p(dti), _p(gti), _p(ws), _stream(dev))
     _native.check(rc, "sihl_od_map_match")
     return dict(det_order=order, dt_match=dtm, dt_ignore=dti, gt_ignore=gti[:, :G])
+
+
+# ---- N4: the per-location MLP towers on the tensor cores -------------------------------------------------
+MLP_CHANNELS = 256                      # the reference's num_channels default; the kernels are built for it
+_MLP_OUT_PADS = (16, 32, 64, 96, 128, 256)
+
+
+def mlp_out_pad(out_features: int) -> int:
+    """Rows the output layer's weight is zero-padded to (tcgen05.mma needs N % 16 == 0)."""
+    for n in _MLP_OUT_PADS:
+        if out_features <= n:
+            return n
+    raise ValueError(f"out_features {out_features} > 256 is not supported by sihl_od_mlp_out")
+
+
+def mlp_hidden(x: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5,
+               out: Optional[Tensor] = None) -> Tensor:
+    """One hidden layer of ``torchvision.ops.MLP(..., norm_layer=LayerNorm, activation_layer=SiLU)`` (ref
+    object_detection.py:51, :56-60): ``SiLU(LayerNorm(x @ weight.T + bias))`` in ONE kernel.  x [M,256] bf16, weight
+    [256,256] bf16, bias / gamma / beta fp32 [256]; returns bf16 [M,256].  Inference only."""
+    x = _req(x, torch.bfloat16, "x", 2)
+    weight = _req(weight, torch.bfloat16, "weight", 2)
+    M, K = x.shape
+    if K != MLP_CHANNELS or tuple(weight.shape) != (MLP_CHANNELS, MLP_CHANNELS):
+        raise ValueError(f"mlp_hidden is built for {MLP_CHANNELS} channels, got x {tuple(x.shape)} weight {tuple(weight.shape)}")
+    dev = x.device
+    with _on(dev):
+        y = out if out is not None else torch.empty((M, K), dtype=torch.bfloat16, device=dev)
+        rc = _lib().sihl_od_mlp_hidden(_p(x), M, K, _p(weight), _p(_req(bias, torch.float32, "bias", 1)),
+                                       _p(_req(gamma, torch.float32, "gamma", 1)), _p(_req(beta, torch.float32, "beta", 1)),
+                                       float(eps), _p(_req(y, torch.bfloat16, "out", 2)), _stream(dev))
+    _native.check(rc, "sihl_od_mlp_hidden")
+    return y
+
+
+def mlp_out(x: Tensor, weight_padded: Tensor, bias_padded: Tensor, out_features: int, out: Optional[Tensor] = None) -> Tensor:
+    """The tower's last ``Linear(256, out_features)``: x [M,256] bf16, ``weight_padded`` [n_pad,256] bf16 with rows
+    >= out_features zero (``mlp_out_pad``), ``bias_padded`` fp32 [n_pad]; returns fp32 [M,out_features]."""
+    x = _req(x, torch.bfloat16, "x", 2)
+    weight_padded = _req(weight_padded, torch.bfloat16, "weight_padded", 2)
+    M, K = x.shape
+    n_pad = int(weight_padded.shape[0])
+    if K != MLP_CHANNELS or weight_padded.shape[1] != K or n_pad not in _MLP_OUT_PADS or not 1 <= out_features <= n_pad:
+        raise ValueError(f"mlp_out: x {tuple(x.shape)}, weight_padded {tuple(weight_padded.shape)}, out_features {out_features}")
+    dev = x.device
+    with _on(dev):
+        y = out if out is not None else torch.empty((M, out_features), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_mlp_out(_p(x), M, K, _p(weight_padded), _p(_req(bias_padded, torch.float32, "bias_padded", 1)),
+                                    n_pad, int(out_features), _p(_req(y, torch.float32, "out", 2)), _stream(dev))
+    _native.check(rc, "sihl_od_mlp_out")
+    return y
