@@ -37,7 +37,8 @@ constexpr int kChunkK = 64;                   // bf16 per 128-byte swizzle row
 constexpr int kChunks = kK / kChunkK;         // 4
 constexpr int kUmmaK = 16;                    // K per tcgen05.mma (bf16)
 constexpr int kXStageBytes = kBlockM * 128;   // one ring slot: 128 rows x 128 B
-constexpr int kThreads = 192;                 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kThreads = 320;                 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kHalfCols = 128;                // columns per epilogue warp of a hidden layer (two warps per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -152,6 +153,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: two fp32 lanes per instruction) and small epilogue helpers ----------------------
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ float lo_of(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float hi_of(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float tanh_fast(float x) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t bf16x2_of(uint64_t v) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(lo_of(v), hi_of(v));
+    return *reinterpret_cast<const uint32_t*>(&b);
+}
+__device__ __forceinline__ void st_global_256(void* dst, const uint32_t* v) {      // one full 32-byte sector per lane
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                 "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight epilogue warps only
+
 __host__ __device__ constexpr int tmem_stage_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
 template <int N>
@@ -159,7 +181,7 @@ struct MlpSmem {
     static constexpr int kStages = (N == 256) ? 5 : 8;
     static constexpr int kWBytes = kChunks * N * 128;
     static constexpr int kRingBytes = kStages * kXStageBytes;
-    static constexpr int kParamBytes = 3 * N * 4;
+    static constexpr int kParamBytes = 3 * N * 4 + 4 * kBlockM * 4;       // bias, gamma/2, beta/2 + the row-statistics exchange
     static constexpr int kBarBytes = (2 * kStages + 1 + 4) * 8 + 16;
     static constexpr int kTotal = 1024 /* alignment slack */ + kWBytes + kRingBytes + kParamBytes + kBarBytes;
 };
@@ -185,13 +207,14 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     constexpr int kStageCols = tmem_stage_cols(N);
     constexpr int kTmemCols = 2 * kStageCols;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // the swizzle atoms need 1024-byte alignment
     uint8_t* sW = base;                                   // 4 chunks x [N rows x 128 B], swizzled by the TMA unit
     uint8_t* sX = sW + L::kWBytes;                        // ring of [128 rows x 128 B] slots
     float* sBias = reinterpret_cast<float*>(sX + L::kRingBytes);
     float* sGamma = sBias + N;
     float* sBeta = sGamma + N;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sBeta + N);
+    float* sStat = sBeta + N;                             // [sum | ssq][half][row]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sStat + 4 * kBlockM);
     uint64_t* empty = full + S;
     uint64_t* w_full = empty + S;
     uint64_t* t_full = w_full + 1;                        // [2] accumulator stage ready for the epilogue
@@ -202,13 +225,13 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
 
     for (int i = threadIdx.x; i < N; i += kThreads) {
         sBias[i] = p.bias[i];
-        sGamma[i] = HIDDEN ? p.gamma[i] : 1.f;
-        sBeta[i] = HIDDEN ? p.beta[i] : 0.f;
+        sGamma[i] = HIDDEN ? 0.5f * p.gamma[i] : 1.f;     // the 1/2 of SiLU's tanh form folded in (exact)
+        sBeta[i] = HIDDEN ? 0.5f * p.beta[i] : 0.f;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(w_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], HIDDEN ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                      // TMEM: one warp allocates and later frees
@@ -262,11 +285,18 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                 tc_commit(&t_full[as]);                   // accumulator complete
             }
         }
-    } else {
-        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = row =====
+    } else if (HIDDEN || warp < 6) {
+        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = row.  Hidden layers: eight warps, the
+        // two warps of a lane quarter take 128 columns each and exchange their partial row sums through shared memory;
+        // the arithmetic is packed fp32x2 (FADD2 / FMUL2 / FFMA2: two columns per issue slot). =====
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         uint32_t t = 0;
+        [[maybe_unused]] float bias_sum = 0.f;
+        if constexpr (HIDDEN) {
+            for (int j = 0; j < kHalfCols; ++j) bias_sum += sBias[half * kHalfCols + j];
+        }
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
             const uint32_t as = t & 1, aph = (t >> 1) & 1;
             mbar_wait(&t_full[as], aph, 4);
@@ -274,63 +304,87 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kStageCols;
             const long long grow = static_cast<long long>(tile) * kBlockM + row;
             if constexpr (HIDDEN) {
+                const int cbase = half * kHalfCols;
                 uint32_t v[32];
-                float sum = 0.f;
+                // pass 1: row sum of the accumulator (the bias sum is a constant of the CTA)
+                uint64_t s2a = 0, s2b = 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    tmem_ld32(taddr + c0, v);
+                for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
+                    tmem_ld32(taddr + cbase + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + sBias[c0 + j];
-                }
-                const float mean = sum * (1.f / N);
-                float ssq = 0.f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    tmem_ld32(taddr + c0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float d = (__uint_as_float(v[j]) + sBias[c0 + j]) - mean;
-                        ssq = __fmaf_rn(d, d, ssq);
+                    for (int j = 0; j < 32; j += 4) {
+                        s2a = add2(s2a, pack2(v[j], v[j + 1]));
+                        s2b = add2(s2b, pack2(v[j + 2], v[j + 3]));
                     }
                 }
-                const float rstd = 1.f / sqrtf(ssq * (1.f / N) + p.eps);
-                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * N;
+                sStat[(0 * 2 + half) * kBlockM + row] = (lo_of(s2a) + hi_of(s2a)) + (lo_of(s2b) + hi_of(s2b)) + bias_sum;
+                epi_sync();
+                const float mean = (sStat[(0 * 2 + 0) * kBlockM + row] + sStat[(0 * 2 + 1) * kBlockM + row]) * (1.f / N);
+                const uint64_t mean2 = pack2f(mean, mean);
+                // pass 2: centred sum of squares
+                uint64_t q2a = 0, q2b = 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    tmem_ld32(taddr + c0, v);
+                for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
+                    tmem_ld32(taddr + cbase + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sBias[cbase + c0 + j]);
+                        const uint64_t d0 = sub2(add2(pack2(v[j], v[j + 1]), b4.x), mean2);
+                        const uint64_t d1 = sub2(add2(pack2(v[j + 2], v[j + 3]), b4.y), mean2);
+                        q2a = fma2(d0, d0, q2a);
+                        q2b = fma2(d1, d1, q2b);
+                    }
+                }
+                sStat[(1 * 2 + half) * kBlockM + row] = (lo_of(q2a) + hi_of(q2a)) + (lo_of(q2b) + hi_of(q2b));
+                epi_sync();
+                const float var = (sStat[(1 * 2 + 0) * kBlockM + row] + sStat[(1 * 2 + 1) * kBlockM + row]) * (1.f / N);
+                const float rstd = 1.f / sqrtf(var + p.eps);
+                const uint64_t rstd2 = pack2f(rstd, rstd);
+                // pass 3: normalise, SiLU, round to bf16, store 64-byte pieces of the row
+                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * N + cbase;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
+                    tmem_ld32(taddr + cbase + c0, v);
                     uint32_t packed[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float y[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const float d = ((__uint_as_float(v[j + u]) + sBias[c0 + j + u]) - mean) * rstd;
-                            const float z = __fmaf_rn(d, sGamma[c0 + j + u], sBeta[c0 + j + u]);
-                            // SiLU(z) = z * sigmoid(z) = h + h * tanh(h), h = z / 2: one MUFU op per element
-                            const float h = 0.5f * z;
-                            float th;
-                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                            y[u] = __fmaf_rn(h, th, h);
-                        }
-                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(y[0], y[1]);
-                        packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                    for (int j = 0; j < 32; j += 4) {
+                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sBias[cbase + c0 + j]);
+                        const ulonglong2 g4 = *reinterpret_cast<const ulonglong2*>(&sGamma[cbase + c0 + j]);     // gamma / 2
+                        const ulonglong2 e4 = *reinterpret_cast<const ulonglong2*>(&sBeta[cbase + c0 + j]);      // beta / 2
+                        // h = SiLU argument / 2;  SiLU(z) = z * sigmoid(z) = h + h * tanh(h): one MUFU op per element
+                        const uint64_t h0 = fma2(mul2(sub2(add2(pack2(v[j], v[j + 1]), b4.x), mean2), rstd2), g4.x, e4.x);
+                        const uint64_t h1 = fma2(mul2(sub2(add2(pack2(v[j + 2], v[j + 3]), b4.y), mean2), rstd2), g4.y, e4.y);
+                        const uint64_t y0 = fma2(h0, pack2f(tanh_fast(lo_of(h0)), tanh_fast(hi_of(h0))), h0);
+                        const uint64_t y1 = fma2(h1, pack2f(tanh_fast(lo_of(h1)), tanh_fast(hi_of(h1))), h1);
+                        packed[(j >> 1)] = bf16x2_of(y0);
+                        packed[(j >> 1) + 1] = bf16x2_of(y1);
                     }
                     if (grow < p.M) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                        st_global_256(orow + c0, packed);
+                        st_global_256(orow + c0 + 16, packed + 8);
                     }
                 }
             } else {
                 uint32_t v[16];
                 float* orow = reinterpret_cast<float*>(p.out) + grow * p.out_cols;
+                const bool vec4 = (p.out_cols & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < N; c0 += 16) {
+                    if (c0 >= p.out_cols) break;                                   // padded columns: nothing to write
                     tmem_ld16(taddr + c0, v);
                     if (grow < p.M) {
+                        if (vec4) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.out_cols) orow[c0 + j] = __uint_as_float(v[j]) + sBias[c0 + j];
+                            for (int j = 0; j < 16; j += 4)
+                                if (c0 + j < p.out_cols)
+                                    *reinterpret_cast<float4*>(orow + c0 + j) =
+                                        make_float4(__uint_as_float(v[j]) + sBias[c0 + j], __uint_as_float(v[j + 1]) + sBias[c0 + j + 1],
+                                                    __uint_as_float(v[j + 2]) + sBias[c0 + j + 2], __uint_as_float(v[j + 3]) + sBias[c0 + j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < p.out_cols) orow[c0 + j] = __uint_as_float(v[j]) + sBias[c0 + j];
+                        }
                     }
                 }
             }

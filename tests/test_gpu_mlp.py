@@ -1,0 +1,119 @@
+"""Row N4: the head's per-location MLP towers on the tensor cores (sihl_od_mlp_hidden / sihl_od_mlp_out)
+against torch.  The reference builds the towers at src/sihl/heads/object_detection.py:51-61 and applies them at :116,
+:121 and :175.  Tolerances: the output layer accumulates bf16 products in fp32 exactly like an fp64 reference on the
+same bf16 operands (<= 2e-5 abs); a hidden layer's result is rounded to bf16 once (half an ulp: 2^-9 relative, plus
+tanh.approx's 2^-11 in SiLU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torchvision import ops as tvops
+
+from sihl_b200 import ops
+from sihl_b200.mlp_tower import PackedTower, run_tower
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(shape, generator=g, device=DEV) * scale
+
+
+def _hidden_ref(x, w, b, gamma, beta, eps=1e-5):
+    pre = (x.double() @ w.double().T + b.double()).float()
+    return F.silu(F.layer_norm(pre, (256,), gamma, beta, eps))
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 300, 128 * 148 + 5, 128 * 400])
+def test_hidden_layer(M):
+    """Single tiles, ragged tails (rows past M are zero-filled by the TMA unit and never stored), one tile per SM plus
+    a tail, and three tiles per CTA (both TMEM stages, ring wrap-around)."""
+    x = _rand((M, 256), 1).bfloat16()
+    w = _rand((256, 256), 2, 1 / 16).bfloat16()
+    b, gamma, beta = _rand((256,), 3), 1 + 0.1 * _rand((256,), 4), 0.1 * _rand((256,), 5)
+    guard = torch.full((M + 2, 256), 7.0, dtype=torch.bfloat16, device=DEV)          # rows M, M+1 must stay untouched
+    y = ops.mlp_hidden(x, w, b, gamma, beta, out=guard[:M])
+    ref = _hidden_ref(x, w, b, gamma, beta)
+    torch.testing.assert_close(y.float(), ref, rtol=2 ** -8, atol=2e-3)
+    assert (guard[M:] == 7.0).all()
+
+
+@pytest.mark.parametrize("out_features", [1, 4, 16, 80, 200])
+@pytest.mark.parametrize("M", [1, 300, 128 * 300 + 17])
+def test_output_layer(out_features, M):
+    x = _rand((M, 256), 6).bfloat16()
+    n_pad = ops.mlp_out_pad(out_features)
+    w = torch.zeros((n_pad, 256), dtype=torch.bfloat16, device=DEV)
+    w[:out_features] = _rand((out_features, 256), 7, 1 / 16).bfloat16()
+    b = torch.zeros((n_pad,), device=DEV)
+    b[:out_features] = _rand((out_features,), 8)
+    guard = torch.full((M + 1, out_features), -3.0, device=DEV)
+    y = ops.mlp_out(x, w, b, out_features, out=guard[:M])
+    ref = (x.double() @ w[:out_features].double().T + b[:out_features].double()).float()
+    torch.testing.assert_close(y, ref, rtol=0, atol=2e-5)
+    assert (guard[M:] == -3.0).all()
+
+
+def test_extreme_rows():
+    """Constant rows (variance 0 -> rstd = 1/sqrt(eps), as torch), large magnitudes, and a row of zeros."""
+    x = torch.zeros((4, 256), device=DEV)
+    x[1] = 1.0
+    x[2] = _rand((256,), 9) * 100
+    x[3, ::2] = 50.0
+    x = x.bfloat16()
+    w = _rand((256, 256), 10, 1 / 16).bfloat16()
+    b, gamma, beta = torch.zeros(256, device=DEV), torch.ones(256, device=DEV), torch.zeros(256, device=DEV)
+    y = ops.mlp_hidden(x, w, b, gamma, beta)
+    ref = _hidden_ref(x, w, b, gamma, beta)
+    assert torch.isfinite(y).all()
+    torch.testing.assert_close(y.float(), ref, rtol=2 ** -8, atol=2e-3)
+
+
+@pytest.mark.parametrize("out_features", [1, 4, 80])
+def test_tower_matches_the_torchvision_module(out_features):
+    """The whole tower (4 hidden layers + output, as the reference builds it) against the torch module: tight against the
+    same module run with bf16 rounding between layers, loose (bf16 chain vs fp32 chain) against the fp32 module."""
+    torch.manual_seed(0)
+    mlp = tvops.MLP(256, [256] * 4 + [out_features], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU).to(DEV).eval()
+    with torch.no_grad():
+        for m in mlp:
+            if isinstance(m, nn.LayerNorm):
+                m.weight.add_(0.1 * torch.randn_like(m.weight)); m.bias.add_(0.1 * torch.randn_like(m.bias))
+    assert PackedTower.supported(mlp)
+    x = _rand((3, 1000, 256), 11)
+    packed = PackedTower(mlp)
+    y = run_tower(packed, x)
+    assert y.shape == (3, 1000, out_features) and y.dtype == torch.float32
+    with torch.no_grad():
+        cur = x.bfloat16().float()
+        mods = [m for m in mlp if not isinstance(m, nn.Dropout)]
+        for i in range(0, len(mods) - 1, 3):
+            lin, ln = mods[i], mods[i + 1]
+            pre = (cur.double() @ lin.weight.bfloat16().double().T + lin.bias.double()).float()
+            cur = F.silu(ln(pre)).bfloat16().float()
+        emu = (cur.double() @ mods[-1].weight.bfloat16().double().T + mods[-1].bias.double()).float()
+        full = mlp(x)
+    torch.testing.assert_close(y, emu, rtol=2e-2, atol=2e-2)           # bf16 roundings may flip an ulp along the chain
+    assert (y - full).abs().max() < 0.1 and (y - full).abs().mean() < 0.01
+    # re-packing follows an optimizer step
+    with torch.no_grad():
+        mlp[0].weight.mul_(0.5)
+    y2 = run_tower(packed, x)
+    assert (y2 - y).abs().max() > 1e-3
+    with torch.no_grad():
+        torch.testing.assert_close(y2, mlp(x), rtol=0, atol=0.1)
+
+
+def test_rejects_what_the_kernels_are_not_built_for():
+    x = torch.zeros((8, 128), dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros((128, 128), dtype=torch.bfloat16, device=DEV)
+    v = torch.zeros((128,), device=DEV)
+    with pytest.raises(ValueError):
+        ops.mlp_hidden(x, w, v, v, v)
+    with pytest.raises(ValueError):
+        ops.mlp_out_pad(300)
+    mlp = tvops.MLP(128, [128, 4], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU)
+    assert not PackedTower.supported(mlp)
+    assert not PackedTower.supported(tvops.MLP(256, [256, 4], norm_layer=None, activation_layer=nn.ReLU))

@@ -1,0 +1,95 @@
+"""Row N4 measurement (developer tool; `python tools/bench_mlp.py [--m 545600] > profiles/r02_n4_mlp.json`):
+one hidden layer (Linear 256->256 + LayerNorm + SiLU), one output layer and the four whole towers of the head at the
+cfg1 location count (640^2, batch 64: M = 545 600), through the tcgen05 kernels and through torch eager (fp32 = what
+the reference runs, and bf16 autocast).  Inputs rotate over 3 buffers (3 x 279 MB > L2); CUDA events; warm-up first."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch import nn
+from torchvision import ops as tvops
+from sihl_b200 import ops
+from sihl_b200.mlp_tower import PackedTower, run_tower
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--m", type=int, default=64 * 8525)
+ap.add_argument("--iters", type=int, default=30)
+ap.add_argument("--classes", type=int, default=80)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+M = args.m
+peaks = {}
+try:
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+HBM = float(peaks.get("hbm_gbs", 6471.1)); TF = float(peaks.get("bf16_tflops", 1660.7))
+
+def timeit(fn, iters=args.iters, warm=5):
+    for i in range(warm): fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+torch.manual_seed(0)
+xs = [torch.randn((M, 256), device=dev).bfloat16() for _ in range(3)]
+ys = [torch.empty((M, 256), dtype=torch.bfloat16, device=dev) for _ in range(3)]
+lin, ln = nn.Linear(256, 256).to(dev), nn.LayerNorm(256).to(dev)
+w, b, g, be = lin.weight.detach().bfloat16().contiguous(), lin.bias.detach().float(), ln.weight.detach().float(), ln.bias.detach().float()
+res = {"M": M, "peaks": {"hbm_gbs": HBM, "bf16_tflops": TF, "source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+ms = timeit(lambda i: ops.mlp_hidden(xs[i % 3], w, b, g, be, out=ys[i % 3]))
+flops, byts = 2.0 * M * 256 * 256, M * 1024.0
+res["hidden_layer"] = {"ms": ms, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / HBM,
+                       "frac_of_tensor_peak": flops / ms / 1e9 / TF, "algorithmic_bytes": byts, "flops": flops}
+with torch.no_grad():
+    xf = [x.float() for x in xs[:2]]
+    seq = nn.Sequential(lin, ln, nn.SiLU())
+    res["hidden_layer"]["torch_eager_fp32_ms"] = timeit(lambda i: seq(xf[i % 2]), iters=10, warm=3)
+    def bf(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return seq(xs[i % 3])
+    res["hidden_layer"]["torch_eager_bf16_autocast_ms"] = timeit(bf, iters=10, warm=3)
+    seq_b = nn.Sequential(lin, ln, nn.SiLU()).bfloat16() if False else None
+    del xf
+torch.cuda.empty_cache()
+
+for n_out in (1, 4, args.classes):
+    n_pad = ops.mlp_out_pad(n_out)
+    wo = torch.zeros((n_pad, 256), dtype=torch.bfloat16, device=dev); wo[:n_out] = torch.randn((n_out, 256), device=dev).bfloat16() / 16
+    bo = torch.zeros((n_pad,), device=dev)
+    outs = [torch.empty((M, n_out), device=dev) for _ in range(3)]
+    ms = timeit(lambda i: ops.mlp_out(xs[i % 3], wo, bo, n_out, out=outs[i % 3]))
+    byts = M * (512.0 + 4 * n_out)
+    res[f"output_layer_{n_out}"] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / HBM, "n_pad": n_pad}
+    del outs
+
+# the four towers of the head (loc, iou: 1; box: 4; cls: classes), 4 hidden layers each
+towers = {n: tvops.MLP(256, [256] * 4 + [o], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU).to(dev).eval()
+          for n, o in (("loc", 1), ("iou", 1), ("box", 4), ("cls", args.classes))}
+packed = {n: PackedTower(m).refresh() for n, m in towers.items()}
+scratch = (ys[0], ys[1])
+def ours(i):
+    for n in towers: run_tower(packed[n], xs[i % 3], scratch)
+ms = timeit(ours, iters=10, warm=3)
+flops = sum(2.0 * M * 256 * (256 * 4 + ops.mlp_out_pad(o)) for o in (1, 1, 4, args.classes))
+res["four_towers"] = {"ms": ms, "tflops": flops / ms / 1e9, "frac_of_tensor_peak": flops / ms / 1e9 / TF, "launches": 4 * 5}
+del ys
+torch.cuda.empty_cache()
+with torch.no_grad():
+    try:
+        xf = xs[0].float()
+        def ref(i):
+            for n in towers: towers[n](xf)
+        res["four_towers"]["torch_eager_fp32_ms"] = timeit(ref, iters=3, warm=1)
+        del xf
+    except torch.OutOfMemoryError as e:
+        res["four_towers"]["torch_eager_fp32_ms"] = None
+    torch.cuda.empty_cache()
+    def refb(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for n in towers: towers[n](xs[i % 3])
+    res["four_towers"]["torch_eager_bf16_autocast_ms"] = timeit(refb, iters=3, warm=1)
+print(json.dumps(res, indent=1))
