@@ -13,13 +13,20 @@
 //     swizzle, mbarrier completion); rows past M are zero-filled by the TMA unit;
 //   * one elected thread issues 16 `tcgen05.mma.cta_group::1.kind::f16` (M=128, N, K=16) per tile into one of two
 //     TMEM accumulator stages (2 x N fp32 columns), `tcgen05.commit` releases ring slots / publishes the accumulator;
-//   * four epilogue warps — one TMEM lane quarter each, thread = row — read the accumulator with `tcgen05.ld`,
-//     add the bias, normalise the row (two-pass mean / variance, fp32, entirely inside the thread: no shuffles, no
-//     shared memory), apply SiLU and write bf16 rows; the other accumulator stage is being filled meanwhile.
+//   * sixteen epilogue warps (hidden layers; four for the narrow output layers) — four per TMEM lane quarter, thread =
+//     row, 64 columns each — read their slice of the accumulator ONCE with `tcgen05.ld` into registers (which frees the
+//     TMEM stage for the tile after next at once), add the bias, take the slice's sum and centred sum of squares,
+//     combine the four slices of a row through one shared-memory exchange per tile (parallel-variance formula),
+//     normalise, apply SiLU as h + h*tanh(h) (h = z/2: one MUFU op per element), round to bf16, and store.  The
+//     arithmetic is packed fp32x2 (FADD2 / FMUL2 / FFMA2).  Stores: a thread's 128-byte piece of its row is 4 x 4
+//     transposed inside the lane quad (SHFL.BFLY) so that every 256-bit store instruction of a warp writes 8 complete
+//     128-byte lines instead of touching 32 (L1 wavefronts per tile: 512 instead of 2 048; measured 9.0k -> 7.6k
+//     cycles per tile).
 //
 // A hidden layer reads 512 B and writes 512 B per location for 131 kFLOP: at M = 545 600 (640^2, batch 64) that is
 // 559 MB and 71.5 GFLOP per layer — HBM-bound at ~87 us, a third of what the unfused Linear + LayerNorm + SiLU kernels
-// move.  Every wait is bounded: a pipeline bug traps instead of hanging the GPU.
+// move; measured 124 us (4.5 TB/s, 577 TFLOP/s): what is left is the epilogue's MIO work per tile (MUFU, LDS, stores),
+// see DESIGN.md.  Every wait is bounded: a pipeline bug traps instead of hanging the GPU.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -37,8 +44,9 @@ constexpr int kChunkK = 64;                   // bf16 per 128-byte swizzle row
 constexpr int kChunks = kK / kChunkK;         // 4
 constexpr int kUmmaK = 16;                    // K per tcgen05.mma (bf16)
 constexpr int kXStageBytes = kBlockM * 128;   // one ring slot: 128 rows x 128 B
-constexpr int kThreads = 320;                 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
-constexpr int kHalfCols = 128;                // columns per epilogue warp of a hidden layer (two warps per TMEM lane quarter)
+constexpr int kThreads = 576;                 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-17: epilogue
+constexpr int kParts = 4;                     // epilogue warps per TMEM lane quarter of a hidden layer
+constexpr int kPartCols = 64;                 // columns each of them owns (held in registers for the whole epilogue)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -142,6 +150,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]),
+          "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]),
+          "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]),
+          "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -172,16 +198,29 @@ __device__ __forceinline__ void st_global_256(void* dst, const uint32_t* v) {   
                  "r"(v[6]), "r"(v[7])
                  : "memory");
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight epilogue warps only
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the sixteen epilogue warps only
 
 __host__ __device__ constexpr int tmem_stage_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
+#ifdef SIHL_MLP_TRACE
+// Developer build only (SIHL_B200_NVCC_EXTRA=-DSIHL_MLP_TRACE, tools/mlp_trace.py): CTA 0 records clock64() at the
+// pipeline's hand-over points, 16 slots per tile.
+constexpr int kTraceTiles = 64;
+__device__ long long g_mlp_trace[kTraceTiles * 16];
+#define MLP_TRACE(tile_no, ev)                                                                   \
+    do {                                                                                         \
+        if (blockIdx.x == 0 && (tile_no) < kTraceTiles) g_mlp_trace[(tile_no) * 16 + (ev)] = clock64(); \
+    } while (0)
+#else
+#define MLP_TRACE(tile_no, ev) do { } while (0)
+#endif
+
 template <int N>
 struct MlpSmem {
-    static constexpr int kStages = (N == 256) ? 5 : 8;
+    static constexpr int kStages = (N == 256) ? 5 : 8;      // N == 256: W takes 128 KB of the 227
     static constexpr int kWBytes = kChunks * N * 128;
     static constexpr int kRingBytes = kStages * kXStageBytes;
-    static constexpr int kParamBytes = 3 * N * 4 + 4 * kBlockM * 4;       // bias, gamma/2, beta/2 + the row-statistics exchange
+    static constexpr int kParamBytes = 3 * N * 4 + 2 * 2 * kParts * kBlockM * 4;   // bias, gamma/2, beta/2 + two row-statistics exchange buffers
     static constexpr int kBarBytes = (2 * kStages + 1 + 4) * 8 + 16;
     static constexpr int kTotal = 1024 /* alignment slack */ + kWBytes + kRingBytes + kParamBytes + kBarBytes;
 };
@@ -213,8 +252,8 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     float* sBias = reinterpret_cast<float*>(sX + L::kRingBytes);
     float* sGamma = sBias + N;
     float* sBeta = sGamma + N;
-    float* sStat = sBeta + N;                             // [sum | ssq][half][row]
-    uint64_t* full = reinterpret_cast<uint64_t*>(sStat + 4 * kBlockM);
+    float* sStat = sBeta + N;                             // [tile parity][sum | M2][part][row]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * kParts * kBlockM);
     uint64_t* empty = full + S;
     uint64_t* w_full = empty + S;
     uint64_t* t_full = w_full + 1;                        // [2] accumulator stage ready for the epilogue
@@ -231,7 +270,7 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(w_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], HIDDEN ? 8 : 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], HIDDEN ? 4 * kParts : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                      // TMEM: one warp allocates and later frees
@@ -253,6 +292,7 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                 for (int c = 0; c < kChunks; ++c, ++it) {
                     const uint32_t s = it % S, ph = (it / S) & 1;
                     mbar_wait(&empty[s], ph ^ 1, 0);
+                    MLP_TRACE(it / kChunks, c);                       // 0..3: slot free, chunk c requested
                     mbar_expect_tx(&full[s], kXStageBytes);
                     tma_load_2d(&map_x, &full[s], sX + s * kXStageBytes, c * kChunkK, tile * kBlockM);
                 }
@@ -267,11 +307,13 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
                 const uint32_t as = t & 1, aph = (t >> 1) & 1;
                 mbar_wait(&t_empty[as], aph ^ 1, 2);
+                MLP_TRACE(t, 4);                                      // 4: accumulator stage free
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * kStageCols;
                 for (int c = 0; c < kChunks; ++c, ++it) {
                     const uint32_t s = it % S, ph = (it / S) & 1;
                     mbar_wait(&full[s], ph, 3);
+                    MLP_TRACE(t, 5 + c);                              // 5..8: chunk c landed, MMAs issued
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(sX + s * kXStageBytes);
                     const uint32_t b_base = smem_u32(sW + c * (N * 128));
@@ -286,84 +328,119 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             }
         }
     } else if (HIDDEN || warp < 6) {
-        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = row.  Hidden layers: eight warps, the
-        // two warps of a lane quarter take 128 columns each and exchange their partial row sums through shared memory;
-        // the arithmetic is packed fp32x2 (FADD2 / FMUL2 / FFMA2: two columns per issue slot). =====
+        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = row.  Hidden layers: sixteen warps, the
+        // four warps of a lane quarter own 64 columns each, read them from TMEM ONCE into registers (which frees the
+        // accumulator stage at once) and exchange their partial row statistics through shared memory; the arithmetic
+        // is packed fp32x2 (FADD2 / FMUL2 / FFMA2: two columns per issue slot). =====
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         uint32_t t = 0;
-        [[maybe_unused]] float bias_sum = 0.f;
-        if constexpr (HIDDEN) {
-            for (int j = 0; j < kHalfCols; ++j) bias_sum += sBias[half * kHalfCols + j];
-        }
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
             const uint32_t as = t & 1, aph = (t >> 1) & 1;
             mbar_wait(&t_full[as], aph, 4);
+            if (warp == 2 && lane == 0) MLP_TRACE(t, 9);              // 9: accumulator complete
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kStageCols;
             const long long grow = static_cast<long long>(tile) * kBlockM + row;
             if constexpr (HIDDEN) {
-                const int cbase = half * kHalfCols;
-                uint32_t v[32];
-                // pass 1: row sum of the accumulator (the bias sum is a constant of the CTA)
+                const int cbase = part * kPartCols;
+                uint32_t v[kPartCols];
+                tmem_ld64(taddr + cbase, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[as]);              // the accumulator stage is free for tile t + 2
+                if (warp == 2 && lane == 0) MLP_TRACE(t, 10);          // 10: accumulator in registers
+                uint64_t x[kPartCols / 2];
+                // statistics of the thread's own 64 columns: x = acc + bias, sum, then the sum of squares about the
+                // LOCAL mean (two passes over registers, no synchronisation in between)
                 uint64_t s2a = 0, s2b = 0;
-#pragma unroll 1
-                for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
-                    tmem_ld32(taddr + cbase + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        s2a = add2(s2a, pack2(v[j], v[j + 1]));
-                        s2b = add2(s2b, pack2(v[j + 2], v[j + 3]));
-                    }
+                for (int j = 0; j < kPartCols; j += 4) {
+                    const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sBias[cbase + j]);
+                    x[j >> 1] = add2(pack2(v[j], v[j + 1]), b4.x);
+                    x[(j >> 1) + 1] = add2(pack2(v[j + 2], v[j + 3]), b4.y);
+                    s2a = add2(s2a, x[j >> 1]);
+                    s2b = add2(s2b, x[(j >> 1) + 1]);
                 }
-                sStat[(0 * 2 + half) * kBlockM + row] = (lo_of(s2a) + hi_of(s2a)) + (lo_of(s2b) + hi_of(s2b)) + bias_sum;
-                epi_sync();
-                const float mean = (sStat[(0 * 2 + 0) * kBlockM + row] + sStat[(0 * 2 + 1) * kBlockM + row]) * (1.f / N);
-                const uint64_t mean2 = pack2f(mean, mean);
-                // pass 2: centred sum of squares
+                const float sum_p = (lo_of(s2a) + hi_of(s2a)) + (lo_of(s2b) + hi_of(s2b));
+                const float mean_p = sum_p * (1.f / kPartCols);
+                const uint64_t mean_p2 = pack2f(mean_p, mean_p);
                 uint64_t q2a = 0, q2b = 0;
-#pragma unroll 1
-                for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
-                    tmem_ld32(taddr + cbase + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sBias[cbase + c0 + j]);
-                        const uint64_t d0 = sub2(add2(pack2(v[j], v[j + 1]), b4.x), mean2);
-                        const uint64_t d1 = sub2(add2(pack2(v[j + 2], v[j + 3]), b4.y), mean2);
-                        q2a = fma2(d0, d0, q2a);
-                        q2b = fma2(d1, d1, q2b);
-                    }
+                for (int j = 0; j < kPartCols / 2; j += 2) {
+                    const uint64_t d0 = sub2(x[j], mean_p2), d1 = sub2(x[j + 1], mean_p2);
+                    q2a = fma2(d0, d0, q2a);
+                    q2b = fma2(d1, d1, q2b);
                 }
-                sStat[(1 * 2 + half) * kBlockM + row] = (lo_of(q2a) + hi_of(q2a)) + (lo_of(q2b) + hi_of(q2b));
+                // one exchange per tile (buffers alternate with the tile parity): the four column slices of a row are
+                // combined with the parallel-variance formula  M2 = sum_q [ M2_q + n_q (mean_q - mean)^2 ]
+                float* stat = sStat + (t & 1) * (2 * kParts * kBlockM);
+                stat[(0 * kParts + part) * kBlockM + row] = sum_p;
+                stat[(1 * kParts + part) * kBlockM + row] = (lo_of(q2a) + hi_of(q2a)) + (lo_of(q2b) + hi_of(q2b));
                 epi_sync();
-                const float var = (sStat[(1 * 2 + 0) * kBlockM + row] + sStat[(1 * 2 + 1) * kBlockM + row]) * (1.f / N);
-                const float rstd = 1.f / sqrtf(var + p.eps);
-                const uint64_t rstd2 = pack2f(rstd, rstd);
-                // pass 3: normalise, SiLU, round to bf16, store 64-byte pieces of the row
-                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * N + cbase;
-#pragma unroll 1
-                for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
-                    tmem_ld32(taddr + cbase + c0, v);
-                    uint32_t packed[16];
+                if (warp == 2 && lane == 0) MLP_TRACE(t, 11);          // 11: row statistics exchanged
+                float sums[kParts], mean = 0.f, m2 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sBias[cbase + c0 + j]);
-                        const ulonglong2 g4 = *reinterpret_cast<const ulonglong2*>(&sGamma[cbase + c0 + j]);     // gamma / 2
-                        const ulonglong2 e4 = *reinterpret_cast<const ulonglong2*>(&sBeta[cbase + c0 + j]);      // beta / 2
-                        // h = SiLU argument / 2;  SiLU(z) = z * sigmoid(z) = h + h * tanh(h): one MUFU op per element
-                        const uint64_t h0 = fma2(mul2(sub2(add2(pack2(v[j], v[j + 1]), b4.x), mean2), rstd2), g4.x, e4.x);
-                        const uint64_t h1 = fma2(mul2(sub2(add2(pack2(v[j + 2], v[j + 3]), b4.y), mean2), rstd2), g4.y, e4.y);
-                        const uint64_t y0 = fma2(h0, pack2f(tanh_fast(lo_of(h0)), tanh_fast(hi_of(h0))), h0);
-                        const uint64_t y1 = fma2(h1, pack2f(tanh_fast(lo_of(h1)), tanh_fast(hi_of(h1))), h1);
-                        packed[(j >> 1)] = bf16x2_of(y0);
-                        packed[(j >> 1) + 1] = bf16x2_of(y1);
-                    }
-                    if (grow < p.M) {
-                        st_global_256(orow + c0, packed);
-                        st_global_256(orow + c0 + 16, packed + 8);
-                    }
+                for (int q = 0; q < kParts; ++q) {
+                    sums[q] = stat[(0 * kParts + q) * kBlockM + row];
+                    mean += sums[q];
+                    m2 += stat[(1 * kParts + q) * kBlockM + row];
                 }
+                mean *= (1.f / N);
+#pragma unroll
+                for (int q = 0; q < kParts; ++q) {
+                    const float dm = sums[q] * (1.f / kPartCols) - mean;
+                    m2 = __fmaf_rn(dm * dm, static_cast<float>(kPartCols), m2);
+                }
+                const float rstd = 1.f / sqrtf(m2 * (1.f / N) + p.eps);
+                const uint64_t mean2 = pack2f(mean, mean);
+                const uint64_t rstd2 = pack2f(rstd, rstd);
+                // normalise, SiLU, round to bf16: the thread's 64 columns are one 128-byte line of the output row
+                uint32_t packed[kPartCols / 2];
+#pragma unroll
+                for (int j = 0; j < kPartCols; j += 4) {
+                    const ulonglong2 g4 = *reinterpret_cast<const ulonglong2*>(&sGamma[cbase + j]);     // gamma / 2
+                    const ulonglong2 e4 = *reinterpret_cast<const ulonglong2*>(&sBeta[cbase + j]);      // beta / 2
+                    // h = SiLU argument / 2;  SiLU(z) = z * sigmoid(z) = h + h * tanh(h): one MUFU op per element
+                    const uint64_t h0 = fma2(mul2(sub2(x[j >> 1], mean2), rstd2), g4.x, e4.x);
+                    const uint64_t h1 = fma2(mul2(sub2(x[(j >> 1) + 1], mean2), rstd2), g4.y, e4.y);
+                    const uint64_t y0 = fma2(h0, pack2f(tanh_fast(lo_of(h0)), tanh_fast(hi_of(h0))), h0);
+                    const uint64_t y1 = fma2(h1, pack2f(tanh_fast(lo_of(h1)), tanh_fast(hi_of(h1))), h1);
+                    packed[j >> 1] = bf16x2_of(y0);
+                    packed[(j >> 1) + 1] = bf16x2_of(y1);
+                }
+                if (warp == 2 && lane == 0) MLP_TRACE(t, 13);          // 13: row computed
+                // store: a thread holds one 128-byte line of its row as four 32-byte pieces.  Written as they are, a
+                // warp-wide 32-byte store touches 32 different lines (32 L1 wavefronts); a 4 x 4 transpose of the pieces
+                // inside every lane quad (two butterfly steps of SHFL.BFLY) makes lanes 4g..4g+3 hold the four pieces
+                // of ONE row, so each store instruction writes 8 complete lines.
+                {
+                    const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                        for (int j = 0; j < 4; j += 2) {                   // step 1: partner lane ^ 1 swaps pieces (j, j+1)
+                            const uint32_t send = b0 ? packed[8 * j + r] : packed[8 * (j + 1) + r];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                            if (b0) packed[8 * j + r] = recv; else packed[8 * (j + 1) + r] = recv;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {                      // step 2: partner lane ^ 2 swaps pieces (j, j+2)
+                            const uint32_t send = b1 ? packed[8 * j + r] : packed[8 * (j + 2) + r];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                            if (b1) packed[8 * j + r] = recv; else packed[8 * (j + 2) + r] = recv;
+                        }
+                    }
+                    // now piece k of this lane = columns [16 q, 16 q + 16) (q = lane & 3) of row (lane & ~3) + k
+                    const long long qrow = static_cast<long long>(tile) * kBlockM + quarter * 32 + (lane & ~3);
+                    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + qrow * N + cbase + 16 * (lane & 3);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (qrow + k < p.M) st_global_256(obase + static_cast<long long>(k) * N, packed + 8 * k);
+                }
+                if (warp == 2 && lane == 0) MLP_TRACE(t, 14);          // 14: stores issued
+                continue;                                              // t_empty was signalled right after the load
             } else {
                 uint32_t v[16];
                 float* orow = reinterpret_cast<float*>(p.out) + grow * p.out_cols;
@@ -490,5 +567,12 @@ SIHL_OD_API int sihl_od_mlp_out(const void* x_bf16, int64_t M, int channels, con
         default: return launch_layer<256, false>(x_bf16, M, w_bf16, p, st);
     }
 }
+
+#ifdef SIHL_MLP_TRACE
+__attribute__((visibility("default"))) int sihl_od_mlp_debug_trace(long long* host_out, int n) {
+    if (n > kTraceTiles * 16) n = kTraceTiles * 16;
+    return cudaMemcpyFromSymbol(host_out, g_mlp_trace, sizeof(long long) * n) == cudaSuccess ? n : -1;
+}
+#endif
 
 }  // extern "C"
