@@ -134,10 +134,41 @@ class ObjectDetection(nn.Module):
         #   DDP's gradient *average* over the ranks equals the gradient of the global-batch loss.
         self.loss_reduction = "local"
         self.process_group = None
+        # "torch": the towers run as the torchvision modules above (fp32 or autocast), in training and inference.
+        # "tcgen05" (SURVEY.md §8f N4): wherever no gradient is being recorded (forward / postprocess / get_saliency under
+        #   no_grad, i.e. validation and serving) the towers run through ``sihl_od_mlp_hidden`` / ``sihl_od_mlp_out`` —
+        #   bf16 operands on the tensor cores, fp32 accumulation and LayerNorm, Linear + LayerNorm + SiLU in one kernel.
+        #   Needs num_channels == 256; training steps keep the torch modules (the kernels produce no gradient).
+        self.mlp_backend = "torch"
+        self._packed_towers: Dict[str, object] = {}
 
     # ------------------------------------------------------------------ helpers
     def _level_sizes(self, inputs: List[Tensor]) -> List[Tuple[int, int]]:
         return [tuple(int(v) for v in inputs[level].shape[2:]) for level in self.levels]
+
+    def _use_tcgen05(self, x: Tensor) -> bool:
+        if self.mlp_backend == "torch":
+            return False
+        if self.mlp_backend != "tcgen05":
+            raise ValueError(f"mlp_backend must be 'torch' or 'tcgen05', got {self.mlp_backend!r}")
+        return x.is_cuda and not torch.is_grad_enabled() and not torch.compiler.is_compiling()
+
+    def _tower(self, name: str, x: Tensor) -> Tensor:
+        """One of the four per-location MLPs (ref :108, :116, :121, :175) on ``x`` [..., C]."""
+        mlp = getattr(self, name)
+        if not self._use_tcgen05(x):
+            return mlp(x)
+        from ..mlp_tower import PackedTower, run_tower
+        packed = self._packed_towers.get(name)
+        if packed is None or packed.mlp is not mlp:
+            if not PackedTower.supported(mlp):
+                raise ValueError(f"mlp_backend='tcgen05' needs num_channels == 256 and the reference's tower structure ({name})")
+            packed = self._packed_towers[name] = PackedTower(mlp)
+        return run_tower(packed, x)
+
+    def _tower_input(self, flat_feats: Tensor) -> Tensor:
+        """The towers' common input: converted to bf16 ONCE when they run on the tensor cores."""
+        return flat_feats.to(torch.bfloat16) if self._use_tcgen05(flat_feats) else flat_feats
 
     def _flat_feats(self, inputs: List[Tensor]) -> Tensor:
         feats = [lateral(inputs[level]) for level, lateral in zip(self.levels, self.laterals)]     # ref :102-105
@@ -158,7 +189,7 @@ class ObjectDetection(nn.Module):
         for lateral, level in zip(self.laterals, self.levels):
             height, width = inputs[level].shape[2:]
             feats = lateral(inputs[level]).flatten(2).transpose(1, 2)
-            scores = self.loc_head(feats).sigmoid().transpose(1, 2).reshape(batch_size, 1, height, width)
+            scores = self._tower("loc_head", feats).sigmoid().transpose(1, 2).reshape(batch_size, 1, height, width)
             scores = functional.interpolate(scores, size=(full_height, full_width))
             output = torch.maximum(output, scores.squeeze(1))
         return output
@@ -172,9 +203,9 @@ class ObjectDetection(nn.Module):
         ``loc_logits.sigmoid()``.  Traceable: under ``torch.compile`` the same kernels run as ``sihl_b200::*`` custom ops
         (``sihl_b200/torch_ops.py``) with fake implementations."""
         (batch_size, _, height, width), device = inputs[0].shape, inputs[0].device
-        flat_feats = self._flat_feats(inputs)
+        flat_feats = self._tower_input(self._flat_feats(inputs))
         levels = self._level_sizes(inputs)
-        loc_logits = self.loc_head(flat_feats).squeeze(2)                                   # ref :108
+        loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                         # ref :108
         compiling = torch.compiler.is_compiling()
         if compiling:
             from .. import torch_ops
@@ -184,8 +215,8 @@ class ObjectDetection(nn.Module):
             top_logits, loc_idxs = ops.topk_locations(loc_logits.detach(), self.max_instances)   # ref :109
         rows = torch.arange(batch_size, device=device).view(batch_size, 1)
         top_feats = flat_feats[rows, loc_idxs]                                              # ref :112
-        class_logits = self.cls_head(top_feats)                                             # ref :116
-        box_raw = self.box_head(top_feats)                                                  # ref :121
+        class_logits = self._tower("cls_head", top_feats)                                   # ref :116
+        box_raw = self._tower("box_head", top_feats)                                        # ref :121
         if compiling:
             num, scores, classes, boxes = torch_ops.decode_rows(top_logits, loc_idxs, class_logits.detach(), box_raw.detach(),
                                                                 level_hw, int(width), int(height))
@@ -208,10 +239,10 @@ class ObjectDetection(nn.Module):
         box of the locations that pass the threshold only — identical results; default: ``"dense"`` for fp32 maps,
         ``"candidate_first"`` for half maps (autocast), which are then read as they are (no fp32 copies)."""
         (_, _, height, width) = inputs[0].shape
-        flat_feats = self._flat_feats(inputs)
-        loc_logits = self.loc_head(flat_feats).squeeze(2)
-        cls_logits = self.cls_head(flat_feats)
-        box_raw = self.box_head(flat_feats)
+        flat_feats = self._tower_input(self._flat_feats(inputs))
+        loc_logits = self._tower("loc_head", flat_feats).squeeze(2)
+        cls_logits = self._tower("cls_head", flat_feats)
+        box_raw = self._tower("box_head", flat_feats)
         if mode is None:
             mode = "dense" if loc_logits.dtype == torch.float32 else "candidate_first"
         return ops.dense_postprocess(loc_logits, cls_logits, box_raw, self._level_sizes(inputs), int(width), int(height),

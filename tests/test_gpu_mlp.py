@@ -117,3 +117,55 @@ def test_rejects_what_the_kernels_are_not_built_for():
     mlp = tvops.MLP(128, [128, 4], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU)
     assert not PackedTower.supported(mlp)
     assert not PackedTower.supported(tvops.MLP(256, [256, 4], norm_layer=None, activation_layer=nn.ReLU))
+
+
+def _head(num_classes=12):
+    from sihl_b200.heads import ObjectDetection
+    torch.manual_seed(0)
+    return ObjectDetection(in_channels=[3] + [64] * 5, num_classes=num_classes, bottom_level=3, top_level=5, num_channels=256,
+                           num_layers=4, max_instances=50).to(DEV).eval()
+
+
+def _pyramid(batch=2, size=256):
+    g = torch.Generator().manual_seed(3)
+    return [torch.randn((batch, 3, size, size), generator=g).to(DEV)] + [
+        torch.randn((batch, 64, size // 2 ** l, size // 2 ** l), generator=g).to(DEV) for l in range(1, 6)]
+
+
+def test_head_inference_through_the_tensor_core_towers():
+    """``mlp_backend = "tcgen05"``: forward / postprocess / get_saliency under no_grad run the towers through the kernels;
+    results agree with the torch towers to bf16-chain accuracy, and a training step (gradients recorded) is untouched."""
+    model, inputs = _head(), _pyramid()
+    with torch.no_grad():
+        model.loc_head[-2].bias.fill_(-1.0)                    # scores around 0.3: candidates exist for postprocess
+        ref_num, ref_scores, ref_cls, ref_boxes = model.forward(inputs)
+        ref_sal = model.get_saliency(inputs)
+        ref_post = model.postprocess(inputs, 0.05, 0.5)
+        model.mlp_backend = "tcgen05"
+        num, scores, cls, boxes = model.forward(inputs)
+        sal = model.get_saliency(inputs)
+        post = model.postprocess(inputs, 0.05, 0.5)
+    assert set(model._packed_towers) == {"loc_head", "cls_head", "box_head"}          # the kernels did run
+    assert scores.shape == ref_scores.shape and boxes.shape == ref_boxes.shape and cls.dtype == torch.int64
+    torch.testing.assert_close(scores, ref_scores, rtol=0, atol=0.02)                 # sorted top-K scores
+    torch.testing.assert_close(sal, ref_sal, rtol=0, atol=0.02)
+    assert (num - ref_num).abs().max() <= 2
+    torch.testing.assert_close(post[1][:, :5], ref_post[1][:, :5], rtol=0, atol=0.02)  # best detections after NMS
+    # gradients recorded -> torch modules, identical to the default backend
+    model.train()
+    tgt = {"classes": [torch.tensor([1, 2], device=DEV), torch.tensor([3], device=DEV)],
+           "boxes": [torch.tensor([[10., 20., 100., 120.], [50., 60., 200., 220.]], device=DEV), torch.tensor([[30., 30., 90., 90.]], device=DEV)]}
+    loss_a, _ = model.training_step(inputs, **tgt)
+    model.mlp_backend = "torch"
+    loss_b, _ = model.training_step(inputs, **tgt)
+    assert loss_a.item() == loss_b.item() and loss_a.requires_grad
+
+
+def test_head_rejects_the_backend_at_other_widths():
+    from sihl_b200.heads import ObjectDetection
+    model = ObjectDetection(in_channels=[3] + [32] * 5, num_classes=4, num_channels=64, num_layers=2).to(DEV).eval()
+    model.mlp_backend = "tcgen05"
+    g = torch.Generator().manual_seed(3)
+    inputs = [torch.randn((1, 3, 64, 64), generator=g).to(DEV)] + [torch.randn((1, 32, 64 // 2 ** l, 64 // 2 ** l), generator=g).to(DEV) for l in range(1, 6)]
+    with torch.no_grad(), pytest.raises(ValueError):
+        model.forward(inputs)

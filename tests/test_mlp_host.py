@@ -1,0 +1,74 @@
+"""Row N4 host logic without a GPU: tower structure recognition, padding rules, C-ABI argument checks."""
+import ctypes
+
+import pytest
+import torch
+from torch import nn
+from torchvision import ops as tvops
+
+from sihl_b200 import _native, ops
+from sihl_b200.mlp_tower import PackedTower, _split
+
+
+def _tower(width=256, layers=4, out=80):
+    return tvops.MLP(width, [width] * layers + [out], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU)
+
+
+def test_recognises_the_reference_tower_and_nothing_else():
+    """ref src/sihl/heads/object_detection.py:51, :56-60: Linear -> LayerNorm -> SiLU -> Dropout, x num_layers, + Linear."""
+    hidden, last = _split(_tower())
+    assert len(hidden) == 4 and last.out_features == 80
+    assert PackedTower.supported(_tower()) and PackedTower.supported(_tower(layers=0, out=1))
+    assert not PackedTower.supported(_tower(width=128))
+    assert not PackedTower.supported(tvops.MLP(256, [256, 4], norm_layer=nn.LayerNorm, activation_layer=nn.ReLU))
+    assert not PackedTower.supported(tvops.MLP(256, [256, 4], norm_layer=None, activation_layer=nn.SiLU))
+    assert not PackedTower.supported(tvops.MLP(256, [256, 4], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU, bias=False))
+    assert not PackedTower.supported(_tower(out=300))
+    assert not PackedTower.supported(nn.Sequential(nn.Linear(256, 256), nn.SiLU()))
+
+
+def test_packing_pads_the_output_layer_and_follows_parameter_updates():
+    mlp = _tower(out=5)
+    packed = PackedTower(mlp).refresh()
+    w, b, n_out = packed.out
+    assert n_out == 5 and tuple(w.shape) == (16, 256) and w.dtype == torch.bfloat16 and (w[5:] == 0).all() and (b[5:] == 0).all()
+    assert len(packed.hidden) == 4 and packed.hidden[0][0].dtype == torch.bfloat16 and packed.hidden[0][4] == pytest.approx(1e-5)
+    first = packed.hidden[0][0]
+    assert packed.refresh().hidden[0][0] is first                      # nothing changed: no re-pack
+    with torch.no_grad():
+        mlp[0].weight.mul_(2.0)
+    assert packed.refresh().hidden[0][0] is not first
+    torch.testing.assert_close(packed.hidden[0][0].float(), mlp[0].weight.detach().bfloat16().float())
+
+
+@pytest.mark.parametrize("out_features,pad", [(1, 16), (4, 16), (16, 16), (17, 32), (80, 96), (97, 128), (129, 256), (256, 256)])
+def test_output_padding_rule(out_features, pad):
+    assert ops.mlp_out_pad(out_features) == pad
+
+
+def test_cabi_rejects_bad_arguments_before_touching_the_device():
+    lib = _native.load()
+    buf = (ctypes.c_char * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.sihl_od_mlp_hidden(p, 128, 128, p, p, p, p, 1e-5, p, None) == 1          # channels != 256
+    assert lib.sihl_od_mlp_hidden(p, -1, 256, p, p, p, p, 1e-5, p, None) == 1
+    assert lib.sihl_od_mlp_hidden(None, 128, 256, p, p, p, p, 1e-5, p, None) == 1
+    assert lib.sihl_od_mlp_hidden(p + 8, 128, 256, p, p, p, p, 1e-5, p, None) == 1      # 16-byte alignment
+    assert lib.sihl_od_mlp_hidden(None, 0, 256, None, None, None, None, 1e-5, None, None) == 0   # empty input: nothing to do
+    assert lib.sihl_od_mlp_out(p, 128, 256, p, p, 24, 4, p, None) == 1                  # n_pad not a supported width
+    assert lib.sihl_od_mlp_out(p, 128, 256, p, p, 16, 17, p, None) == 1                 # out_cols > n_pad
+    assert lib.sihl_od_mlp_out(p, 128, 64, p, p, 16, 4, p, None) == 1
+    assert lib.sihl_od_mlp_out(None, 0, 256, None, None, 16, 4, None, None) == 0
+
+
+def test_head_backend_switch_is_validated():
+    from sihl_b200.heads import ObjectDetection
+    model = ObjectDetection(in_channels=[3] + [8] * 5, num_classes=3, num_channels=16, num_layers=1)
+    assert model.mlp_backend == "torch"
+    x = torch.zeros((1, 4, 16))
+    assert model._use_tcgen05(x) is False
+    model.mlp_backend = "tcgen05"
+    assert model._use_tcgen05(x) is False                              # CPU tensor: the torch modules
+    model.mlp_backend = "cutlass"
+    with pytest.raises(ValueError):
+        model._use_tcgen05(x)

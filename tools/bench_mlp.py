@@ -92,4 +92,23 @@ with torch.no_grad():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             for n in towers: towers[n](xs[i % 3])
     res["four_towers"]["torch_eager_bf16_autocast_ms"] = timeit(refb, iters=3, warm=1)
+
+# the head's forward (ref :99-122) at cfg1: laterals + loc tower on every location + top-K + cls / box towers on K rows + decode
+del xs, towers, packed
+torch.cuda.empty_cache()
+from sihl_b200.heads import ObjectDetection
+B, size = 64, 640
+model = ObjectDetection(in_channels=[3, 64, 128, 256, 256, 256], num_classes=args.classes, num_channels=256, num_layers=4).to(dev).eval()
+g = torch.Generator(device=dev); g.manual_seed(0)
+inputs = [torch.randn((B, c, max(1, size // 2 ** l), max(1, size // 2 ** l)), generator=g, device=dev) if l >= 3 or l == 0 else torch.empty((B, c, 1, 1), device=dev)
+          for l, c in enumerate(model.in_channels)]
+with torch.no_grad():
+    model.mlp_backend = "torch"
+    t_torch = timeit(lambda i: model.forward(inputs), iters=5, warm=2)
+    model.mlp_backend = "tcgen05"
+    t_tc = timeit(lambda i: model.forward(inputs), iters=10, warm=3)
+    feats = model._flat_feats(inputs)
+    t_lat = timeit(lambda i: model._flat_feats(inputs), iters=10, warm=3)
+res["head_forward_cfg1"] = {"batch": B, "image": size, "locations": int(feats.shape[1]), "torch_towers_ms": t_torch, "tcgen05_towers_ms": t_tc,
+                            "laterals_and_concat_ms": t_lat, "speedup": t_torch / t_tc}
 print(json.dumps(res, indent=1))
