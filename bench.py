@@ -75,6 +75,7 @@ def parse_args():
                     help="timed regions of --steps steps each; the line reports the median region (SURVEY.md §8d), min/max "
                          "and per-rank times beside it")
     ap.add_argument("--skip-half-maps", action="store_true", help="do not also time the step on bf16 head outputs")
+    ap.add_argument("--skip-mlp", action="store_true", help="do not also time the MLP towers in front of the path (row N4)")
     ap.add_argument("--skip-train-tail", action="store_true", help="do not time the drop-in head's training tail with backward")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--e2e-lanes", type=int, default=2, help="end-to-end steps in flight (own stream + buffers each)")
@@ -614,6 +615,11 @@ def run_ours(args, w, world, rank, local_rank):
             del h_pipes, h_outs
         del hsets
 
+    # ---- row N4: the per-location MLP towers in FRONT of the path, on the tensor cores (extra line, never the headline)
+    mlp_line = None
+    if not multi and not args.skip_mlp:
+        mlp_line = mlp_towers_line(B * A, C, dev)
+
     # ---- the drop-in head's training tail WITH gradients (what ObjectDetection.training_step runs around its MLPs)
     train_tail = None
     if not multi and not args.skip_train_tail:
@@ -636,7 +642,8 @@ def run_ours(args, w, world, rank, local_rank):
                                                 "steps_in_flight": n_lanes, "decode_mode": args.decode_mode,
                                                 "positives_per_image": P_bar, "candidates_per_image": cand_mean,
                                                 "detections_per_image": det_mean}),
-        "timing": timing, "train_with_backward": train_tail, "half_maps": half_maps, "cpu_affinity": affinity,
+        "timing": timing, "train_with_backward": train_tail, "half_maps": half_maps, "mlp_towers": mlp_line,
+        "cpu_affinity": affinity,
         "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi and not fused else 0)) * args.steps,
         "allreduce": (("fused" if fused else "nccl") if multi else None), "allreduce_check": allreduce_check,
         "allreduce_fallback": (fallback_note[0] if fallback_note else None), "roofline": roofline, "roofline_step": roofline_step,
@@ -644,6 +651,65 @@ def run_ours(args, w, world, rank, local_rank):
         "losses_check": losses,
     }
     print(json.dumps(line), flush=True)
+
+
+def mlp_towers_line(M, C, dev):
+    """the head's four ``ops.MLP(256 -> 256 x 4 -> out, LayerNorm, SiLU)`` towers (ref
+    object_detection.py:51-61) over the step's M = B * A locations through ``sihl_od_mlp_hidden`` / ``sihl_od_mlp_out``
+    (tcgen05 + TMA + TMEM; bf16 operands, fp32 accumulate / normalise), and one hidden layer as torch eager fp32 (what the
+    reference runs) and bf16 autocast.  Inputs rotate over 3 buffers (> L2); CUDA events."""
+    import torch
+    from torch import nn
+    from torchvision import ops as tvops
+    from sihl_b200 import ops
+    from sihl_b200.mlp_tower import PackedTower, run_tower
+
+    def timeit(fn, iters, warm=3):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    torch.manual_seed(0)
+    xs = [torch.randn((M, 256), device=dev).bfloat16() for _ in range(3)]
+    ys = [torch.empty((M, 256), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    towers = {n: tvops.MLP(256, [256] * 4 + [o], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU).to(dev).eval()
+              for n, o in (("loc", 1), ("iou", 1), ("box", 4), ("cls", C))}
+    packed = {n: PackedTower(m).refresh() for n, m in towers.items()}
+    w, b, g, be, eps = packed["loc"].hidden[0]
+    ms = timeit(lambda i: ops.mlp_hidden(xs[i % 3], w, b, g, be, eps, out=ys[i & 1]), 30, 10)
+    peak_hbm, src = measured_peaks()
+    byts, flops = M * 1024.0, 2.0 * M * 256 * 256
+    line = {"locations": M, "dtype": "bf16 operands, f32 accumulate", "note": "row N4, extra line: inference only; the path's "
+            "own kernels have no dense contraction",
+            "hidden_layer": {"ms": ms, "algorithmic_bytes": byts, "flops": flops, "gbs": byts / ms / 1e6, "tflops": flops / ms / 1e9,
+                             "roofline": {"bound": "hbm", "achieved": byts / ms / 1e6, "peak": peak_hbm, "unit": "GB/s",
+                                          "frac": byts / ms / 1e6 / peak_hbm, "peak_source": src}}}
+    scratch = (ys[0], ys[1])
+
+    def four(i):
+        for n in towers:
+            run_tower(packed[n], xs[i % 3], scratch)
+    line["four_towers_ms"] = timeit(four, 5, 2)
+    line["gpu_launches_per_call"] = 4 * 5
+    with torch.no_grad():
+        seq = nn.Sequential(towers["loc"][0], towers["loc"][1], towers["loc"][2])
+        xf = xs[0].float()
+        line["hidden_layer"]["torch_eager_fp32_ms"] = timeit(lambda i: seq(xf), 3, 1)
+
+        def bf(i):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return seq(xs[i % 3])
+        line["hidden_layer"]["torch_eager_bf16_autocast_ms"] = timeit(bf, 3, 1)
+    del xs, ys, xf
+    torch.cuda.empty_cache()
+    return line
 
 
 def train_tail_with_backward(w, x, levels, dev, reps=300):
