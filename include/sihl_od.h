@@ -513,6 +513,18 @@ SIHL_OD_API int sihl_od_mlp_hidden(const void *x_bf16, int64_t m, int channels, 
 SIHL_OD_API int sihl_od_mlp_out(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
                     int n_pad, int out_cols, float *y, void *stream);
 
+/* The laterals in front of the towers (ref object_detection.py:52-55, :102-105): Conv2dNormActivation(C_in, 256, 1,
+ * activation_layer=None) = 1x1 conv + BatchNorm, per level, then "b c h w -> b (h w) c" and the concatenation over
+ * the levels.  Inference (BatchNorm folded into weight and bias by the caller), C_in == 256:
+ *   sihl_od_lateral_rows:   x [B, C, HW] fp32 (NCHW level) -> rows [B*HW, C] bf16   (C % 64 == 0)
+ *   sihl_od_lateral_linear: y = rows W^T + bias on the tensor cores (same kernel family as the towers), bf16, row
+ *       m = b*rows_per_image + i written at row b*out_rows_per_image + out_row_offset + i of y [B*out_rows_per_image, 256]:
+ *       every level lands directly in its slice of the concatenated [B, A, 256] feature tensor the towers read. */
+SIHL_OD_API int sihl_od_lateral_rows(const float *x_nchw, int batch, int channels, int64_t hw, void *rows_bf16, void *stream);
+SIHL_OD_API int sihl_od_lateral_linear(const void *rows_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
+                           int64_t rows_per_image, int64_t out_rows_per_image, int64_t out_row_offset,
+                           void *y_bf16, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,19 +137,6 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32() {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"          // same asm block: the registers are not read before the load has landed
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
@@ -234,14 +221,24 @@ struct MlpParams {
     int n_tiles;
     int out_cols;
     float eps;
+    long long rows_per_image;       // kLinear: see the row formula above
+    long long out_rows_per_image;
+    long long out_row_offset;
 };
 
-// HIDDEN = true:  bias + LayerNorm + SiLU -> bf16 [M,N]   (N == 256)
-// HIDDEN = false: bias                    -> fp32 [M,out_cols], out_cols <= N
-template <int N, bool HIDDEN>
+// MODE kHidden:  bias + LayerNorm + SiLU -> bf16 [M,N]   (N == 256; the towers' hidden layers)
+// MODE kOutF32:  bias                    -> fp32 [M,out_cols], out_cols <= N   (the towers' last Linear)
+// MODE kLinear:  bias                    -> bf16 rows of N == 256, row m written at
+//                (m / rows_per_image) * out_rows_per_image + out_row_offset + m % rows_per_image   (the laterals: 1x1 conv
+//                with the BatchNorm folded in, each level landing in its slice of the concatenated [B, A, 256] features)
+constexpr int kHidden = 0, kOutF32 = 1, kLinear = 2;
+template <int N, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const MlpParams p) {
     using L = MlpSmem<N>;
+    constexpr bool HIDDEN = MODE == kHidden;
+    constexpr bool WIDE = MODE != kOutF32;                // sixteen epilogue warps, bf16 rows of 256
+    static_assert(!WIDE || N == 256, "the wide epilogue is built for 256 output columns");
     constexpr int S = L::kStages;
     constexpr int kStageCols = tmem_stage_cols(N);
     constexpr int kTmemCols = 2 * kStageCols;
@@ -270,7 +267,7 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(w_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], HIDDEN ? 4 * kParts : 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], WIDE ? 4 * kParts : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                      // TMEM: one warp allocates and later frees
@@ -327,7 +324,7 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                 tc_commit(&t_full[as]);                   // accumulator complete
             }
         }
-    } else if (HIDDEN || warp < 6) {
+    } else if (WIDE || warp < 6) {
         // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = row.  Hidden layers: sixteen warps, the
         // four warps of a lane quarter own 64 columns each, read them from TMEM ONCE into registers (which frees the
         // accumulator stage at once) and exchange their partial row statistics through shared memory; the arithmetic
@@ -343,7 +340,7 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kStageCols;
             const long long grow = static_cast<long long>(tile) * kBlockM + row;
-            if constexpr (HIDDEN) {
+            if constexpr (WIDE) {
                 const int cbase = part * kPartCols;
                 uint32_t v[kPartCols];
                 tmem_ld64(taddr + cbase, v);
@@ -363,6 +360,8 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                     s2a = add2(s2a, x[j >> 1]);
                     s2b = add2(s2b, x[(j >> 1) + 1]);
                 }
+                uint32_t packed[kPartCols / 2];
+                if constexpr (HIDDEN) {
                 const float sum_p = (lo_of(s2a) + hi_of(s2a)) + (lo_of(s2b) + hi_of(s2b));
                 const float mean_p = sum_p * (1.f / kPartCols);
                 const uint64_t mean_p2 = pack2f(mean_p, mean_p);
@@ -397,7 +396,6 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                 const uint64_t mean2 = pack2f(mean, mean);
                 const uint64_t rstd2 = pack2f(rstd, rstd);
                 // normalise, SiLU, round to bf16: the thread's 64 columns are one 128-byte line of the output row
-                uint32_t packed[kPartCols / 2];
 #pragma unroll
                 for (int j = 0; j < kPartCols; j += 4) {
                     const ulonglong2 g4 = *reinterpret_cast<const ulonglong2*>(&sGamma[cbase + j]);     // gamma / 2
@@ -409,6 +407,10 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                     const uint64_t y1 = fma2(h1, pack2f(tanh_fast(lo_of(h1)), tanh_fast(hi_of(h1))), h1);
                     packed[j >> 1] = bf16x2_of(y0);
                     packed[(j >> 1) + 1] = bf16x2_of(y1);
+                }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kPartCols / 2; ++j) packed[j] = bf16x2_of(x[j]);       // kLinear: bias only
                 }
                 if (warp == 2 && lane == 0) MLP_TRACE(t, 13);          // 13: row computed
                 // store: a thread holds one 128-byte line of its row as four 32-byte pieces.  Written as they are, a
@@ -434,10 +436,19 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                     }
                     // now piece k of this lane = columns [16 q, 16 q + 16) (q = lane & 3) of row (lane & ~3) + k
                     const long long qrow = static_cast<long long>(tile) * kBlockM + quarter * 32 + (lane & ~3);
-                    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + qrow * N + cbase + 16 * (lane & 3);
+                    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + cbase + 16 * (lane & 3);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (qrow + k < p.M) st_global_256(obase + static_cast<long long>(k) * N, packed + 8 * k);
+                    for (int k = 0; k < 4; ++k) {
+                        const long long m = qrow + k;
+                        if (m < p.M) {
+                            long long orow_k = m;
+                            if constexpr (MODE == kLinear) {
+                                const long long img = m / p.rows_per_image;
+                                orow_k = img * p.out_rows_per_image + p.out_row_offset + (m - img * p.rows_per_image);
+                            }
+                            st_global_256(obase + orow_k * N, packed + 8 * k);
+                        }
+                    }
                 }
                 if (warp == 2 && lane == 0) MLP_TRACE(t, 14);          // 14: stores issued
                 continue;                                              // t_empty was signalled right after the load
@@ -479,6 +490,37 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     }
 }
 
+// NCHW fp32 feature map -> rows of channels in bf16: x [B, C, HW] -> y [B * HW, C] (the A operand of the lateral GEMM).
+// 64 x 64 tiles through shared memory: reads coalesced along HW, 16-byte writes coalesced along C.  HBM-bound (6 B / element).
+__global__ void __launch_bounds__(256) k_nchw_to_rows_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, long long HW) {
+    __shared__ float tile[64][65];
+    const long long hw0 = static_cast<long long>(blockIdx.x) * 64;
+    const int c0 = blockIdx.y * 64;
+    const float* xb = x + static_cast<long long>(blockIdx.z) * C * HW;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;                 // 64 x 4
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int c = ty + 4 * r;
+        tile[c][tx] = (hw0 + tx < HW) ? xb[static_cast<long long>(c0 + c) * HW + hw0 + tx] : 0.f;
+    }
+    __syncthreads();
+    const int chunk = threadIdx.x & 7, rr = threadIdx.x >> 3;               // 8 chunks of 8 channels x 32 rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int h = rr + 32 * pass;
+        if (hw0 + h < HW) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(tile[chunk * 8 + 2 * q][h], tile[chunk * 8 + 2 * q + 1][h]);
+                w4[q] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+            __nv_bfloat16* dst = y + (static_cast<long long>(blockIdx.z) * HW + hw0 + h) * C + c0 + chunk * 8;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -515,11 +557,11 @@ int sm_count() {
     return n;
 }
 
-template <int N, bool HIDDEN>
+template <int N, int MODE>
 int launch_layer(const void* x, long long M, const void* w, const MlpParams& p_in, cudaStream_t stream) {
     using L = MlpSmem<N>;
     // per launch: the attribute belongs to the current device's context, and a process may drive several
-    if (cudaFuncSetAttribute(k_mlp_layer<N, HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) return SIHL_OD_ECUDA;
+    if (cudaFuncSetAttribute(k_mlp_layer<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) return SIHL_OD_ECUDA;
     CUtensorMap map_x, map_w;
     if (!make_map(&map_x, x, static_cast<unsigned long long>(M), kBlockM) || !make_map(&map_w, w, N, N)) return SIHL_OD_ECUDA;
     MlpParams p = p_in;
@@ -528,7 +570,7 @@ int launch_layer(const void* x, long long M, const void* w, const MlpParams& p_i
     const int sms = sm_count();
     if (sms <= 0) return SIHL_OD_ECUDA;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    k_mlp_layer<N, HIDDEN><<<grid, kThreads, L::kTotal, stream>>>(map_x, map_w, p);
+    k_mlp_layer<N, MODE><<<grid, kThreads, L::kTotal, stream>>>(map_x, map_w, p);
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 
@@ -546,7 +588,7 @@ SIHL_OD_API int sihl_od_mlp_hidden(const void* x_bf16, int64_t M, int channels, 
         return SIHL_OD_EINVAL;
     MlpParams p{};
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.out = y_bf16; p.eps = eps; p.out_cols = kK;
-    return launch_layer<256, true>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
+    return launch_layer<256, kHidden>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
 }
 
 SIHL_OD_API int sihl_od_mlp_out(const void* x_bf16, int64_t M, int channels, const void* w_bf16, const float* bias, int n_pad, int out_cols,
@@ -559,12 +601,12 @@ SIHL_OD_API int sihl_od_mlp_out(const void* x_bf16, int64_t M, int channels, con
     p.bias = bias; p.out = y; p.out_cols = out_cols;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (n_pad) {
-        case 16: return launch_layer<16, false>(x_bf16, M, w_bf16, p, st);
-        case 32: return launch_layer<32, false>(x_bf16, M, w_bf16, p, st);
-        case 64: return launch_layer<64, false>(x_bf16, M, w_bf16, p, st);
-        case 96: return launch_layer<96, false>(x_bf16, M, w_bf16, p, st);
-        case 128: return launch_layer<128, false>(x_bf16, M, w_bf16, p, st);
-        default: return launch_layer<256, false>(x_bf16, M, w_bf16, p, st);
+        case 16: return launch_layer<16, kOutF32>(x_bf16, M, w_bf16, p, st);
+        case 32: return launch_layer<32, kOutF32>(x_bf16, M, w_bf16, p, st);
+        case 64: return launch_layer<64, kOutF32>(x_bf16, M, w_bf16, p, st);
+        case 96: return launch_layer<96, kOutF32>(x_bf16, M, w_bf16, p, st);
+        case 128: return launch_layer<128, kOutF32>(x_bf16, M, w_bf16, p, st);
+        default: return launch_layer<256, kOutF32>(x_bf16, M, w_bf16, p, st);
     }
 }
 
@@ -574,5 +616,27 @@ __attribute__((visibility("default"))) int sihl_od_mlp_debug_trace(long long* ho
     return cudaMemcpyFromSymbol(host_out, g_mlp_trace, sizeof(long long) * n) == cudaSuccess ? n : -1;
 }
 #endif
+
+SIHL_OD_API int sihl_od_lateral_rows(const float* x_nchw, int batch, int channels, int64_t hw, void* rows_bf16, void* stream) {
+    if (batch < 0 || channels <= 0 || (channels & 63) != 0 || hw < 0 || batch > 65535) return SIHL_OD_EINVAL;
+    if (batch == 0 || hw == 0) return SIHL_OD_OK;
+    if (!x_nchw || !rows_bf16 || !aligned16(rows_bf16)) return SIHL_OD_EINVAL;
+    const dim3 grid(static_cast<unsigned>((hw + 63) / 64), static_cast<unsigned>(channels / 64), static_cast<unsigned>(batch));
+    k_nchw_to_rows_bf16<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_nchw, static_cast<__nv_bfloat16*>(rows_bf16), channels, hw);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
+SIHL_OD_API int sihl_od_lateral_linear(const void* rows_bf16, int64_t M, int channels, const void* w_bf16, const float* bias, int64_t rows_per_image,
+                                       int64_t out_rows_per_image, int64_t out_row_offset, void* y_bf16, void* stream) {
+    if (channels != kK || M < 0 || M > 0x7FFFFF00LL || rows_per_image <= 0 || out_rows_per_image < rows_per_image || out_row_offset < 0 ||
+        out_row_offset + rows_per_image > out_rows_per_image)
+        return SIHL_OD_EINVAL;
+    if (M == 0) return SIHL_OD_OK;
+    if (!rows_bf16 || !w_bf16 || !bias || !y_bf16 || !aligned16(rows_bf16) || !aligned16(w_bf16) || !aligned16(y_bf16)) return SIHL_OD_EINVAL;
+    MlpParams p{};
+    p.bias = bias; p.out = y_bf16; p.out_cols = kK;
+    p.rows_per_image = rows_per_image; p.out_rows_per_image = out_rows_per_image; p.out_row_offset = out_row_offset;
+    return launch_layer<256, kLinear>(rows_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

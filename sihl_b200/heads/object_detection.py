@@ -170,6 +170,57 @@ class ObjectDetection(nn.Module):
         """The towers' common input: converted to bf16 ONCE when they run on the tensor cores."""
         return flat_feats.to(torch.bfloat16) if self._use_tcgen05(flat_feats) else flat_feats
 
+    def _folded_laterals(self):
+        """Per level (W', b') with the BatchNorm of ``Conv2dNormActivation`` folded into the 1x1 conv (eval semantics:
+        running statistics), W' bf16 [256, C_in], b' fp32; re-folded when a parameter or buffer changes.  None when the
+        laterals cannot run on the tensor-core path (training-mode BatchNorm, other widths, a conv with bias / stride)."""
+        if self.training or self.num_channels != ops.MLP_CHANNELS:
+            return None
+        tensors = []
+        for lateral in self.laterals:
+            conv, bn = lateral[0], lateral[1]
+            if not (isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and len(lateral) == 2 and conv.bias is None
+                    and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.in_channels == ops.MLP_CHANNELS
+                    and bn.track_running_stats and bn.affine and conv.groups == 1):
+                return None
+            tensors += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        if getattr(self, "_folded_key", None) != key:
+            with torch.no_grad():
+                folded = []
+                for lateral in self.laterals:
+                    conv, bn = lateral[0], lateral[1]
+                    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+                    w = (conv.weight.float()[:, :, 0, 0] * scale[:, None]).to(torch.bfloat16).contiguous()
+                    b = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+                    folded.append((w, b))
+            self._folded, self._folded_key = folded, key
+        return self._folded
+
+    def _flat_feats_tensor_cores(self, inputs: List[Tensor]) -> Optional[Tensor]:
+        """ref :102-105 for the tcgen05 backend: every level's lateral as one GEMM writing bf16 straight into its slice of
+        the concatenated [B, A, 256] features (no fp32 feature maps, no cat, no cast pass).  None if not applicable."""
+        folded = self._folded_laterals()
+        if folded is None or any(inputs[level].dtype != torch.float32 for level in self.levels):
+            return None
+        sizes = self._level_sizes(inputs)
+        batch, device = inputs[self.bottom_level].shape[0], inputs[self.bottom_level].device
+        flat = torch.empty((batch, sum(h * w for h, w in sizes), ops.MLP_CHANNELS), dtype=torch.bfloat16, device=device)
+        offset = 0
+        for level, (h, w), (wt, bias) in zip(self.levels, sizes, folded):
+            rows = ops.lateral_rows(inputs[level].contiguous())
+            ops.lateral_linear(rows, wt, bias, h * w, flat, offset)
+            offset += h * w
+        return flat
+
+    def _tower_feats(self, inputs: List[Tensor]) -> Tensor:
+        """The towers' common input [B, A, C] (ref :102-105), bf16 when they run on the tensor cores."""
+        if self._use_tcgen05(inputs[self.bottom_level]):
+            flat = self._flat_feats_tensor_cores(inputs)
+            if flat is not None:
+                return flat
+        return self._tower_input(self._flat_feats(inputs))
+
     def _flat_feats(self, inputs: List[Tensor]) -> Tensor:
         feats = [lateral(inputs[level]) for level, lateral in zip(self.levels, self.laterals)]     # ref :102-105
         return torch.cat([x.flatten(2).transpose(1, 2) for x in feats], 1)
@@ -203,7 +254,7 @@ class ObjectDetection(nn.Module):
         ``loc_logits.sigmoid()``.  Traceable: under ``torch.compile`` the same kernels run as ``sihl_b200::*`` custom ops
         (``sihl_b200/torch_ops.py``) with fake implementations."""
         (batch_size, _, height, width), device = inputs[0].shape, inputs[0].device
-        flat_feats = self._tower_input(self._flat_feats(inputs))
+        flat_feats = self._tower_feats(inputs)
         levels = self._level_sizes(inputs)
         loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                         # ref :108
         compiling = torch.compiler.is_compiling()
@@ -239,7 +290,7 @@ class ObjectDetection(nn.Module):
         box of the locations that pass the threshold only — identical results; default: ``"dense"`` for fp32 maps,
         ``"candidate_first"`` for half maps (autocast), which are then read as they are (no fp32 copies)."""
         (_, _, height, width) = inputs[0].shape
-        flat_feats = self._tower_input(self._flat_feats(inputs))
+        flat_feats = self._tower_feats(inputs)
         loc_logits = self._tower("loc_head", flat_feats).squeeze(2)
         cls_logits = self._tower("cls_head", flat_feats)
         box_raw = self._tower("box_head", flat_feats)

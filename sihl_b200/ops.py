@@ -825,3 +825,37 @@ def mlp_out(x: Tensor, weight_padded: Tensor, bias_padded: Tensor, out_features:
                                     n_pad, int(out_features), _p(_req(y, torch.float32, "out", 2)), _stream(dev))
     _native.check(rc, "sihl_od_mlp_out")
     return y
+
+
+def lateral_rows(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """One NCHW fp32 pyramid level [B, C, H, W] -> its locations as bf16 rows [B*H*W, C] (C % 64 == 0): the layout the
+    tensor-core layers read (ref object_detection.py:105 does ``rearrange(x, "b c h w -> b (h w) c")`` after the conv)."""
+    x = _req(x, torch.float32, "x", 4)
+    B, C, H, W = x.shape
+    if C % 64:
+        raise ValueError(f"lateral_rows needs channels % 64 == 0, got {C}")
+    dev = x.device
+    with _on(dev):
+        y = out if out is not None else torch.empty((B * H * W, C), dtype=torch.bfloat16, device=dev)
+        rc = _lib().sihl_od_lateral_rows(_p(x), B, C, H * W, _p(_req(y, torch.bfloat16, "out", 2)), _stream(dev))
+    _native.check(rc, "sihl_od_lateral_rows")
+    return y
+
+
+def lateral_linear(rows: Tensor, weight: Tensor, bias: Tensor, rows_per_image: int, out: Tensor, out_row_offset: int) -> Tensor:
+    """``rows @ weight.T + bias`` (bf16 [M,256] x bf16 [256,256], fp32 bias) written into ``out`` [B, A, 256] bf16 at
+    ``out[b, out_row_offset + i]`` for row ``b * rows_per_image + i``: a lateral (1x1 conv with its BatchNorm folded in,
+    ref object_detection.py:52-55) landing in its slice of the concatenated features (ref :105)."""
+    rows = _req(rows, torch.bfloat16, "rows", 2)
+    weight = _req(weight, torch.bfloat16, "weight", 2)
+    out = _req(out, torch.bfloat16, "out", 3)
+    M, K = rows.shape
+    if K != MLP_CHANNELS or tuple(weight.shape) != (K, K) or out.shape[2] != K or M % rows_per_image or M // rows_per_image != out.shape[0]:
+        raise ValueError(f"lateral_linear: rows {tuple(rows.shape)}, weight {tuple(weight.shape)}, out {tuple(out.shape)}, "
+                         f"rows_per_image {rows_per_image}")
+    dev = rows.device
+    with _on(dev):
+        rc = _lib().sihl_od_lateral_linear(_p(rows), M, K, _p(weight), _p(_req(bias, torch.float32, "bias", 1)), int(rows_per_image),
+                                           int(out.shape[1]), int(out_row_offset), _p(out), _stream(dev))
+    _native.check(rc, "sihl_od_lateral_linear")
+    return out

@@ -169,3 +169,50 @@ def test_head_rejects_the_backend_at_other_widths():
     inputs = [torch.randn((1, 3, 64, 64), generator=g).to(DEV)] + [torch.randn((1, 32, 64 // 2 ** l, 64 // 2 ** l), generator=g).to(DEV) for l in range(1, 6)]
     with torch.no_grad(), pytest.raises(ValueError):
         model.forward(inputs)
+
+
+@pytest.mark.parametrize("hw", [(80, 80), (5, 5), (13, 7)])
+def test_lateral_rows_is_the_rearrange_of_the_reference(hw):
+    """ref :105 ``rearrange(x, "b c h w -> b (h w) c")`` + bf16 rounding, for sizes that are and are not multiples of 64."""
+    h, w = hw
+    x = _rand((3, 256, h, w), 21)
+    rows = ops.lateral_rows(x)
+    want = x.flatten(2).transpose(1, 2).reshape(-1, 256).bfloat16()
+    assert torch.equal(rows, want)
+
+
+def test_lateral_linear_lands_in_its_slice_of_the_concatenated_features():
+    B, A = 3, 700
+    out = torch.full((B, A, 256), 9.0, dtype=torch.bfloat16, device=DEV)
+    wt = _rand((256, 256), 22, 1 / 16).bfloat16()
+    bias = _rand((256,), 23)
+    for hw_l, off in ((400, 0), (100, 400), (150, 500)):                     # 650 of the 700 rows per image get written
+        rows = _rand((B * hw_l, 256), 24 + off).bfloat16()
+        ops.lateral_linear(rows, wt, bias, hw_l, out, off)
+        ref = (rows.double() @ wt.double().T + bias.double()).float().reshape(B, hw_l, 256)
+        torch.testing.assert_close(out[:, off:off + hw_l].float(), ref, rtol=2 ** -8, atol=2e-3)
+    assert (out[:, 650:] == 9.0).all()
+
+
+def test_head_laterals_on_the_tensor_cores_match_conv_plus_batchnorm():
+    """Eval-mode laterals (1x1 conv + BatchNorm with non-trivial running statistics) through lateral_rows + lateral_linear
+    against the torch modules; in training mode (batch statistics) the path is not taken."""
+    from sihl_b200.heads import ObjectDetection
+    torch.manual_seed(1)
+    model = ObjectDetection(in_channels=[3, 16, 32, 256, 256, 256], num_classes=5, num_channels=256, num_layers=1).to(DEV)
+    with torch.no_grad():
+        for lat in model.laterals:
+            lat[1].running_mean.normal_(0, 0.5); lat[1].running_var.uniform_(0.5, 2.0)
+            lat[1].weight.normal_(1, 0.2); lat[1].bias.normal_(0, 0.2)
+    model.eval()
+    g = torch.Generator().manual_seed(5)
+    inputs = [torch.randn((2, c, max(1, 96 // 2 ** l), max(1, 96 // 2 ** l)), generator=g).to(DEV) for l, c in enumerate(model.in_channels)]
+    model.mlp_backend = "tcgen05"
+    with torch.no_grad():
+        flat = model._tower_feats(inputs)
+        ref = model._flat_feats(inputs)
+    assert flat.dtype == torch.bfloat16 and flat.shape == ref.shape
+    torch.testing.assert_close(flat.float(), ref, rtol=2e-2, atol=2e-2)       # bf16 operands and result
+    model.train()
+    with torch.no_grad():
+        assert model._folded_laterals() is None

@@ -109,6 +109,16 @@ with torch.no_grad():
     t_tc = timeit(lambda i: model.forward(inputs), iters=10, warm=3)
     feats = model._flat_feats(inputs)
     t_lat = timeit(lambda i: model._flat_feats(inputs), iters=10, warm=3)
+    t_lat_tc = timeit(lambda i: model._tower_feats(inputs), iters=10, warm=3)
+    lvl = inputs[3]
+    rows = ops.lateral_rows(lvl)
+    t_rows = timeit(lambda i: ops.lateral_rows(lvl, out=rows), iters=20, warm=3)
+    wt, bias = model._folded_laterals()[0]
+    flat_tc = model._tower_feats(inputs)
+    t_lin = timeit(lambda i: ops.lateral_linear(rows, wt, bias, lvl.shape[2] * lvl.shape[3], flat_tc, 0), iters=20, warm=3)
 res["head_forward_cfg1"] = {"batch": B, "image": size, "locations": int(feats.shape[1]), "torch_towers_ms": t_torch, "tcgen05_towers_ms": t_tc,
-                            "laterals_and_concat_ms": t_lat, "speedup": t_torch / t_tc}
+                            "laterals_and_concat_ms": t_lat, "speedup": t_torch / t_tc,
+                            "laterals_tensor_cores_ms": t_lat_tc,
+                            "level3_rows_kernel": {"ms": t_rows, "gbs": lvl.numel() * 6 / t_rows / 1e6, "frac_of_hbm_peak": lvl.numel() * 6 / t_rows / 1e6 / HBM},
+                            "level3_linear_kernel": {"ms": t_lin, "gbs": rows.numel() * 4 / t_lin / 1e6, "frac_of_hbm_peak": rows.numel() * 4 / t_lin / 1e6 / HBM}}
 print(json.dumps(res, indent=1))
