@@ -216,3 +216,21 @@ def test_head_laterals_on_the_tensor_cores_match_conv_plus_batchnorm():
     model.train()
     with torch.no_grad():
         assert model._folded_laterals() is None
+
+
+@pytest.mark.parametrize("backend", ["torch", "tcgen05"])
+def test_graphed_forward_replays_the_same_detections(backend):
+    """sihl_b200.serving.GraphedInference: forward captured once, replayed on new inputs — same outputs as the eager call."""
+    from sihl_b200.serving import GraphedInference
+    model = _head()
+    model.mlp_backend = backend
+    a, b = _pyramid(), [t * 0.5 + 0.1 for t in _pyramid()]
+    graphed = GraphedInference(model.forward, a)
+    for inputs in (a, b, a):
+        with torch.no_grad():
+            want = [t.clone() for t in model.forward(inputs)]
+        got = graphed(inputs)
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+    with pytest.raises(ValueError):
+        graphed([t[:1] for t in a])

@@ -121,4 +121,22 @@ res["head_forward_cfg1"] = {"batch": B, "image": size, "locations": int(feats.sh
                             "laterals_tensor_cores_ms": t_lat_tc,
                             "level3_rows_kernel": {"ms": t_rows, "gbs": lvl.numel() * 6 / t_rows / 1e6, "frac_of_hbm_peak": lvl.numel() * 6 / t_rows / 1e6 / HBM},
                             "level3_linear_kernel": {"ms": t_lin, "gbs": rows.numel() * 4 / t_lin / 1e6, "frac_of_hbm_peak": rows.numel() * 4 / t_lin / 1e6 / HBM}}
+
+# small-batch serving: eager (one host launch per kernel) vs one CUDA graph per call
+from sihl_b200.serving import GraphedInference
+del inputs, feats, rows, flat_tc
+torch.cuda.empty_cache()
+res["serving_latency_ms"] = {}
+for b in (1, 8):
+    small = [torch.randn((b, c, max(1, size // 2 ** l), max(1, size // 2 ** l)), generator=g, device=dev) if l >= 3 or l == 0 else torch.empty((b, c, 1, 1), device=dev)
+             for l, c in enumerate(model.in_channels)]
+    entry = {}
+    with torch.no_grad():
+        for backend in ("torch", "tcgen05"):
+            model.mlp_backend = backend
+            entry[f"{backend}_towers_eager"] = timeit(lambda i: model.forward(small), iters=30, warm=5)
+            graphed = GraphedInference(model.forward, small)
+            entry[f"{backend}_towers_graph"] = timeit(lambda i: graphed(small), iters=100, warm=10)
+            del graphed
+    res["serving_latency_ms"][f"batch_{b}"] = entry
 print(json.dumps(res, indent=1))
