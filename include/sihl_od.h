@@ -513,6 +513,20 @@ SIHL_OD_API int sihl_od_mlp_hidden(const void *x_bf16, int64_t m, int channels, 
 SIHL_OD_API int sihl_od_mlp_out(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
                     int n_pad, int out_cols, float *y, void *stream);
 
+/* Training path of a hidden layer (bf16 mixed precision, like autocast): the forward additionally stores every row's
+ * LayerNorm statistics, row_stats [M,2] = (mean, rstd); the backward of LayerNorm + SiLU is one HBM-bound kernel over
+ * rows: v = x W^T + bias (the pre-activation, recomputed by the caller with sihl_od_lateral_linear(rows = x, identity row
+ * map)), dy -> dv [M,256] bf16 and per-CTA partial column sums partials [partial_rows,3,256] fp32 = (d gamma, d beta,
+ * d bias) to be summed over partial_rows = sihl_od_mlp_bwd_partial_rows().  The two gradient GEMMs are plain matrix
+ * products: dx = dv W (sihl_od_lateral_linear with W^T, zero bias) and dW = dv^T x (library GEMM). */
+SIHL_OD_API int sihl_od_mlp_hidden_train(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
+                             const float *gamma, const float *beta, float eps, void *y_bf16, float *row_stats,
+                             void *stream);
+SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void);
+SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void *v_bf16, const void *dy_bf16, const float *row_stats, const float *gamma,
+                           const float *beta, int64_t m, int channels, void *dv_bf16, float *partials,
+                           int partial_rows, void *stream);
+
 /* The laterals in front of the towers (ref object_detection.py:52-55, :102-105): Conv2dNormActivation(C_in, 256, 1,
  * activation_layer=None) = 1x1 conv + BatchNorm, per level, then "b c h w -> b (h w) c" and the concatenation over
  * the levels.  Inference (BatchNorm folded into weight and bias by the caller), C_in == 256:

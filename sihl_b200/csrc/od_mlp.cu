@@ -221,6 +221,7 @@ struct MlpParams {
     int n_tiles;
     int out_cols;
     float eps;
+    float* row_stats;               // kHidden, optional: [M,2] = (mean, rstd) of every row's LayerNorm, kept for the backward
     long long rows_per_image;       // kLinear: see the row formula above
     long long out_rows_per_image;
     long long out_row_offset;
@@ -393,6 +394,8 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                     m2 = __fmaf_rn(dm * dm, static_cast<float>(kPartCols), m2);
                 }
                 const float rstd = 1.f / sqrtf(m2 * (1.f / N) + p.eps);
+                if (p.row_stats != nullptr && part == 0 && grow < p.M)
+                    *reinterpret_cast<float2*>(p.row_stats + 2 * grow) = make_float2(mean, rstd);
                 const uint64_t mean2 = pack2f(mean, mean);
                 const uint64_t rstd2 = pack2f(rstd, rstd);
                 // normalise, SiLU, round to bf16: the thread's 64 columns are one 128-byte line of the output row
@@ -521,6 +524,81 @@ __global__ void __launch_bounds__(256) k_nchw_to_rows_bf16(const float* __restri
     }
 }
 
+// Backward of LayerNorm + SiLU for the towers' training path: one warp per row, lane = 8 columns.
+//   n = (v - mean) rstd, z = n gamma + beta, dz = dy * SiLU'(z), dn = dz gamma,
+//   dv = rstd (dn - mean_j(dn) - n mean_j(dn n));  column sums of dz n, dz, dv = d gamma, d beta, d bias
+// v is the layer's pre-activation (x W^T + b, recomputed by the linear mode of the layer kernel, bf16), (mean, rstd) come
+// from the forward.  Every CTA writes its partial column sums to partials[blockIdx.x][3][256] (summed by the caller:
+// deterministic, no atomics).  HBM-bound: 2 x 512 B read + 512 B written per row.
+constexpr int kBwdWarps = 8;
+__global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dy,
+                                                                         const float* __restrict__ row_stats, const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta, long long M, __nv_bfloat16* __restrict__ dv,
+                                                                         float* __restrict__ partials) {
+    __shared__ float red[kBwdWarps][3][kK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = lane * 8;
+    float g[8], be[8], acc_g[8], acc_b[8], acc_v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; acc_g[j] = acc_b[j] = acc_v[j] = 0.f; }
+    const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps;
+    for (long long row = static_cast<long long>(blockIdx.x) * kBwdWarps + warp; row < M; row += stride) {
+        const uint4 v4 = *reinterpret_cast<const uint4*>(v + row * kK + c0);
+        const uint4 d4 = *reinterpret_cast<const uint4*>(dy + row * kK + c0);
+        const float2 st = *reinterpret_cast<const float2*>(row_stats + 2 * row);
+        const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+        float n[8], dn[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[q]));
+            const float2 df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[q]));
+            const float vv[2] = {vf.x, vf.y}, dd[2] = {df.x, df.y};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * q + u;
+                n[j] = (vv[u] - st.x) * st.y;
+                const float z = __fmaf_rn(n[j], g[j], be[j]);
+                const float sg = 1.f / (1.f + __expf(-z));
+                const float dz = dd[u] * (sg * __fmaf_rn(z, 1.f - sg, 1.f));
+                acc_g[j] = __fmaf_rn(dz, n[j], acc_g[j]);
+                acc_b[j] += dz;
+                dn[j] = dz * g[j];
+                s1 += dn[j];
+                s2 = __fmaf_rn(dn[j], n[j], s2);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float a = s1 * (1.f / kK), b = s2 * (1.f / kK);
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float o2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * q + u;
+                o2[u] = st.y * (dn[j] - a - n[j] * b);
+                acc_v[j] += o2[u];
+            }
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(o2[0], o2[1]);
+            ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
+        }
+        *reinterpret_cast<uint4*>(dv + row * kK + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[warp][0][c0 + j] = acc_g[j]; red[warp][1][c0 + j] = acc_b[j]; red[warp][2][c0 + j] = acc_v[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * kK; i += kBwdWarps * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdWarps; ++w) t += red[w][i / kK][i % kK];
+        partials[static_cast<long long>(blockIdx.x) * 3 * kK + i] = t;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -589,6 +667,33 @@ SIHL_OD_API int sihl_od_mlp_hidden(const void* x_bf16, int64_t M, int channels, 
     MlpParams p{};
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.out = y_bf16; p.eps = eps; p.out_cols = kK;
     return launch_layer<256, kHidden>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
+}
+
+SIHL_OD_API int sihl_od_mlp_hidden_train(const void* x_bf16, int64_t M, int channels, const void* w_bf16, const float* bias, const float* gamma,
+                                         const float* beta, float eps, void* y_bf16, float* row_stats, void* stream) {
+    if (channels != kK || M < 0 || M > 0x7FFFFF00LL) return SIHL_OD_EINVAL;
+    if (M == 0) return SIHL_OD_OK;
+    if (!x_bf16 || !w_bf16 || !bias || !gamma || !beta || !y_bf16 || !row_stats || !aligned16(x_bf16) || !aligned16(w_bf16) || !aligned16(y_bf16) ||
+        (reinterpret_cast<uintptr_t>(row_stats) & 7u))
+        return SIHL_OD_EINVAL;
+    MlpParams p{};
+    p.bias = bias; p.gamma = gamma; p.beta = beta; p.out = y_bf16; p.eps = eps; p.out_cols = kK; p.row_stats = row_stats;
+    return launch_layer<256, kHidden>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
+}
+
+SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void) { const int sms = sm_count(); return sms > 0 ? 4 * sms : 0; }
+
+SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void* v_bf16, const void* dy_bf16, const float* row_stats, const float* gamma, const float* beta, int64_t M,
+                                       int channels, void* dv_bf16, float* partials, int partial_rows, void* stream) {
+    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows()) return SIHL_OD_EINVAL;
+    if (!partials || !gamma || !beta) return SIHL_OD_EINVAL;
+    if (M > 0 && (!v_bf16 || !dy_bf16 || !row_stats || !dv_bf16 || !aligned16(v_bf16) || !aligned16(dy_bf16) || !aligned16(dv_bf16) ||
+                  (reinterpret_cast<uintptr_t>(row_stats) & 7u)))
+        return SIHL_OD_EINVAL;
+    k_mlp_hidden_bwd_rows<<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(v_bf16), static_cast<const __nv_bfloat16*>(dy_bf16), row_stats, gamma, beta, M,
+        static_cast<__nv_bfloat16*>(dv_bf16), partials);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 
 SIHL_OD_API int sihl_od_mlp_out(const void* x_bf16, int64_t M, int channels, const void* w_bf16, const float* bias, int n_pad, int out_cols,

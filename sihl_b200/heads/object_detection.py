@@ -138,7 +138,10 @@ class ObjectDetection(nn.Module):
         # "tcgen05" (SURVEY.md §8f N4): wherever no gradient is being recorded (forward / postprocess / get_saliency under
         #   no_grad, i.e. validation and serving) the towers run through ``sihl_od_mlp_hidden`` / ``sihl_od_mlp_out`` —
         #   bf16 operands on the tensor cores, fp32 accumulation and LayerNorm, Linear + LayerNorm + SiLU in one kernel.
-        #   Needs num_channels == 256; training steps keep the torch modules (the kernels produce no gradient).
+        #   Needs num_channels == 256; training steps keep the torch modules.
+        # "tcgen05+train": additionally the towers of ``training_step`` run in bf16 mixed precision (what Lightning's
+        #   precision="bf16-mixed" gives the torch towers): forward on the tensor cores, recomputing backward
+        #   (``mlp_tower._HiddenLayerFn``); parameter gradients and LayerNorm statistics stay fp32.
         self.mlp_backend = "torch"
         self._packed_towers: Dict[str, object] = {}
 
@@ -149,13 +152,22 @@ class ObjectDetection(nn.Module):
     def _use_tcgen05(self, x: Tensor) -> bool:
         if self.mlp_backend == "torch":
             return False
-        if self.mlp_backend != "tcgen05":
-            raise ValueError(f"mlp_backend must be 'torch' or 'tcgen05', got {self.mlp_backend!r}")
+        if self.mlp_backend not in ("tcgen05", "tcgen05+train"):
+            raise ValueError(f"mlp_backend must be 'torch', 'tcgen05' or 'tcgen05+train', got {self.mlp_backend!r}")
         return x.is_cuda and not torch.is_grad_enabled() and not torch.compiler.is_compiling()
+
+    def _use_tcgen05_training(self, x: Tensor) -> bool:
+        return (self.mlp_backend == "tcgen05+train" and x.is_cuda and torch.is_grad_enabled() and x.shape[0] > 0
+                and not torch.compiler.is_compiling())
 
     def _tower(self, name: str, x: Tensor) -> Tensor:
         """One of the four per-location MLPs (ref :108, :116, :121, :175) on ``x`` [..., C]."""
         mlp = getattr(self, name)
+        if self._use_tcgen05_training(x):
+            from ..mlp_tower import PackedTower, run_tower_train
+            if not PackedTower.supported(mlp):
+                raise ValueError(f"mlp_backend='tcgen05+train' needs num_channels == 256 and the reference's tower structure ({name})")
+            return run_tower_train(mlp, x)
         if not self._use_tcgen05(x):
             return mlp(x)
         from ..mlp_tower import PackedTower, run_tower
@@ -342,11 +354,11 @@ class ObjectDetection(nn.Module):
             st.grad_scale = float(self._world_size())      # DDP averages the gradients of W ranks (see loss_reduction)
 
         flat_feats = self._flat_feats(inputs)                                               # ref :151-154
-        loc_logits = self.loc_head(flat_feats).squeeze(2)                                   # ref :157
-        iou_preds = self.iou_head(flat_feats).squeeze(2)                                    # ref :175
+        loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                         # ref :157
+        iou_preds = self._tower("iou_head", flat_feats).squeeze(2)                          # ref :175
         o2m_feats = flat_feats.reshape(batch_size * st.A, -1).index_select(0, st.pos_index)  # ref :184 (+ padding rows)
-        box_raw = self.box_head(o2m_feats)                                                  # ref :189
-        class_logits = self.cls_head(o2m_feats)                                             # ref :200
+        box_raw = self._tower("box_head", o2m_feats)                                        # ref :189
+        class_logits = self._tower("cls_head", o2m_feats)                                   # ref :200
         out = _TrainLoss.apply(loc_logits, iou_preds, box_raw, class_logits, st, reduce_sums)
         self.last_assignment, self.last_rel_iou, self.last_train_state = st.assignment, st.rel_iou, st
         metrics = {"location_loss": out[0], "box_loss": out[1], "class_loss": out[2], "iou_loss": out[3]}

@@ -5,7 +5,10 @@ activation_layer=nn.SiLU)`` (ref src/sihl/heads/object_detection.py:51, :56-60),
 ``Linear, LayerNorm, SiLU, Dropout`` x num_layers ``+ Linear, Dropout``.  :class:`PackedTower` reads those modules'
 parameters once (bf16 weights, fp32 bias / gamma / beta, the last weight zero-padded to a tensor-core friendly row count)
 and re-packs when any parameter's version counter moves; :func:`run_tower` chains ``ops.mlp_hidden`` x num_layers and
-``ops.mlp_out`` over two ping-pong activation buffers.  Inference only — no autograd graph is recorded.
+``ops.mlp_out`` over two ping-pong activation buffers (inference: no autograd graph is recorded).
+:func:`run_tower_train` is the training path: the same kernels behind ``torch.autograd.Function`` nodes with a recomputing
+backward, bf16 mixed precision (activations and operands bf16; accumulation, LayerNorm statistics and every parameter
+gradient fp32) — the precision Lightning's ``precision="bf16-mixed"`` gives the torch towers.
 """
 from __future__ import annotations
 
@@ -94,3 +97,67 @@ def run_tower(packed: PackedTower, x: Tensor, scratch: Optional[Tuple[Tensor, Te
     w, b, n_out = packed.out
     y = ops.mlp_out(cur, w, b, n_out)
     return y.reshape(*lead, n_out)
+
+
+# ---- training path: bf16 mixed precision (what Lightning's precision="bf16-mixed" gives the torch towers) ---------------
+class _HiddenLayerFn(torch.autograd.Function):
+    """``SiLU(LayerNorm(x W^T + b))`` with the forward on the tensor cores and a recomputing backward:
+    v = x W^T + b again (tensor cores), LayerNorm + SiLU backward over rows (one HBM-bound kernel), dx = dv W (tensor
+    cores), dW = dv^T x (a plain library GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, eps):
+        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        b32, g32, be32 = bias.detach().float().contiguous(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        y, stats = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps)
+        ctx.save_for_backward(x, w16, b32, g32, be32, stats)
+        ctx.param_dtypes = (weight.dtype, bias.dtype, gamma.dtype, beta.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16, b32, g32, be32, stats = ctx.saved_tensors
+        dy = dy.to(torch.bfloat16).contiguous()
+        v = ops.linear_bf16(x, w16, b32)                                     # recompute the pre-activation
+        dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd(v, dy, stats, g32, be32)
+        del v
+        dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None
+        dw = torch.matmul(dv.t(), x).float()                                 # [out, in]
+        wd, bd, gd, bed = ctx.param_dtypes
+        return dx, dw.to(wd), dbias.to(bd), dgamma.to(gd), dbeta.to(bed), None
+
+
+class _OutLayerFn(torch.autograd.Function):
+    """The tower's last Linear: forward on the tensor cores (fp32 result), backward as bf16 matrix products."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        n_out = weight.shape[0]
+        n_pad = ops.mlp_out_pad(n_out)
+        w = torch.zeros((n_pad, ops.MLP_CHANNELS), dtype=torch.bfloat16, device=x.device)
+        w[:n_out] = weight.detach().to(torch.bfloat16)
+        b = torch.zeros((n_pad,), dtype=torch.float32, device=x.device)
+        b[:n_out] = bias.detach().float()
+        ctx.save_for_backward(x, w[:n_out])
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return ops.mlp_out(x, w, b, n_out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w16 = ctx.saved_tensors
+        d16 = dout.to(torch.bfloat16)
+        dx = torch.matmul(d16, w16) if ctx.needs_input_grad[0] else None      # [M, 256] bf16
+        dw = torch.matmul(d16.t(), x).float()
+        wd, bd = ctx.param_dtypes
+        return dx, dw.to(wd), dout.float().sum(0).to(bd)
+
+
+def run_tower_train(mlp: nn.Sequential, x: Tensor) -> Tensor:
+    """``mlp(x)`` with gradients, bf16 activations / operands and fp32 accumulation, statistics and parameters' gradients."""
+    hidden, last = _split(mlp)
+    lead = x.shape[:-1]
+    cur = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+    for lin, ln in hidden:
+        cur = _HiddenLayerFn.apply(cur, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps))
+    y = _OutLayerFn.apply(cur, last.weight, last.bias)
+    return y.reshape(*lead, last.out_features)

@@ -859,3 +859,52 @@ def lateral_linear(rows: Tensor, weight: Tensor, bias: Tensor, rows_per_image: i
                                            int(out.shape[1]), int(out_row_offset), _p(out), _stream(dev))
     _native.check(rc, "sihl_od_lateral_linear")
     return out
+
+
+def linear_bf16(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """``x @ weight.T + bias`` for x [M,256] bf16, weight [256,256] bf16, bias fp32 -> bf16 [M,256] (the linear mode of the
+    tensor-core layer kernel with the identity row map)."""
+    M = int(x.shape[0])
+    out = torch.empty((1, M, MLP_CHANNELS), dtype=torch.bfloat16, device=x.device)
+    if M:
+        lateral_linear(x, weight, bias, M, out, 0)
+    return out[0]
+
+
+def mlp_hidden_train(x: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
+    """:func:`mlp_hidden` that also returns every row's LayerNorm statistics [M,2] = (mean, rstd) for the backward."""
+    x = _req(x, torch.bfloat16, "x", 2)
+    weight = _req(weight, torch.bfloat16, "weight", 2)
+    M, K = x.shape
+    if K != MLP_CHANNELS or tuple(weight.shape) != (K, K):
+        raise ValueError(f"mlp_hidden_train is built for {MLP_CHANNELS} channels, got x {tuple(x.shape)} weight {tuple(weight.shape)}")
+    dev = x.device
+    with _on(dev):
+        y = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
+        stats = torch.empty((M, 2), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_mlp_hidden_train(_p(x), M, K, _p(weight), _p(_req(bias, torch.float32, "bias", 1)),
+                                             _p(_req(gamma, torch.float32, "gamma", 1)), _p(_req(beta, torch.float32, "beta", 1)),
+                                             float(eps), _p(y), _p(stats), _stream(dev))
+    _native.check(rc, "sihl_od_mlp_hidden_train")
+    return y, stats
+
+
+def mlp_hidden_bwd(v: Tensor, dy: Tensor, row_stats: Tensor, gamma: Tensor, beta: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Backward of LayerNorm + SiLU over rows: pre-activation ``v`` [M,256] bf16, upstream ``dy`` [M,256] bf16, the forward's
+    ``row_stats`` -> (dv bf16 [M,256], d_gamma, d_beta, d_bias fp32 [256])."""
+    v = _req(v, torch.bfloat16, "v", 2)
+    dy = _req(dy, torch.bfloat16, "dy", 2)
+    M, K = v.shape
+    if K != MLP_CHANNELS or dy.shape != v.shape or tuple(row_stats.shape) != (M, 2):
+        raise ValueError(f"mlp_hidden_bwd: v {tuple(v.shape)}, dy {tuple(dy.shape)}, row_stats {tuple(row_stats.shape)}")
+    dev = v.device
+    with _on(dev):
+        n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
+        dv = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
+        partials = torch.empty((n_part, 3, K), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_mlp_hidden_bwd(_p(v), _p(dy), _p(_req(row_stats, torch.float32, "row_stats", 2)),
+                                           _p(_req(gamma, torch.float32, "gamma", 1)), _p(_req(beta, torch.float32, "beta", 1)),
+                                           M, K, _p(dv), _p(partials), n_part, _stream(dev))
+    _native.check(rc, "sihl_od_mlp_hidden_bwd")
+    sums = partials.sum(0)
+    return dv, sums[0], sums[1], sums[2]

@@ -93,6 +93,34 @@ with torch.no_grad():
             for n in towers: towers[n](xs[i % 3])
     res["four_towers"]["torch_eager_bf16_autocast_ms"] = timeit(refb, iters=3, warm=1)
 
+# training: one tower (loc: 4 hidden + 1 output column) forward + backward over M locations
+from sihl_b200.mlp_tower import run_tower_train
+tower = towers["loc"].train()
+xt = xs[0].float().requires_grad_(True)
+gy = torch.randn((M, 1), device=dev)
+def train_ours(i):
+    tower.zero_grad(set_to_none=True); xt.grad = None
+    run_tower_train(tower, xt).backward(gy)
+def train_torch(i):
+    tower.zero_grad(set_to_none=True); xt.grad = None
+    tower(xt).backward(gy)
+def train_autocast(i):
+    tower.zero_grad(set_to_none=True); xt.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = tower(xt)
+    out.backward(gy.to(out.dtype))
+res["tower_forward_backward"] = {"ms": timeit(train_ours, iters=5, warm=2)}
+torch.cuda.empty_cache()
+try:
+    res["tower_forward_backward"]["torch_eager_fp32_ms"] = timeit(train_torch, iters=3, warm=1)
+except torch.OutOfMemoryError:
+    res["tower_forward_backward"]["torch_eager_fp32_ms"] = None
+torch.cuda.empty_cache()
+res["tower_forward_backward"]["torch_eager_bf16_autocast_ms"] = timeit(train_autocast, iters=3, warm=1)
+del xt, gy
+tower.eval()
+torch.cuda.empty_cache()
+
 # the head's forward (ref :99-122) at cfg1: laterals + loc tower on every location + top-K + cls / box towers on K rows + decode
 del xs, towers, packed
 torch.cuda.empty_cache()
