@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(256) k_nchw_to_rows_bf16(const float* __restri
 // from the forward.  Every CTA writes its partial column sums to partials[blockIdx.x][3][256] (summed by the caller:
 // deterministic, no atomics).  HBM-bound: 2 x 512 B read + 512 B written per row.
 constexpr int kBwdWarps = 8;
+constexpr int kBwdRows = 2;                   // rows per warp and iteration: both rows' loads are in flight before the arithmetic
 __global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dy,
                                                                          const float* __restrict__ row_stats, const float* __restrict__ gamma,
                                                                          const float* __restrict__ beta, long long M, __nv_bfloat16* __restrict__ dv,
@@ -541,52 +542,62 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __
     float g[8], be[8], acc_g[8], acc_b[8], acc_v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { g[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; acc_g[j] = acc_b[j] = acc_v[j] = 0.f; }
-    const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps;
-    for (long long row = static_cast<long long>(blockIdx.x) * kBwdWarps + warp; row < M; row += stride) {
-        const uint4 v4 = *reinterpret_cast<const uint4*>(v + row * kK + c0);
-        const uint4 d4 = *reinterpret_cast<const uint4*>(dy + row * kK + c0);
-        const float2 st = *reinterpret_cast<const float2*>(row_stats + 2 * row);
-        const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
-        float n[8], dn[8], s1 = 0.f, s2 = 0.f;
+    const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps * kBwdRows;
+    for (long long row0 = (static_cast<long long>(blockIdx.x) * kBwdWarps + warp) * kBwdRows; row0 < M; row0 += stride) {
+        uint4 v4[kBwdRows], d4[kBwdRows];
+        float2 st[kBwdRows];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[q]));
-            const float2 df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[q]));
-            const float vv[2] = {vf.x, vf.y}, dd[2] = {df.x, df.y};
+        for (int r = 0; r < kBwdRows; ++r) {
+            const long long row = row0 + r < M ? row0 + r : M - 1;          // the tail repeats the last row (not stored, not summed)
+            v4[r] = *reinterpret_cast<const uint4*>(v + row * kK + c0);
+            d4[r] = *reinterpret_cast<const uint4*>(dy + row * kK + c0);
+            st[r] = *reinterpret_cast<const float2*>(row_stats + 2 * row);
+        }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = 2 * q + u;
-                n[j] = (vv[u] - st.x) * st.y;
-                const float z = __fmaf_rn(n[j], g[j], be[j]);
-                const float sg = 1.f / (1.f + __expf(-z));
-                const float dz = dd[u] * (sg * __fmaf_rn(z, 1.f - sg, 1.f));
-                acc_g[j] = __fmaf_rn(dz, n[j], acc_g[j]);
-                acc_b[j] += dz;
-                dn[j] = dz * g[j];
-                s1 += dn[j];
-                s2 = __fmaf_rn(dn[j], n[j], s2);
+        for (int r = 0; r < kBwdRows; ++r) {
+            const bool live = row0 + r < M;
+            const uint32_t vw[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w}, dw[4] = {d4[r].x, d4[r].y, d4[r].z, d4[r].w};
+            float n[8], dn[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[q]));
+                const float2 df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[q]));
+                const float vv[2] = {vf.x, vf.y}, dd[2] = {live ? df.x : 0.f, live ? df.y : 0.f};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = 2 * q + u;
+                    n[j] = (vv[u] - st[r].x) * st[r].y;
+                    const float z = __fmaf_rn(n[j], g[j], be[j]);
+                    const float sg = __fmaf_rn(0.5f, tanh_fast(0.5f * z), 0.5f);          // sigmoid(z), one MUFU op
+                    const float dz = dd[u] * (sg * __fmaf_rn(z, 1.f - sg, 1.f));           // dy * SiLU'(z)
+                    acc_g[j] = __fmaf_rn(dz, n[j], acc_g[j]);
+                    acc_b[j] += dz;
+                    dn[j] = dz * g[j];
+                    s1 += dn[j];
+                    s2 = __fmaf_rn(dn[j], n[j], s2);
+                }
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        const float a = s1 * (1.f / kK), b = s2 * (1.f / kK);
-        uint32_t ow[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float o2[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = 2 * q + u;
-                o2[u] = st.y * (dn[j] - a - n[j] * b);
-                acc_v[j] += o2[u];
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
-            const __nv_bfloat162 p2 = __floats2bfloat162_rn(o2[0], o2[1]);
-            ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
+            const float a = s1 * (1.f / kK), b = s2 * (1.f / kK);
+            uint32_t ow[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float o2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = 2 * q + u;
+                    o2[u] = st[r].y * (dn[j] - a - n[j] * b);
+                    acc_v[j] += o2[u];
+                }
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(o2[0], o2[1]);
+                ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
+            }
+            if (live) *reinterpret_cast<uint4*>(dv + (row0 + r) * kK + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
-        *reinterpret_cast<uint4*>(dv + row * kK + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[warp][0][c0 + j] = acc_g[j]; red[warp][1][c0 + j] = acc_b[j]; red[warp][2][c0 + j] = acc_v[j]; }
@@ -596,6 +607,20 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __
 #pragma unroll
         for (int w = 0; w < kBwdWarps; ++w) t += red[w][i / kK][i % kK];
         partials[static_cast<long long>(blockIdx.x) * 3 * kK + i] = t;
+    }
+}
+
+// bf16 -> fp32 of a contiguous array (the gradient handed back to the fp32 laterals): 16-byte loads, 2 x 16-byte stores.
+__global__ void __launch_bounds__(256) k_bf16_to_f32(const uint4* __restrict__ src, float4* __restrict__ dst, long long n_vec8) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec8; i += stride) {
+        const uint4 w = src[i];
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.z));
+        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.w));
+        dst[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+        dst[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
     }
 }
 
@@ -681,7 +706,17 @@ SIHL_OD_API int sihl_od_mlp_hidden_train(const void* x_bf16, int64_t M, int chan
     return launch_layer<256, kHidden>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
 }
 
-SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void) { const int sms = sm_count(); return sms > 0 ? 4 * sms : 0; }
+SIHL_OD_API int sihl_od_bf16_to_f32(const void* src_bf16, int64_t n, float* dst, void* stream) {
+    if (n < 0 || (n & 7) != 0) return SIHL_OD_EINVAL;
+    if (n == 0) return SIHL_OD_OK;
+    if (!src_bf16 || !dst || !aligned16(src_bf16) || !aligned16(dst)) return SIHL_OD_EINVAL;
+    const int sms = sm_count();
+    if (sms <= 0) return SIHL_OD_ECUDA;
+    k_bf16_to_f32<<<sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src_bf16), reinterpret_cast<float4*>(dst), n / 8);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
+SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void) { const int sms = sm_count(); return sms > 0 ? 8 * sms : 0; }
 
 SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void* v_bf16, const void* dy_bf16, const float* row_stats, const float* gamma, const float* beta, int64_t M,
                                        int channels, void* dv_bf16, float* partials, int partial_rows, void* stream) {

@@ -152,11 +152,27 @@ class _OutLayerFn(torch.autograd.Function):
         return dx, dw.to(wd), dout.float().sum(0).to(bd)
 
 
+class _ToBf16Fn(torch.autograd.Function):
+    """fp32 -> bf16 at the tower's entrance; the backward hands the gradient back in fp32 (one full-width kernel)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.src_dtype = x.dtype
+        return x.to(torch.bfloat16)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        return ops.bf16_to_f32(g) if ctx.src_dtype == torch.float32 and g.dtype == torch.bfloat16 else g.to(ctx.src_dtype)
+
+
 def run_tower_train(mlp: nn.Sequential, x: Tensor) -> Tensor:
     """``mlp(x)`` with gradients, bf16 activations / operands and fp32 accumulation, statistics and parameters' gradients."""
     hidden, last = _split(mlp)
     lead = x.shape[:-1]
-    cur = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+    cur = x.reshape(-1, x.shape[-1]).contiguous()
+    if cur.dtype != torch.bfloat16:
+        cur = _ToBf16Fn.apply(cur)
     for lin, ln in hidden:
         cur = _HiddenLayerFn.apply(cur, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps))
     y = _OutLayerFn.apply(cur, last.weight, last.bias)

@@ -908,3 +908,16 @@ def mlp_hidden_bwd(v: Tensor, dy: Tensor, row_stats: Tensor, gamma: Tensor, beta
     _native.check(rc, "sihl_od_mlp_hidden_bwd")
     sums = partials.sum(0)
     return dv, sums[0], sums[1], sums[2]
+
+
+def bf16_to_f32(t: Tensor) -> Tensor:
+    """fp32 copy of a contiguous bf16 tensor whose element count is a multiple of 8 (full-width loads and stores)."""
+    t = _req(t, torch.bfloat16, "t")
+    if t.numel() % 8:
+        return t.float()
+    dev = t.device
+    with _on(dev):
+        out = torch.empty(t.shape, dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_bf16_to_f32(_p(t), t.numel(), _p(out), _stream(dev))
+    _native.check(rc, "sihl_od_bf16_to_f32")
+    return out

@@ -150,6 +150,25 @@ res["head_forward_cfg1"] = {"batch": B, "image": size, "locations": int(feats.sh
                             "level3_rows_kernel": {"ms": t_rows, "gbs": lvl.numel() * 6 / t_rows / 1e6, "frac_of_hbm_peak": lvl.numel() * 6 / t_rows / 1e6 / HBM},
                             "level3_linear_kernel": {"ms": t_lin, "gbs": rows.numel() * 4 / t_lin / 1e6, "frac_of_hbm_peak": rows.numel() * 4 / t_lin / 1e6 / HBM}}
 
+# the drop-in head's whole training step (ref :124-217) + backward at cfg1: laterals (torch) + four towers + the hot path
+from sihl_b200 import synth
+gt = synth.gt_batch_np(3, B, size, size, args.classes, 100)
+tb = [torch.from_numpy(b_).to(dev) for b_, _ in gt.per_image()]
+tc = [torch.from_numpy(c_).to(dev) for _, c_ in gt.per_image()]
+model.train()
+def train_step(i):
+    model.zero_grad(set_to_none=True)
+    loss, _ = model.training_step(inputs, classes=tc, boxes=tb)
+    loss.backward()
+res["head_training_step_cfg1"] = {}
+for backend in ("tcgen05+train", "torch"):
+    model.mlp_backend = backend
+    torch.cuda.empty_cache()
+    res["head_training_step_cfg1"][backend.replace("+", "_") + "_ms"] = timeit(train_step, iters=3 if backend == "torch" else 6, warm=2)
+model.zero_grad(set_to_none=True)
+model.eval()
+torch.cuda.empty_cache()
+
 # small-batch serving: eager (one host launch per kernel) vs one CUDA graph per call
 from sihl_b200.serving import GraphedInference
 del inputs, feats, rows, flat_tc
