@@ -72,3 +72,33 @@ def test_head_backend_switch_is_validated():
     model.mlp_backend = "cutlass"
     with pytest.raises(ValueError):
         model._use_tcgen05(x)
+
+
+def test_cabi_training_and_lateral_entries_reject_bad_arguments():
+    lib = _native.load()
+    buf = (ctypes.c_char * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.sihl_od_mlp_hidden_train(p, 128, 256, p, p, p, p, 1e-5, p, None, None) == 1        # row_stats missing
+    assert lib.sihl_od_mlp_hidden_train(p, 128, 64, p, p, p, p, 1e-5, p, p, None) == 1
+    assert lib.sihl_od_mlp_hidden_train(None, 0, 256, None, None, None, None, 1e-5, None, None, None) == 0
+    assert lib.sihl_od_mlp_hidden_bwd(p, p, p, p, p, 128, 256, p, p, 3, None) == 1                 # wrong number of partial rows
+    assert lib.sihl_od_mlp_hidden_bwd(p, p, p, p, p, 128, 128, p, p, 8, None) == 1
+    assert lib.sihl_od_bf16_to_f32(p, 12, p, None) == 1                                            # n % 8
+    assert lib.sihl_od_bf16_to_f32(p + 2, 16, p, None) == 1                                        # alignment
+    assert lib.sihl_od_bf16_to_f32(None, 0, None, None) == 0
+    assert lib.sihl_od_lateral_rows(p, 2, 100, 64, p, None) == 1                                   # channels % 64
+    assert lib.sihl_od_lateral_rows(p, 0, 256, 64, p, None) == 0
+    assert lib.sihl_od_lateral_linear(p, 128, 256, p, p, 0, 128, 0, p, None) == 1                  # rows_per_image <= 0
+    assert lib.sihl_od_lateral_linear(p, 128, 256, p, p, 64, 100, 50, p, None) == 1                # slice leaves the image
+    assert lib.sihl_od_lateral_linear(p, 128, 128, p, p, 64, 64, 0, p, None) == 1
+
+
+def test_training_backend_is_only_used_when_gradients_are_recorded():
+    from sihl_b200.heads import ObjectDetection
+    model = ObjectDetection(in_channels=[3] + [8] * 5, num_classes=3, num_channels=16, num_layers=1)
+    model.mlp_backend = "tcgen05+train"
+    x = torch.zeros((1, 4, 16))
+    assert model._use_tcgen05_training(x) is False                     # CPU tensor
+    assert model._use_tcgen05(x) is False
+    out = model._tower("loc_head", x)                                  # -> the torch module
+    assert out.shape == (1, 4, 1) and out.requires_grad
