@@ -707,7 +707,23 @@ def mlp_towers_line(M, C, dev):
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return seq(xs[i % 3])
         line["hidden_layer"]["torch_eager_bf16_autocast_ms"] = timeit(bf, 3, 1)
-    del xs, ys, xf
+    # training path of one tower (loc: 4 hidden layers + 1 output column): forward on the tensor cores + recomputing backward
+    from sihl_b200.mlp_tower import run_tower_train
+    tower = towers["loc"].train()
+    xt = xf.requires_grad_(True)
+    gy = torch.randn((M, 1), device=dev)
+
+    def train(run):
+        def step(i):
+            tower.zero_grad(set_to_none=True)
+            xt.grad = None
+            run(xt).backward(gy)
+        return step
+    line["tower_forward_backward"] = {"ms": timeit(train(lambda t: run_tower_train(tower, t)), 5, 2),
+                                      "torch_eager_fp32_ms": timeit(train(tower), 2, 1),
+                                      "precision": "bf16 operands / activations, fp32 accumulation, statistics and parameter gradients"}
+    tower.eval()
+    del xs, ys, xf, xt, gy
     torch.cuda.empty_cache()
     return line
 
