@@ -354,6 +354,10 @@ class ObjectDetection(nn.Module):
             st.grad_scale = float(self._world_size())      # DDP averages the gradients of W ranks (see loss_reduction)
 
         flat_feats = self._flat_feats(inputs)                                               # ref :151-154
+        if self._use_tcgen05_training(flat_feats):
+            # one bf16 copy feeds all four towers; their input gradients are accumulated in bf16 and handed back once
+            from ..mlp_tower import _ToBf16Fn
+            flat_feats = _ToBf16Fn.apply(flat_feats)
         loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                         # ref :157
         iou_preds = self._tower("iou_head", flat_feats).squeeze(2)                          # ref :175
         o2m_feats = flat_feats.reshape(batch_size * st.A, -1).index_select(0, st.pos_index)  # ref :184 (+ padding rows)

@@ -121,7 +121,7 @@ class _HiddenLayerFn(torch.autograd.Function):
         v = ops.linear_bf16(x, w16, b32)                                     # recompute the pre-activation
         dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd(v, dy, stats, g32, be32)
         del v
-        dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None
+        dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None   # dv W
         dw = torch.matmul(dv.t(), x).float()                                 # [out, in]
         wd, bd, gd, bed = ctx.param_dtypes
         return dx, dw.to(wd), dbias.to(bd), dgamma.to(gd), dbeta.to(bed), None
