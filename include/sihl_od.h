@@ -537,6 +537,18 @@ SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void *v_bf16, const void *dy_bf16, 
  *       m = b*rows_per_image + i written at row b*out_rows_per_image + out_row_offset + i of y [B*out_rows_per_image, 256]:
  *       every level lands directly in its slice of the concatenated [B, A, 256] feature tensor the towers read. */
 SIHL_OD_API int sihl_od_lateral_rows(const float *x_nchw, int batch, int channels, int64_t hw, void *rows_bf16, void *stream);
+/* Training path of a lateral (batch-statistics BatchNorm, bf16 mixed precision).  Forward: the batch statistics of the
+ * conv output follow from the input's first and second moments (mean = W s / M, E[y^2] = diag(W G W^T) / M with s = sum of
+ * rows, G = rows^T rows), so the conv + BatchNorm is again ONE folded sihl_od_lateral_linear pass.  Backward over rows
+ * [M,256] bf16 with n = the normalised conv output (recomputed with sihl_od_lateral_linear):
+ *   sihl_od_bn_bwd_colsums: partials [partial_rows,2,256] = per-CTA sums over rows of (dz, dz*n)
+ *   sihl_od_bn_bwd_apply:   dy = scale * (dz - mean_dz - n * mean_dzn)
+ *   sihl_od_rows_to_nchw:   rows [B*HW, C] bf16 -> x [B, C, HW] fp32 (the input gradient handed back to the neck) */
+SIHL_OD_API int sihl_od_bn_bwd_colsums(const void *dz_bf16, const void *n_bf16, int64_t m, int channels, float *partials,
+                           int partial_rows, void *stream);
+SIHL_OD_API int sihl_od_bn_bwd_apply(const void *dz_bf16, const void *n_bf16, const float *scale, const float *mean_dz,
+                         const float *mean_dzn, int64_t m, int channels, void *dy_bf16, void *stream);
+SIHL_OD_API int sihl_od_rows_to_nchw(const void *rows_bf16, int batch, int channels, int64_t hw, float *x_nchw, void *stream);
 SIHL_OD_API int sihl_od_lateral_linear(const void *rows_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
                            int64_t rows_per_image, int64_t out_rows_per_image, int64_t out_row_offset,
                            void *y_bf16, void *stream);

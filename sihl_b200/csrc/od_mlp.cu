@@ -624,6 +624,100 @@ __global__ void __launch_bounds__(256) k_bf16_to_f32(const uint4* __restrict__ s
     }
 }
 
+// ---- training path of the laterals (1x1 conv + batch-statistics BatchNorm over rows [M,256]) ---------------------------------
+// Backward of the BatchNorm, reductions over ROWS (per channel): same skeleton as k_mlp_hidden_bwd_rows (warp per row,
+// lane = 8 channels, register accumulators, per-CTA partials).
+//   pass 1 (k_bn_bwd_colsums): partials[cta][0][c] = sum_m dz[m,c], partials[cta][1][c] = sum_m dz[m,c] n[m,c]
+//   pass 2 (k_bn_bwd_apply):   dy[m,c] = scale[c] (dz[m,c] - mean_dz[c] - n[m,c] mean_dzn[c])
+// n = (y - mean) invstd is the normalised conv output (recomputed by the caller with the linear mode of the layer kernel).
+__global__ void __launch_bounds__(kBwdWarps * 32) k_bn_bwd_colsums(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ n,
+                                                                    long long M, float* __restrict__ partials) {
+    __shared__ float red[kBwdWarps][2][kK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = lane * 8;
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps;
+    for (long long row = static_cast<long long>(blockIdx.x) * kBwdWarps + warp; row < M; row += stride) {
+        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + row * kK + c0);
+        const uint4 n4 = *reinterpret_cast<const uint4*>(n + row * kK + c0);
+        const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, nw[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[q]));
+            const float2 nf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nw[q]));
+            a0[2 * q] += df.x; a0[2 * q + 1] += df.y;
+            a1[2 * q] = __fmaf_rn(df.x, nf.x, a1[2 * q]); a1[2 * q + 1] = __fmaf_rn(df.y, nf.y, a1[2 * q + 1]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[warp][0][c0 + j] = a0[j]; red[warp][1][c0 + j] = a1[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kK; i += kBwdWarps * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdWarps; ++w) t += red[w][i / kK][i % kK];
+        partials[static_cast<long long>(blockIdx.x) * 2 * kK + i] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ n,
+                                                       const float* __restrict__ scale, const float* __restrict__ mean_dz,
+                                                       const float* __restrict__ mean_dzn, long long M, __nv_bfloat16* __restrict__ dy) {
+    const int lane = threadIdx.x & 31;
+    const int c0 = lane * 8;
+    float sc[8], m0[8], m1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; m0[j] = mean_dz[c0 + j]; m1[j] = mean_dzn[c0 + j]; }
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
+        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + row * kK + c0);
+        const uint4 n4 = *reinterpret_cast<const uint4*>(n + row * kK + c0);
+        const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, nw[4] = {n4.x, n4.y, n4.z, n4.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[q]));
+            const float2 nf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nw[q]));
+            const float o0 = sc[2 * q] * (df.x - m0[2 * q] - nf.x * m1[2 * q]);
+            const float o1 = sc[2 * q + 1] * (df.y - m0[2 * q + 1] - nf.y * m1[2 * q + 1]);
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(o0, o1);
+            ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
+        }
+        *reinterpret_cast<uint4*>(dy + row * kK + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// rows of channels in bf16 -> NCHW fp32: y [B*HW, C] -> x [B, C, HW] (the gradient handed back to the neck).
+__global__ void __launch_bounds__(256) k_rows_to_nchw_f32(const __nv_bfloat16* __restrict__ y, float* __restrict__ x, int C, long long HW) {
+    __shared__ float tile[64][65];                                           // [hw][c]
+    const long long hw0 = static_cast<long long>(blockIdx.x) * 64;
+    const int c0 = blockIdx.y * 64;
+    const int chunk = threadIdx.x & 7, rr = threadIdx.x >> 3;               // 8 chunks of 8 channels x 32 rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int h = rr + 32 * pass;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (hw0 + h < HW) w = *reinterpret_cast<const uint4*>(y + (static_cast<long long>(blockIdx.z) * HW + hw0 + h) * C + c0 + chunk * 8);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[q]));
+            tile[h][chunk * 8 + 2 * q] = f.x;
+            tile[h][chunk * 8 + 2 * q + 1] = f.y;
+        }
+    }
+    __syncthreads();
+    float* xb = x + static_cast<long long>(blockIdx.z) * C * HW;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;                 // 64 x 4
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int c = ty + 4 * r;
+        if (hw0 + tx < HW) xb[static_cast<long long>(c0 + c) * HW + hw0 + tx] = tile[tx][c];
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -763,6 +857,38 @@ SIHL_OD_API int sihl_od_lateral_rows(const float* x_nchw, int batch, int channel
     if (!x_nchw || !rows_bf16 || !aligned16(rows_bf16)) return SIHL_OD_EINVAL;
     const dim3 grid(static_cast<unsigned>((hw + 63) / 64), static_cast<unsigned>(channels / 64), static_cast<unsigned>(batch));
     k_nchw_to_rows_bf16<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_nchw, static_cast<__nv_bfloat16*>(rows_bf16), channels, hw);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
+SIHL_OD_API int sihl_od_rows_to_nchw(const void* rows_bf16, int batch, int channels, int64_t hw, float* x_nchw, void* stream) {
+    if (batch < 0 || channels <= 0 || (channels & 63) != 0 || hw < 0 || batch > 65535) return SIHL_OD_EINVAL;
+    if (batch == 0 || hw == 0) return SIHL_OD_OK;
+    if (!rows_bf16 || !x_nchw || !aligned16(rows_bf16)) return SIHL_OD_EINVAL;
+    const dim3 grid(static_cast<unsigned>((hw + 63) / 64), static_cast<unsigned>(channels / 64), static_cast<unsigned>(batch));
+    k_rows_to_nchw_f32<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(rows_bf16), x_nchw, channels, hw);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
+SIHL_OD_API int sihl_od_bn_bwd_colsums(const void* dz_bf16, const void* n_bf16, int64_t M, int channels, float* partials, int partial_rows,
+                                       void* stream) {
+    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows() || !partials) return SIHL_OD_EINVAL;
+    if (M > 0 && (!dz_bf16 || !n_bf16 || !aligned16(dz_bf16) || !aligned16(n_bf16))) return SIHL_OD_EINVAL;
+    k_bn_bwd_colsums<<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dz_bf16), static_cast<const __nv_bfloat16*>(n_bf16), M, partials);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
+SIHL_OD_API int sihl_od_bn_bwd_apply(const void* dz_bf16, const void* n_bf16, const float* scale, const float* mean_dz, const float* mean_dzn,
+                                     int64_t M, int channels, void* dy_bf16, void* stream) {
+    if (channels != kK || M < 0) return SIHL_OD_EINVAL;
+    if (M == 0) return SIHL_OD_OK;
+    if (!dz_bf16 || !n_bf16 || !scale || !mean_dz || !mean_dzn || !dy_bf16 || !aligned16(dz_bf16) || !aligned16(n_bf16) || !aligned16(dy_bf16))
+        return SIHL_OD_EINVAL;
+    const int sms = sm_count();
+    if (sms <= 0) return SIHL_OD_ECUDA;
+    k_bn_bwd_apply<<<sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dz_bf16),
+                                                                          static_cast<const __nv_bfloat16*>(n_bf16), scale, mean_dz, mean_dzn, M,
+                                                                          static_cast<__nv_bfloat16*>(dy_bf16));
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 

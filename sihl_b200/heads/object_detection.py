@@ -225,6 +225,37 @@ class ObjectDetection(nn.Module):
             offset += h * w
         return flat
 
+    def _flat_feats_training(self, inputs: List[Tensor]) -> Tensor:
+        """ref :151-154 inside ``training_step``.  Backend "tcgen05+train": one bf16 [B, A, 256] tensor feeds all four
+        towers (their input gradients are accumulated in bf16); when the laterals have the reference's structure at 256
+        channels and are in training mode, they run on the tensor-core path too (``mlp_tower._LateralsTrainFn``: batch
+        statistics from the input's moments, conv + BatchNorm as one folded GEMM per level) and the modules' running
+        statistics are updated here exactly as ``nn.BatchNorm2d`` does."""
+        probe = inputs[self.bottom_level]
+        if not self._use_tcgen05_training(probe):
+            return self._flat_feats(inputs)
+        from ..mlp_tower import _LateralsTrainFn, _ToBf16Fn
+        fusable = self.training and self.num_channels == ops.MLP_CHANNELS and all(
+            isinstance(lat[0], nn.Conv2d) and isinstance(lat[1], nn.BatchNorm2d) and len(lat) == 2 and lat[0].bias is None
+            and lat[0].kernel_size == (1, 1) and lat[0].stride == (1, 1) and lat[0].groups == 1
+            and lat[0].in_channels == ops.MLP_CHANNELS and lat[1].affine and lat[1].track_running_stats
+            and lat[1].momentum is not None and inputs[level].dtype == torch.float32
+            for lat, level in zip(self.laterals, self.levels))
+        if not fusable:
+            return _ToBf16Fn.apply(self._flat_feats(inputs))
+        args = []
+        for lat, level in zip(self.laterals, self.levels):
+            args += [inputs[level], lat[0].weight, lat[1].weight, lat[1].bias]
+        out = _LateralsTrainFn.apply(tuple(float(lat[1].eps) for lat in self.laterals), *args)
+        with torch.no_grad():
+            for i, (lat, level) in enumerate(zip(self.laterals, self.levels)):
+                bn, mean, var = lat[1], out[1 + 2 * i], out[2 + 2 * i]
+                count = inputs[level].shape[0] * inputs[level].shape[2] * inputs[level].shape[3]
+                bn.running_mean.mul_(1 - bn.momentum).add_(mean.to(bn.running_mean.dtype), alpha=bn.momentum)
+                bn.running_var.mul_(1 - bn.momentum).add_((var * (count / max(count - 1, 1))).to(bn.running_var.dtype), alpha=bn.momentum)
+                bn.num_batches_tracked += 1
+        return out[0]
+
     def _tower_feats(self, inputs: List[Tensor]) -> Tensor:
         """The towers' common input [B, A, C] (ref :102-105), bf16 when they run on the tensor cores."""
         if self._use_tcgen05(inputs[self.bottom_level]):
@@ -353,11 +384,7 @@ class ObjectDetection(nn.Module):
         if reduce_sums is not None:
             st.grad_scale = float(self._world_size())      # DDP averages the gradients of W ranks (see loss_reduction)
 
-        flat_feats = self._flat_feats(inputs)                                               # ref :151-154
-        if self._use_tcgen05_training(flat_feats):
-            # one bf16 copy feeds all four towers; their input gradients are accumulated in bf16 and handed back once
-            from ..mlp_tower import _ToBf16Fn
-            flat_feats = _ToBf16Fn.apply(flat_feats)
+        flat_feats = self._flat_feats_training(inputs)                                      # ref :151-154
         loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                         # ref :157
         iou_preds = self._tower("iou_head", flat_feats).squeeze(2)                          # ref :175
         o2m_feats = flat_feats.reshape(batch_size * st.A, -1).index_select(0, st.pos_index)  # ref :184 (+ padding rows)

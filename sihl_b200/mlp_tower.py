@@ -122,7 +122,7 @@ class _HiddenLayerFn(torch.autograd.Function):
         dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd(v, dy, stats, g32, be32)
         del v
         dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None   # dv W
-        dw = torch.matmul(dv.t(), x).float()                                 # [out, in]
+        dw = torch.mm(dv.t(), x, out_dtype=torch.float32)                    # [out, in], fp32 out of the bf16 GEMM
         wd, bd, gd, bed = ctx.param_dtypes
         return dx, dw.to(wd), dbias.to(bd), dgamma.to(gd), dbeta.to(bed), None
 
@@ -147,7 +147,7 @@ class _OutLayerFn(torch.autograd.Function):
         x, w16 = ctx.saved_tensors
         d16 = dout.to(torch.bfloat16)
         dx = torch.matmul(d16, w16) if ctx.needs_input_grad[0] else None      # [M, 256] bf16
-        dw = torch.matmul(d16.t(), x).float()
+        dw = torch.mm(d16.t(), x, out_dtype=torch.float32)
         wd, bd = ctx.param_dtypes
         return dx, dw.to(wd), dout.float().sum(0).to(bd)
 
@@ -177,3 +177,70 @@ def run_tower_train(mlp: nn.Sequential, x: Tensor) -> Tensor:
         cur = _HiddenLayerFn.apply(cur, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps))
     y = _OutLayerFn.apply(cur, last.weight, last.bias)
     return y.reshape(*lead, last.out_features)
+
+
+class _LateralsTrainFn(torch.autograd.Function):
+    """All laterals in training mode — per level ``Conv2d(256, 256, 1, bias=False)`` + batch-statistics ``BatchNorm2d`` (ref
+    object_detection.py:52-55, :102-105) — each written straight into its slice of the concatenated bf16 features.
+
+    Forward: the conv output is never materialised.  Its batch mean and variance follow from the input's first and second
+    moments (mean = W s / M, E[y^2] = diag(W G W^T) / M with s = sum of the rows, G = rows^T rows, fp32), so conv +
+    BatchNorm is one GEMM pass with folded weights, like the eval path.  Backward: the normalised conv output is recomputed
+    by the same GEMM, the BatchNorm backward runs over rows in two HBM-bound kernels, the conv's dgrad is the tensor-core
+    GEMM (+ the layout change back to NCHW fp32) and its wgrad a library GEMM.  Also returns every level's (mean, biased
+    variance) so the caller can update the modules' running statistics exactly as torch does.
+
+    ``apply(eps_per_level, x_0, w_0, gamma_0, beta_0, x_1, ...)`` -> (flat [B, A, 256] bf16, mean_0, var_0, mean_1, ...)."""
+
+    @staticmethod
+    def forward(ctx, eps, *tensors):
+        n_levels = len(tensors) // 4
+        xs, ws, gs, bs = tensors[0::4], tensors[1::4], tensors[2::4], tensors[3::4]
+        B = xs[0].shape[0]
+        sizes = [(int(x.shape[2]), int(x.shape[3])) for x in xs]
+        flat = torch.empty((B, sum(h * w for h, w in sizes), ops.MLP_CHANNELS), dtype=torch.bfloat16, device=xs[0].device)
+        saved, stats, offset = [], [], 0
+        for lvl in range(n_levels):
+            h, w = sizes[lvl]
+            M = B * h * w
+            rows = ops.lateral_rows(xs[lvl].detach().contiguous())
+            w16 = ws[lvl].detach()[:, :, 0, 0].to(torch.bfloat16).contiguous()
+            wf = w16.float()
+            s = rows.sum(0, dtype=torch.float32)
+            gram = torch.mm(rows.t(), rows, out_dtype=torch.float32)
+            mean = (wf @ s) / M
+            var = ((((wf @ gram) * wf).sum(1) / M) - mean * mean).clamp_min(0.0)
+            invstd = torch.rsqrt(var + eps[lvl])
+            scale = gs[lvl].detach().float() * invstd
+            ops.lateral_linear(rows, (wf * scale[:, None]).to(torch.bfloat16).contiguous(),
+                               (bs[lvl].detach().float() - mean * scale).contiguous(), h * w, flat, offset)
+            saved += [rows, w16, mean, invstd, scale]
+            stats += [mean, var]
+            offset += h * w
+        ctx.save_for_backward(*saved)
+        ctx.sizes, ctx.batch = sizes, B
+        ctx.dtypes = [(ws[l].dtype, gs[l].dtype, bs[l].dtype) for l in range(n_levels)]
+        ctx.mark_non_differentiable(*stats)
+        return (flat, *stats)
+
+    @staticmethod
+    def backward(ctx, dflat, *_unused):
+        saved = ctx.saved_tensors
+        B, grads, offset = ctx.batch, [None], 0
+        dflat = dflat.to(torch.bfloat16)
+        for lvl, (h, w) in enumerate(ctx.sizes):
+            rows, w16, mean, invstd, scale = saved[5 * lvl:5 * lvl + 5]
+            M = B * h * w
+            dz = dflat[:, offset:offset + h * w].reshape(M, -1).contiguous()
+            wf = w16.float()
+            n = ops.linear_bf16(rows, (wf * invstd[:, None]).to(torch.bfloat16).contiguous(), (-mean * invstd).contiguous())
+            dy, dgamma, dbeta = ops.bn_bwd_rows(dz, n, scale)
+            del n, dz
+            dx = None
+            if ctx.needs_input_grad[1 + 4 * lvl]:
+                dx = ops.rows_to_nchw(ops.linear_bf16(dy, w16.t().contiguous(), torch.zeros_like(mean)), B, h, w)
+            dw = torch.mm(dy.t(), rows, out_dtype=torch.float32)[:, :, None, None]
+            wd, gd, bd = ctx.dtypes[lvl]
+            grads += [dx, dw.to(wd), dgamma.to(gd), dbeta.to(bd)]
+            offset += h * w
+        return tuple(grads)

@@ -10,6 +10,8 @@ per function; the same citations are in the header next to each C entry point.
 """
 from __future__ import annotations
 
+import collections
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -67,7 +69,16 @@ def _req(t: Tensor, dtype, name: str, ndim: Optional[int] = None, pinned_ok: boo
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     if ndim is not None and t.dim() != ndim:
         raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
-    return t if t.is_contiguous() else t.contiguous()
+    if t.is_contiguous():
+        return t
+    # a contiguous COPY: callers pass `_p(_req(...))` straight into a C call, so nothing else references the copy — keep
+    # the last few alive here, or the allocator could hand its block to the next temporary before the kernel is enqueued
+    t = t.contiguous()
+    _KEEPALIVE.append(t)
+    return t
+
+
+_KEEPALIVE: "collections.deque" = collections.deque(maxlen=16)
 
 
 def _req_map(t: Tensor, name: str, ndim: Optional[int] = None, pinned_ok: bool = False) -> Tuple[Tensor, int]:
@@ -921,3 +932,43 @@ def bf16_to_f32(t: Tensor) -> Tensor:
         rc = _lib().sihl_od_bf16_to_f32(_p(t), t.numel(), _p(out), _stream(dev))
     _native.check(rc, "sihl_od_bf16_to_f32")
     return out
+
+
+def rows_to_nchw(rows: Tensor, batch: int, height: int, width: int) -> Tensor:
+    """bf16 rows [B*H*W, C] -> fp32 NCHW [B, C, H, W] (inverse layout of :func:`lateral_rows`; C % 64 == 0)."""
+    rows = _req(rows, torch.bfloat16, "rows", 2)
+    C = int(rows.shape[1])
+    if C % 64 or rows.shape[0] != batch * height * width:
+        raise ValueError(f"rows_to_nchw: rows {tuple(rows.shape)} for batch {batch}, {height}x{width}")
+    dev = rows.device
+    with _on(dev):
+        x = torch.empty((batch, C, height, width), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_rows_to_nchw(_p(rows), batch, C, height * width, _p(x), _stream(dev))
+    _native.check(rc, "sihl_od_rows_to_nchw")
+    return x
+
+
+def bn_bwd_rows(dz: Tensor, n: Tensor, scale: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backward of a batch-statistics BatchNorm over rows: ``dz`` [M,256] bf16 (gradient of the normalised + affine
+    output), ``n`` [M,256] bf16 (normalised conv output), ``scale`` = gamma * invstd fp32 [256] -> (dy bf16 [M,256] =
+    gradient of the conv output, d_gamma, d_beta fp32 [256])."""
+    dz = _req(dz, torch.bfloat16, "dz", 2)
+    n = _req(n, torch.bfloat16, "n", 2)
+    M, K = dz.shape
+    if K != MLP_CHANNELS or n.shape != dz.shape:
+        raise ValueError(f"bn_bwd_rows: dz {tuple(dz.shape)}, n {tuple(n.shape)}")
+    dev = dz.device
+    with _on(dev):
+        n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
+        partials = torch.empty((n_part, 2, K), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_bn_bwd_colsums(_p(dz), _p(n), M, K, _p(partials), n_part, _stream(dev))
+        _native.check(rc, "sihl_od_bn_bwd_colsums")
+        sums = partials.sum(0)
+        d_beta, d_gamma = sums[0], sums[1]
+        dy = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
+        # named, so that they outlive the launch: a temporary inside the argument list is freed (and its block handed to the
+        # next temporary) before the kernel is enqueued
+        mean_dz, mean_dzn, scale = (d_beta / M).contiguous(), (d_gamma / M).contiguous(), _req(scale, torch.float32, "scale", 1)
+        rc = _lib().sihl_od_bn_bwd_apply(_p(dz), _p(n), _p(scale), _p(mean_dz), _p(mean_dzn), M, K, _p(dy), _stream(dev))
+    _native.check(rc, "sihl_od_bn_bwd_apply")
+    return dy, d_gamma, d_beta

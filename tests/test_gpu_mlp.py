@@ -318,3 +318,62 @@ def test_head_training_step_with_tensor_core_towers():
         if ga[n].norm() > 1e-6:
             assert _cos(ga[n], gb[n]) > 0.98, (n, _cos(ga[n], gb[n]))
     assert _cos(ia, ib) > 0.98
+
+
+def test_training_laterals_on_the_tensor_core_path_match_conv_plus_batchnorm():
+    """Training-mode laterals (1x1 conv + batch-statistics BatchNorm, ref :52-55, :102-105) through _LateralsTrainFn against
+    the torch modules: output, every gradient (input, conv weight, BatchNorm weight and bias) and the running statistics."""
+    import copy
+    from sihl_b200.heads import ObjectDetection
+    torch.manual_seed(2)
+    model = ObjectDetection(in_channels=[3, 16, 32, 256, 256, 256], num_classes=5, num_channels=256, num_layers=1).to(DEV).train()
+    with torch.no_grad():
+        for lat in model.laterals:
+            lat[1].weight.normal_(1, 0.2); lat[1].bias.normal_(0, 0.2)
+    ref = copy.deepcopy(model)
+    g = torch.Generator().manual_seed(6)
+    base = [torch.randn((3, c, max(1, 96 // 2 ** l), max(1, 96 // 2 ** l)), generator=g).to(DEV) * 1.5 + 0.3 for l, c in enumerate(model.in_channels)]
+    xa = [t.clone().requires_grad_(True) for t in base]
+    xb = [t.clone().requires_grad_(True) for t in base]
+    model.mlp_backend = "tcgen05+train"
+    flat = model._flat_feats_training(xa)
+    want = ref._flat_feats(xb)
+    assert flat.dtype == torch.bfloat16 and flat.shape == want.shape
+    torch.testing.assert_close(flat.float(), want, rtol=2e-2, atol=3e-2)
+    gout = _rand(tuple(want.shape), 51)
+    flat.backward(gout.bfloat16())
+    want.backward(gout)
+    for lvl in (3, 4, 5):
+        assert _cos(xa[lvl].grad, xb[lvl].grad) > 0.995 and _rel_l2(xa[lvl].grad, xb[lvl].grad) < 0.1, lvl
+    for (na, pa), (nb, pb) in zip(model.laterals.named_parameters(), ref.laterals.named_parameters()):
+        assert na == nb and _cos(pa.grad, pb.grad) > 0.995 and _rel_l2(pa.grad, pb.grad) < 0.1, (na, _cos(pa.grad, pb.grad))
+    for la, lb in zip(model.laterals, ref.laterals):
+        torch.testing.assert_close(la[1].running_mean, lb[1].running_mean, rtol=2e-2, atol=2e-3)
+        torch.testing.assert_close(la[1].running_var, lb[1].running_var, rtol=2e-2, atol=2e-3)
+        assert int(la[1].num_batches_tracked) == int(lb[1].num_batches_tracked) == 1
+
+
+def test_head_training_step_with_tensor_core_laterals_and_towers():
+    """The whole drop-in training step with laterals AND towers on the tensor-core path (256-channel pyramid) against the
+    torch modules: loss within 2 %, parameter gradients in the same direction."""
+    import copy
+    from sihl_b200.heads import ObjectDetection
+    torch.manual_seed(4)
+    model = ObjectDetection(in_channels=[3, 16, 32, 256, 256, 256], num_classes=6, num_channels=256, num_layers=2, max_instances=20).to(DEV).train()
+    ref = copy.deepcopy(model)
+    model.mlp_backend = "tcgen05+train"
+    g = torch.Generator().manual_seed(8)
+    inputs = [torch.randn((2, c, max(1, 128 // 2 ** l), max(1, 128 // 2 ** l)), generator=g).to(DEV) for l, c in enumerate(model.in_channels)]
+    tgt = {"classes": [torch.tensor([1, 2], device=DEV), torch.tensor([3], device=DEV)],
+           "boxes": [torch.tensor([[10., 20., 100., 120.], [50., 60., 110., 90.]], device=DEV), torch.tensor([[30., 30., 90., 90.]], device=DEV)]}
+    loss, _ = model.training_step(inputs, **tgt)
+    loss.backward()
+    ref_loss, _ = ref.training_step(inputs, **tgt)
+    ref_loss.backward()
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=2e-2)
+    checked = 0
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        if q.grad is not None and q.grad.norm() > 1e-6:
+            assert p.grad is not None and _cos(p.grad, q.grad) > 0.97, (n, _cos(p.grad, q.grad))
+            checked += 1
+    assert checked > 20
