@@ -377,3 +377,36 @@ def test_head_training_step_with_tensor_core_laterals_and_towers():
             assert p.grad is not None and _cos(p.grad, q.grad) > 0.97, (n, _cos(p.grad, q.grad))
             checked += 1
     assert checked > 20
+
+
+def test_optimizer_trajectory_with_the_tensor_core_training_path():
+    """Fifteen AdamW steps on one batch, torch modules vs ``mlp_backend = "tcgen05+train"`` from the same initial weights: both
+    losses fall and stay within a few percent of each other (bf16 mixed precision vs fp32), running statistics follow."""
+    import copy
+    from sihl_b200.heads import ObjectDetection
+    torch.manual_seed(7)
+    a = ObjectDetection(in_channels=[3, 16, 32, 256, 256, 256], num_classes=6, num_channels=256, num_layers=2, max_instances=20).to(DEV).train()
+    b = copy.deepcopy(a)
+    b.mlp_backend = "tcgen05+train"
+    g = torch.Generator().manual_seed(9)
+    inputs = [torch.randn((2, c, max(1, 128 // 2 ** l), max(1, 128 // 2 ** l)), generator=g).to(DEV) for l, c in enumerate(a.in_channels)]
+    tgt = {"classes": [torch.tensor([1, 2], device=DEV), torch.tensor([3], device=DEV)],
+           "boxes": [torch.tensor([[10., 20., 100., 120.], [50., 60., 110., 90.]], device=DEV), torch.tensor([[30., 30., 90., 90.]], device=DEV)]}
+    curves = []
+    for model in (a, b):
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4)
+        losses = []
+        for _ in range(15):
+            opt.zero_grad(set_to_none=True)
+            loss, _ = model.training_step(inputs, **tgt)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        curves.append(losses)
+    la, lb = curves
+    assert la[-1] < 0.9 * la[0] and lb[-1] < 0.9 * lb[0], (la, lb)
+    for x, y in zip(la, lb):
+        assert y == pytest.approx(x, rel=0.06), (la, lb)
+    for ma, mb in zip(a.laterals, b.laterals):
+        torch.testing.assert_close(mb[1].running_mean, ma[1].running_mean, rtol=5e-2, atol=5e-3)
+        torch.testing.assert_close(mb[1].running_var, ma[1].running_var, rtol=5e-2, atol=5e-3)
