@@ -8,8 +8,12 @@ max_detection_thresholds=[1, 10, K], backend="faster_coco_eval")`` (ref src/sihl
 ``torchmetrics==1.6.1`` and ``faster-coco-eval==1.6.5`` (``requirements.lock:21,129``), the latter a C++ port of
 ``pycocotools.cocoeval.COCOeval``.  This file restates that published algorithm — ``COCOeval.evaluateImg`` (greedy
 matching), ``COCOeval.accumulate`` (precision / recall tables) and ``COCOeval.summarize`` with torchmetrics' key names —
-in plain Python loops over numpy arrays; no golden vector of the real libraries exists to pin it.  Known-answer cases
-(perfect detections, one false positive, a missed object) are checked in ``tests/test_map_oracle.py``.
+in plain Python loops over numpy arrays.  The reference's own tests hold no value for this step
+(``tests/heads/test_object_detection.py:72-80`` only asserts that the metrics dict is non-empty), and neither library can be
+run here to generate fixtures; the anchors are (a) the ONE published input/output vector of the real library, the example
+in ``MeanAveragePrecision``'s docstring (``TORCHMETRICS_DOC_EXAMPLE`` below: all 12 summary values), and (b) known-answer
+cases in closed form (perfect detections, greedy order across IoU thresholds, a missed object + a false positive, the
+area-range ignore rules), all in ``tests/test_map_oracle.py``.  One published vector is not a pin: the label stays.
 
 Conventions restated from torchmetrics' ``_get_coco_format`` / faster_coco_eval: boxes xyxy -> xywh with w, h computed in
 fp32; areas = w * h in double; iscrowd = 0; detections of an image sorted by score descending with a stable sort;
@@ -24,6 +28,16 @@ import numpy as np
 IOU_THRESHOLDS = np.linspace(0.5, 0.95, 10)
 RECALL_THRESHOLDS = np.linspace(0.0, 1.0, 101)
 AREA_RANGES = ((0.0, 1e5 ** 2), (0.0, 32.0 ** 2), (32.0 ** 2, 96.0 ** 2), (96.0 ** 2, 1e5 ** 2))   # all, small, medium, large
+
+
+# The one published input/output vector of the real library this path replaces: the example in the docstring of
+# ``torchmetrics.detection.mean_ap.MeanAveragePrecision`` (torchmetrics 1.6.x, the version the reference pins in
+# requirements.lock) — one detection, one ground-truth box, IoU 304 / 392 = 0.7755, so 6 of the 10 IoU thresholds match.
+TORCHMETRICS_DOC_EXAMPLE = dict(
+    det_boxes=[[258.0, 41.0, 606.0, 285.0]], det_scores=[0.536], det_classes=[0],
+    gt_boxes=[[214.0, 41.0, 562.0, 285.0]], gt_classes=[0],
+    want={"map": 0.6, "map_50": 1.0, "map_75": 1.0, "map_small": -1.0, "map_medium": -1.0, "map_large": 0.6,
+          "mar_1": 0.6, "mar_10": 0.6, "mar_100": 0.6, "mar_small": -1.0, "mar_medium": -1.0, "mar_large": 0.6})
 
 
 def _wh32(b: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

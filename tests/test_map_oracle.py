@@ -69,6 +69,15 @@ def test_area_ranges_ignore_rules():
     assert s["map_small"] == pytest.approx(1.0) and s["map_large"] == pytest.approx(1.0) and s["map_medium"] == -1.0
 
 
+def test_published_torchmetrics_docstring_example():
+    e = mo.TORCHMETRICS_DOC_EXAMPLE
+    im, m = _image(e["det_boxes"], e["det_scores"], e["det_classes"], e["gt_boxes"], e["gt_classes"])
+    assert (m["dt_match"][0][:6, 0] == 0).all() and (m["dt_match"][0][6:, 0] == -1).all()
+    s = _summary([im], [0])
+    for k, v in e["want"].items():
+        assert s[k] == pytest.approx(v, abs=1e-6), k
+
+
 def test_metrics_accumulate_equals_the_oracle_on_random_matches():
     """The vectorised host half of DetectionMAP (cumulative sums per category) == the loop restatement, fed with the
     same random match tables (several images, categories, ties in the scores, categories without gt / without dets)."""
