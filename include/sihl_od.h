@@ -528,6 +528,13 @@ SIHL_OD_API int sihl_od_bf16_to_f32(const void *src_bf16, int64_t n, float *dst,
 SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void *v_bf16, const void *dy_bf16, const float *row_stats, const float *gamma,
                            const float *beta, int64_t m, int channels, void *dv_bf16, float *partials,
                            int partial_rows, void *stream);
+/* The same backward for a tower's LAST hidden layer when the Linear behind it has one output (the location and IoU towers,
+ * ref object_detection.py:56, :60): the upstream gradient is the outer product dy[m,:] = bf16(dout[m]) * w_out[:] (dout fp32
+ * [m] = gradient of the tower's output, w_out bf16 [256] = that Linear's weight row), formed in registers instead of being
+ * materialised as an [M,256] matrix by a K = 1 library GEMM and read back. */
+SIHL_OD_API int sihl_od_mlp_hidden_bwd_rank1(const void *v_bf16, const float *dout, const void *w_out_bf16, const float *row_stats,
+                                 const float *gamma, const float *beta, int64_t m, int channels, void *dv_bf16,
+                                 float *partials, int partial_rows, void *stream);
 
 /* The laterals in front of the towers (ref object_detection.py:52-55, :102-105): Conv2dNormActivation(C_in, 256, 1,
  * activation_layer=None) = 1x1 conv + BatchNorm, per level, then "b c h w -> b (h w) c" and the concatenation over
@@ -548,6 +555,18 @@ SIHL_OD_API int sihl_od_bn_bwd_colsums(const void *dz_bf16, const void *n_bf16, 
                            int partial_rows, void *stream);
 SIHL_OD_API int sihl_od_bn_bwd_apply(const void *dz_bf16, const void *n_bf16, const float *scale, const float *mean_dz,
                          const float *mean_dzn, int64_t m, int channels, void *dy_bf16, void *stream);
+/* _map variants: dz is one level's slice of the gradient of the concatenated [B, dz_rows_per_image, 256] features, read in
+ * place — row m of the level is row (m / rows_per_image) * dz_rows_per_image + dz_row_offset + m % rows_per_image of dz. */
+SIHL_OD_API int sihl_od_bn_bwd_colsums_map(const void *dz_bf16, int64_t rows_per_image, int64_t dz_rows_per_image,
+                               int64_t dz_row_offset, const void *n_bf16, int64_t m, int channels, float *partials,
+                               int partial_rows, void *stream);
+SIHL_OD_API int sihl_od_bn_bwd_apply_map(const void *dz_bf16, int64_t rows_per_image, int64_t dz_rows_per_image,
+                             int64_t dz_row_offset, const void *n_bf16, const float *scale, const float *mean_dz,
+                             const float *mean_dzn, int64_t m, int channels, void *dy_bf16, void *stream);
+/* Column sums of bf16 rows [m,256] in fp32 — the first moment s of a lateral's input (see above): per-CTA partials
+ * [partial_rows,256], partial_rows = sihl_od_mlp_bwd_partial_rows(), summed by the caller. */
+SIHL_OD_API int sihl_od_rows_colsum(const void *rows_bf16, int64_t m, int channels, float *partials, int partial_rows,
+                        void *stream);
 SIHL_OD_API int sihl_od_rows_to_nchw(const void *rows_bf16, int batch, int channels, int64_t hw, float *x_nchw, void *stream);
 SIHL_OD_API int sihl_od_lateral_linear(const void *rows_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
                            int64_t rows_per_image, int64_t out_rows_per_image, int64_t out_row_offset,

@@ -73,6 +73,10 @@ _SIGNATURES = {
     "sihl_od_mlp_hidden_bwd": (I, [P, P, P, P, P, I64, I, P, P, I, P]),
     "sihl_od_lateral_rows": (I, [P, I, I, I64, P, P]),
     "sihl_od_rows_to_nchw": (I, [P, I, I, I64, P, P]),
+    "sihl_od_mlp_hidden_bwd_rank1": (I, [P, P, P, P, P, P, I64, I, P, P, I, P]),
+    "sihl_od_bn_bwd_colsums_map": (I, [P, I64, I64, I64, P, I64, I, P, I, P]),
+    "sihl_od_bn_bwd_apply_map": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, P]),
+    "sihl_od_rows_colsum": (I, [P, I64, I, P, I, P]),
     "sihl_od_bn_bwd_colsums": (I, [P, P, I64, I, P, I, P]),
     "sihl_od_bn_bwd_apply": (I, [P, P, P, P, P, I64, I, P, P]),
     "sihl_od_lateral_linear": (I, [P, I64, I, P, P, I64, I64, I64, P, P]),

@@ -530,27 +530,39 @@ __global__ void __launch_bounds__(256) k_nchw_to_rows_bf16(const float* __restri
 // v is the layer's pre-activation (x W^T + b, recomputed by the linear mode of the layer kernel, bf16), (mean, rstd) come
 // from the forward.  Every CTA writes its partial column sums to partials[blockIdx.x][3][256] (summed by the caller:
 // deterministic, no atomics).  HBM-bound: 2 x 512 B read + 512 B written per row.
+//
+// RANK1: the layer is the tower's LAST hidden layer and the Linear behind it has ONE output (the location and the IoU
+// tower, ref :56, :60), so the upstream gradient is the outer product dy[m,:] = bf16(dout[m]) * w_out[:] (rounded to bf16
+// like the library GEMM it replaces would): read as 4 B per row + one weight row instead of a materialised [M,256] matrix.
 constexpr int kBwdWarps = 8;
 constexpr int kBwdRows = 2;                   // rows per warp and iteration: both rows' loads are in flight before the arithmetic
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+template <bool RANK1>
 __global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dy,
+                                                                         const float* __restrict__ dout, const __nv_bfloat16* __restrict__ w_out,
                                                                          const float* __restrict__ row_stats, const float* __restrict__ gamma,
                                                                          const float* __restrict__ beta, long long M, __nv_bfloat16* __restrict__ dv,
                                                                          float* __restrict__ partials) {
     __shared__ float red[kBwdWarps][3][kK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = lane * 8;
-    float g[8], be[8], acc_g[8], acc_b[8], acc_v[8];
+    float g[8], be[8], acc_g[8], acc_b[8], acc_v[8], wo[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { g[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; acc_g[j] = acc_b[j] = acc_v[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+        g[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; acc_g[j] = acc_b[j] = acc_v[j] = 0.f;
+        wo[j] = RANK1 ? __bfloat162float(w_out[c0 + j]) : 0.f;
+    }
     const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps * kBwdRows;
     for (long long row0 = (static_cast<long long>(blockIdx.x) * kBwdWarps + warp) * kBwdRows; row0 < M; row0 += stride) {
         uint4 v4[kBwdRows], d4[kBwdRows];
         float2 st[kBwdRows];
+        float dcol[kBwdRows];
 #pragma unroll
         for (int r = 0; r < kBwdRows; ++r) {
             const long long row = row0 + r < M ? row0 + r : M - 1;          // the tail repeats the last row (not stored, not summed)
             v4[r] = *reinterpret_cast<const uint4*>(v + row * kK + c0);
-            d4[r] = *reinterpret_cast<const uint4*>(dy + row * kK + c0);
+            if constexpr (RANK1) { dcol[r] = bf16_round(dout[row]); d4[r] = make_uint4(0, 0, 0, 0); }
+            else { d4[r] = *reinterpret_cast<const uint4*>(dy + row * kK + c0); dcol[r] = 0.f; }
             st[r] = *reinterpret_cast<const float2*>(row_stats + 2 * row);
         }
 #pragma unroll
@@ -562,7 +574,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __
             for (int q = 0; q < 4; ++q) {
                 const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[q]));
                 const float2 df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[q]));
-                const float vv[2] = {vf.x, vf.y}, dd[2] = {live ? df.x : 0.f, live ? df.y : 0.f};
+                const float up[2] = {RANK1 ? bf16_round(dcol[r] * wo[2 * q]) : df.x, RANK1 ? bf16_round(dcol[r] * wo[2 * q + 1]) : df.y};
+                const float vv[2] = {vf.x, vf.y}, dd[2] = {live ? up[0] : 0.f, live ? up[1] : 0.f};
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int j = 2 * q + u;
@@ -630,7 +643,17 @@ __global__ void __launch_bounds__(256) k_bf16_to_f32(const uint4* __restrict__ s
 //   pass 1 (k_bn_bwd_colsums): partials[cta][0][c] = sum_m dz[m,c], partials[cta][1][c] = sum_m dz[m,c] n[m,c]
 //   pass 2 (k_bn_bwd_apply):   dy[m,c] = scale[c] (dz[m,c] - mean_dz[c] - n[m,c] mean_dzn[c])
 // n = (y - mean) invstd is the normalised conv output (recomputed by the caller with the linear mode of the layer kernel).
-__global__ void __launch_bounds__(kBwdWarps * 32) k_bn_bwd_colsums(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ n,
+// dz may be a slice of a larger [B, rows_out, 256] tensor (one level of the concatenated features' gradient): row m of the
+// level is row (m / rows_per_image) * dz_rows_per_image + dz_row_offset + m % rows_per_image of dz — read in place, no copy.
+struct RowMap {
+    unsigned rows_per_image;
+    long long src_rows_per_image, src_row_offset;
+    __device__ __forceinline__ long long operator()(long long m) const {
+        const unsigned img = static_cast<unsigned>(m) / rows_per_image;              // M < 2^31 (checked by the caller)
+        return static_cast<long long>(img) * src_rows_per_image + src_row_offset + (static_cast<unsigned>(m) - img * rows_per_image);
+    }
+};
+__global__ void __launch_bounds__(kBwdWarps * 32) k_bn_bwd_colsums(const __nv_bfloat16* __restrict__ dz, const RowMap map, const __nv_bfloat16* __restrict__ n,
                                                                     long long M, float* __restrict__ partials) {
     __shared__ float red[kBwdWarps][2][kK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -640,7 +663,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_bn_bwd_colsums(const __nv_bf
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
     const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps;
     for (long long row = static_cast<long long>(blockIdx.x) * kBwdWarps + warp; row < M; row += stride) {
-        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + row * kK + c0);
+        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + map(row) * kK + c0);
         const uint4 n4 = *reinterpret_cast<const uint4*>(n + row * kK + c0);
         const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, nw[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
@@ -662,7 +685,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_bn_bwd_colsums(const __nv_bf
     }
 }
 
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ n,
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, const RowMap map, const __nv_bfloat16* __restrict__ n,
                                                        const float* __restrict__ scale, const float* __restrict__ mean_dz,
                                                        const float* __restrict__ mean_dzn, long long M, __nv_bfloat16* __restrict__ dy) {
     const int lane = threadIdx.x & 31;
@@ -672,7 +695,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
     for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; m0[j] = mean_dz[c0 + j]; m1[j] = mean_dzn[c0 + j]; }
     const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
     for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
-        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + row * kK + c0);
+        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + map(row) * kK + c0);
         const uint4 n4 = *reinterpret_cast<const uint4*>(n + row * kK + c0);
         const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, nw[4] = {n4.x, n4.y, n4.z, n4.w};
         uint32_t ow[4];
@@ -686,6 +709,41 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
             ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
         }
         *reinterpret_cast<uint4*>(dy + row * kK + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// Column sums of bf16 rows [M,256] in fp32 (the first moment of a lateral's input, see sihl_od_lateral_linear's training
+// notes): per-CTA partials [gridDim.x][256], summed by the caller (deterministic).  HBM-bound, 512 B per row.
+__global__ void __launch_bounds__(kBwdWarps * 32) k_rows_colsum(const __nv_bfloat16* __restrict__ x, long long M, float* __restrict__ partials) {
+    __shared__ float red[kBwdWarps][kK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = lane * 8;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    const long long stride = static_cast<long long>(gridDim.x) * kBwdWarps * 4;
+    for (long long row0 = (static_cast<long long>(blockIdx.x) * kBwdWarps + warp) * 4; row0 < M; row0 += stride) {
+        uint4 r4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) r4[r] = row0 + r < M ? *reinterpret_cast<const uint4*>(x + (row0 + r) * kK + c0) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t w[4] = {r4[r].x, r4[r].y, r4[r].z, r4[r].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+                a[2 * q] += f.x; a[2 * q + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][c0 + j] = a[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kK; i += kBwdWarps * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdWarps; ++w) t += red[w][i];
+        partials[static_cast<long long>(blockIdx.x) * kK + i] = t;
     }
 }
 
@@ -819,8 +877,22 @@ SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void* v_bf16, const void* dy_bf16, 
     if (M > 0 && (!v_bf16 || !dy_bf16 || !row_stats || !dv_bf16 || !aligned16(v_bf16) || !aligned16(dy_bf16) || !aligned16(dv_bf16) ||
                   (reinterpret_cast<uintptr_t>(row_stats) & 7u)))
         return SIHL_OD_EINVAL;
-    k_mlp_hidden_bwd_rows<<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(v_bf16), static_cast<const __nv_bfloat16*>(dy_bf16), row_stats, gamma, beta, M,
+    k_mlp_hidden_bwd_rows<false><<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(v_bf16), static_cast<const __nv_bfloat16*>(dy_bf16), nullptr, nullptr, row_stats, gamma, beta, M,
+        static_cast<__nv_bfloat16*>(dv_bf16), partials);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
+SIHL_OD_API int sihl_od_mlp_hidden_bwd_rank1(const void* v_bf16, const float* dout, const void* w_out_bf16, const float* row_stats, const float* gamma,
+                                             const float* beta, int64_t M, int channels, void* dv_bf16, float* partials, int partial_rows,
+                                             void* stream) {
+    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows()) return SIHL_OD_EINVAL;
+    if (!partials || !gamma || !beta || !w_out_bf16) return SIHL_OD_EINVAL;
+    if (M > 0 && (!v_bf16 || !dout || !row_stats || !dv_bf16 || !aligned16(v_bf16) || !aligned16(dv_bf16) ||
+                  (reinterpret_cast<uintptr_t>(row_stats) & 7u) || (reinterpret_cast<uintptr_t>(dout) & 3u)))
+        return SIHL_OD_EINVAL;
+    k_mlp_hidden_bwd_rows<true><<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(v_bf16), nullptr, dout, static_cast<const __nv_bfloat16*>(w_out_bf16), row_stats, gamma, beta, M,
         static_cast<__nv_bfloat16*>(dv_bf16), partials);
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
@@ -869,26 +941,53 @@ SIHL_OD_API int sihl_od_rows_to_nchw(const void* rows_bf16, int batch, int chann
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 
+static bool row_map_ok(int64_t M, int64_t rows_per_image, int64_t src_rows_per_image, int64_t src_row_offset) {
+    return M <= 0x7FFFFF00LL && rows_per_image > 0 && rows_per_image <= 0x7FFFFF00LL && src_rows_per_image >= rows_per_image && src_row_offset >= 0 &&
+           src_row_offset + rows_per_image <= src_rows_per_image && M % rows_per_image == 0;
+}
+
+SIHL_OD_API int sihl_od_bn_bwd_colsums_map(const void* dz_bf16, int64_t rows_per_image, int64_t dz_rows_per_image, int64_t dz_row_offset,
+                                           const void* n_bf16, int64_t M, int channels, float* partials, int partial_rows, void* stream) {
+    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows() || !partials) return SIHL_OD_EINVAL;
+    if (M > 0 && (!dz_bf16 || !n_bf16 || !aligned16(dz_bf16) || !aligned16(n_bf16) || !row_map_ok(M, rows_per_image, dz_rows_per_image, dz_row_offset)))
+        return SIHL_OD_EINVAL;
+    const RowMap map{static_cast<unsigned>(M > 0 ? rows_per_image : 1), dz_rows_per_image, dz_row_offset};
+    k_bn_bwd_colsums<<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dz_bf16), map, static_cast<const __nv_bfloat16*>(n_bf16), M, partials);
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
 SIHL_OD_API int sihl_od_bn_bwd_colsums(const void* dz_bf16, const void* n_bf16, int64_t M, int channels, float* partials, int partial_rows,
                                        void* stream) {
-    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows() || !partials) return SIHL_OD_EINVAL;
-    if (M > 0 && (!dz_bf16 || !n_bf16 || !aligned16(dz_bf16) || !aligned16(n_bf16))) return SIHL_OD_EINVAL;
-    k_bn_bwd_colsums<<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dz_bf16), static_cast<const __nv_bfloat16*>(n_bf16), M, partials);
+    return sihl_od_bn_bwd_colsums_map(dz_bf16, M > 0 ? M : 1, M > 0 ? M : 1, 0, n_bf16, M, channels, partials, partial_rows, stream);
+}
+
+SIHL_OD_API int sihl_od_bn_bwd_apply_map(const void* dz_bf16, int64_t rows_per_image, int64_t dz_rows_per_image, int64_t dz_row_offset,
+                                         const void* n_bf16, const float* scale, const float* mean_dz, const float* mean_dzn, int64_t M, int channels,
+                                         void* dy_bf16, void* stream) {
+    if (channels != kK || M < 0) return SIHL_OD_EINVAL;
+    if (M == 0) return SIHL_OD_OK;
+    if (!dz_bf16 || !n_bf16 || !scale || !mean_dz || !mean_dzn || !dy_bf16 || !aligned16(dz_bf16) || !aligned16(n_bf16) || !aligned16(dy_bf16) ||
+        !row_map_ok(M, rows_per_image, dz_rows_per_image, dz_row_offset))
+        return SIHL_OD_EINVAL;
+    const int sms = sm_count();
+    if (sms <= 0) return SIHL_OD_ECUDA;
+    const RowMap map{static_cast<unsigned>(rows_per_image), dz_rows_per_image, dz_row_offset};
+    k_bn_bwd_apply<<<sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dz_bf16), map,
+                                                                          static_cast<const __nv_bfloat16*>(n_bf16), scale, mean_dz, mean_dzn, M,
+                                                                          static_cast<__nv_bfloat16*>(dy_bf16));
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 
 SIHL_OD_API int sihl_od_bn_bwd_apply(const void* dz_bf16, const void* n_bf16, const float* scale, const float* mean_dz, const float* mean_dzn,
                                      int64_t M, int channels, void* dy_bf16, void* stream) {
-    if (channels != kK || M < 0) return SIHL_OD_EINVAL;
-    if (M == 0) return SIHL_OD_OK;
-    if (!dz_bf16 || !n_bf16 || !scale || !mean_dz || !mean_dzn || !dy_bf16 || !aligned16(dz_bf16) || !aligned16(n_bf16) || !aligned16(dy_bf16))
-        return SIHL_OD_EINVAL;
-    const int sms = sm_count();
-    if (sms <= 0) return SIHL_OD_ECUDA;
-    k_bn_bwd_apply<<<sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dz_bf16),
-                                                                          static_cast<const __nv_bfloat16*>(n_bf16), scale, mean_dz, mean_dzn, M,
-                                                                          static_cast<__nv_bfloat16*>(dy_bf16));
+    return sihl_od_bn_bwd_apply_map(dz_bf16, M > 0 ? M : 1, M > 0 ? M : 1, 0, n_bf16, scale, mean_dz, mean_dzn, M, channels, dy_bf16, stream);
+}
+
+SIHL_OD_API int sihl_od_rows_colsum(const void* rows_bf16, int64_t M, int channels, float* partials, int partial_rows, void* stream) {
+    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows() || !partials) return SIHL_OD_EINVAL;
+    if (M > 0 && (!rows_bf16 || !aligned16(rows_bf16))) return SIHL_OD_EINVAL;
+    k_rows_colsum<<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(rows_bf16), M, partials);
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 

@@ -152,6 +152,41 @@ class _OutLayerFn(torch.autograd.Function):
         return dx, dw.to(wd), dout.float().sum(0).to(bd)
 
 
+class _LastHiddenOutFn(torch.autograd.Function):
+    """A tower's last hidden layer AND its single-output Linear (the location and IoU towers, ref :56, :60) as one node: the
+    backward never materialises the [M,256] gradient between the two — ``d16[:, None] * w_out`` would come out of a K = 1
+    library GEMM only to be read back by the LayerNorm + SiLU backward, which forms it in registers instead
+    (``ops.mlp_hidden_bwd_rank1``).  Same arithmetic and roundings as ``_OutLayerFn`` after ``_HiddenLayerFn``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, eps, w_out, b_out):
+        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        b32, g32, be32 = bias.detach().float().contiguous(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        y, stats = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps)
+        n_pad = ops.mlp_out_pad(1)
+        wo = torch.zeros((n_pad, ops.MLP_CHANNELS), dtype=torch.bfloat16, device=x.device)
+        wo[:1] = w_out.detach().to(torch.bfloat16)
+        bo = torch.zeros((n_pad,), dtype=torch.float32, device=x.device)
+        bo[:1] = b_out.detach().float()
+        ctx.save_for_backward(x, w16, b32, g32, be32, stats, y, wo)
+        ctx.param_dtypes = (weight.dtype, bias.dtype, gamma.dtype, beta.dtype, w_out.dtype, b_out.dtype)
+        return ops.mlp_out(y, wo, bo, 1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w16, b32, g32, be32, stats, y, wo = ctx.saved_tensors
+        dcol = dout.reshape(-1).float().contiguous()                          # [M] fp32
+        d16 = dcol.to(torch.bfloat16)
+        v = ops.linear_bf16(x, w16, b32)                                     # recompute the pre-activation
+        dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd_rank1(v, dcol, wo[0], stats, g32, be32)
+        del v
+        dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(dv.t(), x, out_dtype=torch.float32)
+        dw_out = torch.mm(d16[None, :], y, out_dtype=torch.float32)          # [1, 256]
+        wd, bd, gd, bed, wod, bod = ctx.param_dtypes
+        return dx, dw.to(wd), dbias.to(bd), dgamma.to(gd), dbeta.to(bed), None, dw_out.to(wod), dcol.sum(0, keepdim=True).to(bod)
+
+
 class _ToBf16Fn(torch.autograd.Function):
     """fp32 -> bf16 at the tower's entrance; the backward hands the gradient back in fp32 (one full-width kernel)."""
 
@@ -173,9 +208,14 @@ def run_tower_train(mlp: nn.Sequential, x: Tensor) -> Tensor:
     cur = x.reshape(-1, x.shape[-1]).contiguous()
     if cur.dtype != torch.bfloat16:
         cur = _ToBf16Fn.apply(cur)
-    for lin, ln in hidden:
+    fuse_last = last.out_features == 1 and len(hidden) > 0
+    for lin, ln in (hidden[:-1] if fuse_last else hidden):
         cur = _HiddenLayerFn.apply(cur, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps))
-    y = _OutLayerFn.apply(cur, last.weight, last.bias)
+    if fuse_last:
+        lin, ln = hidden[-1]
+        y = _LastHiddenOutFn.apply(cur, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps), last.weight, last.bias)
+    else:
+        y = _OutLayerFn.apply(cur, last.weight, last.bias)
     return y.reshape(*lead, last.out_features)
 
 
@@ -206,7 +246,7 @@ class _LateralsTrainFn(torch.autograd.Function):
             rows = ops.lateral_rows(xs[lvl].detach().contiguous())
             w16 = ws[lvl].detach()[:, :, 0, 0].to(torch.bfloat16).contiguous()
             wf = w16.float()
-            s = rows.sum(0, dtype=torch.float32)
+            s = ops.rows_colsum(rows)
             gram = torch.mm(rows.t(), rows, out_dtype=torch.float32)
             mean = (wf @ s) / M
             var = ((((wf @ gram) * wf).sum(1) / M) - mean * mean).clamp_min(0.0)
@@ -227,15 +267,14 @@ class _LateralsTrainFn(torch.autograd.Function):
     def backward(ctx, dflat, *_unused):
         saved = ctx.saved_tensors
         B, grads, offset = ctx.batch, [None], 0
-        dflat = dflat.to(torch.bfloat16)
+        dflat = dflat.to(torch.bfloat16).contiguous()                         # [B, A, 256]: every level reads its slice in place
         for lvl, (h, w) in enumerate(ctx.sizes):
             rows, w16, mean, invstd, scale = saved[5 * lvl:5 * lvl + 5]
-            M = B * h * w
-            dz = dflat[:, offset:offset + h * w].reshape(M, -1).contiguous()
             wf = w16.float()
             n = ops.linear_bf16(rows, (wf * invstd[:, None]).to(torch.bfloat16).contiguous(), (-mean * invstd).contiguous())
-            dy, dgamma, dbeta = ops.bn_bwd_rows(dz, n, scale)
-            del n, dz
+            dy, dgamma, dbeta = ops.bn_bwd_rows(dflat, n, scale, dz_rows_per_image=int(dflat.shape[1]), dz_row_offset=offset,
+                                                rows_per_image=h * w)
+            del n
             dx = None
             if ctx.needs_input_grad[1 + 4 * lvl]:
                 dx = ops.rows_to_nchw(ops.linear_bf16(dy, w16.t().contiguous(), torch.zeros_like(mean)), B, h, w)

@@ -921,6 +921,46 @@ def mlp_hidden_bwd(v: Tensor, dy: Tensor, row_stats: Tensor, gamma: Tensor, beta
     return dv, sums[0], sums[1], sums[2]
 
 
+def mlp_hidden_bwd_rank1(v: Tensor, dout: Tensor, w_out: Tensor, row_stats: Tensor, gamma: Tensor, beta: Tensor
+                         ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """:func:`mlp_hidden_bwd` for a tower's last hidden layer when the Linear behind it has ONE output: the upstream
+    gradient ``bf16(dout)[:, None] * w_out[None, :]`` (``dout`` fp32 [M], ``w_out`` bf16 [256]) is formed in registers
+    instead of being materialised by a K = 1 GEMM."""
+    v = _req(v, torch.bfloat16, "v", 2)
+    dout = _req(dout, torch.float32, "dout", 1)
+    w_out = _req(w_out, torch.bfloat16, "w_out", 1)
+    M, K = v.shape
+    if K != MLP_CHANNELS or dout.shape[0] != M or w_out.shape[0] != K or tuple(row_stats.shape) != (M, 2):
+        raise ValueError(f"mlp_hidden_bwd_rank1: v {tuple(v.shape)}, dout {tuple(dout.shape)}, w_out {tuple(w_out.shape)}, "
+                         f"row_stats {tuple(row_stats.shape)}")
+    dev = v.device
+    with _on(dev):
+        n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
+        dv = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
+        partials = torch.empty((n_part, 3, K), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_mlp_hidden_bwd_rank1(_p(v), _p(dout), _p(w_out), _p(_req(row_stats, torch.float32, "row_stats", 2)),
+                                                 _p(_req(gamma, torch.float32, "gamma", 1)), _p(_req(beta, torch.float32, "beta", 1)),
+                                                 M, K, _p(dv), _p(partials), n_part, _stream(dev))
+    _native.check(rc, "sihl_od_mlp_hidden_bwd_rank1")
+    sums = partials.sum(0)
+    return dv, sums[0], sums[1], sums[2]
+
+
+def rows_colsum(rows: Tensor) -> Tensor:
+    """fp32 column sums [256] of bf16 rows [M,256]: one HBM-bound pass (the first moment of a lateral's input)."""
+    rows = _req(rows, torch.bfloat16, "rows", 2)
+    M, K = rows.shape
+    if K != MLP_CHANNELS:
+        raise ValueError(f"rows_colsum is built for {MLP_CHANNELS} channels, got {tuple(rows.shape)}")
+    dev = rows.device
+    with _on(dev):
+        n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
+        partials = torch.empty((n_part, K), dtype=torch.float32, device=dev)
+        rc = _lib().sihl_od_rows_colsum(_p(rows), M, K, _p(partials), n_part, _stream(dev))
+    _native.check(rc, "sihl_od_rows_colsum")
+    return partials.sum(0)
+
+
 def bf16_to_f32(t: Tensor) -> Tensor:
     """fp32 copy of a contiguous bf16 tensor whose element count is a multiple of 8 (full-width loads and stores)."""
     t = _req(t, torch.bfloat16, "t")
@@ -948,27 +988,43 @@ def rows_to_nchw(rows: Tensor, batch: int, height: int, width: int) -> Tensor:
     return x
 
 
-def bn_bwd_rows(dz: Tensor, n: Tensor, scale: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-    """Backward of a batch-statistics BatchNorm over rows: ``dz`` [M,256] bf16 (gradient of the normalised + affine
-    output), ``n`` [M,256] bf16 (normalised conv output), ``scale`` = gamma * invstd fp32 [256] -> (dy bf16 [M,256] =
-    gradient of the conv output, d_gamma, d_beta fp32 [256])."""
-    dz = _req(dz, torch.bfloat16, "dz", 2)
+def bn_bwd_rows(dz: Tensor, n: Tensor, scale: Tensor, dz_rows_per_image: Optional[int] = None, dz_row_offset: int = 0,
+                rows_per_image: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backward of a batch-statistics BatchNorm over rows: ``dz`` bf16 (gradient of the normalised + affine output),
+    ``n`` [M,256] bf16 (normalised conv output), ``scale`` = gamma * invstd fp32 [256] -> (dy bf16 [M,256] = gradient of
+    the conv output, d_gamma, d_beta fp32 [256]).
+
+    ``dz`` is either [M,256], or — with ``rows_per_image`` / ``dz_rows_per_image`` / ``dz_row_offset`` — the whole
+    contiguous [B, dz_rows_per_image, 256] gradient of the concatenated features, of which this level is the slice
+    ``[:, dz_row_offset : dz_row_offset + rows_per_image]`` (read in place: no strided copy)."""
     n = _req(n, torch.bfloat16, "n", 2)
-    M, K = dz.shape
-    if K != MLP_CHANNELS or n.shape != dz.shape:
-        raise ValueError(f"bn_bwd_rows: dz {tuple(dz.shape)}, n {tuple(n.shape)}")
-    dev = dz.device
+    M, K = n.shape
+    if rows_per_image is None:
+        dz = _req(dz, torch.bfloat16, "dz", 2)
+        if dz.shape != n.shape:
+            raise ValueError(f"bn_bwd_rows: dz {tuple(dz.shape)}, n {tuple(n.shape)}")
+        rows_per_image, dz_rows_per_image, dz_row_offset = max(M, 1), max(M, 1), 0
+    else:
+        dz = _req(dz, torch.bfloat16, "dz", 3)
+        if (dz.shape[2] != K or dz.shape[1] != dz_rows_per_image or dz.shape[0] * rows_per_image != M or dz_row_offset < 0
+                or dz_row_offset + rows_per_image > dz_rows_per_image):
+            raise ValueError(f"bn_bwd_rows: dz {tuple(dz.shape)}, n {tuple(n.shape)}, slice {dz_row_offset}+{rows_per_image}")
+    if K != MLP_CHANNELS:
+        raise ValueError(f"bn_bwd_rows is built for {MLP_CHANNELS} channels, got {K}")
+    dev = n.device
     with _on(dev):
         n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
         partials = torch.empty((n_part, 2, K), dtype=torch.float32, device=dev)
-        rc = _lib().sihl_od_bn_bwd_colsums(_p(dz), _p(n), M, K, _p(partials), n_part, _stream(dev))
-        _native.check(rc, "sihl_od_bn_bwd_colsums")
+        rc = _lib().sihl_od_bn_bwd_colsums_map(_p(dz), int(rows_per_image), int(dz_rows_per_image), int(dz_row_offset), _p(n), M, K,
+                                               _p(partials), n_part, _stream(dev))
+        _native.check(rc, "sihl_od_bn_bwd_colsums_map")
         sums = partials.sum(0)
         d_beta, d_gamma = sums[0], sums[1]
         dy = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
         # named, so that they outlive the launch: a temporary inside the argument list is freed (and its block handed to the
         # next temporary) before the kernel is enqueued
         mean_dz, mean_dzn, scale = (d_beta / M).contiguous(), (d_gamma / M).contiguous(), _req(scale, torch.float32, "scale", 1)
-        rc = _lib().sihl_od_bn_bwd_apply(_p(dz), _p(n), _p(scale), _p(mean_dz), _p(mean_dzn), M, K, _p(dy), _stream(dev))
-    _native.check(rc, "sihl_od_bn_bwd_apply")
+        rc = _lib().sihl_od_bn_bwd_apply_map(_p(dz), int(rows_per_image), int(dz_rows_per_image), int(dz_row_offset), _p(n), _p(scale),
+                                             _p(mean_dz), _p(mean_dzn), M, K, _p(dy), _stream(dev))
+    _native.check(rc, "sihl_od_bn_bwd_apply_map")
     return dy, d_gamma, d_beta

@@ -292,6 +292,72 @@ def test_tower_training_path_against_the_torch_module():
         assert _rel_l2(ours[n], p.grad) < 0.1, (n, _rel_l2(ours[n], p.grad))
 
 
+@pytest.mark.parametrize("M", [1, 300, 128 * 150 + 7])
+def test_rank1_backward_equals_the_materialised_outer_product(M):
+    """``ops.mlp_hidden_bwd_rank1`` (upstream gradient bf16(dout) x w_out formed in registers) == ``ops.mlp_hidden_bwd`` on
+    the [M,256] matrix the K = 1 library GEMM produces: same roundings, same accumulation order -> bit-equal."""
+    v = _rand((M, 256), 51).bfloat16()
+    x = _rand((M, 256), 52).bfloat16()
+    gamma, beta = 1 + 0.1 * _rand((256,), 53), 0.1 * _rand((256,), 54)
+    w16 = _rand((256, 256), 55, 1 / 16).bfloat16()
+    _, stats = ops.mlp_hidden_train(x, w16, _rand((256,), 56), gamma, beta)
+    dout = _rand((M,), 57)
+    w_out = _rand((1, 256), 58, 1 / 16).bfloat16()
+    dy = torch.matmul(dout.to(torch.bfloat16)[:, None], w_out)
+    want = ops.mlp_hidden_bwd(v, dy.contiguous(), stats, gamma, beta)
+    got = ops.mlp_hidden_bwd_rank1(v, dout, w_out[0], stats, gamma, beta)
+    for name, a, b in zip(("dv", "dgamma", "dbeta", "dbias"), got, want):
+        assert torch.equal(a, b), name
+
+
+def test_single_output_tower_fuses_its_last_two_layers():
+    """A tower with one output (location / IoU head) runs its last hidden layer and the output Linear as one autograd node
+    (``_LastHiddenOutFn``): same loss and parameter gradients as the torchvision module, like the 4-output tower above."""
+    from sihl_b200 import mlp_tower
+    torch.manual_seed(1)
+    mlp = tvops.MLP(256, [256] * 4 + [1], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU).to(DEV)
+    x = _rand((2, 3000, 256), 61).requires_grad_(True)
+    tgt = _rand((2, 3000, 1), 62)
+    out = mlp_tower.run_tower_train(mlp, x)
+    assert type(out.grad_fn.next_functions[0][0]).__name__.startswith("_LastHiddenOutFn") or "_LastHiddenOutFn" in str(out.grad_fn.next_functions)
+    loss = F.mse_loss(out, tgt)
+    loss.backward()
+    ours = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+    dx = x.grad.clone()
+    mlp.zero_grad(); x.grad = None
+    ref_loss = F.mse_loss(mlp(x), tgt)
+    ref_loss.backward()
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=2e-2)
+    assert _cos(dx, x.grad) > 0.995 and _rel_l2(dx, x.grad) < 0.1
+    for n, p in mlp.named_parameters():
+        assert ours[n].shape == p.grad.shape, n
+        assert _cos(ours[n], p.grad) > 0.995, (n, _cos(ours[n], p.grad))
+        assert _rel_l2(ours[n], p.grad) < 0.1, (n, _rel_l2(ours[n], p.grad))
+
+
+@pytest.mark.parametrize("M", [1, 5, 4099, 128 * 900])
+def test_rows_colsum(M):
+    rows = _rand((M, 256), 71).bfloat16()
+    got = ops.rows_colsum(rows)
+    want = rows.double().sum(0)
+    torch.testing.assert_close(got.double(), want, rtol=1e-5, atol=1e-3 * max(1.0, M ** 0.5) * 1e-2)
+
+
+def test_bn_backward_reads_its_level_in_place():
+    """``ops.bn_bwd_rows`` on one level's slice of the [B, A, 256] gradient read in place == the same call on a contiguous
+    copy of the slice (bit-equal), and it does not touch its neighbours' rows."""
+    B, A, off, hw = 3, 700, 123, 400
+    dflat = _rand((B, A, 256), 81).bfloat16()
+    n = _rand((B * hw, 256), 82).bfloat16()
+    scale = 1 + 0.1 * _rand((256,), 83)
+    want = ops.bn_bwd_rows(dflat[:, off:off + hw].reshape(B * hw, 256).contiguous(), n, scale)
+    got = ops.bn_bwd_rows(dflat, n, scale, dz_rows_per_image=A, dz_row_offset=off, rows_per_image=hw)
+    for name, a, b in zip(("dy", "dgamma", "dbeta"), got, want):
+        assert torch.equal(a, b), name
+    with pytest.raises(ValueError):
+        ops.bn_bwd_rows(dflat, n, scale, dz_rows_per_image=A, dz_row_offset=A - hw + 1, rows_per_image=hw)
+
+
 def test_head_training_step_with_tensor_core_towers():
     """``mlp_backend = "tcgen05+train"``: the drop-in training step with the towers in bf16 mixed precision — loss within
     2 % of the fp32 towers, gradients of towers, laterals and inputs in the same direction."""

@@ -21,7 +21,7 @@ def step():
     loss.backward()
 for _ in range(3): step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:28]
@@ -30,3 +30,11 @@ print(f"total device ms per step ~ {tot:.2f}")
 for e in rows:
     if e.device_time_total > 0:
         print(f"{e.device_time_total / 3e3:8.3f} ms  x{e.count // 3:4d}  {e.key[:110]}")
+
+# second view: ATen ops by input shape (SELF device time only, so nested ops are not counted twice): the torch "glue"
+# between the head's own kernels
+print("\n# self device time by (op, input shapes)")
+rows = sorted(prof.key_averages(group_by_input_shape=True), key=lambda e: -e.self_device_time_total)[:45]
+for e in rows:
+    if e.self_device_time_total > 0:
+        print(f"{e.self_device_time_total / 3e3:8.3f} ms  x{e.count // 3:4d}  {e.key[:60]:60s} {str(e.input_shapes)[:110]}")
