@@ -523,6 +523,10 @@ SIHL_OD_API int sihl_od_mlp_hidden_train(const void *x_bf16, int64_t m, int chan
                              const float *gamma, const float *beta, float eps, void *y_bf16, float *row_stats,
                              void *stream);
 SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void);
+/* Grid (= rows of partials) the two sihl_od_mlp_hidden_bwd* entries are tuned for: two persistent CTAs per SM, each
+ * streaming its rows through a shared-memory ring (cp.async.bulk + mbarrier).  They accept any partial_rows in
+ * [1, sihl_od_mlp_bwd_partial_rows()] and write exactly that many rows of partials. */
+SIHL_OD_API int sihl_od_mlp_hidden_bwd_partial_rows(void);
 /* bf16 -> fp32 of n contiguous values (n % 8 == 0): the towers' input gradient handed back to the fp32 laterals. */
 SIHL_OD_API int sihl_od_bf16_to_f32(const void *src_bf16, int64_t n, float *dst, void *stream);
 SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void *v_bf16, const void *dy_bf16, const float *row_stats, const float *gamma,

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "sihl_od_mlp_out": (I, [P, I64, I, P, P, I, I, P, P]),
     "sihl_od_mlp_hidden_train": (I, [P, I64, I, P, P, P, P, F, P, P, P]),
     "sihl_od_mlp_bwd_partial_rows": (I, []),
+    "sihl_od_mlp_hidden_bwd_partial_rows": (I, []),
     "sihl_od_bf16_to_f32": (I, [P, I64, P, P]),
     "sihl_od_mlp_hidden_bwd": (I, [P, P, P, P, P, I64, I, P, P, I, P]),
     "sihl_od_lateral_rows": (I, [P, I, I, I64, P, P]),

@@ -33,6 +33,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/sihl_od.h"
 
@@ -623,6 +624,198 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_mlp_hidden_bwd_rows(const __
     }
 }
 
+// The same backward with the rows streamed through a shared-memory ring by the TMA unit (the default; the register-staged
+// kernel above is kept as the A/B, SIHL_MLP_BWD_RING=0).  k_mlp_hidden_bwd_rows holds ~106 registers per thread, so two
+// CTAs = 16 warps fit on an SM and every warp's loads are exposed once per iteration: measured 200 us per [537 600, 256]
+// layer = 4.1 TB/s for 825 MB.  Here the TMA unit keeps kRingStages x 32 rows of v and dy (one contiguous
+// cp.async.bulk each, completion on an mbarrier) in flight per CTA regardless of what the warps hold in registers;
+// the eight warps take 4 rows each per stage (lane = 8 columns, conflict-free LDS.128) and hand the stage back through an
+// `empty` mbarrier; thread 0 refills a stage at the top of the next iteration (a ninth, dedicated producer warp would cap
+// the kernel at 96 registers per thread and spill).  Row statistics (8 B per row) and, RANK1, dout (4 B per row) are plain broadcast loads one
+// stage ahead.  Same arithmetic, and the same row -> (CTA, warp) order for both variants of RANK1, so they stay bit-equal.
+constexpr int kRingRows = 32;
+constexpr int kRingStages = 3;
+constexpr int kRingThreads = kBwdWarps * 32;
+constexpr int kRingArrBytes = kRingRows * kK * 2;                           // 16 KB: 32 rows of one operand
+template <bool RANK1> __host__ __device__ constexpr int ring_stage_bytes() { return RANK1 ? kRingArrBytes : 2 * kRingArrBytes; }
+template <bool RANK1> __host__ __device__ constexpr int ring_smem_bytes() { return kRingStages * ring_stage_bytes<RANK1>() + 2 * kRingStages * 8 + 128; }
+static_assert(kRingStages * kRingArrBytes >= kBwdWarps * 3 * kK * 4, "the final reduction reuses the ring");
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool RANK1>
+__global__ void __launch_bounds__(kRingThreads, 2) k_mlp_hidden_bwd_ring(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dy,
+                                                                          const float* __restrict__ dout, const __nv_bfloat16* __restrict__ w_out,
+                                                                          const float* __restrict__ row_stats, const float* __restrict__ gamma,
+                                                                          const float* __restrict__ beta, long long M, __nv_bfloat16* __restrict__ dv,
+                                                                          float* __restrict__ partials) {
+    extern __shared__ uint8_t ring_raw[];
+    uint8_t* ring = ring_raw + ((128u - (smem_u32(ring_raw) & 127u)) & 127u);
+    constexpr int kStageBytes = ring_stage_bytes<RANK1>();
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kRingStages * kStageBytes);
+    uint64_t* empty = full + kRingStages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = static_cast<int>((M + kRingRows - 1) / kRingRows);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRingStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kBwdWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int c0 = lane * 8;
+    uint64_t acc_g2[4], acc_b2[4], acc_v2[4];                    // columns (c0 + 2q, c0 + 2q + 1)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc_g2[q] = acc_b2[q] = acc_v2[q] = 0ull;
+
+    auto issue = [&](int stage, int c) {                         // thread 0 only
+        const long long row0 = static_cast<long long>(c) * kRingRows;
+        const uint32_t bytes = static_cast<uint32_t>((M - row0 < kRingRows ? M - row0 : kRingRows) * kK * 2);
+        mbar_expect_tx(&full[stage], RANK1 ? bytes : 2 * bytes);
+        bulk_g2s(ring + stage * kStageBytes, v + row0 * kK, bytes, &full[stage]);
+        if constexpr (!RANK1) bulk_g2s(ring + stage * kStageBytes + kRingArrBytes, dy + row0 * kK, bytes, &full[stage]);
+    };
+    if (threadIdx.x == 0)
+        for (int st0 = 0; st0 < kRingStages; ++st0) {
+            const long long c = static_cast<long long>(blockIdx.x) + static_cast<long long>(st0) * gridDim.x;
+            if (c < n_chunks) issue(st0, static_cast<int>(c));
+        }
+    {
+        // ===== consumers: warp w owns rows 4w .. 4w+3 of every stage =====
+        constexpr int kWarpRows = kRingRows / kBwdWarps;         // 4
+        uint64_t g2[4], be2[4], wo2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            g2[q] = pack2f(gamma[c0 + 2 * q], gamma[c0 + 2 * q + 1]);
+            be2[q] = pack2f(beta[c0 + 2 * q], beta[c0 + 2 * q + 1]);
+            wo2[q] = RANK1 ? pack2f(__bfloat162float(w_out[c0 + 2 * q]), __bfloat162float(w_out[c0 + 2 * q + 1])) : 0ull;
+        }
+        float2 st_next[kWarpRows];
+        float dc_next[kWarpRows];
+        auto load_side = [&](int c) {                           // broadcast loads (every lane the same address), one stage ahead
+#pragma unroll
+            for (int r = 0; r < kWarpRows; ++r) {
+                const long long row = static_cast<long long>(c) * kRingRows + warp * kWarpRows + r;
+                const bool ok = c < n_chunks && row < M;
+                st_next[r] = ok ? *reinterpret_cast<const float2*>(row_stats + 2 * row) : make_float2(0.f, 0.f);
+                dc_next[r] = (RANK1 && ok) ? bf16_round(dout[row]) : 0.f;
+            }
+        };
+        load_side(blockIdx.x);
+        int s = 0, rs = -1;                                      // rs: the stage consumed last iteration, to be refilled
+        uint32_t ph = 0, rph = 0;
+        for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+            if (threadIdx.x == 0 && rs >= 0) {
+                const long long cn = static_cast<long long>(c) + static_cast<long long>(kRingStages - 1) * gridDim.x;
+                if (cn < n_chunks) {
+                    mbar_wait(&empty[rs], rph, 20);              // all eight warps have read it
+                    issue(rs, static_cast<int>(cn));
+                }
+            }
+            float2 st[kWarpRows];
+            float dcol[kWarpRows];
+#pragma unroll
+            for (int r = 0; r < kWarpRows; ++r) { st[r] = st_next[r]; dcol[r] = dc_next[r]; }
+            load_side(c + static_cast<int>(gridDim.x));
+            mbar_wait(&full[s], ph, 21);
+            const uint8_t* sv = ring + s * kStageBytes + (warp * kWarpRows) * (kK * 2) + lane * 16;
+            const long long row_base = static_cast<long long>(c) * kRingRows + warp * kWarpRows;
+            // two rows at a time, in lockstep: the two rows' arithmetic and their 2 x 2 x 5 reduction shuffles are independent
+            // instruction streams the scheduler can interleave (16 consumer warps per SM: the kernel is bound by issue
+            // latency, not by the 825 MB it moves)
+#pragma unroll
+            for (int r0 = 0; r0 < kWarpRows; r0 += 2) {
+                if (row_base + r0 >= M) break;                   // warp-uniform: both rows past M
+                // packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: columns 2q, 2q+1 per instruction), as in the forward epilogue
+                uint64_t n[2][4], dn[2][4], s1[2] = {0ull, 0ull}, s2[2] = {0ull, 0ull};
+                bool live[2];
+                const uint64_t half2 = pack2f(0.5f, 0.5f), one2 = pack2f(1.f, 1.f);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = r0 + h;
+                    live[h] = row_base + r < M;                  // a row past M holds stale shared memory: contributes exact zeros
+                    const uint4 v4 = *reinterpret_cast<const uint4*>(sv + r * (kK * 2));
+                    uint4 d4 = make_uint4(0, 0, 0, 0);
+                    if constexpr (!RANK1) d4 = *reinterpret_cast<const uint4*>(sv + kRingArrBytes + r * (kK * 2));
+                    const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+                    const uint64_t mean2 = pack2f(st[r].x, st[r].x), rstd2 = pack2f(st[r].y, st[r].y), dcol2 = pack2f(dcol[r], dcol[r]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // bf16 -> fp32 is a 16-bit shift: (low half << 16, high half & 0xffff0000)
+                        uint64_t vv = pack2(vw[q] << 16, vw[q] & 0xffff0000u);
+                        uint64_t dd;
+                        if constexpr (RANK1) {
+                            const uint32_t rounded = bf16x2_of(mul2(dcol2, wo2[q]));                  // bf16(bf16(dout) * w_out), like the GEMM
+                            dd = pack2(rounded << 16, rounded & 0xffff0000u);
+                        } else {
+                            dd = pack2(dw[q] << 16, dw[q] & 0xffff0000u);
+                        }
+                        if (!live[h]) { vv = 0ull; dd = 0ull; }
+                        n[h][q] = mul2(sub2(vv, mean2), rstd2);
+                        const uint64_t z = fma2(n[h][q], g2[q], be2[q]);
+                        const uint64_t hz = mul2(z, half2);
+                        const uint64_t sg = fma2(half2, pack2f(tanh_fast(lo_of(hz)), tanh_fast(hi_of(hz))), half2);   // sigmoid(z), one MUFU op each
+                        const uint64_t dz = mul2(dd, mul2(sg, fma2(z, sub2(one2, sg), one2)));                        // dy * SiLU'(z)
+                        acc_g2[q] = fma2(dz, n[h][q], acc_g2[q]);
+                        acc_b2[q] = add2(acc_b2[q], dz);
+                        dn[h][q] = mul2(dz, g2[q]);
+                        s1[h] = add2(s1[h], dn[h][q]);
+                        s2[h] = fma2(dn[h][q], n[h][q], s2[h]);
+                    }
+                }
+                float r1[2], r2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { r1[h] = lo_of(s1[h]) + hi_of(s1[h]); r2[h] = lo_of(s2[h]) + hi_of(s2[h]); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        r1[h] += __shfl_xor_sync(0xffffffffu, r1[h], o);
+                        r2[h] += __shfl_xor_sync(0xffffffffu, r2[h], o);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = r0 + h;
+                    const float a = r1[h] * (1.f / kK), b = r2[h] * (1.f / kK);
+                    const uint64_t a2 = pack2f(a, a), nb2 = pack2f(-b, -b), rstd2 = pack2f(st[r].y, st[r].y);
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint64_t o2 = mul2(rstd2, fma2(n[h][q], nb2, sub2(dn[h][q], a2)));      // rstd (dn - a - n b)
+                        acc_v2[q] = add2(acc_v2[q], o2);
+                        ow[q] = bf16x2_of(o2);
+                    }
+                    if (live[h]) *reinterpret_cast<uint4*>(dv + (row_base + r) * kK + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);               // this warp has read its rows of the stage
+            rs = s; rph = ph;
+            if (++s == kRingStages) { s = 0; ph ^= 1; }
+        }
+    }
+    __syncthreads();                                             // every stage consumed: the ring is free for the reduction
+    float* red = reinterpret_cast<float*>(ring);                 // [warp][3][256]
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<float2*>(&red[(warp * 3 + 0) * kK + c0 + 2 * q]) = make_float2(lo_of(acc_g2[q]), hi_of(acc_g2[q]));
+            *reinterpret_cast<float2*>(&red[(warp * 3 + 1) * kK + c0 + 2 * q]) = make_float2(lo_of(acc_b2[q]), hi_of(acc_b2[q]));
+            *reinterpret_cast<float2*>(&red[(warp * 3 + 2) * kK + c0 + 2 * q]) = make_float2(lo_of(acc_v2[q]), hi_of(acc_v2[q]));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * kK; i += kRingThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdWarps; ++w) t += red[w * 3 * kK + i];
+        partials[static_cast<long long>(blockIdx.x) * 3 * kK + i] = t;
+    }
+}
+
 // bf16 -> fp32 of a contiguous array (the gradient handed back to the fp32 laterals): 16-byte loads, 2 x 16-byte stores.
 __global__ void __launch_bounds__(256) k_bf16_to_f32(const uint4* __restrict__ src, float4* __restrict__ dst, long long n_vec8) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -829,6 +1022,25 @@ int launch_layer(const void* x, long long M, const void* w, const MlpParams& p_i
     return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
 }
 
+// Either kernel writes partials[gridDim.x][3][256]; any partial_rows in [1, 8 x SMs] is a valid grid.
+template <bool RANK1>
+int launch_hidden_bwd(const void* v, const void* dy, const float* dout, const void* w_out, const float* row_stats, const float* gamma,
+                             const float* beta, int64_t M, void* dv, float* partials, int partial_rows, cudaStream_t st) {
+    static const bool use_ring = [] { const char* e = getenv("SIHL_MLP_BWD_RING"); return e == nullptr || atoi(e) != 0; }();
+    if (use_ring) {
+        if (cudaFuncSetAttribute(k_mlp_hidden_bwd_ring<RANK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem_bytes<RANK1>()) != cudaSuccess)
+            return SIHL_OD_ECUDA;
+        k_mlp_hidden_bwd_ring<RANK1><<<partial_rows, kRingThreads, ring_smem_bytes<RANK1>(), st>>>(
+            static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(dy), dout, static_cast<const __nv_bfloat16*>(w_out), row_stats, gamma,
+            beta, M, static_cast<__nv_bfloat16*>(dv), partials);
+    } else {
+        k_mlp_hidden_bwd_rows<RANK1><<<partial_rows, kBwdWarps * 32, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(dy), dout, static_cast<const __nv_bfloat16*>(w_out), row_stats, gamma,
+            beta, M, static_cast<__nv_bfloat16*>(dv), partials);
+    }
+    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -870,31 +1082,29 @@ SIHL_OD_API int sihl_od_bf16_to_f32(const void* src_bf16, int64_t n, float* dst,
 
 SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void) { const int sms = sm_count(); return sms > 0 ? 8 * sms : 0; }
 
+SIHL_OD_API int sihl_od_mlp_hidden_bwd_partial_rows(void) { const int sms = sm_count(); return sms > 0 ? 2 * sms : 0; }
+
 SIHL_OD_API int sihl_od_mlp_hidden_bwd(const void* v_bf16, const void* dy_bf16, const float* row_stats, const float* gamma, const float* beta, int64_t M,
                                        int channels, void* dv_bf16, float* partials, int partial_rows, void* stream) {
-    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows()) return SIHL_OD_EINVAL;
+    if (channels != kK || M < 0 || M > 0x7FFFFF00LL || partial_rows <= 0 || partial_rows > sihl_od_mlp_bwd_partial_rows()) return SIHL_OD_EINVAL;
     if (!partials || !gamma || !beta) return SIHL_OD_EINVAL;
     if (M > 0 && (!v_bf16 || !dy_bf16 || !row_stats || !dv_bf16 || !aligned16(v_bf16) || !aligned16(dy_bf16) || !aligned16(dv_bf16) ||
                   (reinterpret_cast<uintptr_t>(row_stats) & 7u)))
         return SIHL_OD_EINVAL;
-    k_mlp_hidden_bwd_rows<false><<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(v_bf16), static_cast<const __nv_bfloat16*>(dy_bf16), nullptr, nullptr, row_stats, gamma, beta, M,
-        static_cast<__nv_bfloat16*>(dv_bf16), partials);
-    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+    return launch_hidden_bwd<false>(v_bf16, dy_bf16, nullptr, nullptr, row_stats, gamma, beta, M, dv_bf16, partials, partial_rows,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 SIHL_OD_API int sihl_od_mlp_hidden_bwd_rank1(const void* v_bf16, const float* dout, const void* w_out_bf16, const float* row_stats, const float* gamma,
                                              const float* beta, int64_t M, int channels, void* dv_bf16, float* partials, int partial_rows,
                                              void* stream) {
-    if (channels != kK || M < 0 || partial_rows <= 0 || partial_rows != sihl_od_mlp_bwd_partial_rows()) return SIHL_OD_EINVAL;
+    if (channels != kK || M < 0 || M > 0x7FFFFF00LL || partial_rows <= 0 || partial_rows > sihl_od_mlp_bwd_partial_rows()) return SIHL_OD_EINVAL;
     if (!partials || !gamma || !beta || !w_out_bf16) return SIHL_OD_EINVAL;
     if (M > 0 && (!v_bf16 || !dout || !row_stats || !dv_bf16 || !aligned16(v_bf16) || !aligned16(dv_bf16) ||
                   (reinterpret_cast<uintptr_t>(row_stats) & 7u) || (reinterpret_cast<uintptr_t>(dout) & 3u)))
         return SIHL_OD_EINVAL;
-    k_mlp_hidden_bwd_rows<true><<<partial_rows, kBwdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(v_bf16), nullptr, dout, static_cast<const __nv_bfloat16*>(w_out_bf16), row_stats, gamma, beta, M,
-        static_cast<__nv_bfloat16*>(dv_bf16), partials);
-    return cudaGetLastError() == cudaSuccess ? SIHL_OD_OK : SIHL_OD_ECUDA;
+    return launch_hidden_bwd<true>(v_bf16, nullptr, dout, w_out_bf16, row_stats, gamma, beta, M, dv_bf16, partials, partial_rows,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 SIHL_OD_API int sihl_od_mlp_out(const void* x_bf16, int64_t M, int channels, const void* w_bf16, const float* bias, int n_pad, int out_cols,

@@ -910,7 +910,7 @@ def mlp_hidden_bwd(v: Tensor, dy: Tensor, row_stats: Tensor, gamma: Tensor, beta
         raise ValueError(f"mlp_hidden_bwd: v {tuple(v.shape)}, dy {tuple(dy.shape)}, row_stats {tuple(row_stats.shape)}")
     dev = v.device
     with _on(dev):
-        n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
+        n_part = int(_lib().sihl_od_mlp_hidden_bwd_partial_rows())
         dv = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
         partials = torch.empty((n_part, 3, K), dtype=torch.float32, device=dev)
         rc = _lib().sihl_od_mlp_hidden_bwd(_p(v), _p(dy), _p(_req(row_stats, torch.float32, "row_stats", 2)),
@@ -935,7 +935,7 @@ def mlp_hidden_bwd_rank1(v: Tensor, dout: Tensor, w_out: Tensor, row_stats: Tens
                          f"row_stats {tuple(row_stats.shape)}")
     dev = v.device
     with _on(dev):
-        n_part = int(_lib().sihl_od_mlp_bwd_partial_rows())
+        n_part = int(_lib().sihl_od_mlp_hidden_bwd_partial_rows())
         dv = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
         partials = torch.empty((n_part, 3, K), dtype=torch.float32, device=dev)
         rc = _lib().sihl_od_mlp_hidden_bwd_rank1(_p(v), _p(dout), _p(w_out), _p(_req(row_stats, torch.float32, "row_stats", 2)),
