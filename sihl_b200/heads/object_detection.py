@@ -385,9 +385,16 @@ class ObjectDetection(nn.Module):
             st.grad_scale = float(self._world_size())      # DDP averages the gradients of W ranks (see loss_reduction)
 
         flat_feats = self._flat_feats_training(inputs)                                      # ref :151-154
-        loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                         # ref :157
-        iou_preds = self._tower("iou_head", flat_feats).squeeze(2)                          # ref :175
-        o2m_feats = flat_feats.reshape(batch_size * st.A, -1).index_select(0, st.pos_index)  # ref :184 (+ padding rows)
+        if self._use_tcgen05_training(flat_feats) and flat_feats.requires_grad:
+            # one autograd node for the three consumers of the features: its backward is one add + one in-place index_add
+            from ..mlp_tower import _FanOutFn
+            loc_in, iou_in, o2m_feats = _FanOutFn.apply(flat_feats.reshape(batch_size * st.A, -1), st.pos_index)
+            loc_logits = self._tower("loc_head", loc_in).reshape(batch_size, st.A)          # ref :157
+            iou_preds = self._tower("iou_head", iou_in).reshape(batch_size, st.A)           # ref :175
+        else:
+            loc_logits = self._tower("loc_head", flat_feats).squeeze(2)                     # ref :157
+            iou_preds = self._tower("iou_head", flat_feats).squeeze(2)                      # ref :175
+            o2m_feats = flat_feats.reshape(batch_size * st.A, -1).index_select(0, st.pos_index)  # ref :184 (+ padding rows)
         box_raw = self._tower("box_head", o2m_feats)                                        # ref :189
         class_logits = self._tower("cls_head", o2m_feats)                                   # ref :200
         out = _TrainLoss.apply(loc_logits, iou_preds, box_raw, class_logits, st, reduce_sums)
