@@ -521,6 +521,8 @@ SIHL_OD_API int sihl_od_mlp_out(const void *x_bf16, int64_t m, int channels, con
  * products: dx = dv W (sihl_od_lateral_linear with W^T, zero bias) and dW = dv^T x (library GEMM). */
 SIHL_OD_API int sihl_od_mlp_hidden_train(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
                              const float *gamma, const float *beta, float eps, void *y_bf16, float *row_stats,
+                             void *v_bf16 /* optional: bf16 [M,256], the pre-activation, stored by the same epilogue so
+                                             that the backward does not have to recompute it */,
                              void *stream);
 SIHL_OD_API int sihl_od_mlp_bwd_partial_rows(void);
 /* Grid (= rows of partials) the two sihl_od_mlp_hidden_bwd* entries are tuned for: two persistent CTAs per SM, each

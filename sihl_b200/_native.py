@@ -67,7 +67,7 @@ _SIGNATURES = {
     "sihl_od_batched_nms": (I, [P, P, P, P, I, I64, F, P, P, P, P]),
     "sihl_od_mlp_hidden": (I, [P, I64, I, P, P, P, P, F, P, P]),
     "sihl_od_mlp_out": (I, [P, I64, I, P, P, I, I, P, P]),
-    "sihl_od_mlp_hidden_train": (I, [P, I64, I, P, P, P, P, F, P, P, P]),
+    "sihl_od_mlp_hidden_train": (I, [P, I64, I, P, P, P, P, F, P, P, P, P]),
     "sihl_od_mlp_bwd_partial_rows": (I, []),
     "sihl_od_mlp_hidden_bwd_partial_rows": (I, []),
     "sihl_od_bf16_to_f32": (I, [P, I64, P, P]),

@@ -223,6 +223,7 @@ struct MlpParams {
     int out_cols;
     float eps;
     float* row_stats;               // kHidden, optional: [M,2] = (mean, rstd) of every row's LayerNorm, kept for the backward
+    void* pre_out;                  // kHiddenPre: bf16 [M,N] = x W^T + bias, the pre-activation, kept for the backward
     long long rows_per_image;       // kLinear: see the row formula above
     long long out_rows_per_image;
     long long out_row_offset;
@@ -233,12 +234,13 @@ struct MlpParams {
 // MODE kLinear:  bias                    -> bf16 rows of N == 256, row m written at
 //                (m / rows_per_image) * out_rows_per_image + out_row_offset + m % rows_per_image   (the laterals: 1x1 conv
 //                with the BatchNorm folded in, each level landing in its slice of the concatenated [B, A, 256] features)
-constexpr int kHidden = 0, kOutF32 = 1, kLinear = 2;
+// MODE kHiddenPre: kHidden that also stores the pre-activation (bf16) -> the training backward does not recompute it
+constexpr int kHidden = 0, kOutF32 = 1, kLinear = 2, kHiddenPre = 3;
 template <int N, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const MlpParams p) {
     using L = MlpSmem<N>;
-    constexpr bool HIDDEN = MODE == kHidden;
+    constexpr bool HIDDEN = MODE == kHidden || MODE == kHiddenPre;
     constexpr bool WIDE = MODE != kOutF32;                // sixteen epilogue warps, bf16 rows of 256
     static_assert(!WIDE || N == 256, "the wide epilogue is built for 256 output columns");
     constexpr int S = L::kStages;
@@ -344,6 +346,58 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             const long long grow = static_cast<long long>(tile) * kBlockM + row;
             if constexpr (WIDE) {
                 const int cbase = part * kPartCols;
+                // store: a thread holds one 128-byte line of its row as four 32-byte pieces.  Written as they are, a
+                // warp-wide 32-byte store touches 32 different lines (32 L1 wavefronts); a 4 x 4 transpose of the pieces
+                // inside every lane quad (two butterfly steps of SHFL.BFLY) makes lanes 4g..4g+3 hold the four pieces
+                // of ONE row, so each store instruction writes 8 complete lines.
+                auto store_rows = [&](uint32_t (&pk)[kPartCols / 2], __nv_bfloat16* out, bool mapped) {
+                    const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                        for (int j = 0; j < 4; j += 2) {                   // step 1: partner lane ^ 1 swaps pieces (j, j+1)
+                            const uint32_t send = b0 ? pk[8 * j + r] : pk[8 * (j + 1) + r];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                            if (b0) pk[8 * j + r] = recv; else pk[8 * (j + 1) + r] = recv;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {                      // step 2: partner lane ^ 2 swaps pieces (j, j+2)
+                            const uint32_t send = b1 ? pk[8 * j + r] : pk[8 * (j + 2) + r];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                            if (b1) pk[8 * j + r] = recv; else pk[8 * (j + 2) + r] = recv;
+                        }
+                    }
+                    // now piece k of this lane = columns [16 q, 16 q + 16) (q = lane & 3) of row (lane & ~3) + k
+                    const long long qrow = static_cast<long long>(tile) * kBlockM + quarter * 32 + (lane & ~3);
+                    __nv_bfloat16* obase = out + cbase + 16 * (lane & 3);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const long long m = qrow + k;
+                        if (m < p.M) {
+                            long long orow_k = m;
+                            if (mapped) {
+                                const long long img = m / p.rows_per_image;
+                                orow_k = img * p.out_rows_per_image + p.out_row_offset + (m - img * p.rows_per_image);
+                            }
+                            st_global_256(obase + orow_k * N, pk + 8 * k);
+                        }
+                    }
+                };
+                if constexpr (MODE == kHiddenPre) {
+                    // first pass over the accumulator: v = bf16(x W^T + bias), the pre-activation the backward needs.  The
+                    // accumulator is read from TMEM again below rather than kept: 64 more live registers would spill, the
+                    // second tcgen05.ld costs a few hundred cycles, and the TMEM stage is not needed before tile t + 2.
+                    uint32_t v0[kPartCols];
+                    tmem_ld64(taddr + cbase, v0);
+                    uint32_t pk0[kPartCols / 2];
+#pragma unroll
+                    for (int j = 0; j < kPartCols; j += 4) {
+                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sBias[cbase + j]);
+                        pk0[j >> 1] = bf16x2_of(add2(pack2(v0[j], v0[j + 1]), b4.x));
+                        pk0[(j >> 1) + 1] = bf16x2_of(add2(pack2(v0[j + 2], v0[j + 3]), b4.y));
+                    }
+                    store_rows(pk0, reinterpret_cast<__nv_bfloat16*>(p.pre_out), false);
+                }
                 uint32_t v[kPartCols];
                 tmem_ld64(taddr + cbase, v);
                 tc_fence_before();
@@ -417,43 +471,7 @@ k_mlp_layer(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
                     for (int j = 0; j < kPartCols / 2; ++j) packed[j] = bf16x2_of(x[j]);       // kLinear: bias only
                 }
                 if (warp == 2 && lane == 0) MLP_TRACE(t, 13);          // 13: row computed
-                // store: a thread holds one 128-byte line of its row as four 32-byte pieces.  Written as they are, a
-                // warp-wide 32-byte store touches 32 different lines (32 L1 wavefronts); a 4 x 4 transpose of the pieces
-                // inside every lane quad (two butterfly steps of SHFL.BFLY) makes lanes 4g..4g+3 hold the four pieces
-                // of ONE row, so each store instruction writes 8 complete lines.
-                {
-                    const bool b0 = lane & 1, b1 = lane & 2;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-                        for (int j = 0; j < 4; j += 2) {                   // step 1: partner lane ^ 1 swaps pieces (j, j+1)
-                            const uint32_t send = b0 ? packed[8 * j + r] : packed[8 * (j + 1) + r];
-                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                            if (b0) packed[8 * j + r] = recv; else packed[8 * (j + 1) + r] = recv;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {                      // step 2: partner lane ^ 2 swaps pieces (j, j+2)
-                            const uint32_t send = b1 ? packed[8 * j + r] : packed[8 * (j + 2) + r];
-                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
-                            if (b1) packed[8 * j + r] = recv; else packed[8 * (j + 2) + r] = recv;
-                        }
-                    }
-                    // now piece k of this lane = columns [16 q, 16 q + 16) (q = lane & 3) of row (lane & ~3) + k
-                    const long long qrow = static_cast<long long>(tile) * kBlockM + quarter * 32 + (lane & ~3);
-                    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + cbase + 16 * (lane & 3);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const long long m = qrow + k;
-                        if (m < p.M) {
-                            long long orow_k = m;
-                            if constexpr (MODE == kLinear) {
-                                const long long img = m / p.rows_per_image;
-                                orow_k = img * p.out_rows_per_image + p.out_row_offset + (m - img * p.rows_per_image);
-                            }
-                            st_global_256(obase + orow_k * N, packed + 8 * k);
-                        }
-                    }
-                }
+                store_rows(packed, reinterpret_cast<__nv_bfloat16*>(p.out), MODE == kLinear);
                 if (warp == 2 && lane == 0) MLP_TRACE(t, 14);          // 14: stores issued
                 continue;                                              // t_empty was signalled right after the load
             } else {
@@ -1059,14 +1077,15 @@ SIHL_OD_API int sihl_od_mlp_hidden(const void* x_bf16, int64_t M, int channels, 
 }
 
 SIHL_OD_API int sihl_od_mlp_hidden_train(const void* x_bf16, int64_t M, int channels, const void* w_bf16, const float* bias, const float* gamma,
-                                         const float* beta, float eps, void* y_bf16, float* row_stats, void* stream) {
+                                         const float* beta, float eps, void* y_bf16, float* row_stats, void* v_bf16, void* stream) {
     if (channels != kK || M < 0 || M > 0x7FFFFF00LL) return SIHL_OD_EINVAL;
     if (M == 0) return SIHL_OD_OK;
     if (!x_bf16 || !w_bf16 || !bias || !gamma || !beta || !y_bf16 || !row_stats || !aligned16(x_bf16) || !aligned16(w_bf16) || !aligned16(y_bf16) ||
-        (reinterpret_cast<uintptr_t>(row_stats) & 7u))
+        (reinterpret_cast<uintptr_t>(row_stats) & 7u) || !aligned16(v_bf16))
         return SIHL_OD_EINVAL;
     MlpParams p{};
-    p.bias = bias; p.gamma = gamma; p.beta = beta; p.out = y_bf16; p.eps = eps; p.out_cols = kK; p.row_stats = row_stats;
+    p.bias = bias; p.gamma = gamma; p.beta = beta; p.out = y_bf16; p.eps = eps; p.out_cols = kK; p.row_stats = row_stats; p.pre_out = v_bf16;
+    if (v_bf16 != nullptr) return launch_layer<256, kHiddenPre>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
     return launch_layer<256, kHidden>(x_bf16, M, w_bf16, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -17,7 +17,14 @@ from typing import List, Optional, Tuple
 import torch
 from torch import Tensor, nn
 
+import os
+
 from . import ops
+
+# Training: keep every hidden layer's pre-activation (bf16 [M,256], written by the forward's epilogue) instead of
+# recomputing it with one more GEMM pass in the backward: +512 B per location and layer of activation memory (2.2 GB at
+# 640^2, batch 64, for the two dense towers) for one HBM round trip less per layer.  SIHL_MLP_SAVE_PRE=0 recomputes.
+SAVE_PRE = os.environ.get("SIHL_MLP_SAVE_PRE", "1") != "0"
 
 
 class PackedTower:
@@ -109,16 +116,20 @@ class _HiddenLayerFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, eps):
         w16 = weight.detach().to(torch.bfloat16).contiguous()
         b32, g32, be32 = bias.detach().float().contiguous(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        y, stats = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps)
-        ctx.save_for_backward(x, w16, b32, g32, be32, stats)
+        if SAVE_PRE:
+            y, stats, v = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps, save_pre=True)
+            ctx.save_for_backward(x, w16, b32, g32, be32, stats, v)
+        else:
+            y, stats = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps)
+            ctx.save_for_backward(x, w16, b32, g32, be32, stats)
         ctx.param_dtypes = (weight.dtype, bias.dtype, gamma.dtype, beta.dtype)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w16, b32, g32, be32, stats = ctx.saved_tensors
+        x, w16, b32, g32, be32, stats, *pre = ctx.saved_tensors
         dy = dy.to(torch.bfloat16).contiguous()
-        v = ops.linear_bf16(x, w16, b32)                                     # recompute the pre-activation
+        v = pre[0] if pre else ops.linear_bf16(x, w16, b32)                  # kept by the forward, or recomputed
         dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd(v, dy, stats, g32, be32)
         del v
         dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None   # dv W
@@ -162,22 +173,25 @@ class _LastHiddenOutFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, eps, w_out, b_out):
         w16 = weight.detach().to(torch.bfloat16).contiguous()
         b32, g32, be32 = bias.detach().float().contiguous(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        y, stats = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps)
+        if SAVE_PRE:
+            y, stats, v = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps, save_pre=True)
+        else:
+            (y, stats), v = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps), None
         n_pad = ops.mlp_out_pad(1)
         wo = torch.zeros((n_pad, ops.MLP_CHANNELS), dtype=torch.bfloat16, device=x.device)
         wo[:1] = w_out.detach().to(torch.bfloat16)
         bo = torch.zeros((n_pad,), dtype=torch.float32, device=x.device)
         bo[:1] = b_out.detach().float()
-        ctx.save_for_backward(x, w16, b32, g32, be32, stats, y, wo)
+        ctx.save_for_backward(x, w16, b32, g32, be32, stats, y, wo, *([v] if v is not None else []))
         ctx.param_dtypes = (weight.dtype, bias.dtype, gamma.dtype, beta.dtype, w_out.dtype, b_out.dtype)
         return ops.mlp_out(y, wo, bo, 1)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w16, b32, g32, be32, stats, y, wo = ctx.saved_tensors
+        x, w16, b32, g32, be32, stats, y, wo, *pre = ctx.saved_tensors
         dcol = dout.reshape(-1).float().contiguous()                          # [M] fp32
         d16 = dcol.to(torch.bfloat16)
-        v = ops.linear_bf16(x, w16, b32)                                     # recompute the pre-activation
+        v = pre[0] if pre else ops.linear_bf16(x, w16, b32)                  # kept by the forward, or recomputed
         dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd_rank1(v, dcol, wo[0], stats, g32, be32)
         del v
         dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None

@@ -882,8 +882,11 @@ def linear_bf16(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     return out[0]
 
 
-def mlp_hidden_train(x: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
-    """:func:`mlp_hidden` that also returns every row's LayerNorm statistics [M,2] = (mean, rstd) for the backward."""
+def mlp_hidden_train(x: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5,
+                     save_pre: bool = False):
+    """:func:`mlp_hidden` that also returns every row's LayerNorm statistics [M,2] = (mean, rstd) for the backward and,
+    with ``save_pre``, the pre-activation ``v = x W^T + b`` (bf16 [M,256], written by the same epilogue) as a third
+    result, so that the backward does not recompute it."""
     x = _req(x, torch.bfloat16, "x", 2)
     weight = _req(weight, torch.bfloat16, "weight", 2)
     M, K = x.shape
@@ -893,11 +896,12 @@ def mlp_hidden_train(x: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, bet
     with _on(dev):
         y = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
         stats = torch.empty((M, 2), dtype=torch.float32, device=dev)
+        v = torch.empty((M, K), dtype=torch.bfloat16, device=dev) if save_pre else None
         rc = _lib().sihl_od_mlp_hidden_train(_p(x), M, K, _p(weight), _p(_req(bias, torch.float32, "bias", 1)),
                                              _p(_req(gamma, torch.float32, "gamma", 1)), _p(_req(beta, torch.float32, "beta", 1)),
-                                             float(eps), _p(y), _p(stats), _stream(dev))
+                                             float(eps), _p(y), _p(stats), _p(v), _stream(dev))
     _native.check(rc, "sihl_od_mlp_hidden_train")
-    return y, stats
+    return (y, stats, v) if save_pre else (y, stats)
 
 
 def mlp_hidden_bwd(v: Tensor, dy: Tensor, row_stats: Tensor, gamma: Tensor, beta: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

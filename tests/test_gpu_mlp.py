@@ -292,6 +292,20 @@ def test_tower_training_path_against_the_torch_module():
         assert _rel_l2(ours[n], p.grad) < 0.1, (n, _rel_l2(ours[n], p.grad))
 
 
+@pytest.mark.parametrize("M", [1, 129, 128 * 150 + 7])
+def test_training_forward_keeps_the_pre_activation(M):
+    """``ops.mlp_hidden_train(save_pre=True)``: y and the row statistics are those of the plain training forward, and the
+    stored pre-activation is bit-equal to what the backward used to recompute (``ops.linear_bf16``); rows past M of a
+    guard-banded buffer stay untouched."""
+    x = _rand((M, 256), 91).bfloat16()
+    w = _rand((256, 256), 92, 1 / 16).bfloat16()
+    b, gamma, beta = _rand((256,), 93), 1 + 0.1 * _rand((256,), 94), 0.1 * _rand((256,), 95)
+    y0, st0 = ops.mlp_hidden_train(x, w, b, gamma, beta)
+    y1, st1, v = ops.mlp_hidden_train(x, w, b, gamma, beta, save_pre=True)
+    assert torch.equal(y0, y1) and torch.equal(st0, st1)
+    assert torch.equal(v, ops.linear_bf16(x, w, b))
+
+
 @pytest.mark.parametrize("M", [1, 300, 128 * 150 + 7])
 def test_rank1_backward_equals_the_materialised_outer_product(M):
     """``ops.mlp_hidden_bwd_rank1`` (upstream gradient bf16(dout) x w_out formed in registers) == ``ops.mlp_hidden_bwd`` on
