@@ -514,11 +514,12 @@ SIHL_OD_API int sihl_od_mlp_out(const void *x_bf16, int64_t m, int channels, con
                     int n_pad, int out_cols, float *y, void *stream);
 
 /* Training path of a hidden layer (bf16 mixed precision, like autocast): the forward additionally stores every row's
- * LayerNorm statistics, row_stats [M,2] = (mean, rstd); the backward of LayerNorm + SiLU is one HBM-bound kernel over
- * rows: v = x W^T + bias (the pre-activation, recomputed by the caller with sihl_od_lateral_linear(rows = x, identity row
- * map)), dy -> dv [M,256] bf16 and per-CTA partial column sums partials [partial_rows,3,256] fp32 = (d gamma, d beta,
- * d bias) to be summed over partial_rows = sihl_od_mlp_bwd_partial_rows().  The two gradient GEMMs are plain matrix
- * products: dx = dv W (sihl_od_lateral_linear with W^T, zero bias) and dW = dv^T x (library GEMM). */
+ * LayerNorm statistics, row_stats [M,2] = (mean, rstd), and — when v_bf16 is given — the pre-activation v = x W^T + bias
+ * (bf16 [M,256]; otherwise the caller recomputes it with sihl_od_lateral_linear(rows = x, identity row map)).  The backward
+ * of LayerNorm + SiLU is one kernel over rows (v, dy streamed through a shared-memory ring by cp.async.bulk): v, dy ->
+ * dv [M,256] bf16 and per-CTA partial column sums partials [partial_rows,3,256] fp32 = (d gamma, d beta, d bias), to be
+ * summed over partial_rows (sihl_od_mlp_hidden_bwd_partial_rows() is the grid the kernel is tuned for).  The two gradient
+ * GEMMs are plain matrix products: dx = dv W (sihl_od_lateral_linear with W^T, zero bias) and dW = dv^T x (library GEMM). */
 SIHL_OD_API int sihl_od_mlp_hidden_train(const void *x_bf16, int64_t m, int channels, const void *w_bf16, const float *bias,
                              const float *gamma, const float *beta, float eps, void *y_bf16, float *row_stats,
                              void *v_bf16 /* optional: bf16 [M,256], the pre-activation, stored by the same epilogue so

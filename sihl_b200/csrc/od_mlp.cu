@@ -546,8 +546,8 @@ __global__ void __launch_bounds__(256) k_nchw_to_rows_bf16(const float* __restri
 // Backward of LayerNorm + SiLU for the towers' training path: one warp per row, lane = 8 columns.
 //   n = (v - mean) rstd, z = n gamma + beta, dz = dy * SiLU'(z), dn = dz gamma,
 //   dv = rstd (dn - mean_j(dn) - n mean_j(dn n));  column sums of dz n, dz, dv = d gamma, d beta, d bias
-// v is the layer's pre-activation (x W^T + b, recomputed by the linear mode of the layer kernel, bf16), (mean, rstd) come
-// from the forward.  Every CTA writes its partial column sums to partials[blockIdx.x][3][256] (summed by the caller:
+// v is the layer's pre-activation (x W^T + b in bf16: kept by the forward, MODE kHiddenPre, or recomputed by the linear mode
+// of the layer kernel), (mean, rstd) come from the forward.  Every CTA writes its partial column sums to partials[blockIdx.x][3][256] (summed by the caller:
 // deterministic, no atomics).  HBM-bound: 2 x 512 B read + 512 B written per row.
 //
 // RANK1: the layer is the tower's LAST hidden layer and the Linear behind it has ONE output (the location and the IoU

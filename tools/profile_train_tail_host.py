@@ -31,6 +31,20 @@ def fwd_bwd():
     out = t._TrainLoss.apply(l, i, b, c, st, None)
     out[4].backward()
 print("leaves + loss fwd + bwd", piece(fwd_bwd))
+# the floor torch itself sets: forward + backward() of a trivial custom Function on four CUDA leaves of the same shapes
+# (no kernels of ours at all): what one `loss.backward()` call costs before it reaches anybody's backward
+class _Nop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, c, d):
+        ctx.save_for_backward(a, b, c, d)
+        return a.new_zeros(5)
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved_tensors
+def nop_fwd_bwd():
+    l, i, b, c = leaves()
+    _Nop.apply(l, i, b, c)[4].backward()
+print("torch floor: 4 leaves + no-op Function + backward()", piece(nop_fwd_bwd))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(300): t.ours()
