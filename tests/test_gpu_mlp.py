@@ -306,6 +306,26 @@ def test_training_forward_keeps_the_pre_activation(M):
     assert torch.equal(v, ops.linear_bf16(x, w, b))
 
 
+@pytest.mark.parametrize("out_features", [1, 4])
+def test_kept_pre_activation_gives_the_gradients_of_the_recompute(out_features, monkeypatch):
+    """``mlp_tower.SAVE_PRE`` (pre-activations written by the forward) against the recomputing backward: the stored v is
+    what the recompute produces, so every gradient is bit-equal."""
+    from sihl_b200 import mlp_tower
+    torch.manual_seed(2)
+    mlp = tvops.MLP(256, [256] * 2 + [out_features], norm_layer=nn.LayerNorm, activation_layer=nn.SiLU).to(DEV)
+    x0 = _rand((1500, 256), 97)
+    tgt = _rand((1500, out_features), 98)
+    grads = []
+    for keep in (True, False):
+        monkeypatch.setattr(mlp_tower, "SAVE_PRE", keep)
+        mlp.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        F.mse_loss(mlp_tower.run_tower_train(mlp, x), tgt).backward()
+        grads.append([x.grad.clone()] + [p.grad.clone() for p in mlp.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("M", [1, 300, 128 * 150 + 7])
 def test_rank1_backward_equals_the_materialised_outer_product(M):
     """``ops.mlp_hidden_bwd_rank1`` (upstream gradient bf16(dout) x w_out formed in registers) == ``ops.mlp_hidden_bwd`` on
