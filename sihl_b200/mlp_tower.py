@@ -27,6 +27,23 @@ from . import ops
 SAVE_PRE = os.environ.get("SIHL_MLP_SAVE_PRE", "1") != "0"
 
 
+def _as(t: Tensor, dtype) -> Tensor:
+    """``t.to(dtype)`` without the dispatcher round trip when there is nothing to convert (the usual case: fp32 parameters)."""
+    return t if t.dtype == dtype else t.to(dtype)
+
+
+def _f32(t: Tensor) -> Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _bf16(t: Tensor) -> Tensor:
+    t = t.detach().to(torch.bfloat16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class PackedTower:
     """bf16 / fp32 copies of one tower's parameters in the layout the kernels take."""
 
@@ -114,8 +131,7 @@ class _HiddenLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, eps):
-        w16 = weight.detach().to(torch.bfloat16).contiguous()
-        b32, g32, be32 = bias.detach().float().contiguous(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        w16, b32, g32, be32 = _bf16(weight), _f32(bias), _f32(gamma), _f32(beta)
         if SAVE_PRE:
             y, stats, v = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps, save_pre=True)
             ctx.save_for_backward(x, w16, b32, g32, be32, stats, v)
@@ -128,14 +144,15 @@ class _HiddenLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w16, b32, g32, be32, stats, *pre = ctx.saved_tensors
-        dy = dy.to(torch.bfloat16).contiguous()
+        dy = _as(dy, torch.bfloat16)
+        dy = dy if dy.is_contiguous() else dy.contiguous()
         v = pre[0] if pre else ops.linear_bf16(x, w16, b32)                  # kept by the forward, or recomputed
         dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd(v, dy, stats, g32, be32)
         del v
-        dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None   # dv W
+        dx = ops.linear_bf16(dv, w16.t().contiguous(), ops.zero_bias(dv.device)) if ctx.needs_input_grad[0] else None   # dv W
         dw = torch.mm(dv.t(), x, out_dtype=torch.float32)                    # [out, in], fp32 out of the bf16 GEMM
         wd, bd, gd, bed = ctx.param_dtypes
-        return dx, dw.to(wd), dbias.to(bd), dgamma.to(gd), dbeta.to(bed), None
+        return dx, _as(dw, wd), _as(dbias, bd), _as(dgamma, gd), _as(dbeta, bed), None
 
 
 class _OutLayerFn(torch.autograd.Function):
@@ -171,8 +188,7 @@ class _LastHiddenOutFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, eps, w_out, b_out):
-        w16 = weight.detach().to(torch.bfloat16).contiguous()
-        b32, g32, be32 = bias.detach().float().contiguous(), gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        w16, b32, g32, be32 = _bf16(weight), _f32(bias), _f32(gamma), _f32(beta)
         if SAVE_PRE:
             y, stats, v = ops.mlp_hidden_train(x, w16, b32, g32, be32, eps, save_pre=True)
         else:
@@ -194,11 +210,11 @@ class _LastHiddenOutFn(torch.autograd.Function):
         v = pre[0] if pre else ops.linear_bf16(x, w16, b32)                  # kept by the forward, or recomputed
         dv, dgamma, dbeta, dbias = ops.mlp_hidden_bwd_rank1(v, dcol, wo[0], stats, g32, be32)
         del v
-        dx = ops.linear_bf16(dv, w16.t().contiguous(), torch.zeros_like(b32)) if ctx.needs_input_grad[0] else None
+        dx = ops.linear_bf16(dv, w16.t().contiguous(), ops.zero_bias(dv.device)) if ctx.needs_input_grad[0] else None
         dw = torch.mm(dv.t(), x, out_dtype=torch.float32)
         dw_out = torch.mm(d16[None, :], y, out_dtype=torch.float32)          # [1, 256]
         wd, bd, gd, bed, wod, bod = ctx.param_dtypes
-        return dx, dw.to(wd), dbias.to(bd), dgamma.to(gd), dbeta.to(bed), None, dw_out.to(wod), dcol.sum(0, keepdim=True).to(bod)
+        return dx, _as(dw, wd), _as(dbias, bd), _as(dgamma, gd), _as(dbeta, bed), None, _as(dw_out, wod), _as(dcol.sum(0, keepdim=True), bod)
 
 
 class _FanOutFn(torch.autograd.Function):
@@ -320,7 +336,7 @@ class _LateralsTrainFn(torch.autograd.Function):
             del n
             dx = None
             if ctx.needs_input_grad[1 + 4 * lvl]:
-                dx = ops.rows_to_nchw(ops.linear_bf16(dy, w16.t().contiguous(), torch.zeros_like(mean)), B, h, w)
+                dx = ops.rows_to_nchw(ops.linear_bf16(dy, w16.t().contiguous(), ops.zero_bias(dy.device)), B, h, w)
             dw = torch.mm(dy.t(), rows, out_dtype=torch.float32)[:, :, None, None]
             wd, gd, bd = ctx.dtypes[lvl]
             grads += [dx, dw.to(wd), dgamma.to(gd), dbeta.to(bd)]

@@ -78,10 +78,16 @@ def test_cabi_training_and_lateral_entries_reject_bad_arguments():
     lib = _native.load()
     buf = (ctypes.c_char * 64)()
     p = ctypes.addressof(buf)
-    assert lib.sihl_od_mlp_hidden_train(p, 128, 256, p, p, p, p, 1e-5, p, None, None) == 1        # row_stats missing
-    assert lib.sihl_od_mlp_hidden_train(p, 128, 64, p, p, p, p, 1e-5, p, p, None) == 1
-    assert lib.sihl_od_mlp_hidden_train(None, 0, 256, None, None, None, None, 1e-5, None, None, None) == 0
-    assert lib.sihl_od_mlp_hidden_bwd(p, p, p, p, p, 128, 256, p, p, 3, None) == 1                 # wrong number of partial rows
+    assert lib.sihl_od_mlp_hidden_train(p, 128, 256, p, p, p, p, 1e-5, p, None, None, None) == 1  # row_stats missing
+    assert lib.sihl_od_mlp_hidden_train(p, 128, 64, p, p, p, p, 1e-5, p, p, None, None) == 1
+    assert lib.sihl_od_mlp_hidden_train(p, 128, 256, p, p, p, p, 1e-5, p, p, p + 2, None) == 1     # v_bf16 misaligned
+    assert lib.sihl_od_mlp_hidden_train(None, 0, 256, None, None, None, None, 1e-5, None, None, None, None) == 0
+    assert lib.sihl_od_mlp_hidden_bwd(p, p, p, p, p, 128, 256, p, p, 0, None) == 1                 # no partial rows
+    assert lib.sihl_od_mlp_hidden_bwd_rank1(p, p, None, p, p, p, 128, 256, p, p, 8, None) == 1     # w_out missing
+    assert lib.sihl_od_bn_bwd_colsums_map(p, 64, 100, 50, p, 128, 256, p, 8, None) == 1            # slice leaves the image (or no GPU)
+    assert lib.sihl_od_bn_bwd_apply_map(p, 64, 100, 50, p, p, p, p, 128, 256, p, None) == 1
+    assert lib.sihl_od_bn_bwd_apply_map(None, 1, 1, 0, None, None, None, None, 0, 256, None, None) == 0
+    assert lib.sihl_od_rows_colsum(p, 128, 128, p, 8, None) == 1                                   # channels
     assert lib.sihl_od_mlp_hidden_bwd(p, p, p, p, p, 128, 128, p, p, 8, None) == 1
     assert lib.sihl_od_bf16_to_f32(p, 12, p, None) == 1                                            # n % 8
     assert lib.sihl_od_bf16_to_f32(p + 2, 16, p, None) == 1                                        # alignment
