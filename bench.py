@@ -46,6 +46,9 @@ WORKLOADS = {
     "cfg1": dict(height=640, width=640, batch=64, classes=80, gt=100, k=100, desc="ObjectDetection head 640x640 b64 P3-P7 C80 G100"),
     "cfg0": dict(height=320, width=320, batch=2, classes=10, gt=20, k=100, desc="examples/object_detection.py head 320x320 b2 C10 G20"),
     "crowd": dict(height=1024, width=1024, batch=8, classes=80, gt=500, k=100, desc="dense-crowd 1024x1024 b8 C80 G500"),
+    # the same geometry at a batch whose kernels are long enough (4 x 57 MB per scan) that launch + ramp + tail stop dominating:
+    # separates "the kernel does not stream at this geometry" from "a 10 us kernel pays 4 us of fixed cost" 
+    "crowd32": dict(height=1024, width=1024, batch=32, classes=80, gt=500, k=100, desc="dense-crowd 1024x1024 b32 C80 G500"),
 }
 SCORE_THR, IOU_THR, TOPK = 0.05, 0.5, 9
 HBM_FALLBACK_GBS = 6650.0
