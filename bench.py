@@ -728,7 +728,45 @@ def mlp_towers_line(M, C, dev):
     tower.eval()
     del xs, ys, xf, xt, gy
     torch.cuda.empty_cache()
+    line["head_training_step"] = head_training_step_line(C, dev, timeit)
+    line["note"] = ("row N4, extra line: the step in FRONT of the path (laterals + four MLP towers) on the tensor cores, inference "
+                    "and (opt-in, bf16 mixed precision) training; the path's own kernels have no dense contraction")
     return line
+
+
+def head_training_step_line(C, dev, timeit):
+    """The drop-in head's whole ``training_step`` + ``backward`` (ref object_detection.py:124-217 with its laterals and four
+    towers, then the hot path) at cfg1's batch on levels 3-5 of a 640x640 input: ``mlp_backend = "tcgen05+train"`` (laterals
+    and towers on the tensor cores, bf16 mixed precision) against the identical module with the torch towers in fp32."""
+    import torch
+    from sihl_b200 import synth
+    from sihl_b200.heads import ObjectDetection
+    B, size = 64, 640
+    torch.manual_seed(0)
+    model = ObjectDetection(in_channels=[3, 64, 128, 256, 256, 256], num_classes=C, num_channels=256, num_layers=4).to(dev).train()
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    inputs = [torch.randn((B, c, size // 2 ** l, size // 2 ** l), generator=g, device=dev) if l >= 3 or l == 0
+              else torch.empty((B, c, 1, 1), device=dev) for l, c in enumerate(model.in_channels)]
+    gt = synth.gt_batch_np(3, B, size, size, C, 100)
+    tb = [torch.from_numpy(b_).to(dev) for b_, _ in gt.per_image()]
+    tc = [torch.from_numpy(c_).to(dev) for _, c_ in gt.per_image()]
+    out = {"batch": B, "image": size, "levels": "3-5", "locations": B * 8400, "gt_per_image": 100,
+           "what": "laterals + four towers + assign + losses, forward and backward, wall clock per step (CUDA events)"}
+
+    def step(i):
+        model.zero_grad(set_to_none=True)
+        loss, _ = model.training_step(inputs, classes=tc, boxes=tb)
+        loss.backward()
+        return loss
+    for backend, iters in (("tcgen05+train", 6), ("torch", 2)):
+        model.mlp_backend = backend
+        out[backend.replace("+", "_") + "_ms"] = timeit(step, iters, 2)
+        out[backend.replace("+", "_") + "_loss"] = float(step(0).detach())
+    out["speedup"] = out["torch_ms"] / out["tcgen05_train_ms"]
+    del model, inputs
+    torch.cuda.empty_cache()
+    return out
 
 
 def train_tail_with_backward(w, x, levels, dev, reps=300):
