@@ -108,3 +108,24 @@ def test_training_backend_is_only_used_when_gradients_are_recorded():
     assert model._use_tcgen05(x) is False
     out = model._tower("loc_head", x)                                  # -> the torch module
     assert out.shape == (1, 4, 1) and out.requires_grad
+
+
+def test_fan_out_node_matches_plain_autograd():
+    """``_FanOutFn`` (one autograd node for the three consumers of the tower features) against what autograd does by itself:
+    same outputs, same input gradient — including repeated index entries (the padding rows repeat row 0) and consumers
+    that receive no gradient."""
+    from sihl_b200.mlp_tower import _FanOutFn
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn((50, 8), generator=g, dtype=torch.float64)
+    idx = torch.tensor([3, 7, 49, 0, 0, 0], dtype=torch.int32)
+    wa, wb, wr = (torch.randn(s, generator=g, dtype=torch.float64) for s in ((50, 8), (50, 8), (6, 8)))
+    for use in ((True, True, True), (True, False, True), (False, False, True), (True, True, False)):
+        x = x0.clone().requires_grad_(True)
+        a, b, rows = _FanOutFn.apply(x, idx)
+        assert torch.equal(a, x0) and torch.equal(b, x0) and torch.equal(rows, x0[idx.long()])
+        loss = sum(((t * w).sum() for t, w, u in zip((a, b, rows), (wa, wb, wr), use) if u))
+        loss.backward()
+        y = x0.clone().requires_grad_(True)
+        ref = sum(((t * w).sum() for t, w, u in zip((y, y, y.index_select(0, idx)), (wa, wb, wr), use) if u))
+        ref.backward()
+        torch.testing.assert_close(x.grad, y.grad, rtol=0, atol=1e-12)
