@@ -81,7 +81,7 @@ def parse_args():
     ap.add_argument("--skip-mlp", action="store_true", help="do not also time the MLP towers in front of the path (row N4)")
     ap.add_argument("--skip-train-tail", action="store_true", help="do not time the drop-in head's training tail with backward")
     ap.add_argument("--e2e-steps", type=int, default=60)
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="end-to-end steps in flight (own stream + buffers each)")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="end-to-end steps in flight (own stream + buffers each)")
     return ap.parse_args()
 
 

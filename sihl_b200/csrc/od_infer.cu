@@ -654,7 +654,9 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
 // (3 shuffles) then lowest index equal to it (3 shuffles), like the TMA consumer.
 // VEC = 4: 16-byte loads (C % 4 == 0, aligned); VEC = 1: any C.
 // ---------------------------------------------------------------------------
-template <int VEC, typename T = float>     // T: element type of the three maps (VEC == 4 needs T == float)
+// HOST: the class / box maps are pinned host memory read in place over PCIe: the candidate's raw box is requested together
+// with its class row (one round trip, not two back to back); own instantiation, the device-memory kernel keeps its registers.
+template <int VEC, typename T = float, bool HOST = false>     // T: element type of the three maps (VEC == 4 needs T == float)
 __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
 {
     const T *t_loc = reinterpret_cast<const T *>(p.loc), *t_cls = reinterpret_cast<const T *>(p.cls);
@@ -699,6 +701,8 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             const int64_t crow = (blk << 5) + src;
             float best = -CUDART_INF_F;
             int arg = 0x7fffffff;
+            float4 raw_early = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HOST && have && gl == 0) raw_early = ldf4(t_box + 4 * crow);
             if (VEC == 4) {
                 const float4 *src4 = reinterpret_cast<const float4 *>(p.cls) + crow * CV;
                 for (int v0 = 0; v0 < CV; v0 += 32) {              // 4 loads in flight per lane and pass
@@ -737,7 +741,7 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             const int ca = __shfl_sync(kFullMask, a, src), cb = __shfl_sync(kFullMask, b, src);
             const int cslot = __shfl_sync(kFullMask, slot, src);
             if (have && gl == 0 && cslot < p.cap) {
-                const float4 raw = ldf4(t_box + 4 * crow);
+                const float4 raw = HOST ? raw_early : ldf4(t_box + 4 * crow);
                 const float4 off = __ldg(p.offsets + ca), sc = __ldg(p.scales + ca);
                 const int64_t o = (int64_t)cb * p.cap + cslot;
                 p.cand_key[o] = ((unsigned long long)__float_as_uint(cs) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ca);
@@ -1085,8 +1089,16 @@ extern "C" int sihl_od_candidate_decode_t(const void *loc_logits_v, const void *
     if (blocks > cap) blocks = cap;
     const bool vec = (num_classes % 4 == 0) && ((reinterpret_cast<uintptr_t>(cls_logits) & 15u) == 0);
     SIHL_CHECK_ARG((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0, "box_raw must be 16-byte aligned");
+    bool host = false;                                             // pinned host maps (zero-copy)
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, cls_logits_v) == cudaSuccess) host = attr.type == cudaMemoryTypeHost;
+        else (void)cudaGetLastError();
+        if (const char *e = getenv("SIHL_HOST_ROWS")) host = host && atoi(e) != 0;                            // developer A/B
+    }
     if (map_dtype == SIHL_OD_F32) {
-        if (vec) k_candidate_decode<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+        if (vec && host) k_candidate_decode<4, float, true><<<(unsigned)blocks, 256, 0, st>>>(p);
+        else if (vec) k_candidate_decode<4><<<(unsigned)blocks, 256, 0, st>>>(p);
         else k_candidate_decode<1><<<(unsigned)blocks, 256, 0, st>>>(p);
     } else {
         // half maps: the score is sigmoid() ROUNDED to the map type (what the reference's `.sigmoid()` returns under

@@ -240,6 +240,23 @@ __device__ __forceinline__ void row_softmax_stats4t(const T *__restrict__ z, int
     *s_out = s;
 }
 
+// q[i] for a run-time i with the array kept in registers (a compare-and-assign loop is turned back into a local-memory
+// index by the compiler): log2(N) rounds of halving selects.
+template <int N>
+__device__ __forceinline__ float pick_reg(const float (&q)[N], int i)
+{
+    float a[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) a[e] = q[e];
+#pragma unroll
+    for (int h = N / 2; h >= 1; h >>= 1) {
+        const bool hi = (i & h) != 0;
+#pragma unroll
+        for (int e = 0; e < h; ++e) a[e] = hi ? a[e + h] : a[e];
+    }
+    return a[0];
+}
+
 // The same with 8 lanes per row: every load instruction covers 128 contiguous bytes of a row.  For maps in device memory
 // this is no better than 4 lanes; for maps left in PINNED HOST memory (read in place over PCIe) the request size is what
 // counts: the link runs out of read tags long before it runs out of bandwidth, and 128-byte reads need half as many.
@@ -271,9 +288,12 @@ __device__ __forceinline__ void row_softmax_stats8t(const T *__restrict__ z, int
 }
 
 // EXCHANGE: the last CTA all-reduces the sums over peer memory before it finalizes (multi-GPU); T: map element type
-template <bool EXCHANGE, typename T = float>
+// HOST: the class / box maps live in pinned host memory and the rows are read in place over PCIe (own instantiation, so
+// that nothing of it touches the register budget or the schedule of the device-memory kernel)
+template <bool EXCHANGE, typename T = float, bool HOST = false>
 __global__ void __launch_bounds__(kPosTileThreads, 8) k_pos_loss_tiles(PosTileParams p, ExchangeParams x)
 {
+    const int host_rows = HOST ? p.host_rows : 0;
     const T *t_cls = reinterpret_cast<const T *>(p.cls), *t_box = reinterpret_cast<const T *>(p.box_raw);
     __shared__ double s_red[2 * 32];
     __shared__ bool s_last;
@@ -303,16 +323,62 @@ __global__ void __launch_bounds__(kPosTileThreads, 8) k_pos_loss_tiles(PosTilePa
             const int32_t flat = __ldg(p.tile_pos_rows + (int64_t)slot * kTile + r_begin + (mine ? lane : 0));
             const int2 ga = __ldg(p.tile_pos_aux + (int64_t)slot * kTile + r_begin + (mine ? lane : 0));
             const float wgt = __int_as_float(ga.y);
-            if (p.box_raw != nullptr && mine) {
+            // host-resident maps: the raw box is REQUESTED here and USED after the class rows have been requested too —
+            // one PCIe round trip per chunk instead of two back to back (the sums do not depend on the order)
+            const bool do_box = p.box_raw != nullptr && mine;
+            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (do_box) raw = ldf4(t_box + 4 * (int64_t)flat);
+            if (!HOST && do_box) {
                 const int a = flat - b * A;
-                acc_box += wgt * pos_box_loss(ldf4(t_box + 4 * (int64_t)flat), __ldg(p.offsets + a), __ldg(p.scales + a),
+                acc_box += wgt * pos_box_loss(raw, __ldg(p.offsets + a), __ldg(p.scales + a),
                                               __ldg(p.gt_boxes + ga.x), p.img_w, p.img_h);                  // ref :197
             }
             if (p.cls != nullptr) {
                 const int64_t tgt64 = __ldg(p.gt_classes + ga.x);
                 const bool tgt_ok = tgt64 >= 0 && tgt64 < p.num_classes;   // out-of-range label: NaN loss, no foreign read
-                float my_m = 0.f, my_se = 1.f;
-                if (p.host_rows) {                                         // 8 lanes per row, 4 rows per pass (see row_softmax_stats8t)
+                float my_m = 0.f, my_se = 1.f, my_zt = 0.f;
+                if (host_rows == 2) {
+                    // WHOLE ROW PER WARP INSTRUCTION (host-resident rows of at most 32 16-byte vectors): lane v loads
+                    // vector v, R rows in flight per warp, and the row crosses the bus ONCE — the statistics and the
+                    // target's logit come from registers.  tools/micro/host_gather_bw.cu: 48.8 GB/s of the link's 55
+                    // for 320-byte rows, against 37-45 GB/s for 8 lanes x 16 B.
+                    constexpr int N = Vec16<T>::N, R = N == 4 ? 4 : 2;
+                    const int CV = p.num_classes / N;
+                    const int tgt_i = tgt_ok ? (int)tgt64 : 0;
+                    for (int r0 = 0; r0 < n; r0 += R) {                    // n is warp-uniform
+                        float q[R][N];
+#pragma unroll
+                        for (int k = 0; k < R; ++k) {
+                            const int r = r0 + k;
+                            const int32_t rflat = __shfl_sync(kFullMask, flat, r < n ? r : 0);
+                            if (lane < CV && r < n) ld_vec16(t_cls + (int64_t)rflat * p.num_classes + lane * N, q[k]);
+                            else {
+#pragma unroll
+                                for (int e = 0; e < N; ++e) q[k][e] = -CUDART_INF_F;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < R; ++k) {
+                            const int r = r0 + k;
+                            if (r >= n) continue;                          // warp-uniform
+                            float m = q[k][0];
+#pragma unroll
+                            for (int e = 1; e < N; ++e) m = fmaxf(m, q[k][e]);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+                            float se = 0.f;
+                            if (lane < CV) {
+#pragma unroll
+                                for (int e = 0; e < N; ++e) se += __expf(q[k][e] - m);
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(kFullMask, se, o);
+                            const int t = __shfl_sync(kFullMask, tgt_i, r);
+                            const float zt = __shfl_sync(kFullMask, pick_reg<N>(q[k], t & (N - 1)), t / N);
+                            if (lane == r) { my_m = m; my_se = se; my_zt = zt; }
+                        }
+                    }
+                } else if (host_rows) {                                  // 8 lanes per row, 4 rows per pass (see row_softmax_stats8t)
                     const int gl8 = lane & 7, grp4 = lane >> 3;
 #pragma unroll
                     for (int pass = 0; pass < 8; ++pass) {
@@ -341,9 +407,15 @@ __global__ void __launch_bounds__(kPosTileThreads, 8) k_pos_loss_tiles(PosTilePa
                     if ((lane >> 3) == pass) { my_m = m_r; my_se = se_r; }
                 }
                 if (mine) {
-                    const float ce = (logf(my_se) + my_m) - ldf(t_cls + (int64_t)flat * p.num_classes + (tgt_ok ? (int)tgt64 : 0));
+                    if (host_rows != 2) my_zt = ldf(t_cls + (int64_t)flat * p.num_classes + (tgt_ok ? (int)tgt64 : 0));
+                    const float ce = (logf(my_se) + my_m) - my_zt;
                     acc_cls += wgt * (tgt_ok ? ce : CUDART_NAN_F);                                          // ref :208
                 }
+            }
+            if (HOST && do_box) {
+                const int a = flat - b * A;
+                acc_box += wgt * pos_box_loss(raw, __ldg(p.offsets + a), __ldg(p.scales + a),
+                                              __ldg(p.gt_boxes + ga.x), p.img_w, p.img_h);                  // ref :197
             }
         }
     } else {
@@ -684,7 +756,9 @@ extern "C" int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, cons
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, cls_logits) == cudaSuccess) p.host_rows = attr.type == cudaMemoryTypeHost;
         else (void)cudaGetLastError();
-        if (const char *e = getenv("SIHL_HOST_ROWS")) p.host_rows = p.host_rows && atoi(e) != 0;             // developer A/B
+        // 2 = whole row per warp instruction (rows of at most 32 vectors), 1 = 8 lanes x 16 B
+        if (p.host_rows && (size_t)num_classes * esz <= 32 * 16) p.host_rows = 2;
+        if (const char *e = getenv("SIHL_HOST_ROWS")) { const int v = atoi(e); if (v >= 0 && v < p.host_rows) p.host_rows = v; }             // developer A/B: 0, 1
     }
     ExchangeParams x;
     x.world = world; x.rank = rank;
@@ -700,7 +774,10 @@ extern "C" int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, cons
     const int64_t cap = (int64_t)kNumSMs * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (world > 1) SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<true, T><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
+    if (p.host_rows) {
+        if (world > 1) SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<true, T, true><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
+        else SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<false, T, true><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
+    } else if (world > 1) SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<true, T><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
     else SIHL_DISPATCH_DTYPE(map_dtype, (k_pos_loss_tiles<false, T><<<(unsigned)blocks, kPosTileThreads, 0, (cudaStream_t)stream>>>(p, x)));
     SIHL_CHECK_LAUNCH("k_pos_loss_tiles");
     return SIHL_OD_OK;

@@ -479,21 +479,25 @@ def test_pipeline_matches_unfused_ops_and_is_replayable(mode):
     np.testing.assert_allclose(results[0][6].cpu().numpy(), o_boxes, rtol=1e-5, atol=1e-4)
 
 
-def test_pipeline_reads_pinned_host_maps_in_place():
+@pytest.mark.parametrize("dtype,C", [(torch.float32, 80), (torch.bfloat16, 80), (torch.float16, 24), (torch.float32, 132),
+                                     (torch.float32, 7)])
+def test_pipeline_reads_pinned_host_maps_in_place(dtype, C):
     """candidate-first pipeline with the class / box maps left in pinned host memory (the kernels gather the rows of the
-    positives and of the candidates over PCIe): bit-identical to the run on device-resident maps."""
+    positives and of the candidates over PCIe): bit-identical to the run on device-resident maps.  The class counts cover
+    the whole-row-per-warp reads (rows of at most 32 16-byte vectors: 80 fp32 / bf16, 24 fp16), the 8-lane reads (132 fp32 =
+    33 vectors) and the element reads (7)."""
     from sihl_b200.pipeline import DetectionHeadPipeline, StepInputs
     W = H = 320
-    B, C, G = 3, 80, 25
+    B, G = 3, 25
     levels = synth.level_sizes(H, W)
     pipe = DetectionHeadPipeline(levels, W, H, B, C, B * G, DEV, decode_mode="candidate_first")
     gt = _gt_dev(synth.gt_batch_np(21, B, H, W, C, G, ragged=True))
     maps = synth.dense_maps_np(22, B, pipe.A, C, loc_mean=-3.0, loc_std=2.0)
-    loc, iou = _t(maps.loc_logits), _t(maps.iou_preds)
+    loc, iou = _t(maps.loc_logits).to(dtype), _t(maps.iou_preds).to(dtype)
     outs = []
     for on_host in (False, True):
-        box = torch.from_numpy(maps.box_raw).pin_memory() if on_host else _t(maps.box_raw)
-        cls = torch.from_numpy(maps.cls_logits).pin_memory() if on_host else _t(maps.cls_logits)
+        box = torch.from_numpy(maps.box_raw).to(dtype).pin_memory() if on_host else _t(maps.box_raw).to(dtype)
+        cls = torch.from_numpy(maps.cls_logits).to(dtype).pin_memory() if on_host else _t(maps.cls_logits).to(dtype)
         out = pipe.new_outputs()
         pipe.step(StepInputs(loc, iou, box, cls, gt), out)
         torch.cuda.synchronize()
@@ -501,7 +505,9 @@ def test_pipeline_reads_pinned_host_maps_in_place():
     a, b = outs
     for name in ("assignment", "rel_iou", "num_instances", "scores", "classes", "boxes"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
-    torch.testing.assert_close(a.losses, b.losses, rtol=1e-6, atol=0)
+    torch.testing.assert_close(a.losses, b.losses, rtol=3e-6, atol=0)     # the row sums associate differently per lane layout
+    if dtype != torch.float32 or C != 80:
+        return
     with pytest.raises(RuntimeError, match="CUDA tensors only"):          # the dense scan streams everything: device only
         ops.dense_decode(loc, torch.from_numpy(maps.cls_logits).pin_memory(), _t(maps.box_raw), pipe.offsets, pipe.scales,
                          W, H, 0.05, pipe.cand, mode="dense")
