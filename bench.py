@@ -541,29 +541,62 @@ def run_ours(args, w, world, rank, local_rank):
         ops.dense_decode(x.loc_logits, x.cls_logits, x.box_raw, pipe.offsets, pipe.scales, W, H, SCORE_THR, pipe.cand,
                          zero_counts=False)
 
+    # The launches are back to back on one stream either way.  Default: `warm` of them captured into ONE CUDA graph
+    # (first node zeroes their counter rows) and replayed — an eager loop pays ~14 us of Python + ctypes +
+    # cudaFuncSetAttribute per call on the host, which is MORE than a 57 MB scan takes on the device (crowd: every ring
+    # shape "measured" 13.9 us that way, r02_decode_sweep_crowd.json), so it would time the host.  --no-graph keeps the loop.
+    graph = None
+    if not args.no_graph:
+        scratch.zero_()
+        decode_once(0)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            scratch[:warm].zero_()
+            for i in range(warm):
+                decode_once(i)
+
+    def batch_of_launches(first):
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(warm):
+                decode_once(first + i)
+
     for _ in range(60):
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         scratch[iters:].zero_()
         w0.record()
-        for i in range(warm):
-            decode_once(iters + i)
+        batch_of_launches(iters)
         w1.record()
         torch.cuda.synchronize()
         settle.append(w0.elapsed_time(w1) / warm)
-        # at least ~40 ms of back-to-back launches: a 57 MB scan settles only after ~15 ms (crowd: 18 us -> 14 us)
+        # at least ~40 ms of back-to-back launches: a 57 MB scan settles only after ~15 ms
         if len(settle) >= 2 and sum(settle) * warm >= 40.0 and abs(settle[-1] - settle[-2]) <= 0.03 * settle[-1]:
             break
+    if graph is None:
+        scratch.zero_()
     if sampler: sampler.mark()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
-    for i in range(iters):
-        decode_once(i)
+    for j in range(iters // warm):
+        batch_of_launches(j * warm)
     k1.record()
     torch.cuda.synchronize()
     if sampler: sampler.mark()
-    pipe.cand.count = counts_saved
-    cand_mean = float(scratch[:iters].float().mean().item())
+    cand_mean = float(scratch[:warm if graph is not None else iters].float().mean().item())
     k_ms = k0.elapsed_time(k1) / iters
+    eager_ms = None
+    if graph is not None:                             # the same launches from a Python loop, for comparison with round 1
+        scratch.zero_()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for i in range(iters):
+            decode_once(i)
+        x1.record()
+        torch.cuda.synchronize()
+        eager_ms = x0.elapsed_time(x1) / iters
+    pipe.cand.count = counts_saved
     # algorithmic bytes per launch: every class logit and location logit read once (4*A*(C+1) per image), the raw
     # box (16 B) read and key 8 + box 16 + class 4 = 28 B written per candidate.  (SURVEY.md §8d counts 16*A for the
     # raw boxes of every location; the kernel reads them for candidates only, so that figure would overstate it.)
@@ -580,6 +613,9 @@ def run_ours(args, w, world, rank, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_dense_decode", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": decode_bytes, "launches_timed": iters,
+                "launch_mode": (f"CUDA graph of {warm} back-to-back launches (+ one memset node), replayed {iters // warm}x"
+                                if graph is not None else "eager loop (host time per call included)"),
+                "eager_loop_ms_per_launch": eager_ms,
                 "warmup_ms_per_launch_by_100": [round(v, 5) for v in settle[:4] + settle[-2:]], "warmup_batches": len(settle)}
     # whole step: train 20A+24G+(16+4C)P + infer 4A(C+1)+16*cand+28K+8 bytes per image — SURVEY.md §8d's figure minus
     # the raw boxes of the locations that are not candidates (never read); the survey's own figure is reported beside it
