@@ -231,7 +231,9 @@ SIHL_OD_API int sihl_od_pos_loss_tiles_exchange(const int32_t *pos_chunks, const
                            double *sums, float *losses, uint32_t *done_counter,
                            void *const *peer_regions, int world, int rank, void *stream);
 
-/* ... and for dense maps of element type map_dtype (box_raw [B*A,4], cls_logits [B*A,C]). */
+/* ... and for dense maps of element type map_dtype (box_raw [B*A,4], cls_logits [B*A,C]).  Both maps may point into
+ * PINNED HOST memory: the positives' rows are then gathered in place over PCIe (one warp instruction per class row when a
+ * row has at most 32 16-byte vectors, the row read once, its raw box requested with it). */
 SIHL_OD_API int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, const int32_t *tile_pos_rows,
                            const int32_t *tile_pos_aux, int batch, int64_t num_anchors,
                            const float *offsets, const float *scales, int img_w, int img_h,
@@ -425,7 +427,9 @@ SIHL_OD_API int sihl_od_candidate_decode(const float *loc_logits, const float *c
                          uint64_t *cand_key, float *cand_box, int32_t *cand_cls, int zero_counts,
                          void *stream);
 
-/* sihl_od_candidate_decode for maps of element type map_dtype (all three maps share it). */
+/* sihl_od_candidate_decode for maps of element type map_dtype (all three maps share it).  cls_logits and box_raw may
+ * point into PINNED HOST memory (cudaHostAlloc / cudaHostRegister, unified addressing): only the candidates' rows are then
+ * read, in place, over PCIe — raw box and class row requested together; loc_logits must be device memory. */
 SIHL_OD_API int sihl_od_candidate_decode_t(const void *loc_logits, const void *cls_logits, const void *box_raw, int map_dtype,
                          int batch, int64_t num_anchors, int num_classes,
                          const float *offsets, const float *scales, int img_w, int img_h, float score_thr,
