@@ -406,11 +406,17 @@ def run_ours(args, w, world, rank, local_rank):
             """Step s goes to lane s % n_lanes: consecutive steps overlap (the HBM-bound decode of one step runs
             next to the latency-bound assignment / NMS kernels of its neighbours)."""
             ln, i = s % n_lanes, s % n_sets
-            with torch.cuda.stream(lane_streams[ln]):
-                if graphs is not None:
-                    graphs[ln][i].replay()
-                else:
+            if graphs is not None:
+                # set_stream, not the `with torch.cuda.stream(...)` context manager: enqueueing a step costs the host
+                # ~11 us with the latter, which is all of cfg0's step; issue_done() puts the main stream back
+                torch.cuda.set_stream(lane_streams[ln])
+                graphs[ln][i].replay()
+            else:
+                with torch.cuda.stream(lane_streams[ln]):
                     full_step(ln, i)
+
+        def issue_done():
+            torch.cuda.set_stream(main)
 
         def drain():
             for ln in range(n_lanes):
@@ -423,13 +429,14 @@ def run_ours(args, w, world, rank, local_rank):
         fork()
         for s in range(n_warmup):
             run_step(s)
+        issue_done()
         drain()
         # R timed regions of exactly n_steps steps each.  Every region: host barrier + synchronize on both sides (the
         # contract), and — with the fused exchange — a DEVICE-side barrier enqueued in front of the start event, so that
         # all GPUs enter the region within an NVLink round trip of each other and the host barrier's rank skew stays
         # outside it.  Reported: the median region of the max-over-ranks times, min / max, and every rank's median.
         start_barrier = getattr(pipes[0], "start_barrier", None) if fused else None
-        per_region, step_no = [], n_warmup
+        per_region, step_no, host_issue = [], n_warmup, []
         for _ in range(max(1, n_regions)):
             barrier()
             if sampler: sampler.mark()
@@ -438,8 +445,11 @@ def run_ours(args, w, world, rank, local_rank):
                 start_barrier[0].device_barrier(start_barrier[1], main)
             e0.record(main)
             fork()
+            h0 = time.perf_counter()
             for s in range(step_no, step_no + n_steps):
                 run_step(s)
+            host_issue.append((time.perf_counter() - h0) * 1e3 / n_steps)
+            issue_done()
             step_no += n_steps
             drain()
             e1.record(main)
@@ -459,7 +469,10 @@ def run_ours(args, w, world, rank, local_rank):
                   "ms_per_step_min": float(region_max.min().item()) / n_steps,
                   "ms_per_step_max": float(region_max.max().item()) / n_steps,
                   "per_rank_ms_per_step_median": [float(v) / n_steps for v in allr.median(dim=1).values.tolist()],
-                  "start": "device-side barrier over NVLink peer memory" if start_barrier is not None else "host barrier"}
+                  "start": "device-side barrier over NVLink peer memory" if start_barrier is not None else "host barrier",
+                  # host wall time to ENQUEUE one step (rank 0, median region): the step is device-bound while this is
+                  # well below ms_per_step
+                  "host_issue_ms_per_step": sorted(host_issue)[len(host_issue) // 2]}
         return ms, pipes, outs, graphs, timing
 
     ms, pipes, outs, graphs, timing = timed_steps(args.decode_mode, args.steps, max(args.warmup, 3), args.regions)
