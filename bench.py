@@ -23,6 +23,9 @@ Prints ONE JSON line (rank 0):
                          the staged copy oracle/_ref/sihl_src; "port" only if neither exists) on the host cores, all
                          threads, bounded sample; ``gpu_eager_reference``: the same code as torch eager on this GPU
 
+  ``config``             the workload, identical in both arms; ``execution`` (graph, streams, steps in flight, decode
+                         mode) and ``workload_stats`` (positives / candidates / detections per image) describe this arm
+
 ``--impl reference``: only that CPU arm (rank 0), same metric/unit/config.
 """
 from __future__ import annotations
@@ -691,10 +694,13 @@ def run_ours(args, w, world, rank, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, args, world, {"cuda_graph": graphs is not None, "streams_per_step": 1 if args.serial else 2,
-                                                "steps_in_flight": n_lanes, "decode_mode": args.decode_mode,
-                                                "positives_per_image": P_bar, "candidates_per_image": cand_mean,
-                                                "detections_per_image": det_mean}),
+        # `config` names the WORKLOAD only and is the same object in both arms (`--impl reference` prints it too); how this
+        # arm executes it, and what the synthetic inputs turned out to contain, sit beside it
+        "config": config_dict(w, args, world),
+        "execution": {"cuda_graph": graphs is not None, "streams_per_step": 1 if args.serial else 2,
+                      "steps_in_flight": n_lanes, "decode_mode": args.decode_mode},
+        "workload_stats": {"positives_per_image": P_bar, "candidates_per_image": cand_mean,
+                           "detections_per_image": det_mean},
         "timing": timing, "train_with_backward": train_tail, "half_maps": half_maps, "mlp_towers": mlp_line,
         "cpu_affinity": affinity,
         "e2e": e2e, "e2e_full_upload": e2e_full, "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi and not fused else 0)) * args.steps,

@@ -18,7 +18,7 @@ for i, f in enumerate(sys.argv[1:]):
         try:
             d = json.load(open(f"gpurun_out/ab_{i}_{r}.json"))
             o = d.get("other_decode_mode") or {}
-            print(f"[{f or 'default'}] run {r}: {d['config']['decode_mode']} {d['ms_per_step']*1e3:.2f} us  other {o.get('ms_per_step', 0)*1e3:.2f} us")
+            print(f"[{f or 'default'}] run {r}: {d['execution']['decode_mode']} {d['ms_per_step']*1e3:.2f} us  other {o.get('ms_per_step', 0)*1e3:.2f} us")
         except Exception as e:
             print(f"[{f}] run {r}: failed {e}")
 PY
