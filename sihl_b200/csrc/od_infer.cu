@@ -654,8 +654,11 @@ __global__ void __launch_bounds__(4 * ROWS) k_dense_decode_tma(DenseDecodeParams
 // (3 shuffles) then lowest index equal to it (3 shuffles), like the TMA consumer.
 // VEC = 4: 16-byte loads (C % 4 == 0, aligned); VEC = 1: any C.
 // ---------------------------------------------------------------------------
-// HOST: the class / box maps are pinned host memory read in place over PCIe: the candidate's raw box is requested together
-// with its class row (one round trip, not two back to back); own instantiation, the device-memory kernel keeps its registers.
+// HOST: the class / box maps are pinned host memory read in place over PCIe (rows of at most 32 16-byte vectors): a
+// candidate's class row is ONE warp instruction (lane v = vector v; up to R candidates of the block in flight), its raw box
+// is requested together with it (one round trip, not two back to back), first-argmax over the warp.  Own instantiation: the
+// device-memory kernel keeps its registers.  PCIe reads are bounded by outstanding requests, not bytes
+// (tools/micro/host_gather_bw.cu), and element loads of half maps would be 2-byte requests.
 template <int VEC, typename T = float, bool HOST = false>     // T: element type of the three maps (VEC == 4 needs T == float)
 __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
 {
@@ -688,6 +691,55 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             slot = base + __popc(peers & ((1u << lane) - 1u));
         }
         const int first = __ffs(m) - 1;
+        if constexpr (HOST) {
+            constexpr int N = Vec16<T>::N, R = N == 4 ? 4 : 2;
+            const int CVW = p.C / N;                               // <= 32 (launcher)
+            for (unsigned rem = m; rem != 0u;) {                   // R candidates per pass: requests first, then the reductions
+                int src[R], cnt = 0;
+                float q[R][N];
+                float4 raw[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    src[k] = first;
+                    if (rem != 0u) { src[k] = __ffs(rem) - 1; rem &= rem - 1u; ++cnt; }
+                    const int64_t crow = (blk << 5) + src[k];
+                    raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (k < cnt && lane < CVW) ld_vec16(t_cls + crow * p.C + lane * N, q[k]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < N; ++e) q[k][e] = -CUDART_INF_F;
+                    }
+                    if (k < cnt && lane == 0) raw[k] = ldf4(t_box + 4 * crow);
+                }
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    if (k >= cnt) continue;                        // warp-uniform
+                    float best = -CUDART_INF_F;
+                    int arg = 0x7fffffff;
+#pragma unroll
+                    for (int e = 0; e < N; ++e)
+                        if (q[k][e] > best) { best = q[k][e]; arg = lane * N + e; }       // ascending index inside the lane: first max
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ob = __shfl_xor_sync(kFullMask, best, o);
+                        const int oa = __shfl_xor_sync(kFullMask, arg, o);
+                        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                    }
+                    if (arg == 0x7fffffff) arg = 0;                // all -inf / NaN row: same convention as below
+                    const float cs = __shfl_sync(kFullMask, s, src[k]);
+                    const int ca = __shfl_sync(kFullMask, a, src[k]), cb = __shfl_sync(kFullMask, b, src[k]);
+                    const int cslot = __shfl_sync(kFullMask, slot, src[k]);
+                    if (lane == 0 && cslot < p.cap) {
+                        const float4 off = __ldg(p.offsets + ca), sc = __ldg(p.scales + ca);
+                        const int64_t o = (int64_t)cb * p.cap + cslot;
+                        p.cand_key[o] = ((unsigned long long)__float_as_uint(cs) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ca);
+                        p.cand_box[o] = make_float4((off.x + sc.x * round_to<T>(expf(raw[k].x))) * p.img_w, (off.y + sc.y * round_to<T>(expf(raw[k].y))) * p.img_h,
+                                                    (off.z + sc.z * round_to<T>(expf(raw[k].z))) * p.img_w, (off.w + sc.w * round_to<T>(expf(raw[k].w))) * p.img_h);
+                        p.cand_cls[o] = arg;
+                    }
+                }
+            }
+        } else
         for (unsigned rem = m; rem != 0u;) {                       // four candidates per pass: peel the four lowest set bits
             int src = first;                                       // lane that owns this group's candidate
             bool have = false;
@@ -701,8 +753,6 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             const int64_t crow = (blk << 5) + src;
             float best = -CUDART_INF_F;
             int arg = 0x7fffffff;
-            float4 raw_early = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (HOST && have && gl == 0) raw_early = ldf4(t_box + 4 * crow);
             if (VEC == 4) {
                 const float4 *src4 = reinterpret_cast<const float4 *>(p.cls) + crow * CV;
                 for (int v0 = 0; v0 < CV; v0 += 32) {              // 4 loads in flight per lane and pass
@@ -741,7 +791,7 @@ __global__ void __launch_bounds__(256) k_candidate_decode(DenseDecodeParams p)
             const int ca = __shfl_sync(kFullMask, a, src), cb = __shfl_sync(kFullMask, b, src);
             const int cslot = __shfl_sync(kFullMask, slot, src);
             if (have && gl == 0 && cslot < p.cap) {
-                const float4 raw = HOST ? raw_early : ldf4(t_box + 4 * crow);
+                const float4 raw = ldf4(t_box + 4 * crow);
                 const float4 off = __ldg(p.offsets + ca), sc = __ldg(p.scales + ca);
                 const int64_t o = (int64_t)cb * p.cap + cslot;
                 p.cand_key[o] = ((unsigned long long)__float_as_uint(cs) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ca);
@@ -1095,16 +1145,21 @@ extern "C" int sihl_od_candidate_decode_t(const void *loc_logits_v, const void *
         if (cudaPointerGetAttributes(&attr, cls_logits_v) == cudaSuccess) host = attr.type == cudaMemoryTypeHost;
         else (void)cudaGetLastError();
         if (const char *e = getenv("SIHL_HOST_ROWS")) host = host && atoi(e) != 0;                            // developer A/B
+        if (const char *e = getenv("SIHL_HOST_CAND")) host = host && atoi(e) != 0;                            // developer A/B (this kernel only)
+        // the whole-row reads need 16-byte rows of at most 32 vectors
+        const size_t row_bytes = (size_t)num_classes * (map_dtype == SIHL_OD_F32 ? 4 : 2);
+        host = host && row_bytes % 16 == 0 && row_bytes <= 32 * 16 && (reinterpret_cast<uintptr_t>(cls_logits_v) & 15u) == 0;
     }
     if (map_dtype == SIHL_OD_F32) {
-        if (vec && host) k_candidate_decode<4, float, true><<<(unsigned)blocks, 256, 0, st>>>(p);
+        if (host) k_candidate_decode<4, float, true><<<(unsigned)blocks, 256, 0, st>>>(p);
         else if (vec) k_candidate_decode<4><<<(unsigned)blocks, 256, 0, st>>>(p);
         else k_candidate_decode<1><<<(unsigned)blocks, 256, 0, st>>>(p);
     } else {
         // half maps: the score is sigmoid() ROUNDED to the map type (what the reference's `.sigmoid()` returns under
         // autocast), which can cross the threshold from below: widen the conservative logit pre-filter accordingly
         if (p.logit_thr > -HUGE_VALF && p.logit_thr < HUGE_VALF) p.logit_thr -= 0.05f * (1.f + fabsf(p.logit_thr));
-        SIHL_DISPATCH_DTYPE(map_dtype, (k_candidate_decode<1, T><<<(unsigned)blocks, 256, 0, st>>>(p)));
+        if (host) SIHL_DISPATCH_DTYPE(map_dtype, (k_candidate_decode<1, T, true><<<(unsigned)blocks, 256, 0, st>>>(p)));
+        else SIHL_DISPATCH_DTYPE(map_dtype, (k_candidate_decode<1, T><<<(unsigned)blocks, 256, 0, st>>>(p)));
     }
     SIHL_CHECK_LAUNCH("k_candidate_decode");
     return SIHL_OD_OK;
