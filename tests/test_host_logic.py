@@ -104,3 +104,24 @@ def test_decode_mode_validation_needs_no_gpu():
     # pinned host maps are only accepted by the gathering (candidate-first) decode: the dense scan is device-only
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         ops.dense_decode(z, torch.zeros(1, 4, 8), torch.zeros(1, 4, 4), z, z, 8, 8, 0.05, None, mode="dense")
+
+
+def test_bench_config_is_the_workload_only_and_shared_by_both_arms():
+    """The driver compares the `config` objects of `bench.py` and `bench.py --impl reference`: it must describe the workload
+    and nothing of how this arm runs it (graphs, lanes, decode mode live in `execution`, input statistics in `workload_stats`)."""
+    import argparse
+    import inspect
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    args = argparse.Namespace(workload="cfg1", allreduce="fused")
+    cfg = bench.config_dict(bench.WORKLOADS["cfg1"], args, 1)
+    assert cfg["workload"].startswith("cfg1") and cfg["anchors"] == 8525 and cfg["global_batch"] == 64
+    assert not {"decode_mode", "cuda_graph", "steps_in_flight", "streams_per_step", "positives_per_image",
+                "candidates_per_image", "detections_per_image", "sample_images_per_step"} & set(cfg)
+    assert "cache" in cfg                                   # the contract: say in `config` how the L2 is kept cold
+    src = inspect.getsource(bench)
+    assert src.count('"config": config_dict(w, args, world),') == 2      # both arms print the same object
+    cfg8 = bench.config_dict(bench.WORKLOADS["cfg1"], args, 8)
+    assert cfg8["global_batch"] == 512 and cfg8["batch_per_gpu"] == 64
