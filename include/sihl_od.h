@@ -429,7 +429,8 @@ SIHL_OD_API int sihl_od_candidate_decode(const float *loc_logits, const float *c
 
 /* sihl_od_candidate_decode for maps of element type map_dtype (all three maps share it).  cls_logits and box_raw may
  * point into PINNED HOST memory (cudaHostAlloc / cudaHostRegister, unified addressing): only the candidates' rows are then
- * read, in place, over PCIe — raw box and class row requested together; loc_logits must be device memory. */
+ * read, in place, over PCIe — raw box and class row requested together; loc_logits must be device memory.  A PAGEABLE
+ * host pointer is refused with SIHL_OD_EINVAL (it would fault in the kernel). */
 SIHL_OD_API int sihl_od_candidate_decode_t(const void *loc_logits, const void *cls_logits, const void *box_raw, int map_dtype,
                          int batch, int64_t num_anchors, int num_classes,
                          const float *offsets, const float *scales, int img_w, int img_h, float score_thr,

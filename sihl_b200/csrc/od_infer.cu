@@ -1141,9 +1141,14 @@ extern "C" int sihl_od_candidate_decode_t(const void *loc_logits_v, const void *
     SIHL_CHECK_ARG((reinterpret_cast<uintptr_t>(box_raw) & 15u) == 0, "box_raw must be 16-byte aligned");
     bool host = false;                                             // pinned host maps (zero-copy)
     {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, cls_logits_v) == cudaSuccess) host = attr.type == cudaMemoryTypeHost;
-        else (void)cudaGetLastError();
+        const void *host_ok_maps[2] = {cls_logits_v, box_raw_v};
+        for (const void *map : host_ok_maps) {       // pageable host memory would fault in the kernel: refuse it here
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, map) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+            SIHL_CHECK_ARG(attr.type != cudaMemoryTypeUnregistered,
+                           "box_raw / cls_logits must be device memory or PINNED host memory (got a pageable host pointer)");
+            if (map == cls_logits_v) host = attr.type == cudaMemoryTypeHost;
+        }
         if (const char *e = getenv("SIHL_HOST_ROWS")) host = host && atoi(e) != 0;                            // developer A/B
         if (const char *e = getenv("SIHL_HOST_CAND")) host = host && atoi(e) != 0;                            // developer A/B (this kernel only)
         // the whole-row reads need 16-byte rows of at most 32 vectors

@@ -752,10 +752,17 @@ extern "C" int sihl_od_pos_loss_tiles_exchange_t(const int32_t *pos_chunks, cons
     SIHL_CHECK_ARG(box_raw == nullptr || (reinterpret_cast<uintptr_t>(box_raw) & (4 * esz - 1)) == 0, "box_raw rows must be aligned");
     p.sums = sums; p.losses = losses; p.done_counter = done_counter;
     p.host_rows = 0;
-    if (cls_logits != nullptr && p.cls_vec4) {                    // pinned host maps (zero-copy): wider row reads
+    const void *host_ok_maps[2] = {cls_logits, box_raw};
+    for (const void *map : host_ok_maps) {               // pageable host memory would fault in the kernel: refuse it here
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, cls_logits) == cudaSuccess) p.host_rows = attr.type == cudaMemoryTypeHost;
-        else (void)cudaGetLastError();
+        if (map == nullptr) continue;
+        if (cudaPointerGetAttributes(&attr, map) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+        SIHL_CHECK_ARG(attr.type != cudaMemoryTypeUnregistered,
+                       "box_raw / cls_logits must be device memory or PINNED host memory (got a pageable host pointer)");
+        if (map == cls_logits) p.host_rows = attr.type == cudaMemoryTypeHost;
+    }
+    if (!p.cls_vec4) p.host_rows = 0;
+    if (p.host_rows) {                                            // pinned host maps (zero-copy): wider row reads
         // 2 = whole row per warp instruction (rows of at most 32 vectors), 1 = 8 lanes x 16 B
         if (p.host_rows && (size_t)num_classes * esz <= 32 * 16) p.host_rows = 2;
         if (const char *e = getenv("SIHL_HOST_ROWS")) { const int v = atoi(e); if (v >= 0 && v < p.host_rows) p.host_rows = v; }             // developer A/B: 0, 1

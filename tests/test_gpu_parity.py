@@ -513,6 +513,30 @@ def test_pipeline_reads_pinned_host_maps_in_place(dtype, C):
                          W, H, 0.05, pipe.cand, mode="dense")
 
 
+def test_c_entries_refuse_pageable_host_maps():
+    """A C-ABI caller that hands a PAGEABLE host pointer for the class / box map gets EINVAL from the entry, not a faulting
+    kernel (the Python layer already refuses unpinned host tensors; device and pinned pointers keep working, see above)."""
+    from sihl_b200 import _native
+    lib = _native.load()
+    W = H = 320
+    B, C = 2, 80
+    levels = synth.level_sizes(H, W)
+    off, sc, _ = ops.anchor_tables(levels, W, H, DEV)
+    A = int(off.shape[0])
+    maps = synth.dense_maps_np(5, B, A, C, loc_mean=-3.0, loc_std=2.0)
+    loc, box = _t(maps.loc_logits), _t(maps.box_raw)
+    cls_pageable = np.ascontiguousarray(maps.cls_logits)              # plain numpy memory: neither device nor pinned
+    cand = ops.CandidateBuffers.allocate(B, A, DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.sihl_od_candidate_decode_t(loc.data_ptr(), cls_pageable.ctypes.data, box.data_ptr(), ops.DTYPE_CODES[torch.float32],
+                                        B, A, C, off.data_ptr(), sc.data_ptr(), W, H, 0.05, cand.count.data_ptr(), cand.capacity,
+                                        cand.key.data_ptr(), cand.box.data_ptr(), cand.cls.data_ptr(), 1, st)
+    with pytest.raises(_native.NativeError, match="PINNED host memory"):
+        _native.check(rc, "sihl_od_candidate_decode_t")
+    torch.cuda.synchronize()                                           # nothing was launched on bad memory: the context is alive
+    assert float(loc.sum().item()) == float(torch.from_numpy(maps.loc_logits).to(DEV).sum().item())
+
+
 # --------------------------------------------------------------------------- N1: QuadrilateralDetection.bbox_matching
 def _quad_check_vs_restatement(anchors_dev, boxes_np_list, topk=9):
     from sihl_b200.heads import quadrilateral_detection as qd
